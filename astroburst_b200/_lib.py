@@ -1,0 +1,141 @@
+"""ctypes loader for libastroburst_cuda.so and the Context wrapper (no torch types cross the ABI)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "lib", "libastroburst_cuda.so")
+
+AB_OK, AB_ERR_INVALID, AB_ERR_CUDA, AB_ERR_UNSUPPORTED, AB_ERR_NOMEM = range(5)
+AB_MAX_FRAMES = 256
+
+
+class AstroBurstError(RuntimeError):
+    """Raised for every non-zero ab_status (the reference's anyhow::Error -> String)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"[ab_status {status}] {message}")
+        self.status = status
+        self.message = message
+
+
+class StackConfigC(C.Structure):
+    _fields_ = [("sigma_low", C.c_float), ("sigma_high", C.c_float),
+                ("max_iterations", C.c_uint32), ("align", C.c_uint32)]
+
+
+class ImageStatsC(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("min", "max", "median", "mad", "sigma", "mean")] + [
+        ("valid_count", C.c_uint64)]
+
+
+class StfParamsC(C.Structure):
+    _fields_ = [("shadow", C.c_double), ("midtone", C.c_double), ("highlight", C.c_double)]
+
+
+def library_path() -> str:
+    return _SO
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+# name -> (restype, argtypes); the test-suite checks this table against include/astroburst_cuda.h
+_vp, _sz, _u64p = C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)
+SIGNATURES = {
+    "ab_abi_version": (C.c_int, []),
+    "ab_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "ab_ctx_destroy": (None, [_vp]),
+    "ab_last_error": (C.c_char_p, [_vp]),
+    "ab_ctx_device": (C.c_int, [_vp]),
+    "ab_ctx_launch_count": (C.c_uint64, [_vp]),
+    "ab_ctx_synchronize": (C.c_int, [_vp]),
+    "ab_host_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
+    "ab_host_free": (C.c_int, [_vp]),
+    "ab_dev_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
+    "ab_dev_free": (C.c_int, [_vp, _vp]),
+    "ab_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, _sz]),
+    "ab_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, _sz]),
+    "ab_stack_sigma_clip": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz, _sz,
+                                      C.POINTER(StackConfigC), _vp, _u64p]),
+    "ab_stack_sigma_clip_dev": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz,
+                                          C.POINTER(StackConfigC), _vp, _vp, _vp]),
+    "ab_sigma_clip_combine": (C.c_int, [_vp, _vp, _sz, C.c_float, C.c_float, C.c_uint32,
+                                        C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(_SO):
+                raise AstroBurstError(
+                    AB_ERR_CUDA,
+                    f"{_SO} is missing: build it with `python -m astroburst_b200.build` "
+                    "(there is no CPU fallback)")
+            l = C.CDLL(_SO)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(l, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = l
+    return _lib
+
+
+class Context:
+    """Owns one `ab_ctx` (one CUDA device, its streams and scratch)."""
+
+    def __init__(self, device: int | None = None):
+        self._h = C.c_void_p()
+        st = lib().ab_ctx_create(-1 if device is None else int(device), C.byref(self._h))
+        if st != AB_OK:
+            self._h = C.c_void_p()
+            raise AstroBurstError(st, "ab_ctx_create failed (no usable CUDA device?)")
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    @property
+    def device(self) -> int:
+        return lib().ab_ctx_device(self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().ab_ctx_launch_count(self._h))
+
+    def check(self, status: int) -> None:
+        if status != AB_OK:
+            msg = lib().ab_last_error(self._h)
+            raise AstroBurstError(status, msg.decode() if msg else "")
+
+    def synchronize(self) -> None:
+        self.check(lib().ab_ctx_synchronize(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            lib().ab_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_context(device: int | None = None) -> Context:
+    """Process-wide context per device (created on first use)."""
+    key = -1 if device is None else int(device)
+    with _default_lock:
+        if key not in _default:
+            _default[key] = Context(device)
+        return _default[key]

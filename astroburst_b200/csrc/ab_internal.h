@@ -1,0 +1,84 @@
+// ab_internal.h -- context object, error plumbing and launch helpers shared by the
+// translation units of libastroburst_cuda.so.  Not part of the public ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+
+#include "astroburst_cuda.h"
+
+constexpr int AB_NUM_COPY_STREAMS = 3;
+
+struct ab_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;                        // default compute stream of the context
+    cudaStream_t copy_streams[AB_NUM_COPY_STREAMS] = {};  // host-buffer pipelines
+    cudaEvent_t copy_events[AB_NUM_COPY_STREAMS] = {};
+    // device scratch reused by host-buffer entry points (grown on demand)
+    void *d_scratch[AB_NUM_COPY_STREAMS] = {};
+    size_t d_scratch_bytes[AB_NUM_COPY_STREAMS] = {};
+    // small device + pinned host blocks for scalars (counters, stats partials)
+    void *d_small = nullptr;
+    void *h_small = nullptr;
+    static constexpr size_t SMALL_BYTES = 1 << 20;
+    std::mutex mu;
+    std::atomic<uint64_t> launches{0};
+    std::string last_error;
+};
+
+inline ab_status ab_fail(ab_ctx *ctx, ab_status st, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->last_error = buf;
+    return st;
+}
+
+#define AB_CUDA(ctx, call)                                                                    \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return ab_fail((ctx), AB_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                \
+                           cudaGetErrorString(e__), __FILE__, __LINE__);                      \
+    } while (0)
+
+#define AB_LAUNCH_CHECK(ctx)                                                                  \
+    do {                                                                                      \
+        (ctx)->launches.fetch_add(1, std::memory_order_relaxed);                              \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess)                                                               \
+            return ab_fail((ctx), AB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",            \
+                           cudaGetErrorString(e__), __FILE__, __LINE__);                      \
+    } while (0)
+
+// RAII device guard: entry points run on the context's device without disturbing the caller's.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+ab_status ab_scratch_reserve(ab_ctx *ctx, int slot, size_t bytes);
+
+// ---- stack.cu
+struct FrameTable {
+    const float *p[AB_MAX_FRAMES];
+};
+ab_status ab_stack_launch(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix,
+                          float sigma_low, float sigma_high, unsigned max_iter, float *d_out,
+                          unsigned long long *d_rejected, cudaStream_t stream);

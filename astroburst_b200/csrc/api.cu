@@ -1,0 +1,262 @@
+// api.cu -- C-ABI entry points of libastroburst_cuda.so: context, memory helpers and the
+// host-buffer / device-buffer stack calls.  See include/astroburst_cuda.h for the contract.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "ab_internal.h"
+
+ab_status ab_scratch_reserve(ab_ctx *ctx, int slot, size_t bytes) {
+    if (ctx->d_scratch_bytes[slot] >= bytes) return AB_OK;
+    if (ctx->d_scratch[slot]) {
+        AB_CUDA(ctx, cudaFree(ctx->d_scratch[slot]));
+        ctx->d_scratch[slot] = nullptr;
+        ctx->d_scratch_bytes[slot] = 0;
+    }
+    cudaError_t e = cudaMalloc(&ctx->d_scratch[slot], bytes);
+    if (e != cudaSuccess)
+        return ab_fail(ctx, AB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes,
+                       cudaGetErrorString(e));
+    ctx->d_scratch_bytes[slot] = bytes;
+    return AB_OK;
+}
+
+extern "C" {
+
+int ab_abi_version(void) { return AB_ABI_VERSION; }
+
+ab_status ab_ctx_create(int device, ab_ctx **out) {
+    if (!out) return AB_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return AB_ERR_CUDA;
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) return AB_ERR_CUDA;
+    }
+    if (device >= count) return AB_ERR_INVALID;
+    ab_ctx *ctx = new (std::nothrow) ab_ctx();
+    if (!ctx) return AB_ERR_NOMEM;
+    ctx->device = device;
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return AB_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < AB_NUM_COPY_STREAMS; ++i) {
+        ok = cudaStreamCreateWithFlags(&ctx->copy_streams[i], cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->copy_events[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc(&ctx->d_small, ab_ctx::SMALL_BYTES) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ctx->h_small, ab_ctx::SMALL_BYTES) == cudaSuccess;
+    if (!ok) {
+        ab_ctx_destroy(ctx);
+        return AB_ERR_CUDA;
+    }
+    *out = ctx;
+    return AB_OK;
+}
+
+void ab_ctx_destroy(ab_ctx *ctx) {
+    if (!ctx) return;
+    {
+        DeviceGuard g(ctx->device);
+        cudaDeviceSynchronize();
+        for (int i = 0; i < AB_NUM_COPY_STREAMS; ++i) {
+            if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
+            if (ctx->copy_events[i]) cudaEventDestroy(ctx->copy_events[i]);
+            if (ctx->copy_streams[i]) cudaStreamDestroy(ctx->copy_streams[i]);
+        }
+        if (ctx->d_small) cudaFree(ctx->d_small);
+        if (ctx->h_small) cudaFreeHost(ctx->h_small);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+const char *ab_last_error(ab_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+int ab_ctx_device(ab_ctx *ctx) { return ctx ? ctx->device : -1; }
+uint64_t ab_ctx_launch_count(ab_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
+
+ab_status ab_ctx_synchronize(ab_ctx *ctx) {
+    if (!ctx) return AB_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    AB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < AB_NUM_COPY_STREAMS; ++i)
+        AB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_streams[i]));
+    return AB_OK;
+}
+
+ab_status ab_host_alloc(size_t bytes, void **out) {
+    if (!out) return AB_ERR_INVALID;
+    return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? AB_OK : AB_ERR_NOMEM;
+}
+ab_status ab_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? AB_OK : AB_ERR_CUDA; }
+
+ab_status ab_dev_alloc(ab_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx || !out) return AB_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess)
+        return ab_fail(ctx, AB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes,
+                       cudaGetErrorString(e));
+    return AB_OK;
+}
+ab_status ab_dev_free(ab_ctx *ctx, void *p) {
+    if (!ctx) return AB_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    AB_CUDA(ctx, cudaFree(p));
+    return AB_OK;
+}
+ab_status ab_memcpy_h2d(ab_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx) return AB_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    AB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    AB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AB_OK;
+}
+ab_status ab_memcpy_d2h(ab_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx) return AB_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    AB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    AB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AB_OK;
+}
+
+// ------------------------------------------------------------------------------- stacking
+static ab_status check_stack_args(ab_ctx *ctx, const void *frames, size_t n_frames,
+                                  const ab_stack_config *cfg, const void *out) {
+    if (!ctx) return AB_ERR_INVALID;
+    if (n_frames == 0) return ab_fail(ctx, AB_ERR_INVALID, "No images to stack");
+    if (!frames || !cfg || !out) return ab_fail(ctx, AB_ERR_INVALID, "null argument");
+    if (cfg->align)
+        return ab_fail(ctx, AB_ERR_UNSUPPORTED,
+                       "align=true (phase-correlation pre-alignment) is not implemented");
+    if (n_frames > AB_MAX_FRAMES)
+        return ab_fail(ctx, AB_ERR_UNSUPPORTED, "n_frames %zu > AB_MAX_FRAMES %d", n_frames,
+                       AB_MAX_FRAMES);
+    return AB_OK;
+}
+
+ab_status ab_stack_sigma_clip_dev(ab_ctx *ctx, const float *const *d_frames, size_t n_frames,
+                                  size_t npix, const ab_stack_config *cfg, float *d_out,
+                                  uint64_t *d_rejected, void *stream) {
+    ab_status st = check_stack_args(ctx, d_frames, n_frames, cfg, d_out);
+    if (st != AB_OK) return st;
+    if (!d_rejected) return ab_fail(ctx, AB_ERR_INVALID, "null d_rejected");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    FrameTable ft;
+    for (size_t f = 0; f < n_frames; ++f) {
+        if (!d_frames[f]) return ab_fail(ctx, AB_ERR_INVALID, "null frame pointer %zu", f);
+        ft.p[f] = d_frames[f];
+    }
+    for (size_t f = n_frames; f < AB_MAX_FRAMES; ++f) ft.p[f] = nullptr;
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    return ab_stack_launch(ctx, ft, (int)n_frames, npix, cfg->sigma_low, cfg->sigma_high,
+                           cfg->max_iterations, d_out, (unsigned long long *)d_rejected, s);
+}
+
+// Host-buffer call: the image is cut into row bands; band k's frames are copied H2D on copy
+// stream k % 3 while band k-1 is being combined and band k-2's result goes back D2H, so with
+// pinned caller memory the call runs at PCIe speed with the kernel hidden behind the copies.
+ab_status ab_stack_sigma_clip(ab_ctx *ctx, const float *const *frames, size_t n_frames,
+                              size_t rows, size_t cols, const ab_stack_config *cfg, float *out,
+                              uint64_t *rejected_pixels) {
+    ab_status st = check_stack_args(ctx, frames, n_frames, cfg, out);
+    if (st != AB_OK) return st;
+    for (size_t f = 0; f < n_frames; ++f)
+        if (!frames[f]) return ab_fail(ctx, AB_ERR_INVALID, "null frame pointer %zu", f);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    if (rejected_pixels) *rejected_pixels = 0;
+    const size_t npix = rows * cols;
+    if (npix == 0) return AB_OK;
+
+    // band size: ~96 MiB of input per band, whole rows, at least one row
+    const size_t target_px = std::max<size_t>((96u << 20) / (n_frames * sizeof(float)), 1);
+    size_t band_rows = std::max<size_t>(target_px / cols, 1);
+    band_rows = std::min(band_rows, rows);
+    const size_t band_px_max = band_rows * cols;
+    const size_t n_bands = (rows + band_rows - 1) / band_rows;
+    const int n_slots = (int)std::min<size_t>(AB_NUM_COPY_STREAMS, n_bands);
+
+    // per slot: n_frames input planes + 1 output plane (256-byte aligned) ; counters in d_small
+    const size_t plane_bytes = ((band_px_max * sizeof(float) + 255) / 256) * 256;
+    for (int s = 0; s < n_slots; ++s) {
+        st = ab_scratch_reserve(ctx, s, plane_bytes * (n_frames + 1));
+        if (st != AB_OK) return st;
+    }
+    unsigned long long *d_rej = reinterpret_cast<unsigned long long *>(ctx->d_small);
+    unsigned long long *h_rej = reinterpret_cast<unsigned long long *>(ctx->h_small);
+    if (n_bands * sizeof(unsigned long long) > 4096)
+        return ab_fail(ctx, AB_ERR_UNSUPPORTED, "too many bands (%zu)", n_bands);
+
+    for (size_t b = 0; b < n_bands; ++b) {
+        const int slot = (int)(b % n_slots);
+        cudaStream_t s = ctx->copy_streams[slot];
+        const size_t r0 = b * band_rows;
+        const size_t nr = std::min(band_rows, rows - r0);
+        const size_t off = r0 * cols, px = nr * cols;
+        char *base = static_cast<char *>(ctx->d_scratch[slot]);
+        FrameTable ft;
+        for (size_t f = 0; f < n_frames; ++f) {
+            float *d = reinterpret_cast<float *>(base + f * plane_bytes);
+            AB_CUDA(ctx, cudaMemcpyAsync(d, frames[f] + off, px * sizeof(float),
+                                         cudaMemcpyHostToDevice, s));
+            ft.p[f] = d;
+        }
+        for (size_t f = n_frames; f < AB_MAX_FRAMES; ++f) ft.p[f] = nullptr;
+        float *d_out = reinterpret_cast<float *>(base + n_frames * plane_bytes);
+        st = ab_stack_launch(ctx, ft, (int)n_frames, px, cfg->sigma_low, cfg->sigma_high,
+                             cfg->max_iterations, d_out, d_rej + b, s);
+        if (st != AB_OK) return st;
+        AB_CUDA(ctx, cudaMemcpyAsync(out + off, d_out, px * sizeof(float),
+                                     cudaMemcpyDeviceToHost, s));
+        AB_CUDA(ctx, cudaMemcpyAsync(h_rej + b, d_rej + b, sizeof(unsigned long long),
+                                     cudaMemcpyDeviceToHost, s));
+    }
+    for (int s = 0; s < n_slots; ++s) AB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_streams[s]));
+    uint64_t total = 0;
+    for (size_t b = 0; b < n_bands; ++b) total += h_rej[b];
+    if (rejected_pixels) *rejected_pixels = total;
+    return AB_OK;
+}
+
+ab_status ab_sigma_clip_combine(ab_ctx *ctx, const float *values, size_t n, float sigma_low,
+                                float sigma_high, uint32_t max_iter, float *mean_out,
+                                uint32_t *rejected_out) {
+    if (!ctx || !mean_out || !rejected_out) return AB_ERR_INVALID;
+    if (n > AB_MAX_FRAMES)
+        return ab_fail(ctx, AB_ERR_UNSUPPORTED, "n %zu > AB_MAX_FRAMES %d", n, AB_MAX_FRAMES);
+    *mean_out = 0.0f;
+    *rejected_out = 0;
+    if (n == 0) return AB_OK;  // combine.rs:21-23
+    if (!values) return ab_fail(ctx, AB_ERR_INVALID, "null values");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    // layout in d_small: [0,8) counter | [64, 64+4) out | [8192, ...) values
+    char *d = static_cast<char *>(ctx->d_small);
+    float *d_vals = reinterpret_cast<float *>(d + 8192);
+    float *d_out = reinterpret_cast<float *>(d + 64);
+    unsigned long long *d_rej = reinterpret_cast<unsigned long long *>(d);
+    AB_CUDA(ctx, cudaMemcpyAsync(d_vals, values, n * sizeof(float), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    FrameTable ft;
+    for (size_t f = 0; f < AB_MAX_FRAMES; ++f) ft.p[f] = f < n ? d_vals + f : nullptr;
+    ab_status st = ab_stack_launch(ctx, ft, (int)n, 1, sigma_low, sigma_high, max_iter, d_out,
+                                   d_rej, ctx->stream);
+    if (st != AB_OK) return st;
+    unsigned long long rej = 0;
+    AB_CUDA(ctx, cudaMemcpyAsync(mean_out, d_out, sizeof(float), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    AB_CUDA(ctx, cudaMemcpyAsync(&rej, d_rej, sizeof(rej), cudaMemcpyDeviceToHost, ctx->stream));
+    AB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *rejected_out = (uint32_t)rej;
+    return AB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+"""GPU parity tests for the sigma-clip stack: CUDA path (through the C ABI) vs the CPU oracle.
+
+Bar: `rejected_pixels` bit-exact; pixels bit-exact on these inputs (the only order-dependent
+step, the f64 sum of f32 samples, is exact for any dynamic range < 2^29) and in any case within
+1e-5 relative (BASELINE.json north_star tolerance).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # north_star: f32 pixel values within 1e-5 relative
+
+
+@pytest.fixture(scope="module")
+def ab():
+    import astroburst_b200 as ab
+
+    ab.default_context()
+    return ab
+
+
+def _assert_pixels(got, want):
+    assert got.shape == want.shape
+    bad = ~(np.isclose(got, want, rtol=REL_TOL, atol=0.0) | (got == want))
+    assert not bad.any(), f"{bad.sum()} pixels outside {REL_TOL} relative"
+    return int((got != want).sum())
+
+
+# ---- the reference's unit tests (combine.rs:199-284) through the CUDA path
+def test_reference_unit_vectors(ab, orc):
+    cases = [
+        ([10.0, 10.1, 9.9, 10.0, 10.2], 3.0, 3.0, 5),
+        ([10.0, 10.1, 9.9, 10.0, 500.0], 3.0, 3.0, 5),
+        ([100.0, 100.2, 99.8, 100.1, 100.0, 5000.0, 99.9], 2.0, 2.0, 5),
+        ([], 3.0, 3.0, 5),
+        ([42.0], 3.0, 3.0, 5),
+    ]
+    for vals, sl, sh, it in cases:
+        got = ab.sigma_clip_combine(vals, sl, sh, it)
+        want = orc.sigma_clip_combine(vals, sl, sh, it)
+        assert got == want, (vals, got, want)
+    mean, rej = ab.sigma_clip_combine([10.0, 10.1, 9.9, 10.0, 10.2], 3.0, 3.0, 5)
+    assert abs(mean - 10.04) < 0.1 and rej == 0
+    mean, rej = ab.sigma_clip_combine([10.0, 10.1, 9.9, 10.0, 500.0], 3.0, 3.0, 5)
+    assert mean < 15.0 and rej > 0
+
+
+def test_stack_identical_and_outlier(ab):
+    img = (np.arange(16, dtype=np.float32) * 10.0).reshape(4, 4)
+    res = ab.stack_images([img, img, img], ab.StackConfig(align=False))
+    assert res.frame_count == 3 and abs(res.image[0, 0]) < 1e-4 and abs(res.image[1, 1] - 50.0) < 1e-4
+    clean = np.full((4, 4), 100.0, np.float32)
+    noisy = clean.copy()
+    noisy[2, 2] = 50000.0
+    res = ab.stack_images([clean, clean, clean, noisy, clean], ab.StackConfig(3.0, 3.0, 5, False))
+    assert abs(res.image[2, 2] - 100.0) < 1.0 and res.rejected_pixels > 0
+
+
+def test_error_behaviour(ab):
+    with pytest.raises(ab.AstroBurstError):  # bail!("No images to stack")
+        ab.stack_images([], ab.StackConfig(align=False))
+    with pytest.raises(ab.AstroBurstError):  # align=true needs phase correlation (not built)
+        ab.stack_images([np.zeros((4, 4), np.float32)], ab.StackConfig())
+
+
+# ---- random single-pixel vectors, every length class (register 8/16/32/64 and deep path)
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 7, 8, 9, 10, 15, 16, 17, 20, 31, 32, 33, 48, 63, 64, 65, 100, 128, 200, 256])
+def test_single_pixel_random(ab, orc, n):
+    rng = np.random.default_rng(n)
+    for trial in range(6):
+        v = rng.normal(1000.0, 12.0, n).astype(np.float32)
+        if trial % 2:
+            v[rng.integers(0, n)] += 20000.0
+        if trial % 3 == 2 and n > 2:
+            v[rng.integers(0, n, max(n // 8, 1))] -= 300.0
+        sl, sh = [(3.0, 3.0), (2.0, 2.5), (1.0, 4.0)][trial % 3]
+        for it in (0, 1, 2, 5, 8):
+            assert ab.sigma_clip_combine(v, sl, sh, it) == orc.sigma_clip_combine(v, sl, sh, it), (n, trial, it)
+
+
+def test_single_pixel_edge_cases(ab, orc):
+    cases = [
+        [5.0, 5.0, 5.0, 5.0],                 # MAD = 0 -> sigma floor 1e-10
+        [1.0, 1.0, 1.0, 1.0, 2.0],            # everything but the mode rejected
+        [0.0, 0.0],
+        [-3.0, 7.0],
+        [1.0, 2.0, 1000.0, 1001.0],           # even n: upper median (combine.rs:38-40)
+        list(np.linspace(-50, 50, 32)),
+        [3.4e38, 3.4e38, -3.4e38, 1.0],       # dev overflows to inf
+    ]
+    for v in cases:
+        for it in (0, 1, 5):
+            for sl, sh in ((3.0, 3.0), (0.5, 0.5), (0.0, 0.0)):
+                assert ab.sigma_clip_combine(v, sl, sh, it) == orc.sigma_clip_combine(v, sl, sh, it), (v, it, sl)
+    # Dynamic range > 2^29: the f64 sum of the survivors is no longer exact, so the result
+    # depends on summation order -- which in the reference is the unspecified permutation left
+    # by select_nth_unstable (combine.rs:39,51).  The CUDA path sums in ascending order.  Once the
+    # clip has removed the huge samples the sum is exact again and must match bit for bit.
+    v = [1e30, -1e30, 1.0, 2.0, 3.0]
+    for it in (1, 5):
+        assert ab.sigma_clip_combine(v, 3.0, 3.0, it) == orc.sigma_clip_combine(v, 3.0, 3.0, it) == (2.0, 2)
+
+
+# ---- whole stacks vs oracle
+@pytest.mark.parametrize("n_frames,rows,cols", [(32, 96, 160), (10, 64, 200), (3, 33, 47), (16, 50, 70),
+                                                (20, 40, 90), (33, 40, 64), (64, 32, 48), (100, 24, 40),
+                                                (256, 16, 24), (1, 8, 8), (2, 8, 8)])
+def test_stack_matches_oracle(ab, orc, n_frames, rows, cols):
+    from astroburst_b200 import synth
+
+    fr = synth.stack_frames(n_frames, rows, cols, seed=n_frames, nan_border=4, cosmic_fraction=2e-3)
+    want, want_rej = orc.stack_images(list(fr), 3.0, 3.0, 5)
+    res = ab.stack_images(list(fr), ab.StackConfig(3.0, 3.0, 5, False))
+    assert res.rejected_pixels == want_rej
+    ndiff = _assert_pixels(res.image, want)
+    assert ndiff == 0, f"{ndiff} pixels not bit-identical"
+
+
+def test_stack_all_nan_pixels_and_ragged(ab, orc):
+    from astroburst_b200 import synth
+
+    fr = synth.stack_frames(12, 40, 40, seed=3, nan_border=0)
+    fr[:, 5, 5] = np.nan           # all-NaN pixel -> 0.0, no rejections (G3)
+    fr[:11, 6, 6] = np.inf         # a single finite sample
+    fr[::2, 7, :] = -np.inf
+    want, want_rej = orc.stack_images(list(fr), 2.5, 3.5, 4)
+    res = ab.stack_images(list(fr), ab.StackConfig(2.5, 3.5, 4, False))
+    assert res.image[5, 5] == 0.0 and res.rejected_pixels == want_rej
+    assert np.array_equal(res.image, want)
+    # ragged frames are cropped to the common minimum (combine.rs:104-113)
+    ragged = [fr[0], fr[1][:38, :], fr[2][:, :36]]
+    want, want_rej = orc.stack_images([f[:38, :36] for f in ragged], 3.0, 3.0, 5)
+    res = ab.stack_images(ragged, ab.StackConfig(3.0, 3.0, 5, False))
+    assert res.image.shape == (38, 36) and np.array_equal(res.image, want) and res.rejected_pixels == want_rej
+
+
+def test_stack_max_iter_and_sigma_sweep(ab, orc):
+    from astroburst_b200 import synth
+
+    fr = list(synth.stack_frames(32, 48, 64, seed=11, nan_border=0, cosmic_fraction=5e-3))
+    for it in (0, 1, 2, 3, 10):
+        for sl, sh in ((3.0, 3.0), (1.5, 2.0)):
+            want, want_rej = orc.stack_images(fr, sl, sh, it)
+            res = ab.stack_images(fr, ab.StackConfig(sl, sh, it, False))
+            assert res.rejected_pixels == want_rej and np.array_equal(res.image, want), (it, sl, sh)
+
+
+# ---- size-independent properties at the BASELINE size (32 x 4096^2), device-resident
+def test_full_size_properties(ab, orc):
+    import torch
+    from astroburst_b200 import synth
+
+    dev = torch.device("cuda:0")
+    n, rows, cols = 32, 4096, 4096
+    frames = synth.stack_frames_torch(n, rows, cols, dev)
+    cfg = ab.StackConfig(3.0, 3.0, 5, False)
+    ctx = ab.default_context(0)
+    out = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+    rej = torch.zeros(1, dtype=torch.int64, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    ab.stack_images_device([f.data_ptr() for f in frames], rows * cols, cfg, out.data_ptr(), rej.data_ptr(), s)
+    torch.cuda.synchronize()
+    # (1) frame-order invariance: the result is a function of the sample multiset
+    perm = torch.randperm(n).tolist()
+    out2 = torch.empty_like(out)
+    rej2 = torch.zeros_like(rej)
+    ab.stack_images_device([frames[i].data_ptr() for i in perm], rows * cols, cfg, out2.data_ptr(), rej2.data_ptr(), s)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2) and int(rej) == int(rej2)
+    # (2) bounded by the finite sample range; finite everywhere
+    st = torch.stack(frames)
+    finite = torch.isfinite(st)
+    lo = torch.where(finite, st, torch.full_like(st, float("inf"))).amin(0)
+    hi = torch.where(finite, st, torch.full_like(st, float("-inf"))).amax(0)
+    assert bool(torch.isfinite(out).all()) and bool((out >= lo).all()) and bool((out <= hi).all())
+    # (3) oracle on sampled row bands of the same input (bit-exact), incl. the NaN border
+    for r0 in (0, 60, 2048, 4096 - 16):
+        band = [f[r0:r0 + 16].cpu().numpy() for f in frames]
+        want, _ = orc.stack_images(band, 3.0, 3.0, 5)
+        assert np.array_equal(out[r0:r0 + 16].cpu().numpy(), want)
+    # (4) host-buffer entry point == device entry point
+    host = [f[:256].cpu().numpy() for f in frames]
+    res = ab.stack_images(host, cfg)
+    assert np.array_equal(res.image, out[:256].cpu().numpy())
+    # (5) stacking n copies of one frame returns it (finite pixels) with no rejections
+    same = [frames[1]] * n
+    ab.stack_images_device([f.data_ptr() for f in same], rows * cols, cfg, out2.data_ptr(), rej2.data_ptr(), s)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, frames[1]) and int(rej2) == 0

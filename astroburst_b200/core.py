@@ -79,7 +79,7 @@ def stack_images(images: Sequence[np.ndarray], config: StackConfig,
 def stack_images_device(frame_ptrs: Sequence[int], npix: int, config: StackConfig, out_ptr: int,
                         rejected_ptr: int, stream: int = 0, ctx: Context | None = None) -> None:
     """Device-resident stack: raw device pointers (e.g. torch `data_ptr()`), enqueued on
-    `stream` (a cudaStream_t handle; 0 = the context's stream) without synchronizing."""
+    `stream` (a cudaStream_t handle; 0 = the CUDA legacy default stream) without synchronizing."""
     ctx = ctx or default_context()
     if len(frame_ptrs) == 0:
         raise AstroBurstError(_lib.AB_ERR_INVALID, "No images to stack")

@@ -28,6 +28,10 @@ struct ab_ctx {
     void *d_small = nullptr;
     void *h_small = nullptr;
     static constexpr size_t SMALL_BYTES = 1 << 20;
+    int stack_variant = 0;     // AB_STACK_VARIANT: 0 warp-autonomous (default), 1 block-barrier, 2 TMA
+    bool force_tma1d = false;  // AB_STACK_FORCE_TMA1D=1: per-frame bulk copies instead of the tensor map
+    unsigned stack_dbg = 0;    // AB_STACK_DBG: timing experiments only (results invalid)
+    void *encode_tmap_fn = nullptr;  // cuTensorMapEncodeTiled, resolved lazily
     std::mutex mu;
     std::atomic<uint64_t> launches{0};
     std::string last_error;

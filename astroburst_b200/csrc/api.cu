@@ -1,6 +1,7 @@
 // api.cu -- C-ABI entry points of libastroburst_cuda.so: context, memory helpers and the
 // host-buffer / device-buffer stack calls.  See include/astroburst_cuda.h for the contract.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -45,6 +46,14 @@ ab_status ab_ctx_create(int device, ab_ctx **out) {
         return AB_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    {
+        const char *e = getenv("AB_STACK_VARIANT");
+        ctx->stack_variant = e ? atoi(e) : 0;
+        e = getenv("AB_STACK_FORCE_TMA1D");
+        ctx->force_tma1d = e && e[0] == '1';
+        e = getenv("AB_STACK_DBG");
+        ctx->stack_dbg = e ? (unsigned)atoi(e) : 0u;
+    }
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < AB_NUM_COPY_STREAMS; ++i) {
         ok = cudaStreamCreateWithFlags(&ctx->copy_streams[i], cudaStreamNonBlocking) == cudaSuccess;
@@ -155,7 +164,7 @@ ab_status ab_stack_sigma_clip_dev(ab_ctx *ctx, const float *const *d_frames, siz
         ft.p[f] = d_frames[f];
     }
     for (size_t f = n_frames; f < AB_MAX_FRAMES; ++f) ft.p[f] = nullptr;
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t s = (cudaStream_t)stream;  // NULL = CUDA legacy default stream
     return ab_stack_launch(ctx, ft, (int)n_frames, npix, cfg->sigma_low, cfg->sigma_high,
                            cfg->max_iterations, d_out, (unsigned long long *)d_rejected, s);
 }

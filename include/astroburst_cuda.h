@@ -9,15 +9,15 @@
  * Conventions
  *  - Images are row-major contiguous f32 (`Array2<f32>::as_slice()`), rows x cols.
  *  - Every function returns an ab_status; 0 is success.  Nothing throws or aborts across the
- *    boundary.  `ab_last_error(ctx)` returns the message of the last failure on that context
- *    for the calling thread.
+ *    boundary.  `ab_last_error(ctx)` returns the message of the last failure on that context.
  *  - Entry points without a `_dev` suffix take HOST buffers, run synchronously (copies
  *    included) and return after the result is in the caller's output buffer, matching the
  *    blocking semantics of the reference functions.  The library never retains or frees
  *    caller memory.
- *  - `_dev` entry points take DEVICE pointers and a `cudaStream_t` (as void*; NULL = the
- *    context's stream); they enqueue work and do NOT synchronize unless documented, so chained
- *    steps (blend -> WB -> SCNR -> tone) stay resident in HBM.
+ *  - `_dev` entry points take DEVICE pointers and a `cudaStream_t` (as void*; NULL = the CUDA
+ *    legacy default stream, as everywhere in the runtime API); they enqueue work and do NOT
+ *    synchronize unless documented, so chained steps (blend -> WB -> SCNR -> tone) stay
+ *    resident in HBM.
  *  - A context is bound to one CUDA device.  Entry points are re-entrant across contexts and
  *    thread-safe on one context (calls on the same context serialize).
  *  - There is no CPU fallback: without a usable CUDA device every call fails with

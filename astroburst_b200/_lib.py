@@ -35,6 +35,27 @@ class StfParamsC(C.Structure):
     _fields_ = [("shadow", C.c_double), ("midtone", C.c_double), ("highlight", C.c_double)]
 
 
+class AutoStfConfigC(C.Structure):
+    _fields_ = [("target_bg", C.c_double), ("shadow_k", C.c_double)]
+
+
+class ScnrConfigC(C.Structure):
+    _fields_ = [("method", C.c_int32), ("amount", C.c_float), ("preserve_luminance", C.c_int32)]
+
+
+class BlendWeightC(C.Structure):
+    _fields_ = [("channel_idx", C.c_uint64), ("r_weight", C.c_double), ("g_weight", C.c_double),
+                ("b_weight", C.c_double)]
+
+
+class LevelsParamsC(C.Structure):
+    _fields_ = [("black", C.c_double), ("gamma", C.c_double), ("white", C.c_double)]
+
+
+class AffineC(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("a", "b", "tx", "c", "d", "ty")]
+
+
 def library_path() -> str:
     return _SO
 
@@ -64,6 +85,41 @@ SIGNATURES = {
                                           C.POINTER(StackConfigC), _vp, _vp, _vp]),
     "ab_sigma_clip_combine": (C.c_int, [_vp, _vp, _sz, C.c_float, C.c_float, C.c_uint32,
                                         C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    # pointwise
+    "ab_apply_stf_u8": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "ab_apply_stf_u8_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "ab_apply_stf_f32": (C.c_int, [_vp, _vp, _sz, _vp, _vp, C.c_int, _vp]),
+    "ab_apply_stf_f32_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, C.c_int, _vp, _vp]),
+    "ab_arcsinh_stretch": (C.c_int, [_vp, _vp, _sz, C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
+    "ab_arcsinh_stretch_dev": (C.c_int, [_vp, _vp, _sz, C.c_float, C.c_float, C.c_float, C.c_float,
+                                         _vp, _vp]),
+    "ab_scale": (C.c_int, [_vp, _vp, _sz, C.c_float, _vp]),
+    "ab_scale_dev": (C.c_int, [_vp, _vp, _sz, C.c_float, _vp, _vp]),
+    "ab_apply_levels": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
+    "ab_apply_levels_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "ab_spline_lut": (C.c_int, [_vp, _sz, _vp]),
+    "ab_apply_curve": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
+    "ab_apply_curve_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "ab_blend_channels": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _sz, _sz, _sz, _vp, _vp, _vp]),
+    "ab_blend_channels_dev": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp]),
+    "ab_apply_scnr": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "ab_apply_scnr_dev": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    # stats
+    "ab_compute_image_stats": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_double, C.c_double, _vp]),
+    "ab_image_stats_dev": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_double, C.c_double, _vp, _vp]),
+    "ab_histogram_u32": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, C.c_double, _vp, _vp]),
+    "ab_histogram_u32_dev": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, C.c_double, _vp, _vp, _vp]),
+    "ab_downsample_histogram": (C.c_int, [_vp, _sz, _sz, _vp]),
+    "ab_auto_stf": (C.c_int, [_vp, _vp, _vp]),
+    "ab_linked_stats": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "ab_select_wb_reference": (C.c_int, [_vp, _vp, _vp, _vp]),
+    # bicubic gathers
+    "ab_warp_affine_bicubic": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp]),
+    "ab_warp_affine_bicubic_dev": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _vp]),
+    "ab_shift_bicubic": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, C.c_double, _vp]),
+    "ab_shift_bicubic_dev": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, C.c_double, _vp, _vp]),
+    "ab_resample_bicubic": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, _vp]),
+    "ab_resample_bicubic_dev": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _vp]),
 }
 
 

@@ -14,10 +14,10 @@
 
 namespace abk {
 
-// [P, npix] f32 view of the frame cube, box = 256 pixels x P frames, no swizzle: the tile lands in
-// shared memory as stage[f][pixel], exactly what the per-thread column reads expect.
+// [P, npix] f32 view of the frame cube, box = box_px pixels x P frames, no swizzle: the tile lands
+// in shared memory as stage[f][pixel], exactly what the per-thread column reads expect.
 bool ab_make_stack_tmap(ab_ctx *ctx, const float *base, size_t npix, size_t plane_stride_elems,
-                        int P, TmapParam *out) {
+                        int P, int box_px, TmapParam *out) {
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -34,7 +34,7 @@ bool ab_make_stack_tmap(ab_ctx *ctx, const float *base, size_t npix, size_t plan
     static_assert(sizeof(CUtensorMap) == sizeof(TmapParam), "CUtensorMap is 128 bytes");
     const cuuint64_t gdim[2] = {(cuuint64_t)npix, (cuuint64_t)P};
     const cuuint64_t gstride[1] = {(cuuint64_t)plane_stride_elems * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)TILE, (cuuint32_t)P};
+    const cuuint32_t box[2] = {(cuuint32_t)box_px, (cuuint32_t)P};
     const cuuint32_t estride[2] = {1, 1};
     CUresult r = reinterpret_cast<encode_fn>(ctx->encode_tmap_fn)(
         reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,

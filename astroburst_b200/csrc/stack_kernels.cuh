@@ -96,6 +96,7 @@ __device__ __forceinline__ double sum_all_reg(const float (&s)[P]) {
 }
 __device__ __forceinline__ double sum_run_mem(const float *s, int stride, int a, int b) {
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll 1
     for (int j = a & ~3; j < b; j += 4) {  // accumulator index = sample index & 3, kept static
         if (j >= a) acc0 += (double)s[j * stride];
         if (j + 1 >= a && j + 1 < b) acc1 += (double)s[(j + 1) * stride];
@@ -107,6 +108,7 @@ __device__ __forceinline__ double sum_run_mem(const float *s, int stride, int a,
 __device__ __forceinline__ double sumsq_run_mem(const float *s, int stride, int a, int b,
                                                 double mean) {
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll 1
     for (int j = a & ~3; j < b; j += 4) {
         if (j >= a) {
             const double d = (double)s[j * stride] - mean;
@@ -410,7 +412,7 @@ __device__ __forceinline__ void drain_batch(WarpQueue<P> &q, unsigned head, unsi
 }
 
 template <int P>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 3)
 stack_warp_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigma_low,
                   float sigma_high, unsigned max_iter, float *__restrict__ out,
                   unsigned long long *__restrict__ rejected_total) {
@@ -459,12 +461,7 @@ stack_warp_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigm
         const unsigned pmask = __ballot_sync(0xffffffffu, park);
         if (pmask) {
             const unsigned c = __popc(pmask);
-            if (count + c > WQ_CAP) {  // make room (only when whole groups park: NaN strips)
-                const unsigned d = count < 32u ? count : 32u;
-                drain_batch<P>(q, head, d, lane, sigma_low, sigma_high, max_iter, out, local_rej);
-                head = (head + d) & (WQ_CAP - 1);
-                count -= d;
-            }
+            // count < 32 here and c <= 32, so the 64-slot ring always has room
             if (park) {
                 const unsigned slot = (head + count + __popc(pmask & ((1u << lane) - 1u))) & (WQ_CAP - 1);
 #pragma unroll
@@ -749,6 +746,130 @@ stack_tma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__ 
     if (tid == 0 && sm.rej_total) atomicAdd(rejected_total, sm.rej_total);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-autonomous variant with TMA staging (the production path for 16-byte aligned frames).
+//
+// Same control structure as stack_warp_kernel, but the 32 x P samples of a warp's next pixel group
+// are fetched by the TMA engine into a warp-private 4 KiB shared-memory stage while the warp sorts
+// the current group out of registers:
+//   * frames at a constant stride (one [P, rows, cols] cube): ONE cp.async.bulk.tensor.2d per
+//     group (box = 32 pixels x P frames, UTMALDG); otherwise P 128-byte cp.async.bulk copies;
+//   * completion on a warp-private mbarrier (complete_tx::bytes); the stage is re-armed by lane 0
+//     right after the warp has copied it to registers, so one stage per warp is enough: the fetch
+//     of group i+1 overlaps the whole sort of group i;
+//   * the loads become conflict-free LDS with immediate offsets: the ~1.5 ALU-pipe instructions
+//     of 64-bit address arithmetic per global load disappear from the pipe that bounds the kernel.
+constexpr int WT_WARPS = 8;  // 8 warps x ~13.1 KiB (P=32) -> 2 blocks / SM = 16 warps
+
+template <int P>
+struct WarpTmaSmem {
+    alignas(128) float stage[P][32];
+    WarpQueue<P> q;
+    alignas(8) unsigned long long full;
+    unsigned pad[30];
+};
+
+template <int P, bool kTensorMap>
+__global__ void __launch_bounds__(WT_WARPS * 32, 2)
+stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__ TmapParam tmap,
+                  size_t n_groups, float sigma_low, float sigma_high, unsigned max_iter,
+                  float *__restrict__ out, unsigned long long *__restrict__ rejected_total) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    WarpTmaSmem<P> &sm = reinterpret_cast<WarpTmaSmem<P> *>(smem_raw)[warp];
+    WarpQueue<P> &q = sm.q;
+    const uint32_t bar = smem_u32(&sm.full);
+    const uint32_t stage_addr = smem_u32(&sm.stage[0][0]);
+    constexpr uint32_t GROUP_BYTES = P * 32 * sizeof(float);
+
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const size_t warp_global = (size_t)blockIdx.x * WT_WARPS + warp;
+    const size_t warp_stride = (size_t)gridDim.x * WT_WARPS;
+
+    auto issue = [&](size_t g) {  // lane 0 only
+        mbar_arrive_expect_tx(bar, GROUP_BYTES);
+        if constexpr (kTensorMap) {
+            tma_load_2d(stage_addr, &tmap, (int)(g * 32), 0, bar);
+        } else {
+#pragma unroll 4
+            for (int f = 0; f < P; ++f)
+                tma_load_1d(stage_addr + f * 128, ft.p[f] + g * 32, 128, bar);
+        }
+    };
+    if (lane == 0 && warp_global < n_groups) issue(warp_global);
+
+    unsigned head = 0, count = 0;  // warp-uniform ring state
+    unsigned local_rej = 0;
+    uint32_t parity = 0;
+    for (size_t g = warp_global; g < n_groups; g += warp_stride, parity ^= 1u) {
+        const size_t p = g * 32 + lane;
+        mbar_wait(bar, parity);
+        float s[P];
+        float probe = 0.0f;
+#pragma unroll
+        for (int f = 0; f < P; ++f) {
+            s[f] = sm.stage[f][lane];
+            probe = fmaf(s[f], 0.0f, probe);  // NaN iff any sample is non-finite
+        }
+        // every lane has consumed its column (probe depends on all 32 loads): refill the stage
+        asm volatile("" ::"f"(probe) : "memory");
+        __syncwarp();
+        if (lane == 0 && g + warp_stride < n_groups) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(g + warp_stride);
+        }
+        int n = P;
+        if (probe != probe) {
+            n = 0;
+#pragma unroll
+            for (int f = 0; f < P; ++f) {
+                const bool fin = fabsf(s[f]) < CUDART_INF_F;
+                n += fin ? 1 : 0;
+                s[f] = fin ? s[f] : CUDART_INF_F;
+            }
+        }
+        float result;
+        unsigned rej, meta;
+        bool park = false;
+        if (phase_a<P>(s, n, sigma_low, sigma_high, max_iter, result, rej, meta)) {
+            __stcs(out + p, result);
+            local_rej += rej;
+        } else {
+            park = true;
+        }
+        const unsigned pmask = __ballot_sync(0xffffffffu, park);
+        if (pmask) {
+            // count < 32 here and at most 32 lanes park, so the 64-slot ring always has room
+            if (park) {
+                const unsigned slot =
+                    (head + count + __popc(pmask & ((1u << lane) - 1u))) & (WQ_CAP - 1);
+#pragma unroll
+                for (int f = 0; f < P; ++f) q.v[f][slot] = s[f];
+                q.meta[slot] = meta;
+                q.lastc[slot] = result;
+                q.rej0[slot] = rej;
+                q.pix[slot] = (unsigned)p;
+            }
+            count += __popc(pmask);
+            __syncwarp();
+            if (count >= 32u) {
+                drain_batch<P>(q, head, 32u, lane, sigma_low, sigma_high, max_iter, out, local_rej);
+                head = (head + 32u) & (WQ_CAP - 1);
+                count -= 32u;
+            }
+        }
+    }
+    if (count) drain_batch<P>(q, head, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
+    const unsigned w = __reduce_add_sync(0xffffffffu, local_rej);
+    if (lane == 0 && w) atomicAdd(rejected_total, (unsigned long long)w);
+}
+
 template <int P>
 ab_status launch_ldg(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, float sh,
                      unsigned max_iter, float *d_out, unsigned long long *d_rej,
@@ -791,16 +912,52 @@ ab_status launch_ldg(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, f
 
 // Host side of the tensor map (stack.cu): encodes a [P, npix] f32 view with a 256 x P box.
 bool ab_make_stack_tmap(ab_ctx *ctx, const float *base, size_t npix, size_t plane_stride_elems,
-                        int P, TmapParam *out);
+                        int P, int box_px, TmapParam *out);
 
 template <int P>
 ab_status launch_tile(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, float sh,
                       unsigned max_iter, float *d_out, unsigned long long *d_rej,
                       cudaStream_t stream) {
+    if (ctx->stack_variant == 0) {
+        bool al = true;
+        for (int f = 0; f < P; ++f) al = al && ((reinterpret_cast<uintptr_t>(ft.p[f]) & 15) == 0);
+        const size_t groups = al && npix < ((size_t)1 << 31) ? npix / 32 : 0;
+        if (groups) {
+            bool cube = P > 1 && !ctx->force_tma1d;
+            const ptrdiff_t stride = P > 1 ? ft.p[1] - ft.p[0] : 0;
+            for (int f = 1; cube && f < P; ++f) cube = (ft.p[f] - ft.p[f - 1]) == stride;
+            cube = cube && stride > 0 && (stride % 4) == 0 && (size_t)stride >= npix;
+            TmapParam tm{};
+            if (cube) cube = ab_make_stack_tmap(ctx, ft.p[0], npix, (size_t)stride, P, 32, &tm);
+            const size_t smem = sizeof(WarpTmaSmem<P>) * WT_WARPS;
+            constexpr int threads = WT_WARPS * 32;
+            auto kern = cube ? stack_wtma_kernel<P, true> : stack_wtma_kernel<P, false>;
+            AB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem));
+            int per_sm = 0;
+            AB_CUDA(ctx,
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+            if (per_sm < 1) per_sm = 1;
+            size_t grid = (size_t)ctx->sm_count * per_sm;
+            const size_t need = (groups + WT_WARPS - 1) / WT_WARPS;
+            if (grid > need) grid = need;
+            kern<<<(unsigned)grid, threads, smem, stream>>>(ft, tm, groups, sl, sh, max_iter, d_out,
+                                                            d_rej);
+            AB_LAUNCH_CHECK(ctx);
+        }
+        const size_t done = groups * 32;
+        if (done < npix) {  // ragged tail (or everything, for unaligned frames): plain loads
+            FrameTable tail;
+            for (int f = 0; f < AB_MAX_FRAMES; ++f) tail.p[f] = f < P ? ft.p[f] + done : nullptr;
+            return launch_ldg<P>(ctx, tail, npix - done, sl, sh, max_iter, d_out + done, d_rej,
+                                 stream);
+        }
+        return AB_OK;
+    }
     bool aligned = true;
     for (int f = 0; f < P; ++f)
         aligned = aligned && ((reinterpret_cast<uintptr_t>(ft.p[f]) & 15) == 0);
-    const size_t full_tiles = aligned && ctx->stack_variant == 2 ? npix / TILE : 0;
+    const size_t full_tiles = aligned && ctx->stack_variant == 3 ? npix / TILE : 0;
     if (full_tiles) {
         // constant frame stride (a [P, rows, cols] cube) -> one 2-D tensor-map TMA per tile
         bool cube = P > 1 && !ctx->force_tma1d;
@@ -809,7 +966,7 @@ ab_status launch_tile(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, 
         cube = cube && stride > 0 && (stride % 4) == 0 && (size_t)stride >= npix &&
                full_tiles * TILE < (size_t)1 << 31;
         TmapParam tm{};
-        if (cube) cube = ab_make_stack_tmap(ctx, ft.p[0], npix, (size_t)stride, P, &tm);
+        if (cube) cube = ab_make_stack_tmap(ctx, ft.p[0], npix, (size_t)stride, P, TILE, &tm);
         const size_t smem = sizeof(StackTmaSmem<P>);
         constexpr int threads = A_THREADS + B_THREADS + PROD_THREADS;
         auto kern = cube ? stack_tma_kernel<P, true> : stack_tma_kernel<P, false>;

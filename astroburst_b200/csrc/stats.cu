@@ -1,0 +1,737 @@
+// stats.cu -- image statistics, 65,536-bin histograms and auto-STF parameters for sm_100a.
+//
+// Reference semantics (paths relative to src-tauri/src/):
+//   core/imaging/stats.rs:11-13    is_valid_pixel (finite && > 1e-7)
+//   core/imaging/stats.rs:15-41    compute_image_stats / _with_known_range (switch at > 4,000,000 px)
+//   core/imaging/stats.rs:43-73    exact path: scan + exact_median_mut + exact_mad_mut
+//   core/imaging/stats.rs:85-210   histogram path: value hist -> median refine + |v - coarse| hist
+//                                  -> MAD refine, rank interpolation
+//   core/imaging/stats.rs:378-444  build_histogram, downsample_histogram
+//   core/imaging/stf.rs:13-47      auto_stf, mtf_balance (host scalar math)
+//   math/median.rs:27-73           even-n averaging medians
+//
+// GPU mapping.  Every pass is one HBM sweep (float4 loads).  Bin indices use the reference's f64
+// expression `((v as f64 - lo) * inv) as usize` evaluated on the FP64 pipe, so integer bin counts
+// are bit-exact.  65,536-bin histograms: each block keeps a 16,384-bin window (64 KiB of shared
+// memory, u32) positioned where its first pixels fall -- astronomical images are sharply peaked at
+// the sky level, so nearly all increments are shared-memory atomics -- and spills the rest to the
+// global u32 histogram (L2-resident, 256 KiB).  The small rank/percentile walks over the
+// histograms are host scalar code, as in the reference.  Exact medians (<= 4 M px) use an MSB-first
+// radix select on the float bit patterns (valid pixels are positive, so bits are monotone).
+// The f64 pixel sum is reduced block-partial by block-partial in a fixed order (deterministic;
+// the reference's rayon reduction order is not).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include <math_constants.h>
+
+#include "ab_internal.h"
+
+namespace {
+
+constexpr float PADDING_THRESHOLD = 1e-7f;  // types/constants.rs:6
+constexpr double MAD_TO_SIGMA = 1.4826;     // types/constants.rs:7
+constexpr unsigned HIST_BINS = 65536;       // stats.rs:8
+constexpr int ST_THREADS = 512;
+constexpr unsigned WIN = 16384;             // shared-memory window bins
+
+__device__ __forceinline__ bool valid_px(float v) {
+    return (fabsf(v) < CUDART_INF_F) && v > PADDING_THRESHOLD;
+}
+
+struct ScanPartial {
+    double sum;
+    unsigned long long count;
+    float mn, mx;
+};
+
+// ---- pass: min / max / sum / count over valid pixels (stats.rs:212-257)
+__global__ void __launch_bounds__(ST_THREADS)
+scan_kernel(const float *__restrict__ data, size_t len, ScanPartial *__restrict__ partials) {
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    double sum = 0.0;
+    unsigned long long cnt = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(data) & 15) == 0;
+    const size_t n4 = vec_ok ? len / 4 : 0;
+    auto acc = [&](float v) {
+        if (valid_px(v)) {
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+            sum += (double)v;
+            ++cnt;
+        }
+    };
+    for (size_t i = tid; i < n4; i += stride) {
+        const float4 v = __ldcs(reinterpret_cast<const float4 *>(data) + i);
+        acc(v.x); acc(v.y); acc(v.z); acc(v.w);
+    }
+    for (size_t i = n4 * 4 + tid; i < len; i += stride) acc(data[i]);
+
+    __shared__ ScanPartial sh[ST_THREADS / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        sum += __shfl_down_sync(0xffffffffu, sum, o);
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = {sum, cnt, mn, mx};
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ScanPartial r = sh[0];
+        for (int w = 1; w < ST_THREADS / 32; ++w) {
+            r.sum += sh[w].sum;
+            r.count += sh[w].count;
+            r.mn = fminf(r.mn, sh[w].mn);
+            r.mx = fmaxf(r.mx, sh[w].mx);
+        }
+        partials[blockIdx.x] = r;
+    }
+}
+
+// ---- generic 65,536-bin histogram pass.  F::operator()(v, idxA, idxB) classifies one pixel:
+// bit 0 of the return value -> count idxA in histogram A (windowed), bit 1 -> count idxB in
+// histogram B (global atomics only: used for the sparse refine histograms), bit 2 -> ++below.
+struct HistPartial {
+    double sum;
+    unsigned long long count;
+    unsigned long long below;
+};
+
+template <typename F>
+__global__ void __launch_bounds__(ST_THREADS)
+hist_kernel(const float *__restrict__ data, size_t len, F f, unsigned *__restrict__ histA,
+            unsigned *__restrict__ histB, HistPartial *__restrict__ partials) {
+    extern __shared__ unsigned win[];
+    __shared__ unsigned s_base;
+    __shared__ unsigned s_min;
+    for (unsigned i = threadIdx.x; i < WIN; i += blockDim.x) win[i] = 0;
+    if (threadIdx.x == 0) s_min = 0xffffffffu;
+    __syncthreads();
+
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(data) & 15) == 0;
+    const size_t n4 = vec_ok ? len / 4 : 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+
+    // position the window from the block's first pixels
+    {
+        unsigned my = 0xffffffffu;
+        if (tid < n4) {
+            const float4 v = reinterpret_cast<const float4 *>(data)[tid];
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                unsigned a = 0, b = 0;
+                if (f(vv[q], a, b) & 1u) my = min(my, a);
+            }
+        } else if (n4 == 0 && tid < len) {
+            unsigned a = 0, b = 0;
+            if (f(data[tid], a, b) & 1u) my = a;
+        }
+        my = __reduce_min_sync(0xffffffffu, my);
+        if ((threadIdx.x & 31) == 0 && my != 0xffffffffu) atomicMin(&s_min, my);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned m = s_min == 0xffffffffu ? 0u : s_min;
+            unsigned base = m > WIN / 8 ? m - WIN / 8 : 0u;
+            if (base + WIN > HIST_BINS) base = HIST_BINS - WIN;
+            s_base = base;
+        }
+        __syncthreads();
+    }
+    const unsigned base = s_base;
+    double sum = 0.0;
+    unsigned long long cnt = 0, below = 0;
+
+    auto one = [&](float v) {
+        unsigned a = 0, b = 0;
+        const unsigned code = f(v, a, b);
+        if (code & 8u) {
+            sum += (double)v;
+            ++cnt;
+        }
+        if (code & 1u) {
+            const unsigned rel = a - base;
+            if (rel < WIN) atomicAdd(&win[rel], 1u);
+            else atomicAdd(&histA[a], 1u);
+        }
+        if (code & 2u) atomicAdd(&histB[b], 1u);
+        if (code & 4u) ++below;
+    };
+    for (size_t i = tid; i < n4; i += stride) {
+        const float4 v = __ldcs(reinterpret_cast<const float4 *>(data) + i);
+        one(v.x); one(v.y); one(v.z); one(v.w);
+    }
+    for (size_t i = n4 * 4 + tid; i < len; i += stride) one(data[i]);
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < WIN; i += blockDim.x) {
+        const unsigned c = win[i];
+        if (c) atomicAdd(&histA[base + i], c);
+    }
+    // deterministic per-block partial of the f64 sum
+    __shared__ HistPartial sh[ST_THREADS / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, o);
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        below += __shfl_down_sync(0xffffffffu, below, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = {sum, cnt, below};
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        HistPartial r = sh[0];
+        for (int w = 1; w < ST_THREADS / 32; ++w) {
+            r.sum += sh[w].sum;
+            r.count += sh[w].count;
+            r.below += sh[w].below;
+        }
+        partials[blockIdx.x] = r;
+    }
+}
+
+// `((x) as usize).min(last)` for x = f64
+__device__ __forceinline__ unsigned bin_of(double x) {
+    const unsigned long long u = (unsigned long long)x;  // saturating, NaN -> 0, like Rust `as`
+    return u > (unsigned long long)(HIST_BINS - 1) ? HIST_BINS - 1 : (unsigned)u;
+}
+
+struct ValueHistF {  // stats.rs:259-297 scan_sum_and_hist; also build_histogram :393-400
+    double lo, inv;
+    __device__ unsigned operator()(float v, unsigned &a, unsigned &) const {
+        if (!valid_px(v)) return 0;
+        a = bin_of(((double)v - lo) * inv);
+        return 1u | 8u;
+    }
+};
+struct RefineDevF {  // stats.rs:119-146
+    double bin_lo, bin_hi, refine_inv, dev_inv;
+    float coarse_med;
+    __device__ unsigned operator()(float v, unsigned &a, unsigned &b) const {
+        if (!valid_px(v)) return 0;
+        unsigned code = 1u;
+        const double vf = (double)v;
+        if (vf >= bin_lo && vf < bin_hi) {
+            b = bin_of((vf - bin_lo) * refine_inv);
+            code |= 2u;
+        }
+        const float d = fabsf(v - coarse_med);  // f32 subtraction
+        a = bin_of((double)d * dev_inv);
+        return code;
+    }
+};
+struct MadRefineF {  // stats.rs:164-193
+    double region_lo, refine_inv;
+    float med, lo_f32, hi_f32;
+    __device__ unsigned operator()(float v, unsigned &, unsigned &b) const {
+        if (!valid_px(v)) return 0;
+        const float dev = fabsf(v - med);
+        if (dev < lo_f32) return 4u;
+        if (dev < hi_f32) {
+            b = bin_of(((double)dev - region_lo) * refine_inv);
+            return 2u;
+        }
+        return 0;
+    }
+};
+
+// ---- radix select on float bit patterns (exact path)
+// key(v) = bits(v) for mode 0, bits(|v - center|) for mode 1; only valid pixels take part.
+__global__ void __launch_bounds__(ST_THREADS)
+radix_hist_kernel(const float *__restrict__ data, size_t len, int mode, float center,
+                  unsigned prefix, unsigned prefix_mask, int shift, unsigned *__restrict__ hist256) {
+    __shared__ unsigned sh[256];
+    if (threadIdx.x < 256) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const float v = data[i];
+        if (!valid_px(v)) continue;
+        const unsigned key = __float_as_uint(mode ? fabsf(v - center) : v);
+        if ((key & prefix_mask) == prefix) atomicAdd(&sh[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 256 && sh[threadIdx.x]) atomicAdd(&hist256[threadIdx.x], sh[threadIdx.x]);
+}
+
+unsigned grid_for(ab_ctx *ctx, size_t len, int per_thread) {
+    size_t blocks = (len / per_thread + ST_THREADS - 1) / ST_THREADS + 1;
+    const size_t cap = (size_t)ctx->sm_count * 3;
+    return (unsigned)(blocks > cap ? cap : blocks);
+}
+
+// k-th smallest (0-based) key among the valid pixels; 4 passes of 8 bits.
+ab_status radix_select(ab_ctx *ctx, const float *d, size_t len, int mode, float center,
+                       unsigned long long k, cudaStream_t s, float *out) {
+    unsigned *d_hist = reinterpret_cast<unsigned *>(static_cast<char *>(ctx->d_small) + 65536);
+    unsigned *h_hist = reinterpret_cast<unsigned *>(static_cast<char *>(ctx->h_small) + 65536);
+    unsigned prefix = 0, mask = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        AB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned), s));
+        radix_hist_kernel<<<grid_for(ctx, len, 8), ST_THREADS, 0, s>>>(d, len, mode, center, prefix,
+                                                                      mask, shift, d_hist);
+        AB_LAUNCH_CHECK(ctx);
+        AB_CUDA(ctx, cudaMemcpyAsync(h_hist, d_hist, 256 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+        AB_CUDA(ctx, cudaStreamSynchronize(s));
+        unsigned long long cum = 0;
+        int b = 0;
+        for (; b < 256; ++b) {
+            if (cum + h_hist[b] > k) break;
+            cum += h_hist[b];
+        }
+        if (b == 256) return ab_fail(ctx, AB_ERR_CUDA, "radix select: rank out of range");
+        k -= cum;
+        prefix |= (unsigned)b << shift;
+        mask |= 0xffu << shift;
+    }
+    float r;
+    std::memcpy(&r, &prefix, 4);
+    *out = r;
+    return AB_OK;
+}
+
+// exact_median_mut / median_f32_mut semantics on the selected order statistics (median.rs:27-63)
+ab_status select_median_pair(ab_ctx *ctx, const float *d, size_t len, int mode, float center,
+                             unsigned long long n, cudaStream_t s, float *left, float *right) {
+    const unsigned long long mid = n / 2;
+    ab_status st = radix_select(ctx, d, len, mode, center, mid, s, right);
+    if (st != AB_OK) return st;
+    *left = *right;
+    if (n % 2 == 0) st = radix_select(ctx, d, len, mode, center, mid - 1, s, left);
+    return st;
+}
+
+void stats_default(ab_image_stats *o) { std::memset(o, 0, sizeof(*o)); }
+
+// stats.rs:299-353 on host copies of the histograms
+size_t find_percentile_bin(const unsigned *hist, size_t bins, unsigned long long total, double pct) {
+    const unsigned long long target = (unsigned long long)std::ceil((double)total * pct);
+    unsigned long long cum = 0;
+    for (size_t i = 0; i < bins; ++i) {
+        cum += hist[i];
+        if (cum >= target) return i;
+    }
+    return bins - 1;
+}
+double interpolate_percentile(const unsigned *hist, size_t bins, unsigned long long total,
+                              double pct, double data_min, double bin_width) {
+    const unsigned long long target = (unsigned long long)std::ceil((double)total * pct);
+    unsigned long long cum = 0;
+    for (size_t i = 0; i < bins; ++i) {
+        const unsigned long long count = hist[i];
+        cum += count;
+        if (cum >= target) {
+            const unsigned long long overshoot = cum - target;
+            const double frac = count > 0 ? 1.0 - ((double)overshoot / (double)count) : 0.5;
+            return data_min + ((double)i + frac) * bin_width;
+        }
+    }
+    return data_min + (double)bins * bin_width;
+}
+double resolve_rank_in_hist(const unsigned *hist, size_t bins, unsigned long long rank,
+                            double region_lo, double sub_bin_width) {
+    if (rank == 0) return region_lo;
+    unsigned long long cum = 0;
+    for (size_t i = 0; i < bins; ++i) {
+        const unsigned long long count = hist[i];
+        cum += count;
+        if (cum >= rank) {
+            const unsigned long long overshoot = cum - rank;
+            const double frac = count > 0 ? 1.0 - ((double)overshoot / (double)count) : 0.5;
+            return region_lo + ((double)i + frac) * sub_bin_width;
+        }
+    }
+    return region_lo + (double)bins * sub_bin_width;
+}
+
+// device scratch layout inside ctx->d_small / h_small (1 MiB each):
+//   [0, 64 KiB)        partials (<= 444 blocks x 24 B)
+//   [64 KiB, 68 KiB)   radix 256-bin histogram
+//   [128 KiB, 384 KiB) histogram A (65,536 x u32)
+//   [384 KiB, 640 KiB) histogram B
+struct Small {
+    char *d, *h;
+    unsigned *dA, *dB, *hA, *hB;
+    explicit Small(ab_ctx *ctx)
+        : d(static_cast<char *>(ctx->d_small)), h(static_cast<char *>(ctx->h_small)) {
+        dA = reinterpret_cast<unsigned *>(d + (128 << 10));
+        dB = reinterpret_cast<unsigned *>(d + (384 << 10));
+        hA = reinterpret_cast<unsigned *>(h + (128 << 10));
+        hB = reinterpret_cast<unsigned *>(h + (384 << 10));
+    }
+};
+
+template <typename F>
+ab_status run_hist(ab_ctx *ctx, const float *d, size_t len, F f, bool wantA, bool wantB,
+                   cudaStream_t s, double *sum, unsigned long long *count,
+                   unsigned long long *below) {
+    Small sm(ctx);
+    const unsigned grid = grid_for(ctx, len, 16);
+    AB_CUDA(ctx, cudaMemsetAsync(sm.dA, 0, 2 * HIST_BINS * sizeof(unsigned), s));
+    static bool attr = false;
+    AB_CUDA(ctx, cudaFuncSetAttribute(hist_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(WIN * sizeof(unsigned))));
+    (void)attr;
+    hist_kernel<F><<<grid, ST_THREADS, WIN * sizeof(unsigned), s>>>(
+        d, len, f, sm.dA, sm.dB, reinterpret_cast<HistPartial *>(sm.d));
+    AB_LAUNCH_CHECK(ctx);
+    AB_CUDA(ctx, cudaMemcpyAsync(sm.h, sm.d, grid * sizeof(HistPartial), cudaMemcpyDeviceToHost, s));
+    if (wantA)
+        AB_CUDA(ctx, cudaMemcpyAsync(sm.hA, sm.dA, HIST_BINS * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    if (wantB)
+        AB_CUDA(ctx, cudaMemcpyAsync(sm.hB, sm.dB, HIST_BINS * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    AB_CUDA(ctx, cudaStreamSynchronize(s));
+    const HistPartial *hp = reinterpret_cast<const HistPartial *>(sm.h);
+    double sm_sum = 0.0;
+    unsigned long long c = 0, b = 0;
+    for (unsigned i = 0; i < grid; ++i) {
+        sm_sum += hp[i].sum;
+        c += hp[i].count;
+        b += hp[i].below;
+    }
+    if (sum) *sum = sm_sum;
+    if (count) *count = c;
+    if (below) *below = b;
+    return AB_OK;
+}
+
+ab_status run_scan(ab_ctx *ctx, const float *d, size_t len, cudaStream_t s, double *mn, double *mx,
+                   double *sum, unsigned long long *count) {
+    Small sm(ctx);
+    const unsigned grid = grid_for(ctx, len, 16);
+    scan_kernel<<<grid, ST_THREADS, 0, s>>>(d, len, reinterpret_cast<ScanPartial *>(sm.d));
+    AB_LAUNCH_CHECK(ctx);
+    AB_CUDA(ctx, cudaMemcpyAsync(sm.h, sm.d, grid * sizeof(ScanPartial), cudaMemcpyDeviceToHost, s));
+    AB_CUDA(ctx, cudaStreamSynchronize(s));
+    const ScanPartial *sp = reinterpret_cast<const ScanPartial *>(sm.h);
+    double lo = DBL_MAX, hi = -DBL_MAX, tot = 0.0;
+    unsigned long long c = 0;
+    for (unsigned i = 0; i < grid; ++i) {
+        if (sp[i].count) {
+            lo = std::fmin(lo, (double)sp[i].mn);
+            hi = std::fmax(hi, (double)sp[i].mx);
+        }
+        tot += sp[i].sum;
+        c += sp[i].count;
+    }
+    *mn = lo;
+    *mx = hi;
+    *sum = tot;
+    *count = c;
+    return AB_OK;
+}
+
+// stats.rs:85-210
+ab_status hist_core(ab_ctx *ctx, const float *d, size_t len, double global_min, double global_max,
+                    cudaStream_t s, ab_image_stats *out) {
+    Small sm(ctx);
+    const double range = std::fmax(global_max - global_min, 1e-30);
+    const double bin_width = range / (double)HIST_BINS;
+    const double inv_bin = (double)HIST_BINS / range;
+
+    double global_sum = 0.0;
+    unsigned long long total_valid = 0;
+    ab_status st = run_hist(ctx, d, len, ValueHistF{global_min, inv_bin}, true, false, s,
+                            &global_sum, &total_valid, nullptr);
+    if (st != AB_OK) return st;
+    if (total_valid == 0) {
+        stats_default(out);
+        return AB_OK;
+    }
+    const unsigned long long n = total_valid;
+    const double mean = global_sum / (double)n;
+    const unsigned long long half_count = (unsigned long long)std::ceil((double)total_valid * 0.5);
+
+    const size_t median_bin = find_percentile_bin(sm.hA, HIST_BINS, total_valid, 0.5);
+    unsigned long long count_before_median = 0;
+    for (size_t i = 0; i < median_bin; ++i) count_before_median += sm.hA[i];
+    const double median_bin_lo = global_min + (double)median_bin * bin_width;
+    const double median_bin_hi = median_bin_lo + bin_width;
+    const double coarse_median =
+        interpolate_percentile(sm.hA, HIST_BINS, total_valid, 0.5, global_min, bin_width);
+
+    const double dev_range = range;
+    const double dev_bw = dev_range / (double)HIST_BINS;
+    const double dev_inv = (double)HIST_BINS / dev_range;
+    const float coarse_med_f32 = (float)coarse_median;
+    const double refine_range = std::fmax(median_bin_hi - median_bin_lo, 1e-30);
+    const double refine_inv = (double)HIST_BINS / refine_range;
+
+    st = run_hist(ctx, d, len,
+                  RefineDevF{median_bin_lo, median_bin_hi, refine_inv, dev_inv, coarse_med_f32},
+                  true, true, s, nullptr, nullptr, nullptr);
+    if (st != AB_OK) return st;
+    const unsigned long long median_rank_in_bin =
+        half_count > count_before_median ? half_count - count_before_median : 0;
+    const double median_refine_bw = refine_range / (double)HIST_BINS;
+    const double median = resolve_rank_in_hist(sm.hB, HIST_BINS, median_rank_in_bin, median_bin_lo,
+                                               median_refine_bw);
+
+    const size_t mad_bin = find_percentile_bin(sm.hA, HIST_BINS, total_valid, 0.5);
+    const size_t expand_lo = mad_bin > 0 ? mad_bin - 1 : 0;
+    const size_t expand_hi = std::min(mad_bin + 2, (size_t)HIST_BINS);
+    const double mad_region_lo = (double)expand_lo * dev_bw;
+    const double mad_region_hi = (double)expand_hi * dev_bw;
+
+    const float exact_med_f32 = (float)median;
+    const double mad_refine_range = std::fmax(mad_region_hi - mad_region_lo, 1e-30);
+    const double mad_refine_inv = (double)HIST_BINS / mad_refine_range;
+    unsigned long long count_below = 0;
+    st = run_hist(ctx, d, len,
+                  MadRefineF{mad_region_lo, mad_refine_inv, exact_med_f32, (float)mad_region_lo,
+                             (float)mad_region_hi},
+                  false, true, s, nullptr, nullptr, &count_below);
+    if (st != AB_OK) return st;
+    const unsigned long long mad_rank = half_count > count_below ? half_count - count_below : 0;
+    const double mad_refine_bw = mad_refine_range / (double)HIST_BINS;
+    const double mad =
+        resolve_rank_in_hist(sm.hB, HIST_BINS, mad_rank, mad_region_lo, mad_refine_bw);
+
+    out->min = global_min;
+    out->max = global_max;
+    out->mean = mean;
+    out->sigma = std::fmax(mad * MAD_TO_SIGMA, 1e-30);
+    out->median = median;
+    out->mad = mad;
+    out->valid_count = n;
+    return AB_OK;
+}
+
+// stats.rs:43-73
+ab_status stats_exact(ab_ctx *ctx, const float *d, size_t len, cudaStream_t s, ab_image_stats *out) {
+    double mn, mx, sum;
+    unsigned long long n;
+    ab_status st = run_scan(ctx, d, len, s, &mn, &mx, &sum, &n);
+    if (st != AB_OK) return st;
+    if (n == 0) {
+        stats_default(out);
+        return AB_OK;
+    }
+    float left, right;
+    st = select_median_pair(ctx, d, len, 0, 0.0f, n, s, &left, &right);
+    if (st != AB_OK) return st;
+    const double median = (n % 2 == 0) ? ((double)left + (double)right) / 2.0 : (double)right;
+    st = select_median_pair(ctx, d, len, 1, (float)median, n, s, &left, &right);
+    if (st != AB_OK) return st;
+    const float mad_f32 = (n % 2 == 0) ? (left + right) / 2.0f : right;
+    const double mad = (double)mad_f32;
+    out->min = mn;
+    out->max = mx;
+    out->mean = sum / (double)n;
+    out->sigma = std::fmax(mad * MAD_TO_SIGMA, 1e-30);
+    out->median = median;
+    out->mad = mad;
+    out->valid_count = n;
+    return AB_OK;
+}
+
+ab_status stats_hist(ab_ctx *ctx, const float *d, size_t len, cudaStream_t s, ab_image_stats *out) {
+    double mn, mx, sum;
+    unsigned long long n;
+    ab_status st = run_scan(ctx, d, len, s, &mn, &mx, &sum, &n);  // scan_minmax, stats.rs:212-231
+    if (st != AB_OK) return st;
+    if (n == 0) {
+        stats_default(out);
+        return AB_OK;
+    }
+    return hist_core(ctx, d, len, mn, mx, s, out);
+}
+
+// mode: 0 compute_image_stats, 1 exact, 2 histogram, 3 with_known_range
+ab_status stats_dispatch(ab_ctx *ctx, const float *d, size_t len, int mode, double kmin, double kmax,
+                         cudaStream_t s, ab_image_stats *out) {
+    if (len == 0) {
+        stats_default(out);
+        return AB_OK;
+    }
+    if (len >= ((size_t)1 << 32))
+        return ab_fail(ctx, AB_ERR_UNSUPPORTED, "images of 2^32 pixels or more are not supported");
+    switch (mode) {
+        case 1:
+            return stats_exact(ctx, d, len, s, out);
+        case 2:
+            return stats_hist(ctx, d, len, s, out);
+        case 3:
+            if (len <= 4000000) return stats_exact(ctx, d, len, s, out);
+            if (!std::isfinite(kmin) || !std::isfinite(kmax) || kmin >= kmax)
+                return stats_hist(ctx, d, len, s, out);
+            return hist_core(ctx, d, len, kmin, kmax, s, out);
+        default:
+            return len > 4000000 ? stats_hist(ctx, d, len, s, out) : stats_exact(ctx, d, len, s, out);
+    }
+}
+
+ab_status upload_plane(ab_ctx *ctx, const float *h, size_t len, float **d) {
+    ab_status st = ab_scratch_reserve(ctx, 0, len * 4 + 256);
+    if (st != AB_OK) return st;
+    *d = static_cast<float *>(ctx->d_scratch[0]);
+    AB_CUDA(ctx, cudaMemcpyAsync(*d, h, len * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return AB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+ab_status ab_image_stats_dev(ab_ctx *ctx, const float *d_data, size_t len, int mode,
+                             double known_min, double known_max, ab_image_stats *out,
+                             void *stream) {
+    if (!ctx || !out || (len && !d_data)) return AB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    return stats_dispatch(ctx, d_data, len, mode, known_min, known_max, (cudaStream_t)stream, out);
+}
+
+ab_status ab_compute_image_stats(ab_ctx *ctx, const float *data, size_t len, int mode,
+                                 double known_min, double known_max, ab_image_stats *out) {
+    if (!ctx || !out || (len && !data)) return AB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    if (len == 0) {
+        stats_default(out);
+        return AB_OK;
+    }
+    float *d = nullptr;
+    ab_status st = upload_plane(ctx, data, len, &d);
+    if (st != AB_OK) return st;
+    return stats_dispatch(ctx, d, len, mode, known_min, known_max, ctx->stream, out);
+}
+
+// build_histogram, stats.rs:378-421: bins = n_bins u32, edges = n_bins + 1 f64 (host outputs)
+static ab_status histogram_impl(ab_ctx *ctx, const float *d, size_t len, size_t n_bins, double dmin,
+                                double dmax, uint32_t *bins, double *edges, cudaStream_t s) {
+    if (n_bins != HIST_BINS)
+        return ab_fail(ctx, AB_ERR_UNSUPPORTED, "only 65536-bin histograms (HISTOGRAM_BINS) are built");
+    const double range = dmax - dmin;
+    if (range < 1e-10) {  // stats.rs:379-387
+        std::memset(bins, 0, n_bins * sizeof(uint32_t));
+        for (size_t i = 0; i <= n_bins; ++i) edges[i] = dmin;
+        return AB_OK;
+    }
+    const double inv = (double)n_bins / range;
+    Small sm(ctx);
+    ab_status st = run_hist(ctx, d, len, ValueHistF{dmin, inv}, true, false, s, nullptr, nullptr, nullptr);
+    if (st != AB_OK) return st;
+    std::memcpy(bins, sm.hA, n_bins * sizeof(uint32_t));
+    const double step = range / (double)n_bins;
+    for (size_t i = 0; i <= n_bins; ++i) edges[i] = dmin + (double)i * step;
+    return AB_OK;
+}
+ab_status ab_histogram_u32_dev(ab_ctx *ctx, const float *d_data, size_t len, size_t n_bins,
+                               double dmin, double dmax, uint32_t *bins, double *edges,
+                               void *stream) {
+    if (!ctx || !bins || !edges || (len && !d_data)) return AB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    return histogram_impl(ctx, d_data, len, n_bins, dmin, dmax, bins, edges, (cudaStream_t)stream);
+}
+ab_status ab_histogram_u32(ab_ctx *ctx, const float *data, size_t len, size_t n_bins, double dmin,
+                           double dmax, uint32_t *bins, double *edges) {
+    if (!ctx || !bins || !edges || (len && !data)) return AB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    float *d = nullptr;
+    if (len) {
+        ab_status st = upload_plane(ctx, data, len, &d);
+        if (st != AB_OK) return st;
+    }
+    return histogram_impl(ctx, d, len, n_bins, dmin, dmax, bins, edges, ctx->stream);
+}
+
+// downsample_histogram, stats.rs:423-444 (host scalar loop over 65,536 bins)
+ab_status ab_downsample_histogram(const uint32_t *src, size_t src_len, size_t target_bins,
+                                  uint32_t *out) {
+    if (!src || !out) return AB_ERR_INVALID;
+    if (target_bins >= src_len) {
+        std::memcpy(out, src, src_len * sizeof(uint32_t));
+        return AB_OK;
+    }
+    const double ratio = (double)src_len / (double)target_bins;
+    for (size_t i = 0; i < target_bins; ++i) {
+        const size_t start = (size_t)((double)i * ratio);
+        const size_t end = std::min((size_t)((double)(i + 1) * ratio), src_len);
+        uint32_t sum = 0;
+        for (size_t j = start; j < end; ++j) {
+            const uint64_t t = (uint64_t)sum + src[j];
+            sum = t > 0xffffffffull ? 0xffffffffu : (uint32_t)t;
+        }
+        out[i] = sum;
+    }
+    return AB_OK;
+}
+
+// auto_stf + mtf_balance, stf.rs:13-47 (host scalar math)
+ab_status ab_auto_stf(const ab_image_stats *st, const ab_auto_stf_config *cfg, ab_stf_params *out) {
+    if (!st || !cfg || !out) return AB_ERR_INVALID;
+    out->shadow = 0.0;
+    out->midtone = 0.5;
+    out->highlight = 1.0;
+    if (st->valid_count == 0) return AB_OK;
+    auto clampd = [](double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); };
+    const double range = std::fmax(st->max - st->min, 1e-30);
+    const double median_norm = (st->median - st->min) / range;
+    const double sigma_norm = st->sigma / range;
+    const double shadow_norm = clampd(median_norm + cfg->shadow_k * sigma_norm, 0.0, 0.98);
+    const double highlight_norm = 1.0;
+    const double clip_range = std::fmax(highlight_norm - shadow_norm, 1e-15);
+    const double m_clipped = clampd((median_norm - shadow_norm) / clip_range, 0.0, 1.0);
+    double midtone;
+    if (m_clipped <= 0.0 || m_clipped >= 1.0) {
+        midtone = 0.5;
+    } else {
+        const double m = m_clipped, t = cfg->target_bg;
+        const double denom = 2.0 * t * m - t - m;
+        midtone = std::fabs(denom) < 1e-15 ? 0.5 : clampd(m * (t - 1.0) / denom, 0.0001, 0.9999);
+    }
+    out->shadow = shadow_norm;
+    out->midtone = midtone;
+    out->highlight = highlight_norm;
+    return AB_OK;
+}
+
+// linked-STF stat merge, cmd/helpers.rs:185-202
+ab_status ab_linked_stats(const ab_image_stats *r, const ab_image_stats *g, const ab_image_stats *b,
+                          ab_image_stats *c) {
+    if (!r || !g || !b || !c) return AB_ERR_INVALID;
+    c->min = std::fmin(std::fmin(r->min, g->min), b->min);
+    c->max = std::fmax(std::fmax(r->max, g->max), b->max);
+    c->mean = (r->mean + g->mean + b->mean) / 3.0;
+    c->median = (r->median + g->median + b->median) / 3.0;
+    c->sigma = std::sqrt((r->sigma * r->sigma + g->sigma * g->sigma + b->sigma * b->sigma) / 3.0);
+    c->mad = (r->mad + g->mad + b->mad) / 3.0;
+    c->valid_count = r->valid_count;
+    return AB_OK;
+}
+
+// select_wb_reference, core/compose/white_balance.rs:3-20
+ab_status ab_select_wb_reference(const ab_image_stats *sr, const ab_image_stats *sg,
+                                 const ab_image_stats *sb, double out3[3]) {
+    if (!sr || !sg || !sb || !out3) return AB_ERR_INVALID;
+    auto stab = [](const ab_image_stats *s) { return s->median > 1e-10 ? s->mad / s->median : DBL_MAX; };
+    const double a = stab(sr), b = stab(sg), c = stab(sb);
+    if (a <= b && a <= c) {
+        const double m = std::fmax(sr->median, 1e-10);
+        out3[0] = 1.0;
+        out3[1] = m / std::fmax(sg->median, 1e-10);
+        out3[2] = m / std::fmax(sb->median, 1e-10);
+    } else if (c <= b) {
+        const double m = std::fmax(sb->median, 1e-10);
+        out3[0] = m / std::fmax(sr->median, 1e-10);
+        out3[1] = m / std::fmax(sg->median, 1e-10);
+        out3[2] = 1.0;
+    } else {
+        const double m = std::fmax(sg->median, 1e-10);
+        out3[0] = m / std::fmax(sr->median, 1e-10);
+        out3[1] = 1.0;
+        out3[2] = m / std::fmax(sb->median, 1e-10);
+    }
+    return AB_OK;
+}
+
+}  // extern "C"

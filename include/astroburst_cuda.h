@@ -159,6 +159,112 @@ ab_status ab_sigma_clip_combine(ab_ctx *ctx, const float *values, size_t n, floa
                                 float sigma_high, uint32_t max_iter, float *mean_out,
                                 uint32_t *rejected_out);
 
+/* ---------------------------------------------------------------- pointwise operators
+ * Each op has a host-buffer form (synchronous, copies included) and a `_dev` form (device
+ * pointers, enqueued on `stream`, no synchronisation).  `len` = rows*cols. */
+
+/* apply_stf, core/imaging/stf.rs:89-102 (== make_stf_u8_fn :122-145): f32 -> u8 */
+ab_status ab_apply_stf_u8(ab_ctx *ctx, const float *data, size_t len, const ab_stf_params *p,
+                          const ab_image_stats *st, uint8_t *out);
+ab_status ab_apply_stf_u8_dev(ab_ctx *ctx, const float *d_data, size_t len,
+                              const ab_stf_params *p, const ab_image_stats *st, uint8_t *d_out,
+                              void *stream);
+/* apply_stf_f32 / apply_stf_inplace, stf.rs:104-120,147-155 (variant 0); the near-duplicate in
+ * core/compose/rgb.rs:191-207 that divides by clip_range (variant 1) */
+ab_status ab_apply_stf_f32(ab_ctx *ctx, const float *data, size_t len, const ab_stf_params *p,
+                           const ab_image_stats *st, int variant, float *out);
+ab_status ab_apply_stf_f32_dev(ab_ctx *ctx, const float *d_data, size_t len,
+                               const ab_stf_params *p, const ab_image_stats *st, int variant,
+                               float *d_out, void *stream);
+/* arcsinh_stretch_with_stats, core/imaging/stretch.rs:10-46 */
+ab_status ab_arcsinh_stretch(ab_ctx *ctx, const float *data, size_t len, float dmin, float dmax,
+                             float factor, float gamma, float *out);
+ab_status ab_arcsinh_stretch_dev(ab_ctx *ctx, const float *d_data, size_t len, float dmin,
+                                 float dmax, float factor, float gamma, float *d_out,
+                                 void *stream);
+/* v * factor: apply_multiplier_inplace core/compose/rgb.rs:127-130, calibrate_channel
+ * cmd/compose/color.rs:21-49 (out may alias data) */
+ab_status ab_scale(ab_ctx *ctx, const float *data, size_t len, float factor, float *out);
+ab_status ab_scale_dev(ab_ctx *ctx, const float *d_data, size_t len, float factor, float *d_out,
+                       void *stream);
+/* apply_levels, core/imaging/curves.rs:31-50 */
+ab_status ab_apply_levels(ab_ctx *ctx, const float *data, size_t len, const ab_levels_params *p,
+                          float *out);
+ab_status ab_apply_levels_dev(ab_ctx *ctx, const float *d_data, size_t len,
+                              const ab_levels_params *p, float *d_out, void *stream);
+/* SplineLut::from_points, curves.rs:70-95 (host scalar math): points_xy = n_pts (x,y) pairs,
+ * lut = AB_CURVE_LUT_SIZE f32 */
+ab_status ab_spline_lut(const double *points_xy, size_t n_pts, float *lut);
+/* apply_curve, curves.rs:186-198 (truncating LUT lookup, no interpolation) */
+ab_status ab_apply_curve(ab_ctx *ctx, const float *data, size_t len, const float *lut, float *out);
+ab_status ab_apply_curve_dev(ab_ctx *ctx, const float *d_data, size_t len, const float *d_lut,
+                             float *d_out, void *stream);
+/* blend_channels, core/compose/channel_blend.rs:13-70.  Weights whose channel_idx >= n_ch are
+ * skipped; pixels beyond a channel's length contribute nothing; no NaN filtering. */
+ab_status ab_blend_channels(ab_ctx *ctx, const float *const *channels, const size_t *channel_lens,
+                            size_t n_ch, const ab_blend_weight *w, size_t n_w, size_t rows,
+                            size_t cols, float *r, float *g, float *b);
+ab_status ab_blend_channels_dev(ab_ctx *ctx, const float *const *d_channels,
+                                const size_t *channel_lens, size_t n_ch, const ab_blend_weight *w,
+                                size_t n_w, size_t rows, size_t cols, float *d_r, float *d_g,
+                                float *d_b, void *stream);
+/* apply_scnr_inplace, core/imaging/scnr.rs:18-53 (the caller checks equal dims, :24-26) */
+ab_status ab_apply_scnr(ab_ctx *ctx, float *r, float *g, float *b, size_t len,
+                        const ab_scnr_config *cfg);
+ab_status ab_apply_scnr_dev(ab_ctx *ctx, float *d_r, float *d_g, float *d_b, size_t len,
+                            const ab_scnr_config *cfg, void *stream);
+
+/* ---------------------------------------------------------------- statistics / histogram / STF
+ * mode: 0 compute_image_stats (core/imaging/stats.rs:15-23: exact select <= 4,000,000 px,
+ *         65,536-bin 3-pass histogram algorithm above), 1 exact path (stats.rs:43-73),
+ *         2 histogram path (stats.rs:75-210), 3 compute_image_stats_with_known_range
+ *         (stats.rs:25-41, uses known_min/known_max).  The result struct is written on the host;
+ *         the call synchronizes (the percentile walks are host scalar code, as in the reference). */
+ab_status ab_compute_image_stats(ab_ctx *ctx, const float *data, size_t len, int mode,
+                                 double known_min, double known_max, ab_image_stats *out);
+ab_status ab_image_stats_dev(ab_ctx *ctx, const float *d_data, size_t len, int mode,
+                             double known_min, double known_max, ab_image_stats *out,
+                             void *stream);
+/* build_histogram / compute_histogram_with_stats, stats.rs:373-421: n_bins must be 65536
+ * (HISTOGRAM_BINS); bins = n_bins u32, edges = n_bins + 1 f64, both HOST buffers */
+ab_status ab_histogram_u32(ab_ctx *ctx, const float *data, size_t len, size_t n_bins, double dmin,
+                           double dmax, uint32_t *bins, double *edges);
+ab_status ab_histogram_u32_dev(ab_ctx *ctx, const float *d_data, size_t len, size_t n_bins,
+                               double dmin, double dmax, uint32_t *bins, double *edges,
+                               void *stream);
+/* downsample_histogram, stats.rs:423-444 (host) */
+ab_status ab_downsample_histogram(const uint32_t *src, size_t src_len, size_t target_bins,
+                                  uint32_t *out);
+/* auto_stf + mtf_balance, core/imaging/stf.rs:13-47 (host scalar math) */
+ab_status ab_auto_stf(const ab_image_stats *st, const ab_auto_stf_config *cfg, ab_stf_params *out);
+/* linked-STF stat merge, cmd/helpers.rs:185-202 (host) */
+ab_status ab_linked_stats(const ab_image_stats *r, const ab_image_stats *g, const ab_image_stats *b,
+                          ab_image_stats *combined);
+/* select_wb_reference, core/compose/white_balance.rs:3-20 (host): out3 = (r, g, b) factors */
+ab_status ab_select_wb_reference(const ab_image_stats *r, const ab_image_stats *g,
+                                 const ab_image_stats *b, double out3[3]);
+
+/* ---------------------------------------------------------------- bicubic gathers
+ * Catmull-Rom sampler of core/imaging/sampling.rs:51-80 (f64 weights, clamp-to-edge taps) under
+ * the three bounds rules of its callers. */
+/* warp_image, core/alignment/affine.rs:663-690: out(x,y) = sample(t(x,y)) if 0 <= s < dim-1 else 0 */
+ab_status ab_warp_affine_bicubic(ab_ctx *ctx, const float *src, size_t src_rows, size_t src_cols,
+                                 const ab_affine *t, size_t out_rows, size_t out_cols, float *out);
+ab_status ab_warp_affine_bicubic_dev(ab_ctx *ctx, const float *d_src, size_t src_rows,
+                                     size_t src_cols, const ab_affine *t, size_t out_rows,
+                                     size_t out_cols, float *d_out, void *stream);
+/* shift_image_subpixel, core/stacking/align.rs:36-57 (== core/alignment/pair.rs:21-39) */
+ab_status ab_shift_bicubic(ab_ctx *ctx, const float *src, size_t rows, size_t cols, double dy,
+                           double dx, float *out);
+ab_status ab_shift_bicubic_dev(ab_ctx *ctx, const float *d_src, size_t rows, size_t cols, double dy,
+                               double dx, float *d_out, void *stream);
+/* resample_image, core/imaging/resample.rs:25-61; target dims of 0 -> AB_ERR_INVALID */
+ab_status ab_resample_bicubic(ab_ctx *ctx, const float *src, size_t src_rows, size_t src_cols,
+                              size_t target_rows, size_t target_cols, float *out);
+ab_status ab_resample_bicubic_dev(ab_ctx *ctx, const float *d_src, size_t src_rows, size_t src_cols,
+                                  size_t target_rows, size_t target_cols, float *d_out,
+                                  void *stream);
+
 #ifdef __cplusplus
 }
 #endif

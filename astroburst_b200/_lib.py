@@ -56,6 +56,22 @@ class AffineC(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("a", "b", "tx", "c", "d", "ty")]
 
 
+class StarC(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("x", "y", "flux", "fwhm", "eccentricity", "peak")] + [
+        ("npix", C.c_uint64), ("snr", C.c_double)]
+
+
+class DetectionInfoC(C.Structure):
+    _fields_ = [("background_median", C.c_double), ("background_sigma", C.c_double),
+                ("threshold_sigma", C.c_double), ("image_width", C.c_uint64),
+                ("image_height", C.c_uint64), ("n_stars", C.c_uint64)]
+
+
+class AlignResultC(C.Structure):
+    _fields_ = [("transform", AffineC), ("matched_stars", C.c_uint64), ("inliers", C.c_uint64),
+                ("residual_px", C.c_double), ("method", C.c_int32)]
+
+
 def library_path() -> str:
     return _SO
 
@@ -120,6 +136,16 @@ SIGNATURES = {
     "ab_shift_bicubic_dev": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, C.c_double, _vp, _vp]),
     "ab_resample_bicubic": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, _vp]),
     "ab_resample_bicubic_dev": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _vp]),
+    # stars / alignment
+    "ab_detect_stars": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, _vp, _sz, _vp]),
+    "ab_detect_stars_dev": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, _vp, _sz, _vp, _vp]),
+    "ab_estimate_background": (C.c_int, [_vp, _vp, _sz, _sz, _sz, C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double)]),
+    "ab_normalize_for_detection": (C.c_int, [_vp, _vp, _sz, _vp]),
+    "ab_align_affine": (C.c_int, [_vp, _vp, _vp, _sz, _sz, C.c_int, _vp]),
+    "ab_align_affine_dev": (C.c_int, [_vp, _vp, _vp, _sz, _sz, C.c_int, _vp, _vp]),
+    "ab_match_stars": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, C.POINTER(C.c_size_t)]),
+    "ab_ransac_affine": (C.c_int, [_vp, _sz, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),
 }
 
 

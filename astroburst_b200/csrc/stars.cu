@@ -1,0 +1,1078 @@
+// stars.cu -- tile background, star detection and the star-based affine aligner for sm_100a.
+//
+// Reference semantics (paths relative to src-tauri/src/):
+//   math/sigma_clip.rs:4-34                  sigma_clipped_stats (kappa 3, 2 iterations per tile)
+//   core/analysis/star_detection.rs:32-84    estimate_background
+//   core/analysis/star_detection.rs:86-258   detect_stars
+//   core/alignment/affine.rs:24-53           normalize_for_detection
+//   core/alignment/affine.rs:129-212         align_channel_affine (+ :214-660 helpers)
+//
+// Work split.  Everything that touches every pixel runs on the GPU:
+//   * normalisation is fused into the loads of the other kernels (never materialised);
+//   * background: one block per tile; the tile's exact medians / MADs come from an MSB-first radix
+//     select over the tile (valid pixels are positive floats, so their bit patterns are monotone),
+//     the sigma-clip `retain` is a shrinking [lo, hi] interval -- no sort, no per-tile buffers;
+//   * threshold + ordered stream compaction of the (few) above-threshold pixels;
+//   * triangle matching: all ref x tgt descriptor pairs (up to 1.17 G compares), votes in a
+//     120 x 120 shared-memory matrix.
+// What is left is per-star scalar work on a sparse pixel list (typically < 1 % of the image): the
+// 8-connected flood fill in the reference's discovery order, f64 moments, the stable flux sort
+// and the 3-px dedup run on the host exactly as the reference does (same summation order, so star
+// parameters are bit-identical), like the reference's own serial loop.  RANSAC (2000 x <= 120
+// points) is host scalar code too; its stream depends on rayon::current_num_threads() in the
+// reference (affine.rs:410), so the thread count is a parameter.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <vector>
+
+#include <math_constants.h>
+
+#include "ab_internal.h"
+
+namespace {
+
+constexpr double MAD_TO_SIGMA = 1.4826;
+constexpr int BG_THREADS = 512;
+
+struct Norm {  // normalize_for_detection fused into loads: v' = clamp((v - lo) * inv, 0, 1) as f32
+    int on;
+    double lo, inv;
+};
+__device__ __forceinline__ float norm_px(const Norm &nm, float v) {
+    if (!nm.on) return v;
+    double x = ((double)v - nm.lo) * nm.inv;
+    x = x < 0.0 ? 0.0 : x;
+    x = x > 1.0 ? 1.0 : x;  // NaN stays NaN (f64::clamp)
+    return (float)x;
+}
+
+// ------------------------------------------------------------------------- background tiles
+struct TileCtx {
+    const float *img;
+    size_t cols;
+    size_t r0, c0, th, tw;
+    Norm nm;
+};
+struct Sel {  // shared scratch of one block
+    unsigned hist[256];
+    unsigned bin, cum;
+    unsigned long long total;
+    unsigned maxkey;
+};
+
+// key of one pixel for the current selection, or false when the pixel is not in the set.
+// mode 0: value; mode 1: |v - median| as f32 via f64 (sigma_clip.rs:15)
+__device__ __forceinline__ bool tile_key(const TileCtx &t, unsigned i, int mode, double median,
+                                         float L, float H, unsigned &key) {
+    const size_t r = t.r0 + i / t.tw, c = t.c0 + i % t.tw;
+    const float v = norm_px(t.nm, __ldg(t.img + r * t.cols + c));
+    if (!((fabsf(v) < CUDART_INF_F) && v > 1e-7f)) return false;
+    if (!(v >= L && v <= H)) return false;
+    key = __float_as_uint(mode ? (float)fabs((double)v - median) : v);
+    return true;
+}
+
+__device__ unsigned long long tile_count(const TileCtx &t, Sel &s, float L, float H) {
+    if (threadIdx.x == 0) s.total = 0;
+    __syncthreads();
+    unsigned c = 0, key;
+    for (unsigned i = threadIdx.x; i < t.th * t.tw; i += blockDim.x)
+        c += tile_key(t, i, 0, 0.0, L, H, key) ? 1u : 0u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s.total, (unsigned long long)c);
+    __syncthreads();
+    const unsigned long long r = s.total;
+    __syncthreads();
+    return r;
+}
+
+// k-th smallest key (0-based); *less = number of keys strictly smaller than the result
+__device__ unsigned tile_select(const TileCtx &t, Sel &s, int mode, double median, float L, float H,
+                                unsigned long long k, unsigned long long *less) {
+    unsigned prefix = 0, mask = 0;
+    unsigned long long below = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        if (threadIdx.x < 256) s.hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < t.th * t.tw; i += blockDim.x) {
+            unsigned key;
+            if (tile_key(t, i, mode, median, L, H, key) && (key & mask) == prefix)
+                atomicAdd(&s.hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long cum = 0;
+            unsigned b = 0;
+            for (; b < 255; ++b) {
+                if (cum + s.hist[b] > k) break;
+                cum += s.hist[b];
+            }
+            s.bin = b;
+            s.cum = (unsigned)cum;
+        }
+        __syncthreads();
+        k -= s.cum;
+        below += s.cum;
+        prefix |= s.bin << shift;
+        mask |= 0xffu << shift;
+        __syncthreads();
+    }
+    *less = below;
+    return prefix;
+}
+
+// largest key strictly below `bound` (exists by construction when called)
+__device__ unsigned tile_max_below(const TileCtx &t, Sel &s, int mode, double median, float L,
+                                   float H, unsigned bound) {
+    if (threadIdx.x == 0) s.maxkey = 0;
+    __syncthreads();
+    unsigned m = 0;
+    for (unsigned i = threadIdx.x; i < t.th * t.tw; i += blockDim.x) {
+        unsigned key;
+        if (tile_key(t, i, mode, median, L, H, key) && key < bound) m = max(m, key);
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMax(&s.maxkey, m);
+    __syncthreads();
+    const unsigned r = s.maxkey;
+    __syncthreads();
+    return r;
+}
+
+// (left, right) = the (n/2 - 1)-th and (n/2)-th order statistics (left == right for odd n)
+__device__ void tile_median_pair(const TileCtx &t, Sel &s, int mode, double median, float L,
+                                 float H, unsigned long long n, float *left, float *right) {
+    const unsigned long long mid = n / 2;
+    unsigned long long less;
+    const unsigned rk = tile_select(t, s, mode, median, L, H, mid, &less);
+    unsigned lk = rk;
+    if (n % 2 == 0 && less == mid) lk = tile_max_below(t, s, mode, median, L, H, rk);
+    *left = __uint_as_float(lk);
+    *right = __uint_as_float(rk);
+}
+
+// exact_median_mut (median.rs:27-44) and the MAD sigma of sigma_clip.rs:14-17
+__device__ double tile_median(const TileCtx &t, Sel &s, float L, float H, unsigned long long n) {
+    float l, r;
+    tile_median_pair(t, s, 0, 0.0, L, H, n, &l, &r);
+    return (n % 2 == 0) ? ((double)l + (double)r) / 2.0 : (double)r;
+}
+__device__ double tile_mad(const TileCtx &t, Sel &s, double median, float L, float H,
+                           unsigned long long n) {
+    float l, r;
+    tile_median_pair(t, s, 1, median, L, H, n, &l, &r);
+    const float m = (n % 2 == 0) ? (l + r) / 2.0f : r;  // median_f32_mut
+    return (double)m;
+}
+
+__global__ void __launch_bounds__(BG_THREADS)
+bg_tiles_kernel(const float *__restrict__ img, size_t rows, size_t cols, size_t step,
+                size_t tiles_x, Norm nm, double *__restrict__ med_out,
+                double *__restrict__ sig_out, int *__restrict__ ok_out) {
+    __shared__ Sel s;
+    const size_t ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
+    TileCtx t;
+    t.img = img;
+    t.cols = cols;
+    t.r0 = ty * step;
+    t.c0 = tx * step;
+    t.th = min(step, rows - t.r0);
+    t.tw = min(step, cols - t.c0);
+    t.nm = nm;
+    float L = -CUDART_INF_F, H = CUDART_INF_F;
+    unsigned long long n = tile_count(t, s, L, H);
+    if (n < 8) {  // star_detection.rs:61-66
+        if (threadIdx.x == 0) ok_out[blockIdx.x] = 0;
+        return;
+    }
+    for (int it = 0; it < 2; ++it) {  // sigma_clipped_stats(&mut vals, 3.0, 2)
+        if (n < 3) break;
+        const double median = tile_median(t, s, L, H, n);
+        const double mad = tile_mad(t, s, median, L, H, n);
+        const double sig = fmax(mad * MAD_TO_SIGMA, 1e-30);
+        const float lo = (float)(median - 3.0 * sig);
+        const float hi = (float)(median + 3.0 * sig);
+        // retain(v >= lo && v <= hi) on the already retained set
+        if (!(lo <= L)) L = lo;  // NaN-safe max
+        if (!(hi >= H)) H = hi;
+        n = tile_count(t, s, L, H);
+    }
+    double median = 0.0, sigma = 1.0;  // sigma_clip.rs:24-26
+    if (n > 0) {
+        median = tile_median(t, s, L, H, n);
+        sigma = fmax(tile_mad(t, s, median, L, H, n) * MAD_TO_SIGMA, 1e-30);
+    }
+    if (threadIdx.x == 0) {
+        med_out[blockIdx.x] = median;
+        sig_out[blockIdx.x] = sigma;
+        ok_out[blockIdx.x] = 1;
+    }
+}
+
+// ------------------------------------------------------------------------- threshold + compaction
+// pass 1: per-row count of pixels with (v as f64) > threshold && finite; pass 2: ordered write.
+__global__ void __launch_bounds__(256)
+row_count_kernel(const float *__restrict__ img, size_t rows, size_t cols, Norm nm, double thr,
+                 unsigned *__restrict__ row_counts) {
+    const size_t r = blockIdx.x;
+    unsigned c = 0;
+    for (size_t x = threadIdx.x; x < cols; x += blockDim.x) {
+        const float v = norm_px(nm, __ldcs(img + r * cols + x));
+        c += ((double)v > thr && fabsf(v) < CUDART_INF_F) ? 1u : 0u;
+    }
+    __shared__ unsigned sh;
+    if (threadIdx.x == 0) sh = 0;
+    __syncthreads();
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sh, c);
+    __syncthreads();
+    if (threadIdx.x == 0) row_counts[r] = sh;
+}
+
+__global__ void __launch_bounds__(256)
+row_compact_kernel(const float *__restrict__ img, size_t rows, size_t cols, Norm nm, double thr,
+                   const unsigned long long *__restrict__ row_offsets, unsigned *__restrict__ out_col,
+                   float *__restrict__ out_val) {
+    const size_t r = blockIdx.x;
+    __shared__ unsigned warp_tot[8];
+    __shared__ unsigned run;
+    if (threadIdx.x == 0) run = 0;
+    __syncthreads();
+    const unsigned long long base = row_offsets[r];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (size_t x0 = 0; x0 < cols; x0 += blockDim.x) {
+        const size_t x = x0 + threadIdx.x;
+        float v = 0.0f;
+        bool fg = false;
+        if (x < cols) {
+            v = norm_px(nm, __ldcs(img + r * cols + x));
+            fg = ((double)v > thr) && (fabsf(v) < CUDART_INF_F);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, fg);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        unsigned before = run;
+        for (int w = 0; w < warp; ++w) before += warp_tot[w];
+        if (fg) {
+            const unsigned long long pos = base + before + __popc(bal & ((1u << lane) - 1u));
+            out_col[pos] = (unsigned)x;
+            out_val[pos] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tot = 0;
+            for (int w = 0; w < 8; ++w) tot += warp_tot[w];
+            run += tot;
+        }
+        __syncthreads();
+    }
+}
+
+// strided sample gather for normalize_for_detection (affine.rs:31-32)
+__global__ void sample_kernel(const float *__restrict__ img, size_t len, size_t step,
+                              float *__restrict__ out, size_t n_out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_out) out[i] = img[i * step];
+}
+
+// normalize_for_detection materialised (only for the standalone ABI entry / tests)
+__global__ void normalize_kernel(const float *__restrict__ img, size_t len, Norm nm,
+                                 float *__restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride)
+        out[i] = norm_px(nm, img[i]);
+}
+
+// ------------------------------------------------------------------------- triangle matching
+constexpr int MAX_STARS = 120;  // affine.rs:8
+// votes[ri * MAX_STARS + ti] over all (ref tri, tgt tri) pairs within tolerance (affine.rs:327-348)
+__global__ void __launch_bounds__(256)
+tri_match_kernel(const double *__restrict__ r_mid, const double *__restrict__ r_long,
+                 const unsigned char *__restrict__ r_sorted, int n_ref, const double *__restrict__ t_mid,
+                 const double *__restrict__ t_long, const unsigned char *__restrict__ t_sorted,
+                 int n_tgt, double tol, unsigned *__restrict__ votes) {
+    extern __shared__ unsigned sv[];  // MAX_STARS x MAX_STARS votes (57.6 KB, opt-in dynamic)
+    for (int i = threadIdx.x; i < MAX_STARS * MAX_STARS; i += blockDim.x) sv[i] = 0;
+    __syncthreads();
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_ref; a += gridDim.x * blockDim.x) {
+        const double rm = r_mid[a], rl = r_long[a];
+        const int r0 = r_sorted[3 * a], r1 = r_sorted[3 * a + 1], r2 = r_sorted[3 * a + 2];
+        for (int b = 0; b < n_tgt; ++b) {
+            const double d_mid = fabs(rm - __ldg(t_mid + b));
+            const double d_long = fabs(rl - __ldg(t_long + b));
+            if (d_mid > tol || d_long > tol) continue;
+            atomicAdd(&sv[r0 * MAX_STARS + t_sorted[3 * b]], 1u);
+            atomicAdd(&sv[r1 * MAX_STARS + t_sorted[3 * b + 1]], 1u);
+            atomicAdd(&sv[r2 * MAX_STARS + t_sorted[3 * b + 2]], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < MAX_STARS * MAX_STARS; i += blockDim.x)
+        if (sv[i]) atomicAdd(&votes[i], sv[i]);
+}
+
+// ------------------------------------------------------------------------- host-side pieces
+struct SparseImage {  // above-threshold pixels in raster order
+    size_t rows = 0, cols = 0;
+    std::vector<unsigned long long> row_off;  // rows + 1
+    std::vector<unsigned> col;
+    std::vector<float> val;
+    // index of pixel (r, c) in the list or -1
+    long long find(size_t r, size_t c) const {
+        const unsigned *b = col.data() + row_off[r], *e = col.data() + row_off[r + 1];
+        const unsigned *it = std::lower_bound(b, e, (unsigned)c);
+        return (it != e && *it == c) ? (long long)(it - col.data()) : -1;
+    }
+};
+
+inline size_t f2us(double x) {  // Rust `f64 as usize`
+    if (!(x > 0.0)) return 0;
+    if (x >= 18446744073709551615.0) return SIZE_MAX;
+    return (size_t)x;
+}
+
+// star_detection.rs:105-248 on the sparse list: identical visiting order, identical f64 sums.
+void flood_fill_stars(const SparseImage &sp, double bg_median, double bg_sigma,
+                      std::vector<ab_star> &out) {
+    const size_t rows = sp.rows, cols = sp.cols;
+    std::vector<char> visited(sp.col.size(), 0);
+    std::vector<ab_star> stars;
+    std::deque<long long> queue;
+    std::vector<long long> comp;
+    static const int DR[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
+    static const int DC[8] = {0, 0, -1, 1, -1, 1, -1, 1};
+    auto row_of = [&](long long idx) {
+        return (size_t)(std::upper_bound(sp.row_off.begin(), sp.row_off.end(),
+                                         (unsigned long long)idx) - sp.row_off.begin() - 1);
+    };
+    for (size_t r = 1; r + 1 < rows; ++r) {
+        for (unsigned long long p = sp.row_off[r]; p < sp.row_off[r + 1]; ++p) {
+            const size_t c = sp.col[p];
+            if (c < 1 || c + 1 >= cols || visited[p]) continue;  // seeds are interior pixels
+            queue.clear();
+            comp.clear();
+            queue.push_back((long long)p);
+            visited[p] = 1;
+            while (!queue.empty()) {
+                const long long cur = queue.front();
+                queue.pop_front();
+                comp.push_back(cur);
+                const size_t cr = row_of(cur), cc = sp.col[cur];
+                for (int k = 0; k < 8; ++k) {
+                    const long long nr = (long long)cr + DR[k], nc = (long long)cc + DC[k];
+                    if (nr < 0 || nc < 0 || nr >= (long long)rows || nc >= (long long)cols) continue;
+                    const long long q = sp.find((size_t)nr, (size_t)nc);
+                    if (q < 0 || visited[q]) continue;
+                    visited[q] = 1;
+                    queue.push_back(q);
+                }
+            }
+            const size_t npix = comp.size();
+            if (npix < 3 || npix > 5000) continue;
+            double sum_flux = 0.0, sum_x = 0.0, sum_y = 0.0, peak_val = 0.0;
+            for (long long q : comp) {
+                const double w = std::fmax((double)sp.val[q] - bg_median, 0.0);
+                sum_flux += w;
+                sum_x += (double)sp.col[q] * w;
+                sum_y += (double)row_of(q) * w;
+                peak_val = std::fmax(peak_val, w);
+            }
+            if (sum_flux <= 0.0) continue;
+            const double cx = sum_x / sum_flux, cy = sum_y / sum_flux;
+            double sum_r2 = 0.0, sum_xx = 0.0, sum_yy = 0.0, sum_xy = 0.0;
+            for (long long q : comp) {
+                const double w = std::fmax((double)sp.val[q] - bg_median, 0.0);
+                const double dx = (double)sp.col[q] - cx;
+                const double dy = (double)row_of(q) - cy;
+                sum_r2 += (dx * dx + dy * dy) * w;
+                sum_xx += dx * dx * w;
+                sum_yy += dy * dy * w;
+                sum_xy += dx * dy * w;
+            }
+            const double sigma_star = std::sqrt(sum_r2 / (2.0 * sum_flux));
+            const double fwhm = sigma_star * 2.3548200450309493;
+            if (fwhm < 0.5 || fwhm > 30.0) continue;
+            const double ixx = sum_xx / sum_flux, iyy = sum_yy / sum_flux, ixy = sum_xy / sum_flux;
+            const double trace = ixx + iyy;
+            const double det = std::fmax(ixx * iyy - ixy * ixy, 0.0);
+            const double disc = std::sqrt(std::fmax((trace * trace / 4.0) - det, 0.0));
+            const double lambda1 = trace / 2.0 + disc;
+            const double lambda2 = std::fmax(trace / 2.0 - disc, 0.0);
+            double ecc = 0.0;
+            if (lambda1 > 1e-15) {
+                ecc = std::sqrt(1.0 - lambda2 / lambda1);
+                ecc = ecc < 0.0 ? 0.0 : (ecc > 1.0 ? 1.0 : ecc);
+            }
+            const double snr = bg_sigma <= DBL_EPSILON ? 0.0 : peak_val / bg_sigma;  // confidence.rs:3-8
+            stars.push_back({cx, cy, sum_flux, fwhm, ecc, peak_val, (uint64_t)npix, snr});
+        }
+    }
+    std::stable_sort(stars.begin(), stars.end(),
+                     [](const ab_star &a, const ab_star &b) { return a.flux > b.flux; });
+    const double dedup_r2 = 9.0, cell = 3.0;
+    std::map<std::pair<size_t, size_t>, std::vector<size_t>> grid;
+    out.clear();
+    for (size_t i = 0; i < stars.size(); ++i) {
+        const ab_star &s = stars[i];
+        const size_t gx = f2us(s.x / cell), gy = f2us(s.y / cell);
+        bool too_close = false;
+        for (size_t ny = (gy ? gy - 1 : 0); ny <= gy + 1 && !too_close; ++ny)
+            for (size_t nx = (gx ? gx - 1 : 0); nx <= gx + 1 && !too_close; ++nx) {
+                auto it = grid.find({ny, nx});
+                if (it == grid.end()) continue;
+                for (size_t j : it->second) {
+                    const double dx = s.x - stars[j].x, dy = s.y - stars[j].y;
+                    if (dx * dx + dy * dy < dedup_r2) {
+                        too_close = true;
+                        break;
+                    }
+                }
+            }
+        if (!too_close) {
+            grid[{gy, gx}].push_back(i);
+            out.push_back(s);
+        }
+    }
+}
+
+// device scratch of the detector inside ctx scratch slot 1
+ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols, Norm nm,
+                           double sigma_threshold, cudaStream_t s, std::vector<ab_star> &stars,
+                           double *bg_median_out, double *bg_sigma_out) {
+    stars.clear();
+    if (rows < 3 || cols < 3) {  // star_detection.rs:89-98
+        *bg_median_out = 0.0;
+        *bg_sigma_out = 1.0;
+        return AB_OK;
+    }
+    if (cols >= ((size_t)1 << 32) || rows >= ((size_t)1 << 31))
+        return ab_fail(ctx, AB_ERR_UNSUPPORTED, "image too large for the detector");
+    const size_t tile_size = std::min(std::max(std::min(rows, cols) / 8, (size_t)32), (size_t)256);
+    const size_t step = std::max(tile_size, (size_t)16);
+    const size_t tiles_y = (rows + step - 1) / step, tiles_x = (cols + step - 1) / step;
+    const size_t n_tiles = tiles_y * tiles_x;
+
+    // scratch slot 1: [med f64 x tiles][sig f64 x tiles][ok int x tiles][row_counts u32 x rows]
+    const size_t off_sig = n_tiles * 8, off_ok = off_sig + n_tiles * 8;
+    const size_t off_rc = (off_ok + n_tiles * 4 + 255) / 256 * 256;
+    const size_t off_ro = (off_rc + rows * 4 + 255) / 256 * 256;
+    const size_t fixed = (off_ro + (rows + 1) * 8 + 255) / 256 * 256;
+    ab_status st = ab_scratch_reserve(ctx, 1, fixed);
+    if (st != AB_OK) return st;
+    char *base = static_cast<char *>(ctx->d_scratch[1]);
+    double *d_med = reinterpret_cast<double *>(base), *d_sig = reinterpret_cast<double *>(base + off_sig);
+    int *d_ok = reinterpret_cast<int *>(base + off_ok);
+    unsigned *d_rc = reinterpret_cast<unsigned *>(base + off_rc);
+    unsigned long long *d_ro = reinterpret_cast<unsigned long long *>(base + off_ro);
+
+    bg_tiles_kernel<<<(unsigned)n_tiles, BG_THREADS, 0, s>>>(d_img, rows, cols, step, tiles_x, nm,
+                                                            d_med, d_sig, d_ok);
+    AB_LAUNCH_CHECK(ctx);
+    std::vector<double> h_med(n_tiles), h_sig(n_tiles);
+    std::vector<int> h_ok(n_tiles);
+    AB_CUDA(ctx, cudaMemcpyAsync(h_med.data(), d_med, n_tiles * 8, cudaMemcpyDeviceToHost, s));
+    AB_CUDA(ctx, cudaMemcpyAsync(h_sig.data(), d_sig, n_tiles * 8, cudaMemcpyDeviceToHost, s));
+    AB_CUDA(ctx, cudaMemcpyAsync(h_ok.data(), d_ok, n_tiles * 4, cudaMemcpyDeviceToHost, s));
+    AB_CUDA(ctx, cudaStreamSynchronize(s));
+    std::vector<double> medians, sigmas;
+    for (size_t t = 0; t < n_tiles; ++t)
+        if (h_ok[t]) {
+            medians.push_back(h_med[t]);
+            sigmas.push_back(h_sig[t]);
+        }
+    double bg_median = 0.0, bg_sigma = 1.0;  // star_detection.rs:70-72
+    if (!medians.empty()) {
+        std::sort(medians.begin(), medians.end());
+        std::sort(sigmas.begin(), sigmas.end());
+        bg_median = medians[medians.size() / 2];
+        bg_sigma = std::fmax(sigmas[sigmas.size() / 2], 1e-10);
+    }
+    *bg_median_out = bg_median;
+    *bg_sigma_out = bg_sigma;
+    const double threshold = bg_median + sigma_threshold * bg_sigma;
+
+    row_count_kernel<<<(unsigned)rows, 256, 0, s>>>(d_img, rows, cols, nm, threshold, d_rc);
+    AB_LAUNCH_CHECK(ctx);
+    std::vector<unsigned> h_rc(rows);
+    AB_CUDA(ctx, cudaMemcpyAsync(h_rc.data(), d_rc, rows * 4, cudaMemcpyDeviceToHost, s));
+    AB_CUDA(ctx, cudaStreamSynchronize(s));
+    SparseImage sp;
+    sp.rows = rows;
+    sp.cols = cols;
+    sp.row_off.resize(rows + 1);
+    sp.row_off[0] = 0;
+    for (size_t r = 0; r < rows; ++r) sp.row_off[r + 1] = sp.row_off[r] + h_rc[r];
+    const size_t nfg = (size_t)sp.row_off[rows];
+    if (nfg) {
+        AB_CUDA(ctx, cudaMemcpyAsync(d_ro, sp.row_off.data(), (rows + 1) * 8, cudaMemcpyHostToDevice, s));
+        const size_t lists = (nfg * 4 + 255) / 256 * 256;
+        st = ab_scratch_reserve(ctx, 2, lists * 2);
+        if (st != AB_OK) return st;
+        unsigned *d_col = reinterpret_cast<unsigned *>(ctx->d_scratch[2]);
+        float *d_val = reinterpret_cast<float *>(static_cast<char *>(ctx->d_scratch[2]) + lists);
+        row_compact_kernel<<<(unsigned)rows, 256, 0, s>>>(d_img, rows, cols, nm, threshold, d_ro, d_col,
+                                                         d_val);
+        AB_LAUNCH_CHECK(ctx);
+        sp.col.resize(nfg);
+        sp.val.resize(nfg);
+        AB_CUDA(ctx, cudaMemcpyAsync(sp.col.data(), d_col, nfg * 4, cudaMemcpyDeviceToHost, s));
+        AB_CUDA(ctx, cudaMemcpyAsync(sp.val.data(), d_val, nfg * 4, cudaMemcpyDeviceToHost, s));
+        AB_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    flood_fill_stars(sp, bg_median, bg_sigma, stars);
+    return AB_OK;
+}
+
+// affine.rs:24-53: percentiles of a strided sample -> (lo, inv_range); on=0 when the reference
+// returns the image unchanged
+ab_status normalize_params(ab_ctx *ctx, const float *d_img, size_t len, cudaStream_t s, Norm *nm) {
+    nm->on = 0;
+    nm->lo = 0.0;
+    nm->inv = 1.0;
+    if (len == 0) return AB_OK;
+    const size_t step = std::max(len / 100000, (size_t)1);
+    const size_t n_s = (len + step - 1) / step;
+    ab_status st = ab_scratch_reserve(ctx, 2, n_s * 4 + 256);
+    if (st != AB_OK) return st;
+    float *d_s = static_cast<float *>(ctx->d_scratch[2]);
+    sample_kernel<<<(unsigned)((n_s + 255) / 256), 256, 0, s>>>(d_img, len, step, d_s, n_s);
+    AB_LAUNCH_CHECK(ctx);
+    std::vector<float> samples(n_s);
+    AB_CUDA(ctx, cudaMemcpyAsync(samples.data(), d_s, n_s * 4, cudaMemcpyDeviceToHost, s));
+    AB_CUDA(ctx, cudaStreamSynchronize(s));
+    size_t w = 0;
+    for (size_t i = 0; i < n_s; ++i)
+        if (std::isfinite(samples[i])) samples[w++] = samples[i];
+    samples.resize(w);
+    if (samples.size() < 100) return AB_OK;
+    std::stable_sort(samples.begin(), samples.end());
+    const double lo = (double)samples[samples.size() / 100];
+    const double hi = (double)samples[samples.size() * 999 / 1000];
+    const double range = hi - lo;
+    if (range < 1e-15) return AB_OK;
+    nm->on = 1;
+    nm->lo = lo;
+    nm->inv = 1.0 / range;
+    return AB_OK;
+}
+
+// ---- aligner host math (affine.rs:272-660), f64 scalar code
+struct Pt {
+    double x, y;
+};
+struct Match {
+    double rx, ry, tx, ty;
+};
+struct Tri {
+    int idx[3];
+    double ratio_mid, ratio_long;
+};
+constexpr double TRIANGLE_TOLERANCE = 0.02;
+constexpr size_t MIN_MATCHES_AFFINE = 6, MIN_MATCHES_RIGID = 4, RANSAC_ITERATIONS = 2000;
+constexpr double RANSAC_INLIER_PX = 3.0, DETECTION_SIGMA = 3.5, MIN_TRIANGLE_SIDE = 15.0;
+constexpr double MIN_INLIER_RATIO = 0.20, MAX_RESIDUAL_PX = 5.0, MAX_OFFSET_FRACTION = 0.40;
+constexpr double MAX_ROTATION_DEG = 30.0, MIN_SCALE = 0.70, MAX_SCALE = 1.40;
+
+inline double pdist(Pt a, Pt b) {
+    const double dx = a.x - b.x, dy = a.y - b.y;
+    return std::sqrt(dx * dx + dy * dy);
+}
+std::vector<Tri> build_triangles(const std::vector<Pt> &s) {
+    std::vector<Tri> tris;
+    const int n = (int)s.size();
+    if (n < 3) return tris;
+    const int limit = std::min(n, 60);
+    for (int i = 0; i < limit; ++i)
+        for (int j = i + 1; j < limit; ++j)
+            for (int k = j + 1; k < limit; ++k) {
+                double sides[3] = {pdist(s[i], s[j]), pdist(s[j], s[k]), pdist(s[i], s[k])};
+                std::stable_sort(sides, sides + 3);
+                if (sides[0] < MIN_TRIANGLE_SIDE) continue;
+                tris.push_back({{i, j, k}, sides[1] / sides[0], sides[2] / sides[0]});
+            }
+    return tris;
+}
+void sort_triangle_vertices(const std::vector<Pt> &s, const int idx[3], unsigned char out[3]) {
+    const int i = idx[0], j = idx[1], k = idx[2];
+    std::pair<int, double> v[3] = {{i, pdist(s[j], s[k])}, {j, pdist(s[i], s[k])}, {k, pdist(s[i], s[j])}};
+    std::stable_sort(v, v + 3, [](const std::pair<int, double> &a, const std::pair<int, double> &b) {
+        return a.second < b.second;
+    });
+    for (int q = 0; q < 3; ++q) out[q] = (unsigned char)v[q].first;
+}
+
+ab_affine aff_identity() { return {1.0, 0.0, 0.0, 0.0, 1.0, 0.0}; }
+inline void amap(const ab_affine &t, double x, double y, double *px, double *py) {
+    *px = t.a * x + t.b * y + t.tx;
+    *py = t.c * x + t.d * y + t.ty;
+}
+bool solve_3x3(const double a[3][3], const double b[3], double x[3]) {
+    const double det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) -
+                       a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+                       a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+    if (std::fabs(det) < 1e-12) return false;
+    const double id = 1.0 / det;
+    const double inv[3][3] = {{(a[1][1] * a[2][2] - a[1][2] * a[2][1]) * id,
+                               (a[0][2] * a[2][1] - a[0][1] * a[2][2]) * id,
+                               (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * id},
+                              {(a[1][2] * a[2][0] - a[1][0] * a[2][2]) * id,
+                               (a[0][0] * a[2][2] - a[0][2] * a[2][0]) * id,
+                               (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * id},
+                              {(a[1][0] * a[2][1] - a[1][1] * a[2][0]) * id,
+                               (a[0][1] * a[2][0] - a[0][0] * a[2][1]) * id,
+                               (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * id}};
+    for (int i = 0; i < 3; ++i) x[i] = inv[i][0] * b[0] + inv[i][1] * b[1] + inv[i][2] * b[2];
+    return true;
+}
+bool solve_ls(const Match *m, size_t n, bool solve_x, double x[3]) {
+    double ata[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, atb[3] = {0, 0, 0};
+    for (size_t q = 0; q < n; ++q) {
+        const double target = solve_x ? m[q].tx : m[q].ty;
+        const double row[3] = {m[q].rx, m[q].ry, 1.0};
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) ata[i][j] += row[i] * row[j];
+            atb[i] += row[i] * target;
+        }
+    }
+    return solve_3x3(ata, atb, x);
+}
+bool fit_affine(const Match *m, size_t n, ab_affine *t) {
+    if (n < 3) return false;
+    double ab[3], cd[3];
+    if (!solve_ls(m, n, true, ab) || !solve_ls(m, n, false, cd)) return false;
+    *t = {ab[0], ab[1], ab[2], cd[0], cd[1], cd[2]};
+    return true;
+}
+bool fit_rigid(const Match *m, size_t n, ab_affine *t) {
+    if (n < 2) return false;
+    double rcx = 0, rcy = 0, tcx = 0, tcy = 0;
+    for (size_t q = 0; q < n; ++q) {
+        rcx += m[q].rx;
+        rcy += m[q].ry;
+        tcx += m[q].tx;
+        tcy += m[q].ty;
+    }
+    const double nf = (double)n;
+    rcx /= nf;
+    rcy /= nf;
+    tcx /= nf;
+    tcy /= nf;
+    double num = 0.0, den = 0.0;
+    for (size_t q = 0; q < n; ++q) {
+        const double drx = m[q].rx - rcx, dry = m[q].ry - rcy, dtx = m[q].tx - tcx, dty = m[q].ty - tcy;
+        num += drx * dty - dry * dtx;
+        den += drx * dtx + dry * dty;
+    }
+    const double theta = std::atan2(num, den), ct = std::cos(theta), sn = std::sin(theta);
+    *t = {ct, -sn, tcx - ct * rcx + sn * rcy, sn, ct, tcy - sn * rcx - ct * rcy};
+    return true;
+}
+double residual(const std::vector<Match> &m, const ab_affine &t) {
+    if (m.empty()) return 0.0;
+    double sum = 0.0;
+    for (const Match &q : m) {
+        double px, py;
+        amap(t, q.rx, q.ry, &px, &py);
+        const double ex = px - q.tx, ey = py - q.ty;
+        sum += std::sqrt(ex * ex + ey * ey);
+    }
+    return sum / (double)m.size();
+}
+bool ransac(const std::vector<Match> &matches, int method, int n_threads_in, ab_align_result *res) {
+    const size_t n = matches.size();
+    const size_t min_sample = method == 0 ? 3 : 2;
+    if (n < min_sample) return false;
+    const size_t num_threads = (size_t)std::max(n_threads_in, 1);
+    const size_t chunk = (RANSAC_ITERATIONS + num_threads - 1) / num_threads;
+    size_t best_inl = 0;
+    ab_affine best_t = aff_identity();
+    std::vector<char> best_mask(n, 0);
+    for (size_t tid = 0; tid < num_threads; ++tid) {  // rayon reduce_with keeps the first maximum
+        uint64_t state = 0xDEADBEEFCAFEBABEull + (uint64_t)tid * 0x9E3779B97F4A7C15ull;
+        auto rnd = [&]() -> size_t {
+            state ^= state << 13;
+            state ^= state >> 7;
+            state ^= state << 17;
+            return (size_t)(state % (uint64_t)n);
+        };
+        size_t lbest = 0;
+        ab_affine lt = aff_identity();
+        std::vector<char> lmask(n, 0), mask(n, 0);
+        for (size_t it = 0; it < chunk; ++it) {
+            size_t sample[3], ns = 0;
+            int attempts = 0;
+            while (ns < min_sample && attempts < 20) {
+                const size_t idx = rnd();
+                bool has = false;
+                for (size_t q = 0; q < ns; ++q) has |= sample[q] == idx;
+                if (!has) sample[ns++] = idx;
+                ++attempts;
+            }
+            if (ns < min_sample) continue;
+            Match sm[3];
+            for (size_t q = 0; q < ns; ++q) sm[q] = matches[sample[q]];
+            ab_affine t;
+            if (!(method == 0 ? fit_affine(sm, ns, &t) : fit_rigid(sm, ns, &t))) continue;
+            std::fill(mask.begin(), mask.end(), 0);
+            size_t inl = 0;
+            for (size_t i = 0; i < n; ++i) {
+                double px, py;
+                amap(t, matches[i].rx, matches[i].ry, &px, &py);
+                const double ex = px - matches[i].tx, ey = py - matches[i].ty;
+                if (std::sqrt(ex * ex + ey * ey) < RANSAC_INLIER_PX) {
+                    ++inl;
+                    mask[i] = 1;
+                }
+            }
+            if (inl > lbest) {
+                lbest = inl;
+                lt = t;
+                lmask = mask;
+            }
+        }
+        if (tid == 0 || lbest > best_inl) {
+            best_inl = lbest;
+            best_t = lt;
+            best_mask = lmask;
+        }
+    }
+    if (best_inl < MIN_MATCHES_RIGID) return false;
+    if ((double)best_inl / (double)n < MIN_INLIER_RATIO) return false;
+    std::vector<Match> inl;
+    for (size_t i = 0; i < n; ++i)
+        if (best_mask[i]) inl.push_back(matches[i]);
+    ab_affine refined;
+    if (!(method == 0 ? fit_affine(inl.data(), inl.size(), &refined)
+                      : fit_rigid(inl.data(), inl.size(), &refined)))
+        refined = best_t;
+    const double res_px = residual(inl, refined);
+    if (res_px > MAX_RESIDUAL_PX) return false;
+    res->transform = refined;
+    res->matched_stars = n;
+    res->inliers = best_inl;
+    res->residual_px = res_px;
+    res->method = method;
+    return true;
+}
+bool sane(const ab_align_result &r, size_t rows, size_t cols) {
+    const ab_affine &t = r.transform;
+    if (std::fabs(t.tx) > (double)cols * MAX_OFFSET_FRACTION ||
+        std::fabs(t.ty) > (double)rows * MAX_OFFSET_FRACTION)
+        return false;
+    if (std::fabs(std::atan2(t.c, t.a) * (180.0 / M_PI)) > MAX_ROTATION_DEG) return false;
+    const double sx = std::sqrt(t.a * t.a + t.c * t.c), sy = std::sqrt(t.b * t.b + t.d * t.d);
+    return !(sx < MIN_SCALE || sx > MAX_SCALE || sy < MIN_SCALE || sy > MAX_SCALE);
+}
+void fallback(ab_align_result *out) {  // affine.rs:243-270; phase correlation is SURVEY N1
+    out->transform = aff_identity();
+    out->matched_stars = 0;
+    out->inliers = 0;
+    out->residual_px = 0.0;
+    out->method = 3;
+}
+
+// match_triangles (affine.rs:320-384): votes on the GPU, greedy 1-1 assignment on the host.
+// Equal-vote pairs are taken in (ref index, tgt index) order (the reference's order is the
+// HashMap iteration order, i.e. unspecified).
+ab_status match_stars(ab_ctx *ctx, const std::vector<Pt> &rs, const std::vector<Pt> &ts,
+                      cudaStream_t s, std::vector<Match> &matches) {
+    matches.clear();
+    const std::vector<Tri> rt = build_triangles(rs), tt = build_triangles(ts);
+    if (rt.empty() || tt.empty()) return AB_OK;
+    auto pack = [](const std::vector<Pt> &st, const std::vector<Tri> &tr, std::vector<double> &mid,
+                   std::vector<double> &lng, std::vector<unsigned char> &srt) {
+        mid.resize(tr.size());
+        lng.resize(tr.size());
+        srt.resize(tr.size() * 3);
+        for (size_t a = 0; a < tr.size(); ++a) {
+            mid[a] = tr[a].ratio_mid;
+            lng[a] = tr[a].ratio_long;
+            sort_triangle_vertices(st, tr[a].idx, &srt[3 * a]);
+        }
+    };
+    std::vector<double> rmid, rlng, tmid, tlng;
+    std::vector<unsigned char> rsrt, tsrt;
+    pack(rs, rt, rmid, rlng, rsrt);
+    pack(ts, tt, tmid, tlng, tsrt);
+    const size_t nr = rt.size(), nt = tt.size();
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t o_rl = al(nr * 8), o_rs = o_rl + al(nr * 8), o_tm = o_rs + al(nr * 3);
+    const size_t o_tl = o_tm + al(nt * 8), o_ts = o_tl + al(nt * 8), o_v = o_ts + al(nt * 3);
+    const size_t total = o_v + MAX_STARS * MAX_STARS * 4;
+    ab_status st = ab_scratch_reserve(ctx, 2, total);
+    if (st != AB_OK) return st;
+    char *b = static_cast<char *>(ctx->d_scratch[2]);
+    AB_CUDA(ctx, cudaMemcpyAsync(b, rmid.data(), nr * 8, cudaMemcpyHostToDevice, s));
+    AB_CUDA(ctx, cudaMemcpyAsync(b + o_rl, rlng.data(), nr * 8, cudaMemcpyHostToDevice, s));
+    AB_CUDA(ctx, cudaMemcpyAsync(b + o_rs, rsrt.data(), nr * 3, cudaMemcpyHostToDevice, s));
+    AB_CUDA(ctx, cudaMemcpyAsync(b + o_tm, tmid.data(), nt * 8, cudaMemcpyHostToDevice, s));
+    AB_CUDA(ctx, cudaMemcpyAsync(b + o_tl, tlng.data(), nt * 8, cudaMemcpyHostToDevice, s));
+    AB_CUDA(ctx, cudaMemcpyAsync(b + o_ts, tsrt.data(), nt * 3, cudaMemcpyHostToDevice, s));
+    AB_CUDA(ctx, cudaMemsetAsync(b + o_v, 0, MAX_STARS * MAX_STARS * 4, s));
+    const unsigned grid = (unsigned)std::min<size_t>((nr + 255) / 256, (size_t)ctx->sm_count * 2);
+    AB_CUDA(ctx, cudaFuncSetAttribute(tri_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      MAX_STARS * MAX_STARS * 4));
+    tri_match_kernel<<<grid, 256, MAX_STARS * MAX_STARS * 4, s>>>(
+        reinterpret_cast<double *>(b), reinterpret_cast<double *>(b + o_rl),
+        reinterpret_cast<unsigned char *>(b + o_rs), (int)nr, reinterpret_cast<double *>(b + o_tm),
+        reinterpret_cast<double *>(b + o_tl), reinterpret_cast<unsigned char *>(b + o_ts), (int)nt,
+        TRIANGLE_TOLERANCE, reinterpret_cast<unsigned *>(b + o_v));
+    AB_LAUNCH_CHECK(ctx);
+    std::vector<unsigned> votes(MAX_STARS * MAX_STARS);
+    AB_CUDA(ctx, cudaMemcpyAsync(votes.data(), b + o_v, votes.size() * 4, cudaMemcpyDeviceToHost, s));
+    AB_CUDA(ctx, cudaStreamSynchronize(s));
+    struct PV {
+        int ri, ti;
+        unsigned v;
+    };
+    std::vector<PV> pairs;
+    for (int ri = 0; ri < (int)rs.size(); ++ri)
+        for (int ti = 0; ti < (int)ts.size(); ++ti)
+            if (votes[ri * MAX_STARS + ti]) pairs.push_back({ri, ti, votes[ri * MAX_STARS + ti]});
+    std::stable_sort(pairs.begin(), pairs.end(), [](const PV &a, const PV &b) { return a.v > b.v; });
+    std::vector<char> ur(rs.size(), 0), ut(ts.size(), 0);
+    for (const PV &p : pairs) {
+        if (ur[p.ri] || ut[p.ti]) continue;
+        ur[p.ri] = 1;
+        ut[p.ti] = 1;
+        matches.push_back({rs[p.ri].x, rs[p.ri].y, ts[p.ti].x, ts[p.ti].y});
+    }
+    return AB_OK;
+}
+
+ab_status align_on_device(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t rows,
+                          size_t cols, int n_threads, cudaStream_t s, ab_align_result *out) {
+    std::vector<ab_star> rst, tst;
+    double bm, bs;
+    Norm nr, nt;
+    ab_status st = normalize_params(ctx, d_ref, rows * cols, s, &nr);
+    if (st != AB_OK) return st;
+    st = detect_on_device(ctx, d_ref, rows, cols, nr, DETECTION_SIGMA, s, rst, &bm, &bs);
+    if (st != AB_OK) return st;
+    st = normalize_params(ctx, d_tgt, rows * cols, s, &nt);
+    if (st != AB_OK) return st;
+    st = detect_on_device(ctx, d_tgt, rows, cols, nt, DETECTION_SIGMA, s, tst, &bm, &bs);
+    if (st != AB_OK) return st;
+    std::vector<Pt> rs, ts;
+    for (size_t i = 0; i < std::min(rst.size(), (size_t)MAX_STARS); ++i) rs.push_back({rst[i].x, rst[i].y});
+    for (size_t i = 0; i < std::min(tst.size(), (size_t)MAX_STARS); ++i) ts.push_back({tst[i].x, tst[i].y});
+    if (rs.size() < MIN_MATCHES_RIGID || ts.size() < MIN_MATCHES_RIGID) {
+        fallback(out);
+        return AB_OK;
+    }
+    std::vector<Match> matches;
+    st = match_stars(ctx, rs, ts, s, matches);
+    if (st != AB_OK) return st;
+    if (matches.size() < MIN_MATCHES_RIGID) {
+        fallback(out);
+        return AB_OK;
+    }
+    ab_align_result r;
+    if (matches.size() >= MIN_MATCHES_AFFINE && ransac(matches, 0, n_threads, &r) && sane(r, rows, cols)) {
+        *out = r;
+        return AB_OK;
+    }
+    if (ransac(matches, 1, n_threads, &r) && sane(r, rows, cols)) {
+        *out = r;
+        return AB_OK;
+    }
+    fallback(out);
+    return AB_OK;
+}
+
+ab_status upload(ab_ctx *ctx, int slot, const float *h, size_t len, float **d) {
+    ab_status st = ab_scratch_reserve(ctx, slot, len * 4 + 256);
+    if (st != AB_OK) return st;
+    *d = static_cast<float *>(ctx->d_scratch[slot]);
+    AB_CUDA(ctx, cudaMemcpyAsync(*d, h, len * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return AB_OK;
+}
+
+void fill_info(ab_detection_info *info, double bm, double bs, double thr, size_t rows, size_t cols,
+               size_t n) {
+    info->background_median = bm;
+    info->background_sigma = bs;
+    info->threshold_sigma = thr;
+    info->image_width = cols;
+    info->image_height = rows;
+    info->n_stars = n;
+}
+
+}  // namespace
+
+extern "C" {
+
+ab_status ab_detect_stars_dev(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols,
+                              double sigma_threshold, ab_star *stars, size_t max_stars,
+                              ab_detection_info *info, void *stream) {
+    if (!ctx || !info || (max_stars && !stars) || (rows * cols && !d_img)) return AB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    std::vector<ab_star> found;
+    double bm, bs;
+    Norm nm{0, 0.0, 1.0};
+    ab_status st = detect_on_device(ctx, d_img, rows, cols, nm, sigma_threshold,
+                                    (cudaStream_t)stream, found, &bm, &bs);
+    if (st != AB_OK) return st;
+    for (size_t i = 0; i < std::min(found.size(), max_stars); ++i) stars[i] = found[i];
+    fill_info(info, bm, bs, sigma_threshold, rows, cols, found.size());
+    return AB_OK;
+}
+
+ab_status ab_detect_stars(ab_ctx *ctx, const float *img, size_t rows, size_t cols,
+                          double sigma_threshold, ab_star *stars, size_t max_stars,
+                          ab_detection_info *info) {
+    if (!ctx || !info || (max_stars && !stars) || (rows * cols && !img)) return AB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    std::vector<ab_star> found;
+    double bm = 0.0, bs = 1.0;
+    if (rows >= 3 && cols >= 3) {
+        float *d = nullptr;
+        ab_status st = upload(ctx, 0, img, rows * cols, &d);
+        if (st != AB_OK) return st;
+        Norm nm{0, 0.0, 1.0};
+        st = detect_on_device(ctx, d, rows, cols, nm, sigma_threshold, ctx->stream, found, &bm, &bs);
+        if (st != AB_OK) return st;
+    }
+    for (size_t i = 0; i < std::min(found.size(), max_stars); ++i) stars[i] = found[i];
+    fill_info(info, bm, bs, sigma_threshold, rows, cols, found.size());
+    return AB_OK;
+}
+
+// estimate_background, star_detection.rs:32-84, for a caller-chosen tile size
+ab_status ab_estimate_background(ab_ctx *ctx, const float *img, size_t rows, size_t cols,
+                                 size_t tile_size, double *median, double *sigma) {
+    if (!ctx || !img || !median || !sigma) return AB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    *median = 0.0;
+    *sigma = 1.0;
+    if (rows == 0 || cols == 0) return AB_OK;
+    float *d = nullptr;
+    ab_status st = upload(ctx, 0, img, rows * cols, &d);
+    if (st != AB_OK) return st;
+    const size_t step = std::max(tile_size, (size_t)16);
+    const size_t tiles_y = (rows + step - 1) / step, tiles_x = (cols + step - 1) / step;
+    const size_t n_tiles = tiles_y * tiles_x;
+    st = ab_scratch_reserve(ctx, 1, n_tiles * 20 + 256);
+    if (st != AB_OK) return st;
+    char *base = static_cast<char *>(ctx->d_scratch[1]);
+    double *d_med = reinterpret_cast<double *>(base), *d_sig = reinterpret_cast<double *>(base + n_tiles * 8);
+    int *d_ok = reinterpret_cast<int *>(base + n_tiles * 16);
+    Norm nm{0, 0.0, 1.0};
+    bg_tiles_kernel<<<(unsigned)n_tiles, BG_THREADS, 0, ctx->stream>>>(d, rows, cols, step, tiles_x,
+                                                                      nm, d_med, d_sig, d_ok);
+    AB_LAUNCH_CHECK(ctx);
+    std::vector<double> h_med(n_tiles), h_sig(n_tiles);
+    std::vector<int> h_ok(n_tiles);
+    AB_CUDA(ctx, cudaMemcpyAsync(h_med.data(), d_med, n_tiles * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    AB_CUDA(ctx, cudaMemcpyAsync(h_sig.data(), d_sig, n_tiles * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    AB_CUDA(ctx, cudaMemcpyAsync(h_ok.data(), d_ok, n_tiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    AB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<double> medians, sigmas;
+    for (size_t t = 0; t < n_tiles; ++t)
+        if (h_ok[t]) {
+            medians.push_back(h_med[t]);
+            sigmas.push_back(h_sig[t]);
+        }
+    if (medians.empty()) return AB_OK;
+    std::sort(medians.begin(), medians.end());
+    std::sort(sigmas.begin(), sigmas.end());
+    *median = medians[medians.size() / 2];
+    *sigma = std::fmax(sigmas[sigmas.size() / 2], 1e-10);
+    return AB_OK;
+}
+
+// normalize_for_detection, affine.rs:24-53 (materialised; the aligner fuses it into its loads)
+ab_status ab_normalize_for_detection(ab_ctx *ctx, const float *img, size_t len, float *out) {
+    if (!ctx || (len && (!img || !out))) return AB_ERR_INVALID;
+    if (len == 0) return AB_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    float *d = nullptr;
+    ab_status st = upload(ctx, 0, img, len, &d);
+    if (st != AB_OK) return st;
+    Norm nm;
+    st = normalize_params(ctx, d, len, ctx->stream, &nm);
+    if (st != AB_OK) return st;
+    if (!nm.on) {
+        std::memcpy(out, img, len * 4);
+        return AB_OK;
+    }
+    st = ab_scratch_reserve(ctx, 1, len * 4 + 256);
+    if (st != AB_OK) return st;
+    float *d_out = static_cast<float *>(ctx->d_scratch[1]);
+    normalize_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(d, len, nm, d_out);
+    AB_LAUNCH_CHECK(ctx);
+    AB_CUDA(ctx, cudaMemcpyAsync(out, d_out, len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    AB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AB_OK;
+}
+
+ab_status ab_align_affine_dev(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t rows,
+                              size_t cols, int n_threads, ab_align_result *out, void *stream) {
+    if (!ctx || !out || !d_ref || !d_tgt) return AB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    return align_on_device(ctx, d_ref, d_tgt, rows, cols, n_threads, (cudaStream_t)stream, out);
+}
+
+ab_status ab_align_affine(ab_ctx *ctx, const float *ref, const float *tgt, size_t rows, size_t cols,
+                          int n_threads, ab_align_result *out) {
+    if (!ctx || !out || !ref || !tgt) return AB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    // both planes side by side in scratch slot 0
+    const size_t plane = (rows * cols * 4 + 255) / 256 * 256;
+    ab_status st = ab_scratch_reserve(ctx, 0, plane * 2 + 256);
+    if (st != AB_OK) return st;
+    float *d_ref = static_cast<float *>(ctx->d_scratch[0]);
+    float *d_tgt = reinterpret_cast<float *>(static_cast<char *>(ctx->d_scratch[0]) + plane);
+    AB_CUDA(ctx, cudaMemcpyAsync(d_ref, ref, rows * cols * 4, cudaMemcpyHostToDevice, ctx->stream));
+    AB_CUDA(ctx, cudaMemcpyAsync(d_tgt, tgt, rows * cols * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return align_on_device(ctx, d_ref, d_tgt, rows, cols, n_threads, ctx->stream, out);
+}
+
+// match_triangles on caller-provided star lists (x, y pairs): matches_out = 4 doubles per match
+ab_status ab_match_stars(ab_ctx *ctx, const double *ref_xy, size_t n_ref, const double *tgt_xy,
+                         size_t n_tgt, double *matches_out, size_t max_matches, size_t *n_matches) {
+    if (!ctx || !n_matches || (n_ref && !ref_xy) || (n_tgt && !tgt_xy)) return AB_ERR_INVALID;
+    if (n_ref > MAX_STARS || n_tgt > MAX_STARS)
+        return ab_fail(ctx, AB_ERR_INVALID, "at most %d stars per list (MAX_STARS)", MAX_STARS);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    std::vector<Pt> rs(n_ref), ts(n_tgt);
+    for (size_t i = 0; i < n_ref; ++i) rs[i] = {ref_xy[2 * i], ref_xy[2 * i + 1]};
+    for (size_t i = 0; i < n_tgt; ++i) ts[i] = {tgt_xy[2 * i], tgt_xy[2 * i + 1]};
+    std::vector<Match> m;
+    ab_status st = match_stars(ctx, rs, ts, ctx->stream, m);
+    if (st != AB_OK) return st;
+    *n_matches = m.size();
+    for (size_t i = 0; i < std::min(m.size(), max_matches); ++i) {
+        matches_out[4 * i] = m[i].rx;
+        matches_out[4 * i + 1] = m[i].ry;
+        matches_out[4 * i + 2] = m[i].tx;
+        matches_out[4 * i + 3] = m[i].ty;
+    }
+    return AB_OK;
+}
+
+// ransac_affine (affine.rs:400-517), host scalar code: method 0 affine / 1 rigid; returns
+// AB_OK with *found = 0 when the reference returns None
+ab_status ab_ransac_affine(const double *matches, size_t n, int method, int n_threads,
+                           ab_align_result *out, int *found) {
+    if (!out || !found || (n && !matches)) return AB_ERR_INVALID;
+    std::vector<Match> m(n);
+    for (size_t i = 0; i < n; ++i)
+        m[i] = {matches[4 * i], matches[4 * i + 1], matches[4 * i + 2], matches[4 * i + 3]};
+    *found = ransac(m, method, n_threads, out) ? 1 : 0;
+    return AB_OK;
+}
+
+}  // extern "C"

@@ -265,6 +265,35 @@ ab_status ab_resample_bicubic_dev(ab_ctx *ctx, const float *d_src, size_t src_ro
                                   size_t target_rows, size_t target_cols, float *d_out,
                                   void *stream);
 
+/* ---------------------------------------------------------------- stars / alignment
+ * detect_stars, core/analysis/star_detection.rs:86-258.  Up to max_stars stars (flux-descending,
+ * deduplicated) are written; info->n_stars is the number found. */
+ab_status ab_detect_stars(ab_ctx *ctx, const float *img, size_t rows, size_t cols,
+                          double sigma_threshold, ab_star *stars, size_t max_stars,
+                          ab_detection_info *info);
+ab_status ab_detect_stars_dev(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols,
+                              double sigma_threshold, ab_star *stars, size_t max_stars,
+                              ab_detection_info *info, void *stream);
+/* estimate_background, star_detection.rs:32-84 */
+ab_status ab_estimate_background(ab_ctx *ctx, const float *img, size_t rows, size_t cols,
+                                 size_t tile_size, double *median, double *sigma);
+/* normalize_for_detection, core/alignment/affine.rs:24-53 */
+ab_status ab_normalize_for_detection(ab_ctx *ctx, const float *img, size_t len, float *out);
+/* align_channel_affine, affine.rs:129-212.  n_threads stands for rayon::current_num_threads(),
+ * which seeds the reference's RANSAC streams (affine.rs:410-416).  The phase-correlation fallback
+ * (affine.rs:243-270, rustfft) is not built: method = 3 (identity) where the reference would try it. */
+ab_status ab_align_affine(ab_ctx *ctx, const float *ref, const float *tgt, size_t rows, size_t cols,
+                          int n_threads, ab_align_result *out);
+ab_status ab_align_affine_dev(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t rows,
+                              size_t cols, int n_threads, ab_align_result *out, void *stream);
+/* build_triangles + match_triangles, affine.rs:279-384, on (x, y) star lists (<= 120 each);
+ * matches_out receives (ref x, ref y, tgt x, tgt y) per match */
+ab_status ab_match_stars(ab_ctx *ctx, const double *ref_xy, size_t n_ref, const double *tgt_xy,
+                         size_t n_tgt, double *matches_out, size_t max_matches, size_t *n_matches);
+/* ransac_affine, affine.rs:400-517 (host scalar code); *found = 0 where the reference returns None */
+ab_status ab_ransac_affine(const double *matches, size_t n, int method, int n_threads,
+                           ab_align_result *out, int *found);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,9 @@ class AlignResultC(C.Structure):
                 ("residual_px", C.c_double), ("method", C.c_int32)]
 
 
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int)
+
+
 def library_path() -> str:
     return _SO
 
@@ -123,6 +126,8 @@ SIGNATURES = {
     # stats
     "ab_compute_image_stats": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_double, C.c_double, _vp]),
     "ab_image_stats_dev": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_double, C.c_double, _vp, _vp]),
+    "ab_image_stats_sharded_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, C.c_int, C.c_double, C.c_double,
+                                             _vp, _vp]),
     "ab_histogram_u32": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, C.c_double, _vp, _vp]),
     "ab_histogram_u32_dev": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, C.c_double, _vp, _vp, _vp]),
     "ab_downsample_histogram": (C.c_int, [_vp, _sz, _sz, _vp]),

@@ -427,10 +427,74 @@ ab_status run_scan(ab_ctx *ctx, const float *d, size_t len, cudaStream_t s, doub
     return AB_OK;
 }
 
+// Cross-rank reduction hook for row-band sharded images: every histogram / counter
+// the algorithm consumes is summed over ranks before the (identical, replicated) host walk.
+// dtype: 0 f64 sum, 1 u64 sum, 2 f64 min, 3 f64 max.  Null = single GPU.
+struct Reducer {
+    ab_allreduce_fn fn = nullptr;
+    void *user = nullptr;
+    bool on() const { return fn != nullptr; }
+    ab_status run(ab_ctx *ctx, void *buf, size_t count, int dtype) const {
+        if (!fn) return AB_OK;
+        if (fn(user, buf, count, dtype) != 0)
+            return ab_fail(ctx, AB_ERR_INVALID, "all-reduce callback failed");
+        return AB_OK;
+    }
+};
+
+// sums a u32 host histogram over ranks (through u64, like the reference's u64 bins)
+ab_status reduce_hist(ab_ctx *ctx, const Reducer &rd, unsigned *h, std::vector<unsigned long long> &wide) {
+    wide.resize(HIST_BINS);
+    for (size_t i = 0; i < HIST_BINS; ++i) wide[i] = h[i];
+    return rd.run(ctx, wide.data(), HIST_BINS, 1);
+}
+
+size_t find_percentile_bin64(const unsigned long long *hist, size_t bins, unsigned long long total,
+                             double pct) {
+    const unsigned long long target = (unsigned long long)std::ceil((double)total * pct);
+    unsigned long long cum = 0;
+    for (size_t i = 0; i < bins; ++i) {
+        cum += hist[i];
+        if (cum >= target) return i;
+    }
+    return bins - 1;
+}
+double interpolate_percentile64(const unsigned long long *hist, size_t bins, unsigned long long total,
+                                double pct, double data_min, double bin_width) {
+    const unsigned long long target = (unsigned long long)std::ceil((double)total * pct);
+    unsigned long long cum = 0;
+    for (size_t i = 0; i < bins; ++i) {
+        const unsigned long long count = hist[i];
+        cum += count;
+        if (cum >= target) {
+            const unsigned long long overshoot = cum - target;
+            const double frac = count > 0 ? 1.0 - ((double)overshoot / (double)count) : 0.5;
+            return data_min + ((double)i + frac) * bin_width;
+        }
+    }
+    return data_min + (double)bins * bin_width;
+}
+double resolve_rank_in_hist64(const unsigned long long *hist, size_t bins, unsigned long long rank,
+                              double region_lo, double sub_bin_width) {
+    if (rank == 0) return region_lo;
+    unsigned long long cum = 0;
+    for (size_t i = 0; i < bins; ++i) {
+        const unsigned long long count = hist[i];
+        cum += count;
+        if (cum >= rank) {
+            const unsigned long long overshoot = cum - rank;
+            const double frac = count > 0 ? 1.0 - ((double)overshoot / (double)count) : 0.5;
+            return region_lo + ((double)i + frac) * sub_bin_width;
+        }
+    }
+    return region_lo + (double)bins * sub_bin_width;
+}
+
 // stats.rs:85-210
 ab_status hist_core(ab_ctx *ctx, const float *d, size_t len, double global_min, double global_max,
-                    cudaStream_t s, ab_image_stats *out) {
+                    cudaStream_t s, ab_image_stats *out, const Reducer &rd = Reducer()) {
     Small sm(ctx);
+    std::vector<unsigned long long> hA, hB;
     const double range = std::fmax(global_max - global_min, 1e-30);
     const double bin_width = range / (double)HIST_BINS;
     const double inv_bin = (double)HIST_BINS / range;
@@ -440,6 +504,9 @@ ab_status hist_core(ab_ctx *ctx, const float *d, size_t len, double global_min, 
     ab_status st = run_hist(ctx, d, len, ValueHistF{global_min, inv_bin}, true, false, s,
                             &global_sum, &total_valid, nullptr);
     if (st != AB_OK) return st;
+    if ((st = reduce_hist(ctx, rd, sm.hA, hA)) != AB_OK) return st;
+    if ((st = rd.run(ctx, &global_sum, 1, 0)) != AB_OK) return st;
+    if ((st = rd.run(ctx, &total_valid, 1, 1)) != AB_OK) return st;
     if (total_valid == 0) {
         stats_default(out);
         return AB_OK;
@@ -448,13 +515,13 @@ ab_status hist_core(ab_ctx *ctx, const float *d, size_t len, double global_min, 
     const double mean = global_sum / (double)n;
     const unsigned long long half_count = (unsigned long long)std::ceil((double)total_valid * 0.5);
 
-    const size_t median_bin = find_percentile_bin(sm.hA, HIST_BINS, total_valid, 0.5);
+    const size_t median_bin = find_percentile_bin64(hA.data(), HIST_BINS, total_valid, 0.5);
     unsigned long long count_before_median = 0;
-    for (size_t i = 0; i < median_bin; ++i) count_before_median += sm.hA[i];
+    for (size_t i = 0; i < median_bin; ++i) count_before_median += hA[i];
     const double median_bin_lo = global_min + (double)median_bin * bin_width;
     const double median_bin_hi = median_bin_lo + bin_width;
     const double coarse_median =
-        interpolate_percentile(sm.hA, HIST_BINS, total_valid, 0.5, global_min, bin_width);
+        interpolate_percentile64(hA.data(), HIST_BINS, total_valid, 0.5, global_min, bin_width);
 
     const double dev_range = range;
     const double dev_bw = dev_range / (double)HIST_BINS;
@@ -467,13 +534,15 @@ ab_status hist_core(ab_ctx *ctx, const float *d, size_t len, double global_min, 
                   RefineDevF{median_bin_lo, median_bin_hi, refine_inv, dev_inv, coarse_med_f32},
                   true, true, s, nullptr, nullptr, nullptr);
     if (st != AB_OK) return st;
+    if ((st = reduce_hist(ctx, rd, sm.hA, hA)) != AB_OK) return st;
+    if ((st = reduce_hist(ctx, rd, sm.hB, hB)) != AB_OK) return st;
     const unsigned long long median_rank_in_bin =
         half_count > count_before_median ? half_count - count_before_median : 0;
     const double median_refine_bw = refine_range / (double)HIST_BINS;
-    const double median = resolve_rank_in_hist(sm.hB, HIST_BINS, median_rank_in_bin, median_bin_lo,
-                                               median_refine_bw);
+    const double median = resolve_rank_in_hist64(hB.data(), HIST_BINS, median_rank_in_bin,
+                                                 median_bin_lo, median_refine_bw);
 
-    const size_t mad_bin = find_percentile_bin(sm.hA, HIST_BINS, total_valid, 0.5);
+    const size_t mad_bin = find_percentile_bin64(hA.data(), HIST_BINS, total_valid, 0.5);
     const size_t expand_lo = mad_bin > 0 ? mad_bin - 1 : 0;
     const size_t expand_hi = std::min(mad_bin + 2, (size_t)HIST_BINS);
     const double mad_region_lo = (double)expand_lo * dev_bw;
@@ -488,10 +557,12 @@ ab_status hist_core(ab_ctx *ctx, const float *d, size_t len, double global_min, 
                              (float)mad_region_hi},
                   false, true, s, nullptr, nullptr, &count_below);
     if (st != AB_OK) return st;
+    if ((st = reduce_hist(ctx, rd, sm.hB, hB)) != AB_OK) return st;
+    if ((st = rd.run(ctx, &count_below, 1, 1)) != AB_OK) return st;
     const unsigned long long mad_rank = half_count > count_below ? half_count - count_below : 0;
     const double mad_refine_bw = mad_refine_range / (double)HIST_BINS;
     const double mad =
-        resolve_rank_in_hist(sm.hB, HIST_BINS, mad_rank, mad_region_lo, mad_refine_bw);
+        resolve_rank_in_hist64(hB.data(), HIST_BINS, mad_rank, mad_region_lo, mad_refine_bw);
 
     out->min = global_min;
     out->max = global_max;
@@ -601,6 +672,46 @@ ab_status ab_compute_image_stats(ab_ctx *ctx, const float *data, size_t len, int
     ab_status st = upload_plane(ctx, data, len, &d);
     if (st != AB_OK) return st;
     return stats_dispatch(ctx, d, len, mode, known_min, known_max, ctx->stream, out);
+}
+
+// Row-band sharded compute_image_stats (histogram algorithm, stats.rs:75-210): `d_data` is this
+// rank's band, the callback sums / mins / maxes host buffers over all ranks.  Every rank returns
+// the same ImageStats.  Bit-identical to the single-GPU result except `mean` (f64 sum order, G9).
+ab_status ab_image_stats_sharded_dev(ab_ctx *ctx, const float *d_data, size_t len,
+                                     ab_allreduce_fn allreduce, void *user, int use_known_range,
+                                     double known_min, double known_max, ab_image_stats *out,
+                                     void *stream) {
+    if (!ctx || !out || !allreduce || (len && !d_data)) return AB_ERR_INVALID;
+    if (len >= ((size_t)1 << 32))
+        return ab_fail(ctx, AB_ERR_UNSUPPORTED, "bands of 2^32 pixels or more are not supported");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    Reducer rd;
+    rd.fn = allreduce;
+    rd.user = user;
+    double mn = known_min, mx = known_max;
+    const bool known = use_known_range && std::isfinite(known_min) && std::isfinite(known_max) &&
+                       known_min < known_max;
+    if (!known) {
+        double sum = 0.0;
+        unsigned long long n = 0;
+        mn = DBL_MAX;
+        mx = -DBL_MAX;
+        if (len) {
+            ab_status st = run_scan(ctx, d_data, len, s, &mn, &mx, &sum, &n);
+            if (st != AB_OK) return st;
+        }
+        ab_status st = rd.run(ctx, &mn, 1, 2);
+        if (st != AB_OK) return st;
+        if ((st = rd.run(ctx, &mx, 1, 3)) != AB_OK) return st;
+        if ((st = rd.run(ctx, &n, 1, 1)) != AB_OK) return st;
+        if (n == 0) {
+            stats_default(out);
+            return AB_OK;
+        }
+    }
+    return hist_core(ctx, d_data, len, mn, mx, s, out, rd);
 }
 
 // build_histogram, stats.rs:378-421: bins = n_bins u32, edges = n_bins + 1 f64 (host outputs)

@@ -225,6 +225,16 @@ ab_status ab_compute_image_stats(ab_ctx *ctx, const float *data, size_t len, int
 ab_status ab_image_stats_dev(ab_ctx *ctx, const float *d_data, size_t len, int mode,
                              double known_min, double known_max, ab_image_stats *out,
                              void *stream);
+/* Row-band sharded image statistics: each rank passes its band; `allreduce` reduces a
+ * HOST buffer in place over all ranks (dtype 0: f64 sum, 1: u64 sum, 2: f64 min, 3: f64 max;
+ * returns 0 on success) -- e.g. a torch.distributed / NCCL all-reduce.  Always the histogram
+ * algorithm (stats.rs:75-210, the one the reference uses above 4,000,000 px); use_known_range
+ * selects compute_image_stats_with_known_range (stats.rs:25-41).  All ranks get the same result. */
+typedef int (*ab_allreduce_fn)(void *user, void *buf, size_t count, int dtype);
+ab_status ab_image_stats_sharded_dev(ab_ctx *ctx, const float *d_data, size_t len,
+                                     ab_allreduce_fn allreduce, void *user, int use_known_range,
+                                     double known_min, double known_max, ab_image_stats *out,
+                                     void *stream);
 /* build_histogram / compute_histogram_with_stats, stats.rs:373-421: n_bins must be 65536
  * (HISTOGRAM_BINS); bins = n_bins u32, edges = n_bins + 1 f64, both HOST buffers */
 ab_status ab_histogram_u32(ab_ctx *ctx, const float *data, size_t len, size_t n_bins, double dmin,

@@ -1,0 +1,92 @@
+"""2-GPU tests (NCCL): row-band sharded stack and sharded image statistics equal the single-GPU
+results.  Skipped unless the box has at least two GPUs (run with `gpurun --gpus 2`)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import astroburst_b200 as ab
+    from astroburst_b200 import parallel, synth
+
+    ctx = ab.default_context(rank)
+    rows, cols, n = 2304, 2048, 16                      # 4.7 Mpx > 4,000,000 -> histogram algorithm
+    frames = synth.stack_frames(n, 96, cols, seed=3, nan_border=4)
+    rng = np.random.default_rng(1)
+    img = rng.normal(1000.0, 12.0, (rows, cols)).astype(np.float32)
+    img[:50] = 0.0
+    img.reshape(-1)[rng.integers(0, rows * cols, 20000)] += rng.uniform(100, 30000, 20000).astype(np.float32)
+    res = {}
+    # --- sharded statistics
+    r0, r1 = parallel.row_band(rows, rank, world)
+    band = torch.from_numpy(img[r0:r1]).to(dev).contiguous()
+    cb = parallel.make_allreduce(device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    st = parallel.compute_image_stats_sharded(band.data_ptr(), band.numel(), cb, stream=s, ctx=ctx)
+    res["stats"] = (st.min, st.max, st.median, st.mad, st.sigma, st.mean, int(st.valid_count))
+    kr = parallel.compute_image_stats_sharded(band.data_ptr(), band.numel(), cb, known_range=(5.0, 40000.0),
+                                              stream=s, ctx=ctx)
+    res["stats_kr"] = (kr.min, kr.max, kr.median, kr.mad, kr.sigma, int(kr.valid_count))
+    # --- sharded stack: each rank combines its row band of all frames, counters are all-reduced
+    f0, f1 = parallel.row_band(96, rank, world)
+    t = [torch.from_numpy(f[f0:f1].copy()).to(dev) for f in frames]
+    out = torch.empty((f1 - f0, cols), dtype=torch.float32, device=dev)
+    rej = torch.zeros(1, dtype=torch.int64, device=dev)
+    ab.stack_images_device([x.data_ptr() for x in t], out.numel(), ab.StackConfig(3.0, 3.0, 5, False),
+                           out.data_ptr(), rej.data_ptr(), s, ctx)
+    parallel.allreduce_rejected(rej)
+    torch.cuda.synchronize()
+    res["stack_band"] = out.cpu().numpy()
+    res["rej"] = int(rej)
+    q.put((rank, res))
+    dist.destroy_process_group()
+
+
+def test_sharded_equals_single_gpu(orc):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import astroburst_b200 as ab
+    from astroburst_b200 import synth
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    rows, cols, n = 2304, 2048, 16
+    rng = np.random.default_rng(1)
+    img = rng.normal(1000.0, 12.0, (rows, cols)).astype(np.float32)
+    img[:50] = 0.0
+    img.reshape(-1)[rng.integers(0, rows * cols, 20000)] += rng.uniform(100, 30000, 20000).astype(np.float32)
+    one = ab.imaging.compute_image_stats(img)
+    want = (one.min, one.max, one.median, one.mad, one.sigma)
+    for r in (0, 1):
+        got = out[r]["stats"]
+        assert got[:5] == want and got[6] == one.valid_count
+        assert abs(got[5] - one.mean) <= 1e-12 * abs(one.mean)
+    o = orc.compute_image_stats_with_known_range(img, 5.0, 40000.0)
+    assert out[0]["stats_kr"] == out[1]["stats_kr"] == (o.min, o.max, o.median, o.mad, o.sigma, o.valid_count)
+    frames = synth.stack_frames(n, 96, cols, seed=3, nan_border=4)
+    want_img, want_rej = orc.stack_images(list(frames), 3.0, 3.0, 5)
+    got_img = np.concatenate([out[0]["stack_band"], out[1]["stack_band"]])
+    assert np.array_equal(got_img, want_img)
+    assert out[0]["rej"] == out[1]["rej"] == want_rej

@@ -1,0 +1,97 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: band partition, the frame->band
+plan and the all-reduce callback the sharded statistics call back into."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_row_band_partition():
+    from astroburst_b200.parallel import row_band
+
+    for rows in (0, 1, 7, 4096, 12451):
+        for world in (1, 2, 3, 8):
+            bands = [row_band(rows, r, world) for r in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == rows
+            assert all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
+            sizes = [b[1] - b[0] for b in bands]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        row_band(10, 3, 2)
+
+
+def test_frame_to_band_plan_covers_everything():
+    from astroburst_b200.parallel import frame_to_band_plan, row_band
+
+    n_frames, rows, world = 256, 4096, 8
+    plan = frame_to_band_plan(n_frames, rows, world)
+    seen = np.zeros((n_frames, rows), np.int32)
+    per_src = [0] * world
+    for src in range(world):
+        for dst in range(world):
+            for f, r0, r1 in plan[src][dst]:
+                assert (r0, r1) == row_band(rows, dst, world)
+                seen[f, r0:r1] += 1
+                per_src[src] += 1
+    assert (seen == 1).all()
+    assert len(set(per_src)) == 1       # 32 frames per rank (config 5)
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from astroburst_b200.parallel import allreduce_rejected, make_allreduce
+
+    cb = make_allreduce()
+    res = {}
+    # what libastroburst_cuda does: hand the callback a raw host buffer
+    hist = np.arange(65536, dtype=np.uint64) * np.uint64(rank + 1)
+    assert cb(None, hist.ctypes.data, hist.size, 1) == 0
+    res["hist_ok"] = bool((hist == np.arange(65536, dtype=np.uint64) * np.uint64(3)).all())
+    s = np.array([1.5 + rank], np.float64)
+    cb(None, s.ctypes.data, 1, 0)
+    res["sum"] = float(s[0])
+    mn = np.array([10.0 - rank], np.float64)
+    mx = np.array([10.0 + rank], np.float64)
+    cb(None, mn.ctypes.data, 1, 2)
+    cb(None, mx.ctypes.data, 1, 3)
+    res["min"], res["max"] = float(mn[0]), float(mx[0])
+    rej = torch.tensor([100 + rank], dtype=torch.int64)
+    res["rej"] = int(allreduce_rejected(rej))
+    # sharded statistics by the reference algorithm on CPU tensors, to pin the data flow the GPU
+    # path follows: band-local histograms summed over ranks == histogram of the whole image
+    rng = np.random.default_rng(0)
+    img = rng.normal(1000, 12, (64, 128)).astype(np.float32)
+    from astroburst_b200.parallel import row_band
+    r0, r1 = row_band(64, rank, world)
+    band = img[r0:r1]
+    lo, hi = float(img.min()), float(img.max())
+    idx = np.minimum(((band.astype(np.float64) - lo) * (65536 / (hi - lo))).astype(np.int64), 65535)
+    h = np.bincount(idx.reshape(-1), minlength=65536).astype(np.uint64)
+    cb(None, h.ctypes.data, h.size, 1)
+    full = np.minimum(((img.astype(np.float64) - lo) * (65536 / (hi - lo))).astype(np.int64), 65535)
+    res["band_hist_ok"] = bool((h == np.bincount(full.reshape(-1), minlength=65536).astype(np.uint64)).all())
+    q.put((rank, res))
+    dist.destroy_process_group()
+
+
+def test_allreduce_callback_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in (0, 1):
+        assert out[r]["hist_ok"] and out[r]["band_hist_ok"]
+        assert out[r]["sum"] == 4.0 and out[r]["min"] == 9.0 and out[r]["max"] == 11.0
+        assert out[r]["rej"] == 201

@@ -374,22 +374,23 @@ stack_tile_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigm
 constexpr int WQ_CAP = 64;         // ring slots per warp (power of two)
 constexpr int WARPS_PER_BLOCK = 8;
 
-template <int P>
+template <int P, int CAP = WQ_CAP>
 struct WarpQueue {
-    float v[P][WQ_CAP];
-    float lastc[WQ_CAP];
-    unsigned meta[WQ_CAP];
-    unsigned rej0[WQ_CAP];
-    unsigned pix[WQ_CAP];  // pixel index relative to the launch (npix < 2^32 per launch)
+    static constexpr int kCap = CAP;
+    float v[P][CAP];
+    float lastc[CAP];
+    unsigned meta[CAP];
+    unsigned rej0[CAP];
+    unsigned pix[CAP];  // pixel index relative to the launch (npix < 2^32 per launch)
 };
 
 // finish `cnt` (<= 32) parked pixels starting at ring position head; lane i takes entry i
-template <int P>
-__device__ __forceinline__ void drain_batch(WarpQueue<P> &q, unsigned head, unsigned cnt, int lane,
+template <int P, int CAP>
+__device__ __forceinline__ void drain_batch(WarpQueue<P, CAP> &q, unsigned head, unsigned cnt, int lane,
                                             float sigma_low, float sigma_high, unsigned max_iter,
                                             float *__restrict__ out, unsigned &local_rej) {
     if ((unsigned)lane < cnt) {
-        const unsigned slot = (head + lane) & (WQ_CAP - 1);
+        const unsigned slot = (head + lane) & (CAP - 1);
         const unsigned meta = q.meta[slot];
         const unsigned it0 = meta >> 16;
         int a, b, n;
@@ -403,7 +404,7 @@ __device__ __forceinline__ void drain_batch(WarpQueue<P> &q, unsigned head, unsi
             b = (meta >> 8) & 0xff;
         }
         unsigned rej = q.rej0[slot];
-        const float r = clip_combine_sorted_mem(&q.v[0][slot], WQ_CAP, n, a, b, it0, q.lastc[slot],
+        const float r = clip_combine_sorted_mem(&q.v[0][slot], CAP, n, a, b, it0, q.lastc[slot],
                                                 rej, sigma_low, sigma_high, max_iter);
         __stcs(out + q.pix[slot], r);
         local_rej += rej;
@@ -411,8 +412,8 @@ __device__ __forceinline__ void drain_batch(WarpQueue<P> &q, unsigned head, unsi
     __syncwarp();
 }
 
-template <int P>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 3)
+template <int P, int kMinBlocks, bool kPrefetch>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, kMinBlocks)
 stack_warp_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigma_low,
                   float sigma_high, unsigned max_iter, float *__restrict__ out,
                   unsigned long long *__restrict__ rejected_total) {
@@ -427,6 +428,14 @@ stack_warp_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigm
     const size_t n_groups = (npix + 31) / 32;
     const size_t warp_global = (size_t)blockIdx.x * WARPS_PER_BLOCK + warp;
     const size_t warp_stride = (size_t)gridDim.x * WARPS_PER_BLOCK;
+    float nxt[kPrefetch ? P : 1];
+    if constexpr (kPrefetch) {
+        const size_t p0 = warp_global * 32 + lane;
+        if (p0 < npix) {
+#pragma unroll
+            for (int f = 0; f < P; ++f) nxt[f] = __ldcs(ft.p[f] + p0);
+        }
+    }
     for (size_t g = warp_global; g < n_groups; g += warp_stride) {
         const size_t p = g * 32 + lane;
         const bool active = p < npix;
@@ -434,11 +443,20 @@ stack_warp_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigm
         float s[P];
         float result = 0.0f;
         unsigned rej = 0, meta = 0;
+        if constexpr (kPrefetch) {
+#pragma unroll
+            for (int f = 0; f < P; ++f) s[f] = nxt[f];
+            const size_t pn = p + warp_stride * 32;  // software pipeline: next group's loads in flight
+            if (pn < npix) {
+#pragma unroll
+                for (int f = 0; f < P; ++f) nxt[f] = __ldcs(ft.p[f] + pn);
+            }
+        }
         if (active) {
             float probe = 0.0f;
 #pragma unroll
             for (int f = 0; f < P; ++f) {
-                s[f] = __ldcs(ft.p[f] + p);
+                if constexpr (!kPrefetch) s[f] = __ldcs(ft.p[f] + p);
                 probe = fmaf(s[f], 0.0f, probe);  // NaN iff any sample is non-finite
             }
             int n = P;
@@ -460,10 +478,10 @@ stack_warp_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigm
         }
         const unsigned pmask = __ballot_sync(0xffffffffu, park);
         if (pmask) {
-            const unsigned c = __popc(pmask);
-            // count < 32 here and c <= 32, so the 64-slot ring always has room
+            // count < 32 here and at most 32 lanes park, so the 64-slot ring always has room
             if (park) {
-                const unsigned slot = (head + count + __popc(pmask & ((1u << lane) - 1u))) & (WQ_CAP - 1);
+                const unsigned slot =
+                    (head + count + __popc(pmask & ((1u << lane) - 1u))) & (WQ_CAP - 1);
 #pragma unroll
                 for (int f = 0; f < P; ++f) q.v[f][slot] = s[f];
                 q.meta[slot] = meta;
@@ -471,21 +489,16 @@ stack_warp_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigm
                 q.rej0[slot] = rej;
                 q.pix[slot] = (unsigned)p;
             }
-            count += c;
+            count += __popc(pmask);
             __syncwarp();
             if (count >= 32u) {
-                drain_batch<P>(q, head, 32u, lane, sigma_low, sigma_high, max_iter, out, local_rej);
+                drain_batch<P, WQ_CAP>(q, head, 32u, lane, sigma_low, sigma_high, max_iter, out, local_rej);
                 head = (head + 32u) & (WQ_CAP - 1);
                 count -= 32u;
             }
         }
     }
-    while (count) {  // leftovers
-        const unsigned d = count < 32u ? count : 32u;
-        drain_batch<P>(q, head, d, lane, sigma_low, sigma_high, max_iter, out, local_rej);
-        head = (head + d) & (WQ_CAP - 1);
-        count -= d;
-    }
+    if (count) drain_batch<P, WQ_CAP>(q, head, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
     const unsigned w = __reduce_add_sync(0xffffffffu, local_rej);
     if (lane == 0 && w) atomicAdd(rejected_total, (unsigned long long)w);
 }
@@ -759,18 +772,19 @@ stack_tma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__ 
 //     of group i+1 overlaps the whole sort of group i;
 //   * the loads become conflict-free LDS with immediate offsets: the ~1.5 ALU-pipe instructions
 //     of 64-bit address arithmetic per global load disappear from the pipe that bounds the kernel.
-constexpr int WT_WARPS = 8;  // 8 warps x ~13.1 KiB (P=32) -> 2 blocks / SM = 16 warps
+constexpr int WT_WARPS = 8;   // 8 warps x ~8.6 KiB (P=32) -> 3 blocks / SM = 24 warps
+constexpr int WT_CAP = 32;    // ring slots per warp; a group that does not fit drains first
 
 template <int P>
 struct WarpTmaSmem {
     alignas(128) float stage[P][32];
-    WarpQueue<P> q;
+    WarpQueue<P, WT_CAP> q;
     alignas(8) unsigned long long full;
     unsigned pad[30];
 };
 
 template <int P, bool kTensorMap>
-__global__ void __launch_bounds__(WT_WARPS * 32, 2)
+__global__ void __launch_bounds__(WT_WARPS * 32, 3)
 stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__ TmapParam tmap,
                   size_t n_groups, float sigma_low, float sigma_high, unsigned max_iter,
                   float *__restrict__ out, unsigned long long *__restrict__ rejected_total) {
@@ -778,7 +792,7 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     WarpTmaSmem<P> &sm = reinterpret_cast<WarpTmaSmem<P> *>(smem_raw)[warp];
-    WarpQueue<P> &q = sm.q;
+    WarpQueue<P, WT_CAP> &q = sm.q;
     const uint32_t bar = smem_u32(&sm.full);
     const uint32_t stage_addr = smem_u32(&sm.stage[0][0]);
     constexpr uint32_t GROUP_BYTES = P * 32 * sizeof(float);
@@ -845,10 +859,16 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
         }
         const unsigned pmask = __ballot_sync(0xffffffffu, park);
         if (pmask) {
-            // count < 32 here and at most 32 lanes park, so the 64-slot ring always has room
+            const unsigned c = __popc(pmask);
+            if (count + c > (unsigned)WT_CAP) {  // make room: finish what is parked (< 32 lanes)
+                drain_batch<P, WT_CAP>(q, head, count, lane, sigma_low, sigma_high, max_iter, out,
+                                       local_rej);
+                head = (head + count) & (WT_CAP - 1);
+                count = 0;
+            }
             if (park) {
                 const unsigned slot =
-                    (head + count + __popc(pmask & ((1u << lane) - 1u))) & (WQ_CAP - 1);
+                    (head + count + __popc(pmask & ((1u << lane) - 1u))) & (WT_CAP - 1);
 #pragma unroll
                 for (int f = 0; f < P; ++f) q.v[f][slot] = s[f];
                 q.meta[slot] = meta;
@@ -856,16 +876,18 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
                 q.rej0[slot] = rej;
                 q.pix[slot] = (unsigned)p;
             }
-            count += __popc(pmask);
+            count += c;
             __syncwarp();
             if (count >= 32u) {
-                drain_batch<P>(q, head, 32u, lane, sigma_low, sigma_high, max_iter, out, local_rej);
-                head = (head + 32u) & (WQ_CAP - 1);
+                drain_batch<P, WT_CAP>(q, head, 32u, lane, sigma_low, sigma_high, max_iter, out,
+                                       local_rej);
+                head = (head + 32u) & (WT_CAP - 1);
                 count -= 32u;
             }
         }
     }
-    if (count) drain_batch<P>(q, head, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
+    if (count)
+        drain_batch<P, WT_CAP>(q, head, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
     const unsigned w = __reduce_add_sync(0xffffffffu, local_rej);
     if (lane == 0 && w) atomicAdd(rejected_total, (unsigned long long)w);
 }
@@ -894,18 +916,19 @@ ab_status launch_ldg(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, f
         return ab_fail(ctx, AB_ERR_UNSUPPORTED, "npix %zu >= 2^32 per launch", npix);
     const size_t smem = sizeof(WarpQueue<P>) * WARPS_PER_BLOCK;
     constexpr int threads = WARPS_PER_BLOCK * 32;
-    AB_CUDA(ctx, cudaFuncSetAttribute(stack_warp_kernel<P>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kern)(FrameTable, size_t, float, float, unsigned, float *, unsigned long long *) =
+        stack_warp_kernel<P, 3, false>;
+    if (ctx->stack_variant == 4) kern = stack_warp_kernel<P, 4, false>;
+    if (ctx->stack_variant == 5) kern = stack_warp_kernel<P, 2, true>;
+    AB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    AB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stack_warp_kernel<P>,
-                                                               threads, smem));
+    AB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     const size_t n_blocks_needed = (npix + threads - 1) / threads;
     size_t grid = (size_t)ctx->sm_count * per_sm;  // persistent: one wave, groups strided
     if (grid > n_blocks_needed) grid = n_blocks_needed;
     if (grid < 1) grid = 1;
-    stack_warp_kernel<P><<<(unsigned)grid, threads, smem, stream>>>(ft, npix, sl, sh, max_iter,
-                                                                   d_out, d_rej);
+    kern<<<(unsigned)grid, threads, smem, stream>>>(ft, npix, sl, sh, max_iter, d_out, d_rej);
     AB_LAUNCH_CHECK(ctx);
     return AB_OK;
 }
@@ -929,6 +952,10 @@ ab_status launch_tile(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, 
             cube = cube && stride > 0 && (stride % 4) == 0 && (size_t)stride >= npix;
             TmapParam tm{};
             if (cube) cube = ab_make_stack_tmap(ctx, ft.p[0], npix, (size_t)stride, P, 32, &tm);
+            // scattered frames: P small bulk copies per group measured slower (1.18 ms) than plain
+            // coalesced loads (0.92 ms) -> only the tensor-map form is used unless forced
+            if (!cube && !ctx->force_tma1d)
+                return launch_ldg<P>(ctx, ft, npix, sl, sh, max_iter, d_out, d_rej, stream);
             const size_t smem = sizeof(WarpTmaSmem<P>) * WT_WARPS;
             constexpr int threads = WT_WARPS * 32;
             auto kern = cube ? stack_wtma_kernel<P, true> : stack_wtma_kernel<P, false>;

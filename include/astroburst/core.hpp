@@ -1,0 +1,145 @@
+// core.hpp -- header-only C++ mirror of the reference's `core::*` functions over the C ABI
+// (include/astroburst_cuda.h).  The reference is compiled Rust and no Rust toolchain exists in the
+// build image, so this is the host-language view of the boundary: same function names, argument
+// meaning and error behaviour (anyhow::Error -> std::runtime_error) as the Rust functions cited.
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../astroburst_cuda.h"
+
+namespace astroburst {
+
+struct Error : std::runtime_error {
+    ab_status status;
+    Error(ab_status st, const std::string &msg) : std::runtime_error(msg), status(st) {}
+};
+
+class Context {
+  public:
+    explicit Context(int device = -1) {
+        if (ab_ctx_create(device, &ctx_) != AB_OK) throw Error(AB_ERR_CUDA, "no usable CUDA device");
+    }
+    ~Context() { ab_ctx_destroy(ctx_); }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    ab_ctx *get() const { return ctx_; }
+    void check(ab_status st) const {
+        if (st != AB_OK) throw Error(st, ab_last_error(ctx_));
+    }
+
+  private:
+    ab_ctx *ctx_ = nullptr;
+};
+
+struct Image {  // Array2<f32>: row-major contiguous
+    size_t rows = 0, cols = 0;
+    std::vector<float> data;
+    Image() = default;
+    Image(size_t r, size_t c) : rows(r), cols(c), data(r * c) {}
+};
+
+namespace core {
+
+namespace stacking {
+// types/stacking.rs:4-28
+struct StackConfig {
+    float sigma_low = 3.0f, sigma_high = 3.0f;
+    size_t max_iterations = 5;
+    bool align = true;
+};
+struct StackResult {
+    Image image;
+    size_t frame_count = 0;
+    uint64_t rejected_pixels = 0;
+    std::vector<std::pair<int, int>> offsets;
+};
+// core/stacking/combine.rs:94-193 (frames are cropped to the common minimum like :104-113)
+inline StackResult stack_images(const Context &ctx, const std::vector<Image> &images,
+                                const StackConfig &config) {
+    if (images.empty()) throw Error(AB_ERR_INVALID, "No images to stack");
+    size_t rows = images[0].rows, cols = images[0].cols;
+    for (const Image &im : images) {
+        rows = im.rows < rows ? im.rows : rows;
+        cols = im.cols < cols ? im.cols : cols;
+    }
+    std::vector<Image> cropped;
+    std::vector<const float *> ptrs;
+    for (const Image &im : images) {
+        if (im.rows == rows && im.cols == cols) {
+            ptrs.push_back(im.data.data());
+        } else {
+            cropped.emplace_back(rows, cols);
+            for (size_t r = 0; r < rows; ++r)
+                std::copy(im.data.begin() + r * im.cols, im.data.begin() + r * im.cols + cols,
+                          cropped.back().data.begin() + r * cols);
+        }
+    }
+    if (!cropped.empty()) {  // rebuild the pointer list in frame order
+        ptrs.clear();
+        size_t k = 0;
+        for (const Image &im : images)
+            ptrs.push_back(im.rows == rows && im.cols == cols ? im.data.data() : cropped[k++].data.data());
+    }
+    StackResult res;
+    res.image = Image(rows, cols);
+    res.frame_count = images.size();
+    res.offsets.assign(images.size(), {0, 0});
+    const ab_stack_config cfg{config.sigma_low, config.sigma_high, (uint32_t)config.max_iterations,
+                              config.align ? 1u : 0u};
+    ctx.check(ab_stack_sigma_clip(ctx.get(), ptrs.data(), ptrs.size(), rows, cols, &cfg,
+                                  res.image.data.data(), &res.rejected_pixels));
+    return res;
+}
+}  // namespace stacking
+
+namespace imaging {
+using ImageStats = ab_image_stats;  // types/image.rs:2-10
+using StfParams = ab_stf_params;    // types/image.rs:35-40
+// core/imaging/stats.rs:15-23
+inline ImageStats compute_image_stats(const Context &ctx, const Image &img) {
+    ImageStats st{};
+    ctx.check(ab_compute_image_stats(ctx.get(), img.data.data(), img.data.size(), 0, 0.0, 0.0, &st));
+    return st;
+}
+// core/imaging/stf.rs:13-39 with AutoStfConfig::default()
+inline StfParams auto_stf(const ImageStats &st, double target_bg = 0.25, double shadow_k = -2.8) {
+    const ab_auto_stf_config cfg{target_bg, shadow_k};
+    StfParams p{};
+    ab_auto_stf(&st, &cfg, &p);
+    return p;
+}
+// core/imaging/stf.rs:89-102
+inline std::vector<uint8_t> apply_stf(const Context &ctx, const Image &img, const StfParams &p,
+                                      const ImageStats &st) {
+    std::vector<uint8_t> out(img.data.size());
+    ctx.check(ab_apply_stf_u8(ctx.get(), img.data.data(), img.data.size(), &p, &st, out.data()));
+    return out;
+}
+}  // namespace imaging
+
+namespace alignment {
+using AffineTransform = ab_affine;  // affine.rs:56-63
+// core/alignment/affine.rs:663-690
+inline Image warp_image(const Context &ctx, const Image &img, const AffineTransform &t,
+                        size_t out_rows, size_t out_cols) {
+    Image out(out_rows, out_cols);
+    ctx.check(ab_warp_affine_bicubic(ctx.get(), img.data.data(), img.rows, img.cols, &t, out_rows,
+                                     out_cols, out.data.data()));
+    return out;
+}
+// core/alignment/affine.rs:129-212
+inline ab_align_result align_channel_affine(const Context &ctx, const Image &reference,
+                                            const Image &target, int n_threads) {
+    ab_align_result r{};
+    ctx.check(ab_align_affine(ctx.get(), reference.data.data(), target.data.data(), reference.rows,
+                              reference.cols, n_threads, &r));
+    return r;
+}
+}  // namespace alignment
+
+}  // namespace core
+}  // namespace astroburst

@@ -39,6 +39,7 @@
 namespace abk {
 
 constexpr double MAD_TO_SIGMA = 1.4826;  // types/constants.rs:7
+constexpr unsigned META_FINAL_ONLY = 0x80000000u;  // parked pixel: only the final mean is left
 constexpr int TILE = 256;                // pixels per block iteration = threads per block
 
 __device__ __forceinline__ void ce(float &a, float &b) {
@@ -60,7 +61,30 @@ struct OemNet {
     CePair pr[kMax];
     int count;
     constexpr OemNet() : pr{}, count(0) {
-        for (int p = 1; p < P; p <<= 1)
+        int p0 = 1;
+        if (P % 16 == 0) {
+            // 16-blocks: the 60-comparator, 10-layer 16-input network (Green; verified over all
+            // 2^16 zero-one inputs by tools/verify_network.py) instead of Batcher's 63
+            constexpr short g[60][2] = {
+                {0, 13}, {1, 12}, {2, 15}, {3, 14}, {4, 8},   {5, 6},   {7, 11},  {9, 10},
+                {0, 5},  {1, 7},  {2, 9},  {3, 4},  {6, 13},  {8, 14},  {10, 15}, {11, 12},
+                {0, 1},  {2, 3},  {4, 5},  {6, 8},  {7, 9},   {10, 11}, {12, 13}, {14, 15},
+                {0, 2},  {1, 3},  {4, 10}, {5, 11}, {6, 7},   {8, 9},   {12, 14}, {13, 15},
+                {1, 2},  {3, 12}, {4, 6},  {5, 7},  {8, 10},  {9, 11},  {13, 14},
+                {1, 4},  {2, 6},  {5, 8},  {7, 10}, {9, 13},  {11, 14},
+                {2, 4},  {3, 6},  {9, 12}, {11, 13},
+                {3, 5},  {6, 8},  {7, 9},  {10, 12},
+                {3, 4},  {5, 6},  {7, 8},  {9, 10}, {11, 12},
+                {6, 7},  {8, 9}};
+            for (int blk = 0; blk < P / 16; ++blk)
+                for (int i = 0; i < 60; ++i) {
+                    pr[count].a = (short)(blk * 16 + g[i][0]);
+                    pr[count].b = (short)(blk * 16 + g[i][1]);
+                    ++count;
+                }
+            p0 = 16;
+        }
+        for (int p = p0; p < P; p <<= 1)
             for (int k = p; k >= 1; k >>= 1)
                 for (int j = k % p; j + k < P; j += 2 * k)
                     for (int i = 0; i < k; ++i)
@@ -85,47 +109,90 @@ __device__ __forceinline__ void sort_network(float (&s)[P]) {
         sort_network_impl<P>(s, std::make_integer_sequence<int, OemHolder<P>::net.count>{});
 }
 
-// f64 sum of s[a..b) (ascending samples), 4 interleaved accumulators keyed by j & 3, combined
-// as (acc0 + acc1) + (acc2 + acc3).  The same order is used by every path.
+// ---- f64 sums of the surviving run s[a..b) of the ascending samples.
+//
+// The reference accumulates `v as f64` (combine.rs:51,90).  Converting every sample costs one
+// F2F.F64.F32 each, and that instruction issues at 16 lanes/clk/SM (measured), so the conversions --
+// not the DADDs -- dominate the mean.  When the run is positive and spans at most a factor of two
+// (s[b-1] <= 2 s[a], the normal case for sky-dominated pixels) every difference s[j] - s[a] is
+// exact in f32 (Sterbenz) and a multiple of ulp(s[a]); their non-negative partial sums stay exact
+// in f32 as long as the total is below 2^24 ulps = 2 * 2^floor(log2 s[a]).  Then
+//     sum = len * s[a] + D        (exact in f64: < 2^31 ulps)
+// is the exact real sum, which is also what the reference's f64 accumulation yields for such a run,
+// so the result is bit-identical.  The certificate is checked per pixel; anything else takes the
+// plain f64 accumulation (4 accumulators keyed by the index relative to a, combined pairwise).
+__device__ __forceinline__ float next_pow2_above(float s0) {  // 2^(floor(log2 s0) + 1), s0 normal > 0
+    return __uint_as_float((__float_as_uint(s0) & 0x7f800000u) + 0x00800000u);
+}
+// Register version (all P samples survive).  Differences are taken around the median so the two
+// one-signed partial sums stay small (a no-reject pixel has |s[j] - med| <= ~4.4 MAD); returns
+// false when the certificate fails -- the caller then parks the pixel for the f64 path of phase B.
 template <int P>
-__device__ __forceinline__ double sum_all_reg(const float (&s)[P]) {
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+__device__ __forceinline__ bool mean_all_reg(const float (&s)[P], float &mean_out) {
+    const float s0 = s[0], c = s[P / 2];
+    float lo[2] = {0.0f, 0.0f}, hi[2] = {0.0f, 0.0f};
 #pragma unroll
-    for (int j = 0; j < P; ++j) acc[j & 3] += (double)s[j];
-    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    for (int j = 0; j < P / 2; ++j) lo[j & 1] += s[j] - c;  // <= 0
+#pragma unroll
+    for (int j = P / 2 + 1; j < P; ++j) hi[j & 1] += s[j] - c;  // >= 0
+    const float d_lo = lo[0] + lo[1], d_hi = hi[0] + hi[1];
+    const float T = next_pow2_above(s0);
+    const bool ok = s0 >= 1.17549435e-38f && s[P - 1] <= 2.0f * s0 && d_hi < T && -d_lo < T;
+    const double sum = (double)P * (double)c + (double)(d_hi + d_lo);
+    mean_out = (float)(sum / (double)P);
+    return ok;
 }
 __device__ __forceinline__ double sum_run_mem(const float *s, int stride, int a, int b) {
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-#pragma unroll 1
-    for (int j = a & ~3; j < b; j += 4) {  // accumulator index = sample index & 3, kept static
-        if (j >= a) acc0 += (double)s[j * stride];
-        if (j + 1 >= a && j + 1 < b) acc1 += (double)s[(j + 1) * stride];
-        if (j + 2 >= a && j + 2 < b) acc2 += (double)s[(j + 2) * stride];
-        if (j + 3 >= a && j + 3 < b) acc3 += (double)s[(j + 3) * stride];
+    const float s0 = s[a * stride];
+    if (s0 >= 1.17549435e-38f && s[(b - 1) * stride] <= 2.0f * s0) {
+        const int mid = (a + b) >> 1;
+        const float c = s[mid * stride];
+        float lo = 0.0f, hi = 0.0f;
+#pragma unroll 2
+        for (int j = a; j < mid; ++j) lo += s[j * stride] - c;
+#pragma unroll 2
+        for (int j = mid + 1; j < b; ++j) hi += s[j * stride] - c;
+        const float T = next_pow2_above(s0);
+        if (hi < T && -lo < T) return (double)(b - a) * (double)c + (double)(hi + lo);
     }
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int j = a;
+#pragma unroll 1
+    for (; j + 4 <= b; j += 4) {
+        acc0 += (double)s[j * stride];
+        acc1 += (double)s[(j + 1) * stride];
+        acc2 += (double)s[(j + 2) * stride];
+        acc3 += (double)s[(j + 3) * stride];
+    }
+    if (j < b) acc0 += (double)s[j * stride];
+    if (j + 1 < b) acc1 += (double)s[(j + 1) * stride];
+    if (j + 2 < b) acc2 += (double)s[(j + 2) * stride];
     return (acc0 + acc1) + (acc2 + acc3);
 }
 __device__ __forceinline__ double sumsq_run_mem(const float *s, int stride, int a, int b,
                                                 double mean) {
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int j = a;
 #pragma unroll 1
-    for (int j = a & ~3; j < b; j += 4) {
-        if (j >= a) {
-            const double d = (double)s[j * stride] - mean;
-            acc0 += d * d;
-        }
-        if (j + 1 >= a && j + 1 < b) {
-            const double d = (double)s[(j + 1) * stride] - mean;
-            acc1 += d * d;
-        }
-        if (j + 2 >= a && j + 2 < b) {
-            const double d = (double)s[(j + 2) * stride] - mean;
-            acc2 += d * d;
-        }
-        if (j + 3 >= a && j + 3 < b) {
-            const double d = (double)s[(j + 3) * stride] - mean;
-            acc3 += d * d;
-        }
+    for (; j + 4 <= b; j += 4) {
+        const double e0 = (double)s[j * stride] - mean, e1 = (double)s[(j + 1) * stride] - mean;
+        const double e2 = (double)s[(j + 2) * stride] - mean, e3 = (double)s[(j + 3) * stride] - mean;
+        acc0 += e0 * e0;
+        acc1 += e1 * e1;
+        acc2 += e2 * e2;
+        acc3 += e3 * e3;
+    }
+    if (j < b) {
+        const double e = (double)s[j * stride] - mean;
+        acc0 += e * e;
+    }
+    if (j + 1 < b) {
+        const double e = (double)s[(j + 1) * stride] - mean;
+        acc1 += e * e;
+    }
+    if (j + 2 < b) {
+        const double e = (double)s[(j + 2) * stride] - mean;
+        acc2 += e * e;
     }
     return (acc0 + acc1) + (acc2 + acc3);
 }
@@ -187,6 +254,26 @@ __device__ __forceinline__ float clip_combine_sorted_mem(const float *s, int str
     return (float)(sum_run_mem(s, stride, a, b) / (double)len);
 }
 
+// meta word of a parked pixel: a | b << 8 | it0 << 16, bit 31 = only the final mean is left
+__device__ __forceinline__ void decode_meta(unsigned meta, int P, unsigned &it0, int &n, int &a,
+                                            int &b) {
+    it0 = (meta >> 16) & 0x7fffu;
+    if (meta & META_FINAL_ONLY) {
+        n = P;
+        a = 0;
+        b = P;
+        it0 = 0xffffffffu;  // >= max_iter: the clip loop is skipped
+    } else if (it0 == 0) {
+        n = (meta >> 8) & 0xff;
+        a = 0;
+        b = n;
+    } else {
+        n = P;
+        a = meta & 0xff;
+        b = (meta >> 8) & 0xff;
+    }
+}
+
 // Phase A on a register array of exactly P finite-or-+inf samples (n of them finite).
 // Returns true when `result`/`rejected` are final; false when the pixel must be finished by
 // phase B, in which case s[] is sorted and meta = a | b << 8 | it0 << 16.
@@ -213,8 +300,10 @@ __device__ __forceinline__ bool phase_a(float (&s)[P], int n, float sigma_low, f
         return true;
     } else {
         if (max_iter == 0) {
-            result = (float)(sum_all_reg<P>(s) / (double)P);
-            return true;
+            if (mean_all_reg<P>(s, result)) return true;
+            meta = 0u | ((unsigned)P << 8) | META_FINAL_ONLY;
+            result = 0.0f;
+            return false;
         }
         // iteration 0: upper median, upper-median MAD (combine.rs:37-48)
         const float med = s[P / 2];
@@ -248,8 +337,10 @@ __device__ __forceinline__ bool phase_a(float (&s)[P], int n, float sigma_low, f
             }
         }
         if (nl + nh == 0) {  // removed == 0 -> loop ends (combine.rs:80-82); mean of everything
-            result = (float)(sum_all_reg<P>(s) / (double)P);
-            return true;
+            if (mean_all_reg<P>(s, result)) return true;
+            meta = 0u | ((unsigned)P << 8) | META_FINAL_ONLY;  // rare: f64 accumulation in phase B
+            result = med;
+            return false;
         }
         if (nl + nh >= P) {  // everything rejected: last center (combine.rs:85-88)
             rejected = P;
@@ -335,17 +426,9 @@ stack_tile_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigm
         if ((unsigned)tid < cnt) {
             const int src = sm.list[tid];
             const unsigned meta = sm.meta[src];
-            const unsigned it0 = meta >> 16;
+            unsigned it0;
             int a, b, n;
-            if (it0 == 0) {
-                n = (meta >> 8) & 0xff;
-                a = 0;
-                b = n;
-            } else {
-                n = P;
-                a = meta & 0xff;
-                b = (meta >> 8) & 0xff;
-            }
+            decode_meta(meta, P, it0, n, a, b);
             unsigned rej = sm.rej0[src];
             const float r = clip_combine_sorted_mem(&sm.col[0][src], TILE, n, a, b, it0,
                                                     sm.lastc[src], rej, sigma_low, sigma_high,
@@ -392,17 +475,9 @@ __device__ __forceinline__ void drain_batch(WarpQueue<P, CAP> &q, unsigned head,
     if ((unsigned)lane < cnt) {
         const unsigned slot = (head + lane) & (CAP - 1);
         const unsigned meta = q.meta[slot];
-        const unsigned it0 = meta >> 16;
+        unsigned it0;
         int a, b, n;
-        if (it0 == 0) {
-            n = (meta >> 8) & 0xff;
-            a = 0;
-            b = n;
-        } else {
-            n = P;
-            a = meta & 0xff;
-            b = (meta >> 8) & 0xff;
-        }
+        decode_meta(meta, P, it0, n, a, b);
         unsigned rej = q.rej0[slot];
         const float r = clip_combine_sorted_mem(&q.v[0][slot], CAP, n, a, b, it0, q.lastc[slot],
                                                 rej, sigma_low, sigma_high, max_iter);
@@ -600,17 +675,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void *tmap,
 static __device__ __noinline__ float finish_parked(const float *s, int stride, unsigned meta, int P,
                                             float last_center, unsigned &rej, float sigma_low,
                                             float sigma_high, unsigned max_iter) {
-    const unsigned it0 = meta >> 16;
+    unsigned it0;
     int a, b, n;
-    if (it0 == 0) {
-        n = (meta >> 8) & 0xff;
-        a = 0;
-        b = n;
-    } else {
-        n = P;
-        a = meta & 0xff;
-        b = (meta >> 8) & 0xff;
-    }
+    decode_meta(meta, P, it0, n, a, b);
     return clip_combine_sorted_mem(s, stride, n, a, b, it0, last_center, rej, sigma_low,
                                    sigma_high, max_iter);
 }

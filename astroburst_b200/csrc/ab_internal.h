@@ -28,10 +28,9 @@ struct ab_ctx {
     void *d_small = nullptr;
     void *h_small = nullptr;
     static constexpr size_t SMALL_BYTES = 1 << 20;
-    int stack_variant = 0;     // AB_STACK_VARIANT: 0 warp TMA (default), 1 block-barrier LDG, 2 warp LDG, 3 block TMA,
-                               // 4 warp LDG 4 blocks/SM, 5 warp LDG + register prefetch
+    int stack_variant = 0;     // AB_STACK_VARIANT: 0 TMA-staged (default), 2 plain coalesced loads
+    int stack_mix = 0;         // AB_STACK_MIX: 0 default compare-exchange mix, 1..7 A/B variants (P = 32)
     bool force_tma1d = false;  // AB_STACK_FORCE_TMA1D=1: per-frame bulk copies instead of the tensor map
-    unsigned stack_dbg = 0;    // AB_STACK_DBG: timing experiments only (results invalid)
     void *encode_tmap_fn = nullptr;  // cuTensorMapEncodeTiled, resolved lazily
     std::mutex mu;
     std::atomic<uint64_t> launches{0};

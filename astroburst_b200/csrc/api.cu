@@ -51,8 +51,8 @@ ab_status ab_ctx_create(int device, ab_ctx **out) {
         ctx->stack_variant = e ? atoi(e) : 0;
         e = getenv("AB_STACK_FORCE_TMA1D");
         ctx->force_tma1d = e && e[0] == '1';
-        e = getenv("AB_STACK_DBG");
-        ctx->stack_dbg = e ? (unsigned)atoi(e) : 0u;
+        e = getenv("AB_STACK_MIX");
+        ctx->stack_mix = e ? atoi(e) : 0;
     }
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < AB_NUM_COPY_STREAMS; ++i) {

@@ -105,8 +105,9 @@ stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, int n_pad
         }
         if (active) {
             unsigned rej = 0;
-            const float r = abk::clip_combine_sorted_mem(col, stride, n, 0, n, 0, nanf(""), rej,
-                                                         sigma_low, sigma_high, max_iter);
+            const float r = abk::clip_combine_sorted_mem(col, stride, n, 0, n, 0, nanf(""), false,
+                                                         0.0f, rej, sigma_low, sigma_high,
+                                                         max_iter);
             __stcs(out + p, r);
             local_rej += rej;
         }

@@ -6,22 +6,27 @@
 // Kernel structure (one thread = one output pixel, P = exact frame count, samples in registers)
 //
 //  phase A  every pixel, straight-line, register-resident:
-//    * P coalesced streaming loads (one 128 B line per warp per frame plane), or P conflict-free
-//      LDS from a TMA-staged tile (kTma variant, see stack_tile_kernel);
-//    * Batcher odd-even merge sorting network (191 compare-exchanges at P=32, FMNMX pairs);
-//      non-finite samples map to +inf and sort last (combine.rs:170-175 drops them);
+//    * P conflict-free LDS from a warp-private TMA-staged tile (stack_wtma_kernel) or P coalesced
+//      streaming loads (stack_warp_kernel: unaligned frames, ragged tails);
+//    * sorting network (185 compare-exchanges at P=32: two 60-comparator 16-sorters + Batcher's
+//      odd-even merge); non-finite samples map to +inf and sort last (combine.rs:170-175 drops
+//      them).  The network is ALU-pipe bound when every compare-exchange is an FMNMX pair
+//      (64 lanes/clk/SM), so a fraction MN/MD of the compare-exchanges computes the upper output
+//      on the FMA pipe instead: lo = FMNMX.min(a, b) and hi = a + b - lo on the integer bit
+//      patterns (two IMADs; exact because lo is bit-identical to a or b).  Measured on B200
+//      (tools/ubench_ce.cu): 5.65 SM-cycles per 32-sort with FMNMX pairs, 4.3 with a 1/2 mix;
 //    * iteration 0 (combine.rs:37-48) from the sorted order: med = s[P/2] (upper median) and,
 //      because |v-med| is V-shaped over sorted samples, the upper-median MAD is
-//      min_t max(med - s[t], s[t+P/2] - med);
-//    * the clip (combine.rs:65-82): dev = v - center is monotone in v, so the rejects are a
-//      prefix and a suffix of the sorted samples -- peeled from both ends with early exit;
-//    * ~80 % of pixels reject nothing at iteration 0, the reference loop then stops
-//      (combine.rs:80-82) and the result is the f64 mean of all P samples.
-//  phase B  only pixels that rejected something (or have non-finite samples): their sorted
-//    samples are parked in shared memory, compacted over the block, and finished by the first
-//    `count` threads with the dynamic-index version of the same algorithm (mean / sample
-//    variance in f64 over the surviving run, peel, repeat).  This keeps the rare, divergent
-//    iterations >= 1 from being executed in lock-step by every warp.
+//      min_t max(med - s[t], s[t+P/2] - med).  The same differences d[j] = s[j] - med feed the
+//      exact f32 sums of the mean;
+//    * the clip (combine.rs:65-82): dev = v - center is monotone in v, so nothing is rejected iff
+//      d[0] >= -sigma_low*sigma and d[P-1] <= sigma_high*sigma.  ~80 % of pixels: the reference
+//      loop stops (combine.rs:80-82) and the result is the f64 mean of all P samples.
+//  phase B  every other pixel (something rejected at iteration 0, non-finite samples, or a sum
+//    the f32 certificate cannot prove exact): the sorted samples are parked in a warp-private ring
+//    in shared memory and finished 32 at a time, one per lane, with the dynamic-index version of
+//    the algorithm (peel the rejects off both ends, mean / sample variance in f64 over the
+//    surviving run, repeat).
 //
 // Arithmetic mirrors the reference expression by expression (f32 compares, f64 sums, casts,
 // 1e-10 floors); compiled with -fmad=false.  The f64 sums run in a fixed 4-way interleaved
@@ -39,19 +44,35 @@
 namespace abk {
 
 constexpr double MAD_TO_SIGMA = 1.4826;  // types/constants.rs:7
-constexpr unsigned META_FINAL_ONLY = 0x80000000u;  // parked pixel: only the final mean is left
-constexpr int TILE = 256;                // pixels per block iteration = threads per block
+// meta word of a parked pixel: a | b << 8 | it0 << 16 | flags
+constexpr unsigned META_FINAL_ONLY = 0x80000000u;  // only the final mean of [0, b) is left
+constexpr unsigned META_SIGMA0 = 0x40000000u;      // all P finite; iteration 0's sigma is in `aux`
 
-__device__ __forceinline__ void ce(float &a, float &b) {
+// Runtime 1 and -1 (kernel parameters): the multiplier of the IMAD form must not be a
+// compile-time constant, or ptxas folds the IMADs back into ALU-pipe IADD3s.
+struct CeConst {
+    int one, mone;
+};
+
+// Compare-exchange.  kImad = false: FMNMX pair (2 ALU-pipe instructions).  kImad = true: FMNMX
+// min on the ALU pipe, hi = a + b - lo in integer arithmetic on the FMA pipe.  Operands are finite
+// or +inf here (never NaN), so lo is always bit-identical to one of the inputs and the integer
+// identity returns the other one exactly, for any signs.
+template <bool kImad>
+__device__ __forceinline__ void ce(float &a, float &b, const CeConst &k) {
     const float lo = fminf(a, b);
-    const float hi = fmaxf(a, b);
+    if constexpr (kImad) {
+        const int t = __float_as_int(a) * k.one + __float_as_int(b);  // independent of the FMNMX
+        b = __int_as_float(__float_as_int(lo) * k.mone + t);
+    } else {
+        b = fmaxf(a, b);
+    }
     a = lo;
-    b = hi;
 }
 
-// Batcher odd-even merge sort network for any compile-time P, generated as a constexpr list of
-// compare-exchange pairs and expanded with a fold expression, so every index is a literal and
-// the array provably stays in registers.
+// Sorting network for any compile-time P, generated as a constexpr list of compare-exchange pairs
+// and expanded with a fold expression, so every index is a literal and the array provably stays
+// in registers.
 struct CePair {
     short a, b;
 };
@@ -99,14 +120,21 @@ template <int P>
 struct OemHolder {
     static constexpr OemNet<P> net{};
 };
-template <int P, int... I>
-__device__ __forceinline__ void sort_network_impl(float (&s)[P], std::integer_sequence<int, I...>) {
-    (ce(s[OemHolder<P>::net.pr[I].a], s[OemHolder<P>::net.pr[I].b]), ...);
+// compare-exchange I takes the IMAD form for an evenly spread fraction MN/MD of the network
+template <int MN, int MD>
+constexpr bool ce_is_imad(int i) {
+    return MN > 0 && ((i * MN) % MD) + MN >= MD;
 }
-template <int P>
-__device__ __forceinline__ void sort_network(float (&s)[P]) {
+template <int P, int MN, int MD, int... I>
+__device__ __forceinline__ void sort_network_impl(float (&s)[P], const CeConst &k,
+                                                  std::integer_sequence<int, I...>) {
+    (ce<ce_is_imad<MN, MD>(I)>(s[OemHolder<P>::net.pr[I].a], s[OemHolder<P>::net.pr[I].b], k), ...);
+}
+template <int P, int MN, int MD>
+__device__ __forceinline__ void sort_network(float (&s)[P], const CeConst &k) {
     if constexpr (P > 1)
-        sort_network_impl<P>(s, std::make_integer_sequence<int, OemHolder<P>::net.count>{});
+        sort_network_impl<P, MN, MD>(s, k,
+                                     std::make_integer_sequence<int, OemHolder<P>::net.count>{});
 }
 
 // ---- f64 sums of the surviving run s[a..b) of the ascending samples.
@@ -114,33 +142,15 @@ __device__ __forceinline__ void sort_network(float (&s)[P]) {
 // The reference accumulates `v as f64` (combine.rs:51,90).  Converting every sample costs one
 // F2F.F64.F32 each, and that instruction issues at 16 lanes/clk/SM (measured), so the conversions --
 // not the DADDs -- dominate the mean.  When the run is positive and spans at most a factor of two
-// (s[b-1] <= 2 s[a], the normal case for sky-dominated pixels) every difference s[j] - s[a] is
-// exact in f32 (Sterbenz) and a multiple of ulp(s[a]); their non-negative partial sums stay exact
-// in f32 as long as the total is below 2^24 ulps = 2 * 2^floor(log2 s[a]).  Then
-//     sum = len * s[a] + D        (exact in f64: < 2^31 ulps)
+// (s[b-1] <= 2 s[a], the normal case for sky-dominated pixels) every difference s[j] - c with c
+// inside the run is exact in f32 (Sterbenz) and a multiple of ulp(s[a]); the one-signed partial
+// sums stay exact in f32 as long as the total is below 2^24 ulps = 2 * 2^floor(log2 s[a]).  Then
+//     sum = len * c + D        (exact in f64: < 2^31 ulps)
 // is the exact real sum, which is also what the reference's f64 accumulation yields for such a run,
 // so the result is bit-identical.  The certificate is checked per pixel; anything else takes the
 // plain f64 accumulation (4 accumulators keyed by the index relative to a, combined pairwise).
 __device__ __forceinline__ float next_pow2_above(float s0) {  // 2^(floor(log2 s0) + 1), s0 normal > 0
     return __uint_as_float((__float_as_uint(s0) & 0x7f800000u) + 0x00800000u);
-}
-// Register version (all P samples survive).  Differences are taken around the median so the two
-// one-signed partial sums stay small (a no-reject pixel has |s[j] - med| <= ~4.4 MAD); returns
-// false when the certificate fails -- the caller then parks the pixel for the f64 path of phase B.
-template <int P>
-__device__ __forceinline__ bool mean_all_reg(const float (&s)[P], float &mean_out) {
-    const float s0 = s[0], c = s[P / 2];
-    float lo[2] = {0.0f, 0.0f}, hi[2] = {0.0f, 0.0f};
-#pragma unroll
-    for (int j = 0; j < P / 2; ++j) lo[j & 1] += s[j] - c;  // <= 0
-#pragma unroll
-    for (int j = P / 2 + 1; j < P; ++j) hi[j & 1] += s[j] - c;  // >= 0
-    const float d_lo = lo[0] + lo[1], d_hi = hi[0] + hi[1];
-    const float T = next_pow2_above(s0);
-    const bool ok = s0 >= 1.17549435e-38f && s[P - 1] <= 2.0f * s0 && d_hi < T && -d_lo < T;
-    const double sum = (double)P * (double)c + (double)(d_hi + d_lo);
-    mean_out = (float)(sum / (double)P);
-    return ok;
 }
 __device__ __forceinline__ double sum_run_mem(const float *s, int stride, int a, int b) {
     const float s0 = s[a * stride];
@@ -199,9 +209,11 @@ __device__ __forceinline__ double sumsq_run_mem(const float *s, int stride, int 
 
 // Dynamic-index sigma_clip_combine on ascending samples s[0..n) (stride `stride`), resumed at
 // iteration `it0` with the surviving run [a, b), `rejected` rejections so far and the last
-// center.  it0 == 0 runs the whole algorithm (combine.rs:14-92).
+// center.  it0 == 0 runs the whole algorithm (combine.rs:14-92); with have_sigma0 iteration 0's
+// center (last_center = upper median) and sigma (sigma0) come from phase A.
 __device__ __forceinline__ float clip_combine_sorted_mem(const float *s, int stride, int n, int a,
                                                          int b, unsigned it0, float last_center,
+                                                         bool have_sigma0, float sigma0,
                                                          unsigned &rejected, float sigma_low,
                                                          float sigma_high, unsigned max_iter) {
     if (n == 0) return 0.0f;         // combine.rs:21-23
@@ -213,16 +225,21 @@ __device__ __forceinline__ float clip_combine_sorted_mem(const float *s, int str
         if (len < 2) break;
         float center, sigma;
         if (it == 0) {
-            const int m = n >> 1;
-            const float med = s[m * stride];
-            float mad = CUDART_INF_F;
-            for (int t = 0; t <= m; ++t) {
-                const float left = med - s[t * stride];
-                const float right = (t + m < n) ? s[(t + m) * stride] - med : CUDART_INF_F;
-                mad = fminf(mad, fmaxf(left, right));
+            if (have_sigma0) {
+                center = last_center;
+                sigma = sigma0;
+            } else {
+                const int m = n >> 1;
+                const float med = s[m * stride];
+                float mad = CUDART_INF_F;
+                for (int t = 0; t <= m; ++t) {
+                    const float left = med - s[t * stride];
+                    const float right = (t + m < n) ? s[(t + m) * stride] - med : CUDART_INF_F;
+                    mad = fminf(mad, fmaxf(left, right));
+                }
+                center = med;
+                sigma = (float)fmax((double)mad * MAD_TO_SIGMA, 1e-10);
             }
-            center = med;
-            sigma = (float)fmax((double)mad * MAD_TO_SIGMA, 1e-10);
         } else {
             const double nn = (double)len;
             const double mean = sum_run_mem(s, stride, a, b) / nn;
@@ -254,216 +271,103 @@ __device__ __forceinline__ float clip_combine_sorted_mem(const float *s, int str
     return (float)(sum_run_mem(s, stride, a, b) / (double)len);
 }
 
-// meta word of a parked pixel: a | b << 8 | it0 << 16, bit 31 = only the final mean is left
-__device__ __forceinline__ void decode_meta(unsigned meta, int P, unsigned &it0, int &n, int &a,
-                                            int &b) {
-    it0 = (meta >> 16) & 0x7fffu;
-    if (meta & META_FINAL_ONLY) {
-        n = P;
-        a = 0;
-        b = P;
-        it0 = 0xffffffffu;  // >= max_iter: the clip loop is skipped
-    } else if (it0 == 0) {
-        n = (meta >> 8) & 0xff;
-        a = 0;
-        b = n;
-    } else {
-        n = P;
-        a = meta & 0xff;
-        b = (meta >> 8) & 0xff;
-    }
+// Out-of-line: one copy of the dynamic-index code per kernel.
+static __device__ __noinline__ float finish_parked(const float *s, int stride, unsigned meta, int P,
+                                                   float last_center, float aux, unsigned &rej,
+                                                   float sigma_low, float sigma_high,
+                                                   unsigned max_iter) {
+    const int n = (int)((meta >> 8) & 0x1ffu);  // finite samples (== P unless the generic case)
+    unsigned it0 = 0;
+    if (meta & META_FINAL_ONLY) it0 = 0xffffffffu;  // >= max_iter: the clip loop is skipped
+    return clip_combine_sorted_mem(s, stride, n, 0, n, it0, last_center,
+                                   (meta & META_SIGMA0) != 0, aux, rej, sigma_low, sigma_high,
+                                   max_iter);
 }
 
 // Phase A on a register array of exactly P finite-or-+inf samples (n of them finite).
-// Returns true when `result`/`rejected` are final; false when the pixel must be finished by
-// phase B, in which case s[] is sorted and meta = a | b << 8 | it0 << 16.
-template <int P>
+// Returns true when `result` is final (such a pixel rejected nothing); false when the pixel must
+// be finished by phase B, in which case s[] is sorted, result = last center, aux = iteration 0's
+// sigma (META_SIGMA0) and meta = n << 8 | flags.
+template <int P, int MN, int MD>
 __device__ __forceinline__ bool phase_a(float (&s)[P], int n, float sigma_low, float sigma_high,
-                                        unsigned max_iter, float &result, unsigned &rejected,
-                                        unsigned &meta) {
-    rejected = 0;
-    sort_network<P>(s);
-    if (n != P) {  // non-finite samples present: rare, finished with dynamic indices
-        if (n == 0) {
-            result = 0.0f;
-            return true;
-        }
-        if (n == 1) {
-            result = s[0];
-            return true;
-        }
-        meta = 0u | ((unsigned)n << 8) | (0u << 16);
-        return false;
-    }
+                                        unsigned max_iter, const CeConst &k, float &result,
+                                        float &aux, unsigned &meta) {
+    aux = 0.0f;
+    meta = 0u;
     if constexpr (P == 1) {
-        result = s[0];
+        result = n ? s[0] : 0.0f;  // combine.rs:21-26
         return true;
     } else {
-        if (max_iter == 0) {
-            if (mean_all_reg<P>(s, result)) return true;
-            meta = 0u | ((unsigned)P << 8) | META_FINAL_ONLY;
-            result = 0.0f;
+        sort_network<P, MN, MD>(s, k);
+        if (n != P) {  // non-finite samples present: rare, finished with dynamic indices
+            result = n ? s[0] : 0.0f;
+            if (n <= 1) return true;
+            meta = (unsigned)n << 8;
             return false;
         }
-        // iteration 0: upper median, upper-median MAD (combine.rs:37-48)
-        const float med = s[P / 2];
-        float mad = CUDART_INF_F;
+        // iteration 0: upper median, upper-median MAD (combine.rs:37-48); the differences
+        // d[j] = s[j] - med also feed the exact f32 sums of the mean (see sum_run_mem)
+        constexpr int H = P / 2;
+        const float med = s[H];
+        float lo_acc[2] = {0.0f, 0.0f}, hi_acc[2] = {0.0f, 0.0f};
+        float mad[2] = {CUDART_INF_F, CUDART_INF_F};
+        float d_first = 0.0f, d_last = 0.0f;
 #pragma unroll
-        for (int t = 0; t < (P + 1) / 2; ++t)
-            mad = fminf(mad, fmaxf(med - s[t], s[t + P / 2] - med));
-        // (for even P the last window pairs s[P/2] with the absent s[P] = +inf: skipped)
-        const float sigma = (float)fmax((double)mad * MAD_TO_SIGMA, 1e-10);
+        for (int t = 0; t < (P + 1) / 2; ++t) {
+            float left = 0.0f, right = 0.0f;
+            if (t < H) {  // (t == H only for odd P: the window that starts at the median)
+                const float dl = s[t] - med;  // <= 0
+                lo_acc[t & 1] += dl;
+                left = -dl;
+                if (t == 0) d_first = dl;
+            }
+            if (t > 0) {  // (t == 0 pairs with the median itself: difference 0)
+                const float dr = s[t + H] - med;  // >= 0
+                hi_acc[t & 1] += dr;
+                right = dr;
+                if (t + H == P - 1) d_last = dr;
+            }
+            mad[t & 1] = fminf(mad[t & 1], fmaxf(left, right));
+        }
+        const float sigma = (float)fmax((double)fminf(mad[0], mad[1]) * MAD_TO_SIGMA, 1e-10);
         const float lo = -sigma_low * sigma;
         const float hi = sigma_high * sigma;
-        // peel the rejects off both ends; checked in groups of 4 so the common case (nothing or
-        // one sample rejected) leaves after the first group
-        int nh = 0, nl = 0;
-        {
-            bool go = true;
-#pragma unroll
-            for (int j = P - 1; j >= 0; --j) {
-                const bool fail = go && !(s[j] - med <= hi);
-                nh += fail ? 1 : 0;
-                go = fail;
-                if (((P - 1 - j) & 3) == 3 && !go) break;
-            }
-            go = true;
-#pragma unroll
-            for (int j = 0; j < P; ++j) {
-                const bool fail = go && !(s[j] - med >= lo);
-                nl += fail ? 1 : 0;
-                go = fail;
-                if ((j & 3) == 3 && !go) break;
-            }
-        }
-        if (nl + nh == 0) {  // removed == 0 -> loop ends (combine.rs:80-82); mean of everything
-            if (mean_all_reg<P>(s, result)) return true;
-            meta = 0u | ((unsigned)P << 8) | META_FINAL_ONLY;  // rare: f64 accumulation in phase B
-            result = med;
-            return false;
-        }
-        if (nl + nh >= P) {  // everything rejected: last center (combine.rs:85-88)
-            rejected = P;
-            result = isfinite(med) ? med : 0.0f;
+        // nothing rejected (combine.rs:65-82) <=> the extreme samples pass; max_iter == 0 never clips
+        const bool keep_all = max_iter == 0 || (d_first >= lo && d_last <= hi);
+        const float d_lo = lo_acc[0] + lo_acc[1], d_hi = hi_acc[0] + hi_acc[1];
+        const float T = next_pow2_above(s[0]);
+        const bool exact = s[0] >= 1.17549435e-38f && s[P - 1] <= 2.0f * s[0] && d_hi < T && -d_lo < T;
+        if (keep_all && exact) {
+            const double sum = (double)P * (double)med + (double)(d_hi + d_lo);
+            result = (float)(sum / (double)P);
             return true;
         }
-        rejected = (unsigned)(nl + nh);
-        meta = (unsigned)nl | ((unsigned)(P - nh) << 8) | (1u << 16);
         result = med;  // last_center carried into phase B
+        aux = sigma;
+        meta = ((unsigned)P << 8) | (keep_all ? META_FINAL_ONLY : META_SIGMA0);
         return false;
     }
-}
-
-// smem layout per block: col[P][TILE] sorted samples parked by phase A (column = thread),
-// list[TILE] compacted thread ids, meta[TILE], lastc[TILE], count.
-template <int P>
-struct StackSmem {
-    float col[P][TILE];
-    float lastc[TILE];
-    unsigned meta[TILE];
-    unsigned rej0[TILE];
-    unsigned short list[TILE];
-    unsigned count[2];
-    unsigned long long rej_total;
-};
-
-template <int P>
-__global__ void __launch_bounds__(TILE)
-stack_tile_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigma_low,
-                  float sigma_high, unsigned max_iter, float *__restrict__ out,
-                  unsigned long long *__restrict__ rejected_total) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    StackSmem<P> &sm = *reinterpret_cast<StackSmem<P> *>(smem_raw);
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        sm.count[0] = 0;
-        sm.count[1] = 0;
-        sm.rej_total = 0;
-    }
-    __syncthreads();
-    unsigned local_rej = 0;
-    unsigned par = 0;
-    const size_t n_tiles = (npix + TILE - 1) / TILE;
-    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1u) {
-        const size_t p = tile * TILE + tid;
-        const bool active = p < npix;
-        if (active) {
-            float s[P];
-            float probe = 0.0f;
-#pragma unroll
-            for (int f = 0; f < P; ++f) {
-                s[f] = __ldcs(ft.p[f] + p);
-                probe = fmaf(s[f], 0.0f, probe);  // NaN iff any sample is non-finite
-            }
-            int n = P;
-            if (probe != probe) {
-                n = 0;
-#pragma unroll
-                for (int f = 0; f < P; ++f) {
-                    const bool fin = fabsf(s[f]) < CUDART_INF_F;
-                    n += fin ? 1 : 0;
-                    s[f] = fin ? s[f] : CUDART_INF_F;
-                }
-            }
-            float result;
-            unsigned rej, meta;
-            if (phase_a<P>(s, n, sigma_low, sigma_high, max_iter, result, rej, meta)) {
-                __stcs(out + p, result);
-                local_rej += rej;
-            } else {
-#pragma unroll
-                for (int f = 0; f < P; ++f) sm.col[f][tid] = s[f];
-                sm.meta[tid] = meta;
-                sm.lastc[tid] = result;
-                sm.rej0[tid] = rej;
-                const unsigned slot = atomicAdd(&sm.count[par], 1u);
-                sm.list[slot] = (unsigned short)tid;
-            }
-        }
-        __syncthreads();
-        const unsigned cnt = sm.count[par];
-        if (tid == 0) sm.count[par ^ 1u] = 0;  // last read before the previous tile's 2nd barrier
-        if ((unsigned)tid < cnt) {
-            const int src = sm.list[tid];
-            const unsigned meta = sm.meta[src];
-            unsigned it0;
-            int a, b, n;
-            decode_meta(meta, P, it0, n, a, b);
-            unsigned rej = sm.rej0[src];
-            const float r = clip_combine_sorted_mem(&sm.col[0][src], TILE, n, a, b, it0,
-                                                    sm.lastc[src], rej, sigma_low, sigma_high,
-                                                    max_iter);
-            __stcs(out + tile * TILE + src, r);
-            local_rej += rej;
-        }
-        __syncthreads();  // phase B done: columns and the list may be overwritten
-    }
-    const unsigned w = __reduce_add_sync(0xffffffffu, local_rej);
-    if ((tid & 31) == 0 && w) atomicAdd(&sm.rej_total, (unsigned long long)w);
-    __syncthreads();
-    if (tid == 0 && sm.rej_total) atomicAdd(rejected_total, sm.rej_total);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warp-autonomous variant: no block-wide synchronisation at all.
+// Warp-autonomous kernels: no block-wide synchronisation at all.
 //
 // Every warp walks its own sequence of 32-pixel groups.  Lanes whose pixel needs phase B park the
 // sorted samples in a warp-private ring in shared memory (column = ring slot, conflict-free); as
 // soon as the ring holds >= 32 parked pixels the warp finishes 32 of them at once, one per lane,
 // so phase B always runs with full lanes and only every ~6th group.  While one warp is in its
-// (FP64 / XU heavy) phase B the other warps of the SM keep the ALU pipe busy with their sorting
-// networks: warps drift apart instead of marching in lock-step, which is what keeps the ALU pipe
-// (the real bound of this kernel) fed.
-constexpr int WQ_CAP = 64;         // ring slots per warp (power of two)
+// (FP64 / XU heavy) phase B the other warps of the SM keep the ALU and FMA pipes busy with their
+// sorting networks: warps drift apart instead of marching in lock-step.
 constexpr int WARPS_PER_BLOCK = 8;
+constexpr int WQ_CAP = 32;  // ring slots per warp; a group that does not fit drains first
 
 template <int P, int CAP = WQ_CAP>
 struct WarpQueue {
     static constexpr int kCap = CAP;
     float v[P][CAP];
     float lastc[CAP];
+    float aux[CAP];
     unsigned meta[CAP];
-    unsigned rej0[CAP];
     unsigned pix[CAP];  // pixel index relative to the launch (npix < 2^32 per launch)
 };
 
@@ -474,23 +378,84 @@ __device__ __forceinline__ void drain_batch(WarpQueue<P, CAP> &q, unsigned head,
                                             float *__restrict__ out, unsigned &local_rej) {
     if ((unsigned)lane < cnt) {
         const unsigned slot = (head + lane) & (CAP - 1);
-        const unsigned meta = q.meta[slot];
-        unsigned it0;
-        int a, b, n;
-        decode_meta(meta, P, it0, n, a, b);
-        unsigned rej = q.rej0[slot];
-        const float r = clip_combine_sorted_mem(&q.v[0][slot], CAP, n, a, b, it0, q.lastc[slot],
-                                                rej, sigma_low, sigma_high, max_iter);
+        unsigned rej = 0;
+        const float r = finish_parked(&q.v[0][slot], CAP, q.meta[slot], P, q.lastc[slot],
+                                      q.aux[slot], rej, sigma_low, sigma_high, max_iter);
         __stcs(out + q.pix[slot], r);
         local_rej += rej;
     }
     __syncwarp();
 }
 
-template <int P, int kMinBlocks, bool kPrefetch>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, kMinBlocks)
+// Non-finite samples -> +inf (they sort last and are not counted in n).  probe is NaN iff any
+// sample of the pixel is non-finite (x * 0 accumulates NaN for +-inf and NaN).
+template <int P>
+__device__ __forceinline__ int drop_non_finite(float (&s)[P], float probe) {
+    int n = P;
+    if (probe != probe) {
+        n = 0;
+#pragma unroll
+        for (int f = 0; f < P; ++f) {
+            const bool fin = fabsf(s[f]) < CUDART_INF_F;
+            n += fin ? 1 : 0;
+            s[f] = fin ? s[f] : CUDART_INF_F;
+        }
+    }
+    return n;
+}
+
+// Shared tail of both kernels: phase A on the registers, store or park, drain when 32 are parked.
+template <int P, int MN, int MD>
+__device__ __forceinline__ void process_group(float (&s)[P], int n, bool active, size_t p, int lane,
+                                              WarpQueue<P> &q, unsigned &head, unsigned &count,
+                                              unsigned &local_rej, float sigma_low, float sigma_high,
+                                              unsigned max_iter, const CeConst &k,
+                                              float *__restrict__ out) {
+    float result, aux;
+    unsigned meta;
+    bool park = false;
+    if (active) {
+        if (phase_a<P, MN, MD>(s, n, sigma_low, sigma_high, max_iter, k, result, aux, meta))
+            __stcs(out + p, result);
+        else
+            park = true;
+    }
+    const unsigned pmask = __ballot_sync(0xffffffffu, park);
+    if (pmask) {
+        const unsigned c = __popc(pmask);
+        if (count + c > (unsigned)WQ_CAP) {  // make room: finish what is parked (< 32 lanes)
+            drain_batch<P, WQ_CAP>(q, head, count, lane, sigma_low, sigma_high, max_iter, out,
+                                   local_rej);
+            head = (head + count) & (WQ_CAP - 1);
+            count = 0;
+        }
+        if (park) {
+            const unsigned slot =
+                (head + count + __popc(pmask & ((1u << lane) - 1u))) & (WQ_CAP - 1);
+#pragma unroll
+            for (int f = 0; f < P; ++f) q.v[f][slot] = s[f];
+            q.meta[slot] = meta;
+            q.lastc[slot] = result;
+            q.aux[slot] = aux;
+            q.pix[slot] = (unsigned)p;
+        }
+        count += c;
+        __syncwarp();
+        if (count >= 32u) {
+            drain_batch<P, WQ_CAP>(q, head, 32u, lane, sigma_low, sigma_high, max_iter, out,
+                                   local_rej);
+            head = (head + 32u) & (WQ_CAP - 1);
+            count -= 32u;
+        }
+    }
+}
+
+// Plain coalesced loads (one 128 B line per warp per frame plane): frames that are not 16-byte
+// aligned, and the ragged tail of the TMA kernel.
+template <int P, int MN, int MD>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 3)
 stack_warp_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigma_low,
-                  float sigma_high, unsigned max_iter, float *__restrict__ out,
+                  float sigma_high, unsigned max_iter, CeConst k, float *__restrict__ out,
                   unsigned long long *__restrict__ rejected_total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpQueue<P> *queues = reinterpret_cast<WarpQueue<P> *>(smem_raw);
@@ -503,127 +468,47 @@ stack_warp_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigm
     const size_t n_groups = (npix + 31) / 32;
     const size_t warp_global = (size_t)blockIdx.x * WARPS_PER_BLOCK + warp;
     const size_t warp_stride = (size_t)gridDim.x * WARPS_PER_BLOCK;
-    float nxt[kPrefetch ? P : 1];
-    if constexpr (kPrefetch) {
-        const size_t p0 = warp_global * 32 + lane;
-        if (p0 < npix) {
-#pragma unroll
-            for (int f = 0; f < P; ++f) nxt[f] = __ldcs(ft.p[f] + p0);
-        }
-    }
     for (size_t g = warp_global; g < n_groups; g += warp_stride) {
         const size_t p = g * 32 + lane;
         const bool active = p < npix;
-        bool park = false;
         float s[P];
-        float result = 0.0f;
-        unsigned rej = 0, meta = 0;
-        if constexpr (kPrefetch) {
-#pragma unroll
-            for (int f = 0; f < P; ++f) s[f] = nxt[f];
-            const size_t pn = p + warp_stride * 32;  // software pipeline: next group's loads in flight
-            if (pn < npix) {
-#pragma unroll
-                for (int f = 0; f < P; ++f) nxt[f] = __ldcs(ft.p[f] + pn);
-            }
-        }
+        int n = P;
         if (active) {
             float probe = 0.0f;
 #pragma unroll
             for (int f = 0; f < P; ++f) {
-                if constexpr (!kPrefetch) s[f] = __ldcs(ft.p[f] + p);
-                probe = fmaf(s[f], 0.0f, probe);  // NaN iff any sample is non-finite
+                s[f] = __ldcs(ft.p[f] + p);
+                probe = fmaf(s[f], 0.0f, probe);
             }
-            int n = P;
-            if (probe != probe) {
-                n = 0;
-#pragma unroll
-                for (int f = 0; f < P; ++f) {
-                    const bool fin = fabsf(s[f]) < CUDART_INF_F;
-                    n += fin ? 1 : 0;
-                    s[f] = fin ? s[f] : CUDART_INF_F;
-                }
-            }
-            if (phase_a<P>(s, n, sigma_low, sigma_high, max_iter, result, rej, meta)) {
-                __stcs(out + p, result);
-                local_rej += rej;
-            } else {
-                park = true;
-            }
+            n = drop_non_finite<P>(s, probe);
         }
-        const unsigned pmask = __ballot_sync(0xffffffffu, park);
-        if (pmask) {
-            // count < 32 here and at most 32 lanes park, so the 64-slot ring always has room
-            if (park) {
-                const unsigned slot =
-                    (head + count + __popc(pmask & ((1u << lane) - 1u))) & (WQ_CAP - 1);
-#pragma unroll
-                for (int f = 0; f < P; ++f) q.v[f][slot] = s[f];
-                q.meta[slot] = meta;
-                q.lastc[slot] = result;
-                q.rej0[slot] = rej;
-                q.pix[slot] = (unsigned)p;
-            }
-            count += __popc(pmask);
-            __syncwarp();
-            if (count >= 32u) {
-                drain_batch<P, WQ_CAP>(q, head, 32u, lane, sigma_low, sigma_high, max_iter, out, local_rej);
-                head = (head + 32u) & (WQ_CAP - 1);
-                count -= 32u;
-            }
-        }
+        process_group<P, MN, MD>(s, n, active, p, lane, q, head, count, local_rej, sigma_low,
+                                 sigma_high, max_iter, k, out);
     }
-    if (count) drain_batch<P, WQ_CAP>(q, head, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
+    if (count)
+        drain_batch<P, WQ_CAP>(q, head, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
     const unsigned w = __reduce_add_sync(0xffffffffu, local_rej);
     if (lane == 0 && w) atomicAdd(rejected_total, (unsigned long long)w);
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA-staged, warp-specialised variant (the production path for 16-byte aligned frames).
+// TMA-staged variant (the production path for 16-byte aligned frames).
 //
-//   * a tile = 256 consecutive pixels of all P frames.  When the frames sit at a constant stride
-//     (one [P, rows, cols] cube: the layout the host-buffer entry point and bench.py use) the
-//     producer warp fetches a tile with ONE 2-D tensor-map TMA (cp.async.bulk.tensor.2d, box
-//     256 x P, UTMALDG); otherwise with P 1-D bulk copies (cp.async.bulk, UBLKCP).  Completion is
-//     signalled on an mbarrier (complete_tx::bytes); stages form a ring;
-//   * 8 "A" warps run phase A on a landed stage: conflict-free LDS with immediate offsets (no
-//     per-load address arithmetic on the ALU pipe, which the sorting network saturates), then
-//     release the stage at once (the samples are in registers), sort, do iteration 0 and either
-//     store the pixel or park the sorted samples in a small double-buffered queue;
-//   * 2 "B" warps finish the parked pixels of tile k with the dynamic-index code while the A warps
-//     are already sorting tile k+1.  No block-wide barrier anywhere, only mbarriers;
-//   * a parked pixel that finds the queue full (NaN strips: every pixel of the tile parks) is
-//     finished by its own thread from a local-memory copy.
-constexpr int TMA_STAGES = 2;
-constexpr int A_THREADS = TILE;  // 8 warps
-constexpr int B_THREADS = 64;    // 2 warps
-constexpr int PROD_THREADS = 32; // 1 warp, one elected lane
-constexpr int QCAP = 96;         // parked pixels per tile before the local-memory fallback
-
-template <int P>
-struct StackTmaSmem {
-    alignas(128) float stage[TMA_STAGES][P][TILE];
-    float q[2][P][QCAP];          // parked sorted samples, column = queue slot
-    float q_lastc[2][QCAP];
-    unsigned q_meta[2][QCAP];     // a | b << 8 | it0 << 16
-    unsigned q_rej0[2][QCAP];
-    unsigned short q_src[2][QCAP];
-    unsigned q_count[2];
-    alignas(8) unsigned long long full_bar[TMA_STAGES];   // TMA bytes landed
-    alignas(8) unsigned long long empty_bar[TMA_STAGES];  // all A warps copied the stage to regs
-    alignas(8) unsigned long long adone_bar[2];           // all A warps finished tile (parity)
-    alignas(8) unsigned long long qfree_bar[2];           // B warps drained queue (parity)
-    unsigned long long rej_total;
-};
-
+// Same control structure, but the 32 x P samples of a warp's next pixel group are fetched by the
+// TMA engine into a warp-private 4 KiB shared-memory stage while the warp sorts the current group
+// out of registers:
+//   * frames at a constant stride (one [P, rows, cols] cube): ONE cp.async.bulk.tensor.2d per
+//     group (box = 32 pixels x P frames, UTMALDG); otherwise P 128-byte cp.async.bulk copies;
+//   * completion on a warp-private mbarrier (complete_tx::bytes); the stage is re-armed by lane 0
+//     right after the warp has copied it to registers, so one stage per warp is enough: the fetch
+//     of group i+1 overlaps the whole sort of group i;
+//   * the loads become conflict-free LDS with immediate offsets: the ~1.5 ALU-pipe instructions
+//     of 64-bit address arithmetic per global load disappear from the pipe that bounds the kernel.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
@@ -642,17 +527,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Latency-critical wait (A warps: data normally already landed).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
-}
-// Wait for the helper roles (B warps, producer): a short sleep between polls keeps the spin from
-// taking issue slots from the A warps.  (A large try_wait suspend-time hint compiles to
-// NANOSLEEP.SYNCS and was measured to oversleep the ~2 us tile period: the TMA ring starved.)
-template <int NS>
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(NS);
 }
 __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void *src, uint32_t bytes,
                                             uint32_t bar) {
@@ -671,195 +548,27 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void *tmap,
         : "memory");
 }
 
-// Out-of-line so the B warps and the (rare) overflow path share one copy of the code.
-static __device__ __noinline__ float finish_parked(const float *s, int stride, unsigned meta, int P,
-                                            float last_center, unsigned &rej, float sigma_low,
-                                            float sigma_high, unsigned max_iter) {
-    unsigned it0;
-    int a, b, n;
-    decode_meta(meta, P, it0, n, a, b);
-    return clip_combine_sorted_mem(s, stride, n, a, b, it0, last_center, rej, sigma_low,
-                                   sigma_high, max_iter);
-}
-
 struct TmapParam {
     alignas(64) unsigned char bytes[128];  // CUtensorMap
 };
 
-template <int P, bool kTensorMap>
-__global__ void __launch_bounds__(A_THREADS + B_THREADS + PROD_THREADS)
-stack_tma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__ TmapParam tmap,
-                 size_t n_tiles, float sigma_low, float sigma_high, unsigned max_iter,
-                 float *__restrict__ out, unsigned long long *__restrict__ rejected_total,
-                 unsigned dbg) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    StackTmaSmem<P> &sm = *reinterpret_cast<StackTmaSmem<P> *>(smem_raw);
-    const int tid = threadIdx.x;
-    constexpr uint32_t SEG_BYTES = TILE * sizeof(float);
-    constexpr uint32_t TILE_BYTES = P * SEG_BYTES;
-
-    if (tid == 0) {
-        for (int st = 0; st < TMA_STAGES; ++st) {
-            mbar_init(smem_u32(&sm.full_bar[st]), 1);
-            mbar_init(smem_u32(&sm.empty_bar[st]), A_THREADS / 32);
-        }
-        for (int q = 0; q < 2; ++q) {
-            mbar_init(smem_u32(&sm.adone_bar[q]), A_THREADS / 32);
-            mbar_init(smem_u32(&sm.qfree_bar[q]), B_THREADS / 32);
-            sm.q_count[q] = 0;
-        }
-        sm.rej_total = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    // tiles of this block: blockIdx.x, blockIdx.x + gridDim.x, ...
-    const size_t my_tiles =
-        (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    unsigned local_rej = 0;
-
-    if (tid >= A_THREADS + B_THREADS) {
-        // ---------------------------------------------------------------- producer (one lane)
-        if (tid == A_THREADS + B_THREADS) {
-            for (size_t k = 0; k < my_tiles; ++k) {
-                const int st = (int)(k % TMA_STAGES);
-                if (k >= TMA_STAGES)
-                    mbar_wait_sleep<20>(smem_u32(&sm.empty_bar[st]),
-                                    (uint32_t)(((k / TMA_STAGES) - 1) & 1));
-                const size_t tile = blockIdx.x + k * gridDim.x;
-                const uint32_t bar = smem_u32(&sm.full_bar[st]);
-                mbar_arrive_expect_tx(bar, TILE_BYTES);
-                if constexpr (kTensorMap) {
-                    tma_load_2d(smem_u32(&sm.stage[st][0][0]), &tmap, (int)(tile * TILE), 0, bar);
-                } else {
-#pragma unroll 4
-                    for (int f = 0; f < P; ++f)
-                        tma_load_1d(smem_u32(&sm.stage[st][f][0]), ft.p[f] + tile * TILE, SEG_BYTES,
-                                    bar);
-                }
-            }
-        }
-    } else if (tid >= A_THREADS) {
-        // ---------------------------------------------------------------- B warps
-        const int bt = tid - A_THREADS;
-        for (size_t k = 0; k < my_tiles; ++k) {
-            const int qb = (int)(k & 1);
-            mbar_wait_sleep<100>(smem_u32(&sm.adone_bar[qb]), (uint32_t)((k >> 1) & 1));
-            unsigned cnt = sm.q_count[qb];
-            if (cnt > QCAP) cnt = QCAP;
-            const size_t tile = blockIdx.x + k * gridDim.x;
-            if (dbg & 2u) cnt = 0;  // timing experiment: B warps skip their work
-            for (unsigned e = bt; e < cnt; e += B_THREADS) {
-                unsigned rej = sm.q_rej0[qb][e];
-                const float r = finish_parked(&sm.q[qb][0][e], QCAP, sm.q_meta[qb][e], P,
-                                              sm.q_lastc[qb][e], rej, sigma_low, sigma_high,
-                                              max_iter);
-                __stcs(out + tile * TILE + sm.q_src[qb][e], r);
-                local_rej += rej;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(B_THREADS) : "memory");
-            if (bt == 0) sm.q_count[qb] = 0;
-            __syncwarp();
-            if ((bt & 31) == 0) mbar_arrive(smem_u32(&sm.qfree_bar[qb]));
-        }
-    } else {
-        // ---------------------------------------------------------------- A warps
-        for (size_t k = 0; k < my_tiles; ++k) {
-            const int st = (int)(k % TMA_STAGES);
-            const int qb = (int)(k & 1);
-            const size_t tile = blockIdx.x + k * gridDim.x;
-            mbar_wait(smem_u32(&sm.full_bar[st]), (uint32_t)((k / TMA_STAGES) & 1));
-            float s[P];
-            float probe = 0.0f;
-#pragma unroll
-            for (int f = 0; f < P; ++f) {
-                s[f] = sm.stage[st][f][tid];
-                probe = fmaf(s[f], 0.0f, probe);  // NaN iff any sample is non-finite
-            }
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(smem_u32(&sm.empty_bar[st]));  // stage may be refilled
-            int n = P;
-            if (probe != probe) {
-                n = 0;
-#pragma unroll
-                for (int f = 0; f < P; ++f) {
-                    const bool fin = fabsf(s[f]) < CUDART_INF_F;
-                    n += fin ? 1 : 0;
-                    s[f] = fin ? s[f] : CUDART_INF_F;
-                }
-            }
-            float result;
-            unsigned rej, meta;
-            if (dbg & 4u) {  // timing experiment: load pipeline only, no sort / clip
-                __stcs(out + tile * TILE + tid, probe + s[0] + s[P - 1]);
-            } else if (phase_a<P>(s, n, sigma_low, sigma_high, max_iter, result, rej, meta)) {
-                __stcs(out + tile * TILE + tid, result);
-                local_rej += rej;
-            } else {
-                // the queue half is free once the B warps drained tile k-2
-                if (k >= 2) mbar_wait(smem_u32(&sm.qfree_bar[qb]), (uint32_t)(((k >> 1) - 1) & 1));
-                const unsigned slot = atomicAdd(&sm.q_count[qb], 1u);
-                if (slot < QCAP) {
-#pragma unroll
-                    for (int f = 0; f < P; ++f) sm.q[qb][f][slot] = s[f];
-                    sm.q_meta[qb][slot] = meta;
-                    sm.q_lastc[qb][slot] = result;
-                    sm.q_rej0[qb][slot] = rej;
-                    sm.q_src[qb][slot] = (unsigned short)tid;
-                } else {  // queue full: finish from a thread-private copy
-                    float loc[P];
-#pragma unroll
-                    for (int f = 0; f < P; ++f) loc[f] = s[f];
-                    const float r = finish_parked(loc, 1, meta, P, result, rej, sigma_low,
-                                                  sigma_high, max_iter);
-                    __stcs(out + tile * TILE + tid, r);
-                    local_rej += rej;
-                }
-            }
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(smem_u32(&sm.adone_bar[qb]));
-        }
-    }
-    const unsigned w = __reduce_add_sync(0xffffffffu, local_rej);
-    if ((tid & 31) == 0 && w) atomicAdd(&sm.rej_total, (unsigned long long)w);
-    __syncthreads();
-    if (tid == 0 && sm.rej_total) atomicAdd(rejected_total, sm.rej_total);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Warp-autonomous variant with TMA staging (the production path for 16-byte aligned frames).
-//
-// Same control structure as stack_warp_kernel, but the 32 x P samples of a warp's next pixel group
-// are fetched by the TMA engine into a warp-private 4 KiB shared-memory stage while the warp sorts
-// the current group out of registers:
-//   * frames at a constant stride (one [P, rows, cols] cube): ONE cp.async.bulk.tensor.2d per
-//     group (box = 32 pixels x P frames, UTMALDG); otherwise P 128-byte cp.async.bulk copies;
-//   * completion on a warp-private mbarrier (complete_tx::bytes); the stage is re-armed by lane 0
-//     right after the warp has copied it to registers, so one stage per warp is enough: the fetch
-//     of group i+1 overlaps the whole sort of group i;
-//   * the loads become conflict-free LDS with immediate offsets: the ~1.5 ALU-pipe instructions
-//     of 64-bit address arithmetic per global load disappear from the pipe that bounds the kernel.
-constexpr int WT_WARPS = 8;   // 8 warps x ~8.6 KiB (P=32) -> 3 blocks / SM = 24 warps
-constexpr int WT_CAP = 32;    // ring slots per warp; a group that does not fit drains first
-
 template <int P>
 struct WarpTmaSmem {
     alignas(128) float stage[P][32];
-    WarpQueue<P, WT_CAP> q;
+    WarpQueue<P> q;
     alignas(8) unsigned long long full;
     unsigned pad[30];
 };
 
-template <int P, bool kTensorMap>
-__global__ void __launch_bounds__(WT_WARPS * 32, 3)
+template <int P, int MN, int MD, bool kTensorMap>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 3)
 stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__ TmapParam tmap,
-                  size_t n_groups, float sigma_low, float sigma_high, unsigned max_iter,
+                  size_t n_groups, float sigma_low, float sigma_high, unsigned max_iter, CeConst k,
                   float *__restrict__ out, unsigned long long *__restrict__ rejected_total) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     WarpTmaSmem<P> &sm = reinterpret_cast<WarpTmaSmem<P> *>(smem_raw)[warp];
-    WarpQueue<P, WT_CAP> &q = sm.q;
     const uint32_t bar = smem_u32(&sm.full);
     const uint32_t stage_addr = smem_u32(&sm.stage[0][0]);
     constexpr uint32_t GROUP_BYTES = P * 32 * sizeof(float);
@@ -870,8 +579,8 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
     }
     __syncwarp();
 
-    const size_t warp_global = (size_t)blockIdx.x * WT_WARPS + warp;
-    const size_t warp_stride = (size_t)gridDim.x * WT_WARPS;
+    const size_t warp_global = (size_t)blockIdx.x * WARPS_PER_BLOCK + warp;
+    const size_t warp_stride = (size_t)gridDim.x * WARPS_PER_BLOCK;
 
     auto issue = [&](size_t g) {  // lane 0 only
         mbar_arrive_expect_tx(bar, GROUP_BYTES);
@@ -896,97 +605,37 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
 #pragma unroll
         for (int f = 0; f < P; ++f) {
             s[f] = sm.stage[f][lane];
-            probe = fmaf(s[f], 0.0f, probe);  // NaN iff any sample is non-finite
+            probe = fmaf(s[f], 0.0f, probe);
         }
-        // every lane has consumed its column (probe depends on all 32 loads): refill the stage
+        // every lane has consumed its column (probe depends on all P loads): refill the stage
         asm volatile("" ::"f"(probe) : "memory");
         __syncwarp();
         if (lane == 0 && g + warp_stride < n_groups) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(g + warp_stride);
         }
-        int n = P;
-        if (probe != probe) {
-            n = 0;
-#pragma unroll
-            for (int f = 0; f < P; ++f) {
-                const bool fin = fabsf(s[f]) < CUDART_INF_F;
-                n += fin ? 1 : 0;
-                s[f] = fin ? s[f] : CUDART_INF_F;
-            }
-        }
-        float result;
-        unsigned rej, meta;
-        bool park = false;
-        if (phase_a<P>(s, n, sigma_low, sigma_high, max_iter, result, rej, meta)) {
-            __stcs(out + p, result);
-            local_rej += rej;
-        } else {
-            park = true;
-        }
-        const unsigned pmask = __ballot_sync(0xffffffffu, park);
-        if (pmask) {
-            const unsigned c = __popc(pmask);
-            if (count + c > (unsigned)WT_CAP) {  // make room: finish what is parked (< 32 lanes)
-                drain_batch<P, WT_CAP>(q, head, count, lane, sigma_low, sigma_high, max_iter, out,
-                                       local_rej);
-                head = (head + count) & (WT_CAP - 1);
-                count = 0;
-            }
-            if (park) {
-                const unsigned slot =
-                    (head + count + __popc(pmask & ((1u << lane) - 1u))) & (WT_CAP - 1);
-#pragma unroll
-                for (int f = 0; f < P; ++f) q.v[f][slot] = s[f];
-                q.meta[slot] = meta;
-                q.lastc[slot] = result;
-                q.rej0[slot] = rej;
-                q.pix[slot] = (unsigned)p;
-            }
-            count += c;
-            __syncwarp();
-            if (count >= 32u) {
-                drain_batch<P, WT_CAP>(q, head, 32u, lane, sigma_low, sigma_high, max_iter, out,
-                                       local_rej);
-                head = (head + 32u) & (WT_CAP - 1);
-                count -= 32u;
-            }
-        }
+        const int n = drop_non_finite<P>(s, probe);
+        process_group<P, MN, MD>(s, n, true, p, lane, sm.q, head, count, local_rej, sigma_low,
+                                 sigma_high, max_iter, k, out);
     }
     if (count)
-        drain_batch<P, WT_CAP>(q, head, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
+        drain_batch<P, WQ_CAP>(sm.q, head, count, lane, sigma_low, sigma_high, max_iter, out,
+                               local_rej);
     const unsigned w = __reduce_add_sync(0xffffffffu, local_rej);
     if (lane == 0 && w) atomicAdd(rejected_total, (unsigned long long)w);
 }
 
-template <int P>
+// ---------------------------------------------------------------------------------------------
+// Launchers.  MN/MD = fraction of compare-exchanges in the IMAD form.
+template <int P, int MN, int MD>
 ab_status launch_ldg(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, float sh,
                      unsigned max_iter, float *d_out, unsigned long long *d_rej,
                      cudaStream_t stream) {
-    if (ctx->stack_variant == 1) {  // block-barrier phase B (kept for A/B measurements)
-        const size_t smem = sizeof(StackSmem<P>);
-        AB_CUDA(ctx, cudaFuncSetAttribute(stack_tile_kernel<P>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        AB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stack_tile_kernel<P>,
-                                                                   TILE, smem));
-        if (per_sm < 1) per_sm = 1;
-        const size_t n_tiles = (npix + TILE - 1) / TILE;
-        size_t grid = (size_t)ctx->sm_count * per_sm;
-        if (grid > n_tiles) grid = n_tiles;
-        stack_tile_kernel<P><<<(unsigned)grid, TILE, smem, stream>>>(ft, npix, sl, sh, max_iter,
-                                                                    d_out, d_rej);
-        AB_LAUNCH_CHECK(ctx);
-        return AB_OK;
-    }
     if (npix >= ((size_t)1 << 32))
         return ab_fail(ctx, AB_ERR_UNSUPPORTED, "npix %zu >= 2^32 per launch", npix);
     const size_t smem = sizeof(WarpQueue<P>) * WARPS_PER_BLOCK;
     constexpr int threads = WARPS_PER_BLOCK * 32;
-    void (*kern)(FrameTable, size_t, float, float, unsigned, float *, unsigned long long *) =
-        stack_warp_kernel<P, 3, false>;
-    if (ctx->stack_variant == 4) kern = stack_warp_kernel<P, 4, false>;
-    if (ctx->stack_variant == 5) kern = stack_warp_kernel<P, 2, true>;
+    auto kern = stack_warp_kernel<P, MN, MD>;
     AB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     AB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -995,93 +644,89 @@ ab_status launch_ldg(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, f
     size_t grid = (size_t)ctx->sm_count * per_sm;  // persistent: one wave, groups strided
     if (grid > n_blocks_needed) grid = n_blocks_needed;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, threads, smem, stream>>>(ft, npix, sl, sh, max_iter, d_out, d_rej);
+    kern<<<(unsigned)grid, threads, smem, stream>>>(ft, npix, sl, sh, max_iter, CeConst{1, -1},
+                                                    d_out, d_rej);
     AB_LAUNCH_CHECK(ctx);
     return AB_OK;
 }
 
-// Host side of the tensor map (stack.cu): encodes a [P, npix] f32 view with a 256 x P box.
+// Host side of the tensor map (stack.cu): encodes a [P, npix] f32 view with a box_px x P box.
 bool ab_make_stack_tmap(ab_ctx *ctx, const float *base, size_t npix, size_t plane_stride_elems,
                         int P, int box_px, TmapParam *out);
 
-template <int P>
-ab_status launch_tile(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, float sh,
-                      unsigned max_iter, float *d_out, unsigned long long *d_rej,
-                      cudaStream_t stream) {
-    if (ctx->stack_variant == 0) {
-        bool al = true;
-        for (int f = 0; f < P; ++f) al = al && ((reinterpret_cast<uintptr_t>(ft.p[f]) & 15) == 0);
-        const size_t groups = al && npix < ((size_t)1 << 31) ? npix / 32 : 0;
-        if (groups) {
-            bool cube = P > 1 && !ctx->force_tma1d;
-            const ptrdiff_t stride = P > 1 ? ft.p[1] - ft.p[0] : 0;
-            for (int f = 1; cube && f < P; ++f) cube = (ft.p[f] - ft.p[f - 1]) == stride;
-            cube = cube && stride > 0 && (stride % 4) == 0 && (size_t)stride >= npix;
-            TmapParam tm{};
-            if (cube) cube = ab_make_stack_tmap(ctx, ft.p[0], npix, (size_t)stride, P, 32, &tm);
-            // scattered frames: P small bulk copies per group measured slower (1.18 ms) than plain
-            // coalesced loads (0.92 ms) -> only the tensor-map form is used unless forced
-            if (!cube && !ctx->force_tma1d)
-                return launch_ldg<P>(ctx, ft, npix, sl, sh, max_iter, d_out, d_rej, stream);
-            const size_t smem = sizeof(WarpTmaSmem<P>) * WT_WARPS;
-            constexpr int threads = WT_WARPS * 32;
-            auto kern = cube ? stack_wtma_kernel<P, true> : stack_wtma_kernel<P, false>;
-            AB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)smem));
-            int per_sm = 0;
-            AB_CUDA(ctx,
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-            if (per_sm < 1) per_sm = 1;
-            size_t grid = (size_t)ctx->sm_count * per_sm;
-            const size_t need = (groups + WT_WARPS - 1) / WT_WARPS;
-            if (grid > need) grid = need;
-            kern<<<(unsigned)grid, threads, smem, stream>>>(ft, tm, groups, sl, sh, max_iter, d_out,
-                                                            d_rej);
-            AB_LAUNCH_CHECK(ctx);
-        }
-        const size_t done = groups * 32;
-        if (done < npix) {  // ragged tail (or everything, for unaligned frames): plain loads
-            FrameTable tail;
-            for (int f = 0; f < AB_MAX_FRAMES; ++f) tail.p[f] = f < P ? ft.p[f] + done : nullptr;
-            return launch_ldg<P>(ctx, tail, npix - done, sl, sh, max_iter, d_out + done, d_rej,
-                                 stream);
-        }
-        return AB_OK;
-    }
-    bool aligned = true;
-    for (int f = 0; f < P; ++f)
-        aligned = aligned && ((reinterpret_cast<uintptr_t>(ft.p[f]) & 15) == 0);
-    const size_t full_tiles = aligned && ctx->stack_variant == 3 ? npix / TILE : 0;
-    if (full_tiles) {
-        // constant frame stride (a [P, rows, cols] cube) -> one 2-D tensor-map TMA per tile
+template <int P, int MN, int MD>
+ab_status launch_mix(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, float sh,
+                     unsigned max_iter, float *d_out, unsigned long long *d_rej,
+                     cudaStream_t stream) {
+    bool al = ctx->stack_variant != 2;  // AB_STACK_VARIANT=2: plain loads everywhere
+    for (int f = 0; f < P; ++f) al = al && ((reinterpret_cast<uintptr_t>(ft.p[f]) & 15) == 0);
+    const size_t groups = al && npix < ((size_t)1 << 31) ? npix / 32 : 0;
+    if (groups) {
         bool cube = P > 1 && !ctx->force_tma1d;
-        ptrdiff_t stride = P > 1 ? ft.p[1] - ft.p[0] : 0;
+        const ptrdiff_t stride = P > 1 ? ft.p[1] - ft.p[0] : 0;
         for (int f = 1; cube && f < P; ++f) cube = (ft.p[f] - ft.p[f - 1]) == stride;
-        cube = cube && stride > 0 && (stride % 4) == 0 && (size_t)stride >= npix &&
-               full_tiles * TILE < (size_t)1 << 31;
+        cube = cube && stride > 0 && (stride % 4) == 0 && (size_t)stride >= npix;
         TmapParam tm{};
-        if (cube) cube = ab_make_stack_tmap(ctx, ft.p[0], npix, (size_t)stride, P, TILE, &tm);
-        const size_t smem = sizeof(StackTmaSmem<P>);
-        constexpr int threads = A_THREADS + B_THREADS + PROD_THREADS;
-        auto kern = cube ? stack_tma_kernel<P, true> : stack_tma_kernel<P, false>;
+        if (cube) cube = ab_make_stack_tmap(ctx, ft.p[0], npix, (size_t)stride, P, 32, &tm);
+        // scattered frames: P small bulk copies per group measured slower (1.18 ms) than plain
+        // coalesced loads (0.92 ms) -> only the tensor-map form is used unless forced
+        if (!cube && !ctx->force_tma1d)
+            return launch_ldg<P, MN, MD>(ctx, ft, npix, sl, sh, max_iter, d_out, d_rej, stream);
+        const size_t smem = sizeof(WarpTmaSmem<P>) * WARPS_PER_BLOCK;
+        constexpr int threads = WARPS_PER_BLOCK * 32;
+        auto kern = cube ? stack_wtma_kernel<P, MN, MD, true> : stack_wtma_kernel<P, MN, MD, false>;
         AB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
         int per_sm = 0;
         AB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
         if (per_sm < 1) per_sm = 1;
         size_t grid = (size_t)ctx->sm_count * per_sm;
-        if (grid > full_tiles) grid = full_tiles;
-        kern<<<(unsigned)grid, threads, smem, stream>>>(ft, tm, full_tiles, sl, sh, max_iter, d_out,
-                                                        d_rej, ctx->stack_dbg);
+        const size_t need = (groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+        if (grid > need) grid = need;
+        kern<<<(unsigned)grid, threads, smem, stream>>>(ft, tm, groups, sl, sh, max_iter,
+                                                        CeConst{1, -1}, d_out, d_rej);
         AB_LAUNCH_CHECK(ctx);
     }
-    const size_t done = full_tiles * TILE;
-    if (done < npix) {  // ragged tail (or everything, for unaligned frames): LDG kernel
+    const size_t done = groups * 32;
+    if (done < npix) {  // ragged tail (or everything, for unaligned frames): plain loads
         FrameTable tail;
         for (int f = 0; f < AB_MAX_FRAMES; ++f) tail.p[f] = f < P ? ft.p[f] + done : nullptr;
-        return launch_ldg<P>(ctx, tail, npix - done, sl, sh, max_iter, d_out + done, d_rej, stream);
+        return launch_ldg<P, MN, MD>(ctx, tail, npix - done, sl, sh, max_iter, d_out + done, d_rej,
+                                     stream);
     }
     return AB_OK;
+}
+
+// Default mix per frame count (tuned on B200 at P = 32).
+constexpr int DEFAULT_MN = 1, DEFAULT_MD = 2;
+
+// P = 32 also carries alternative mixes (AB_STACK_MIX=1..7) for A/B measurements; they are
+// instantiated in stack_inst_mix*.cu.
+#define AB_MIX_LIST(X) X(1, 0, 1) X(2, 1, 3) X(3, 2, 5) X(4, 3, 5) X(5, 2, 3) X(6, 3, 4) X(7, 1, 1)
+#define AB_MIX_EXTERN(idx, mn, md)                                                               \
+    extern template ab_status launch_mix<32, mn, md>(ab_ctx *, const FrameTable &, size_t, float, \
+                                                     float, unsigned, float *,                   \
+                                                     unsigned long long *, cudaStream_t);
+AB_MIX_LIST(AB_MIX_EXTERN)
+#undef AB_MIX_EXTERN
+
+template <int P>
+ab_status launch_tile(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, float sh,
+                      unsigned max_iter, float *d_out, unsigned long long *d_rej,
+                      cudaStream_t stream) {
+    if constexpr (P == 32) {
+#define AB_MIX_CASE(idx, mn, md)                                                                 \
+    case idx:                                                                                    \
+        return launch_mix<32, mn, md>(ctx, ft, npix, sl, sh, max_iter, d_out, d_rej, stream);
+        switch (ctx->stack_mix) {
+            AB_MIX_LIST(AB_MIX_CASE)
+            default:
+                break;
+        }
+#undef AB_MIX_CASE
+    }
+    return launch_mix<P, DEFAULT_MN, DEFAULT_MD>(ctx, ft, npix, sl, sh, max_iter, d_out, d_rej,
+                                                 stream);
 }
 
 }  // namespace abk

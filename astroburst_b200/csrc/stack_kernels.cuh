@@ -137,6 +137,24 @@ __device__ __forceinline__ void sort_network(float (&s)[P], const CeConst &k) {
                                      std::make_integer_sequence<int, OemHolder<P>::net.count>{});
 }
 
+// ---- x / n for a small positive integer n, correctly rounded, without the f64 division routine.
+// r = RN(1/n) from a table; q = RN(x r); rem = x - n q exactly (fma); q' = RN(q + rem r) is the
+// correctly rounded quotient (Markstein).  Checked against the hardware division for 5e8 operands
+// over n = 1..256 on the host.
+struct RcpTable {
+    double r[AB_MAX_FRAMES + 1];
+    constexpr RcpTable() : r{} {
+        r[0] = 0.0;
+        for (int i = 1; i <= AB_MAX_FRAMES; ++i) r[i] = 1.0 / (double)i;
+    }
+};
+static __constant__ RcpTable g_rcp = RcpTable();
+__device__ __forceinline__ double div_small(double x, int n) {
+    const double r = g_rcp.r[n], dn = (double)n;
+    const double q = x * r;
+    return fma(fma(-q, dn, x), r, q);
+}
+
 // ---- f64 sums of the surviving run s[a..b) of the ascending samples.
 //
 // The reference accumulates `v as f64` (combine.rs:51,90).  Converting every sample costs one
@@ -158,9 +176,9 @@ __device__ __forceinline__ double sum_run_mem(const float *s, int stride, int a,
         const int mid = (a + b) >> 1;
         const float c = s[mid * stride];
         float lo = 0.0f, hi = 0.0f;
-#pragma unroll 2
+#pragma unroll 1
         for (int j = a; j < mid; ++j) lo += s[j * stride] - c;
-#pragma unroll 2
+#pragma unroll 1
         for (int j = mid + 1; j < b; ++j) hi += s[j * stride] - c;
         const float T = next_pow2_above(s0);
         if (hi < T && -lo < T) return (double)(b - a) * (double)c + (double)(hi + lo);
@@ -232,20 +250,21 @@ __device__ __forceinline__ float clip_combine_sorted_mem(const float *s, int str
                 const int m = n >> 1;
                 const float med = s[m * stride];
                 float mad = CUDART_INF_F;
+#pragma unroll 1
                 for (int t = 0; t <= m; ++t) {
                     const float left = med - s[t * stride];
                     const float right = (t + m < n) ? s[(t + m) * stride] - med : CUDART_INF_F;
                     mad = fminf(mad, fmaxf(left, right));
                 }
                 center = med;
-                sigma = (float)fmax((double)mad * MAD_TO_SIGMA, 1e-10);
+                sigma = fmaxf((float)((double)mad * MAD_TO_SIGMA), 1e-10f);
             }
         } else {
-            const double nn = (double)len;
-            const double mean = sum_run_mem(s, stride, a, b) / nn;
+            const double mean = div_small(sum_run_mem(s, stride, a, b), len);
             const double ss = sumsq_run_mem(s, stride, a, b, mean);
             center = (float)mean;
-            sigma = (float)fmax(sqrt(ss / fmax(nn - 1.0, 1.0)), 1e-10);
+            // (float)max(sd, 1e-10) == max((float)sd, (float)1e-10): rounding is monotone
+            sigma = fmaxf((float)sqrt(div_small(ss, len > 2 ? len - 1 : 1)), 1e-10f);
             mean_known = true;
             mean_cur = mean;
         }
@@ -268,30 +287,186 @@ __device__ __forceinline__ float clip_combine_sorted_mem(const float *s, int str
     const int len = b - a;
     if (len == 0) return isfinite(last_center) ? last_center : 0.0f;  // combine.rs:85-88
     if (mean_known) return (float)mean_cur;  // same run, same summation order as the last pass
-    return (float)(sum_run_mem(s, stride, a, b) / (double)len);
+    return (float)div_small(sum_run_mem(s, stride, a, b), len);
 }
 
 // Out-of-line: one copy of the dynamic-index code per kernel.
-static __device__ __noinline__ float finish_parked(const float *s, int stride, unsigned meta, int P,
-                                                   float last_center, float aux, unsigned &rej,
-                                                   float sigma_low, float sigma_high,
-                                                   unsigned max_iter) {
-    const int n = (int)((meta >> 8) & 0x1ffu);  // finite samples (== P unless the generic case)
-    unsigned it0 = 0;
-    if (meta & META_FINAL_ONLY) it0 = 0xffffffffu;  // >= max_iter: the clip loop is skipped
-    return clip_combine_sorted_mem(s, stride, n, 0, n, it0, last_center,
-                                   (meta & META_SIGMA0) != 0, aux, rej, sigma_low, sigma_high,
-                                   max_iter);
+static __device__ __noinline__ float finish_dynamic(const float *s, int stride, int n, int a, int b,
+                                                    unsigned it0, float last_center,
+                                                    bool have_sigma0, float sigma0, unsigned &rej,
+                                                    float sigma_low, float sigma_high,
+                                                    unsigned max_iter) {
+    return clip_combine_sorted_mem(s, stride, n, a, b, it0, last_center, have_sigma0, sigma0, rej,
+                                   sigma_low, sigma_high, max_iter);
 }
 
-// Phase A on a register array of exactly P finite-or-+inf samples (n of them finite).
-// Returns true when `result` is final (such a pixel rejected nothing); false when the pixel must
-// be finished by phase B, in which case s[] is sorted, result = last center, aux = iteration 0's
-// sigma (META_SIGMA0) and meta = n << 8 | flags.
+// Phase B of a META_SIGMA0 pixel (all P samples finite, something rejected at iteration 0).
+// The sorted samples are re-read into registers with immediate offsets; the surviving run [a, b)
+// almost always keeps the "core" [E, P-E), so the passes of iterations >= 1 run over the core with
+// literal register indices (no loop, address or predicate instructions) and only the few edge
+// elements [a, E) and [P-E, b) are visited with dynamic indices in shared memory.  The core's exact
+// f32 difference sums (see sum_run_mem) do not depend on the iteration and are taken once.  A run
+// that loses core elements continues in the dynamic-index code at the same iteration.
+template <int P>
+__device__ __forceinline__ float finish_static(const float *col, int stride, float med, float sigma0,
+                                               unsigned &rej, float sigma_low, float sigma_high,
+                                               unsigned max_iter) {
+    constexpr int H = P / 2;
+    constexpr int E = P >= 24 ? 3 : (P >= 12 ? 2 : (P >= 6 ? 1 : 0));
+    constexpr int C0 = E, C1 = P - E;
+    float s[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) s[j] = col[j * stride];
+    float lo_acc[2] = {0.0f, 0.0f}, hi_acc[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int j = C0; j < H; ++j) lo_acc[j & 1] += s[j] - med;  // <= 0
+#pragma unroll
+    for (int j = H + 1; j < C1; ++j) hi_acc[j & 1] += s[j] - med;  // >= 0
+    const float core_lo = lo_acc[0] + lo_acc[1], core_hi = hi_acc[0] + hi_acc[1];
+
+    int a = 0, b = P;
+    float center = med, sigma = sigma0;
+    for (unsigned it = 0;;) {
+        const float lo = -sigma_low * sigma;
+        const float hi = sigma_high * sigma;
+        int na = a, nb = b;
+#pragma unroll 1
+        while (na < nb && !(col[na * stride] - center >= lo)) ++na;
+#pragma unroll 1
+        while (nb > na && !(col[(nb - 1) * stride] - center <= hi)) --nb;
+        const int removed = (b - a) - (nb - na);
+        rej += (unsigned)removed;
+        a = na;
+        b = nb;
+        const int len = b - a;
+        // removed == 0 at iteration >= 1: the loop ends and the final mean is the mean just used
+        // as center (same run); `center` holds its f32 value already
+        if (removed == 0 && it > 0) return center;
+        if (len == 0) return isfinite(center) ? center : 0.0f;  // combine.rs:85-88
+        ++it;
+        if (a > C0 || b < C1)  // the run lost core elements: rare, dynamic indices from here on
+            return finish_dynamic(col, stride, P, a, b, removed ? it : 0xffffffffu, center, false,
+                                  0.0f, rej, sigma_low, sigma_high, max_iter);
+        // mean of the run: the next iteration's center (combine.rs:49-53) or, when the loop is
+        // over, the result (combine.rs:90-91).  Exact sum = core sums + edge differences when
+        // the f32 certificate holds, else the f64 accumulation.
+        float d_lo = core_lo, d_hi = core_hi;
+#pragma unroll 1
+        for (int j = a; j < C0; ++j) d_lo += col[j * stride] - med;
+#pragma unroll 1
+        for (int j = C1; j < b; ++j) d_hi += col[j * stride] - med;
+        const float sa = col[a * stride];
+        const float T = next_pow2_above(sa);
+        double sum;
+        if (sa >= 1.17549435e-38f && col[(b - 1) * stride] <= 2.0f * sa && d_hi < T && -d_lo < T)
+            sum = (double)len * (double)med + (double)(d_hi + d_lo);
+        else
+            sum = sum_run_mem(col, stride, a, b);
+        const double mean = div_small(sum, len);
+        center = (float)mean;
+        if (removed == 0 || it >= max_iter || len < 2) return center;
+        // sample standard deviation of the run (combine.rs:54-60)
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = C0; j < C1; ++j) {
+            const double e = (double)s[j] - mean;
+            acc[j & 3] += e * e;
+        }
+#pragma unroll 1
+        for (int j = a; j < C0; ++j) {
+            const double e = (double)col[j * stride] - mean;
+            acc[0] += e * e;
+        }
+#pragma unroll 1
+        for (int j = C1; j < b; ++j) {
+            const double e = (double)col[j * stride] - mean;
+            acc[1] += e * e;
+        }
+        const double ss = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        sigma = fmaxf((float)sqrt(div_small(ss, len > 2 ? len - 1 : 1)), 1e-10f);
+    }
+}
+
+// Iteration 0 and the no-reject mean on the first N sorted samples of s[] (all finite; s[N..P) are
+// the +inf stand-ins of dropped samples).  Returns true when `result` is final (such a pixel
+// rejected nothing); false when the pixel must be finished by phase B: result = last center,
+// aux = iteration 0's sigma and meta = N << 8 | flags.
+template <int P, int N>
+__device__ __forceinline__ bool phase_a_tail(const float (&s)[P], float sigma_low, float sigma_high,
+                                             unsigned max_iter, float &result, float &aux,
+                                             unsigned &meta) {
+    static_assert(N >= 2 && N <= P, "phase_a_tail needs 2 <= N <= P");
+    // upper median, upper-median MAD (combine.rs:37-48); the differences d[j] = s[j] - med also
+    // feed the exact f32 sums of the mean (see sum_run_mem)
+    constexpr int H = N / 2;
+    const float med = s[H];
+    float lo_acc[2] = {0.0f, 0.0f}, hi_acc[2] = {0.0f, 0.0f};
+    float mad[2] = {CUDART_INF_F, CUDART_INF_F};
+    float d_first = 0.0f, d_last = 0.0f;
+#pragma unroll
+    for (int t = 0; t < (N + 1) / 2; ++t) {
+        float left = 0.0f, right = 0.0f;
+        if (t < H) {  // (t == H only for odd N: the window that starts at the median)
+            const float dl = s[t] - med;  // <= 0
+            lo_acc[t & 1] += dl;
+            left = -dl;
+            if (t == 0) d_first = dl;
+        }
+        if (t > 0) {  // (t == 0 pairs with the median itself: difference 0)
+            const float dr = s[t + H] - med;  // >= 0
+            hi_acc[t & 1] += dr;
+            right = dr;
+            if (t + H == N - 1) d_last = dr;
+        }
+        mad[t & 1] = fminf(mad[t & 1], fmaxf(left, right));
+    }
+    // (float)max(x, 1e-10) == max((float)x, (float)1e-10): rounding is monotone
+    const float sigma = fmaxf((float)((double)fminf(mad[0], mad[1]) * MAD_TO_SIGMA), 1e-10f);
+    const float lo = -sigma_low * sigma;
+    const float hi = sigma_high * sigma;
+    // nothing rejected (combine.rs:65-82) <=> the extreme samples pass; max_iter == 0 never clips
+    const bool keep_all = max_iter == 0 || (d_first >= lo && d_last <= hi);
+    const float d_lo = lo_acc[0] + lo_acc[1], d_hi = hi_acc[0] + hi_acc[1];
+    const float T = next_pow2_above(s[0]);
+    const bool exact = s[0] >= 1.17549435e-38f && s[N - 1] <= 2.0f * s[0] && d_hi < T && -d_lo < T;
+    if (keep_all && exact) {
+        const double sum = (double)N * (double)med + (double)(d_hi + d_lo);
+        result = (float)div_small(sum, N);
+        return true;
+    }
+    result = med;  // last_center carried into phase B
+    aux = sigma;
+    meta = ((unsigned)N << 8) | (keep_all ? META_FINAL_ONLY : META_SIGMA0);
+    return false;
+}
+
+// Frame-uniform gaps (the NaN borders registration leaves: every pixel of a region misses the
+// same frames) make n warp-uniform; up to MAX_MISSING dropped samples are then handled by a
+// register-resident tail specialised on n instead of the dynamic-index code.
+constexpr int MAX_MISSING = 8;
+template <int P, int K>
+__device__ __forceinline__ bool phase_a_uniform(const float (&s)[P], int n, float sigma_low,
+                                                float sigma_high, unsigned max_iter, float &result,
+                                                float &aux, unsigned &meta, bool &handled) {
+    if constexpr (K > MAX_MISSING || P - K < 2) {
+        handled = false;
+        return false;
+    } else {
+        if (n == P - K) {
+            handled = true;
+            return phase_a_tail<P, P - K>(s, sigma_low, sigma_high, max_iter, result, aux, meta);
+        }
+        return phase_a_uniform<P, K + 1>(s, n, sigma_low, sigma_high, max_iter, result, aux, meta,
+                                         handled);
+    }
+}
+
+// Phase A on a register array of exactly P finite-or-+inf samples (n of them finite; n_uni = n
+// when every lane of the warp has the same n, else -1).
 template <int P, int MN, int MD>
-__device__ __forceinline__ bool phase_a(float (&s)[P], int n, float sigma_low, float sigma_high,
-                                        unsigned max_iter, const CeConst &k, float &result,
-                                        float &aux, unsigned &meta) {
+__device__ __forceinline__ bool phase_a(float (&s)[P], int n, int n_uni, float sigma_low,
+                                        float sigma_high, unsigned max_iter, const CeConst &k,
+                                        float &result, float &aux, unsigned &meta) {
     aux = 0.0f;
     meta = 0u;
     if constexpr (P == 1) {
@@ -299,52 +474,17 @@ __device__ __forceinline__ bool phase_a(float (&s)[P], int n, float sigma_low, f
         return true;
     } else {
         sort_network<P, MN, MD>(s, k);
-        if (n != P) {  // non-finite samples present: rare, finished with dynamic indices
-            result = n ? s[0] : 0.0f;
-            if (n <= 1) return true;
-            meta = (unsigned)n << 8;
-            return false;
+        if (n == P) return phase_a_tail<P, P>(s, sigma_low, sigma_high, max_iter, result, aux, meta);
+        if (n == n_uni) {  // warp-uniform branch
+            bool handled;
+            const bool done = phase_a_uniform<P, 1>(s, n, sigma_low, sigma_high, max_iter, result,
+                                                    aux, meta, handled);
+            if (handled) return done;
         }
-        // iteration 0: upper median, upper-median MAD (combine.rs:37-48); the differences
-        // d[j] = s[j] - med also feed the exact f32 sums of the mean (see sum_run_mem)
-        constexpr int H = P / 2;
-        const float med = s[H];
-        float lo_acc[2] = {0.0f, 0.0f}, hi_acc[2] = {0.0f, 0.0f};
-        float mad[2] = {CUDART_INF_F, CUDART_INF_F};
-        float d_first = 0.0f, d_last = 0.0f;
-#pragma unroll
-        for (int t = 0; t < (P + 1) / 2; ++t) {
-            float left = 0.0f, right = 0.0f;
-            if (t < H) {  // (t == H only for odd P: the window that starts at the median)
-                const float dl = s[t] - med;  // <= 0
-                lo_acc[t & 1] += dl;
-                left = -dl;
-                if (t == 0) d_first = dl;
-            }
-            if (t > 0) {  // (t == 0 pairs with the median itself: difference 0)
-                const float dr = s[t + H] - med;  // >= 0
-                hi_acc[t & 1] += dr;
-                right = dr;
-                if (t + H == P - 1) d_last = dr;
-            }
-            mad[t & 1] = fminf(mad[t & 1], fmaxf(left, right));
-        }
-        const float sigma = (float)fmax((double)fminf(mad[0], mad[1]) * MAD_TO_SIGMA, 1e-10);
-        const float lo = -sigma_low * sigma;
-        const float hi = sigma_high * sigma;
-        // nothing rejected (combine.rs:65-82) <=> the extreme samples pass; max_iter == 0 never clips
-        const bool keep_all = max_iter == 0 || (d_first >= lo && d_last <= hi);
-        const float d_lo = lo_acc[0] + lo_acc[1], d_hi = hi_acc[0] + hi_acc[1];
-        const float T = next_pow2_above(s[0]);
-        const bool exact = s[0] >= 1.17549435e-38f && s[P - 1] <= 2.0f * s[0] && d_hi < T && -d_lo < T;
-        if (keep_all && exact) {
-            const double sum = (double)P * (double)med + (double)(d_hi + d_lo);
-            result = (float)(sum / (double)P);
-            return true;
-        }
-        result = med;  // last_center carried into phase B
-        aux = sigma;
-        meta = ((unsigned)P << 8) | (keep_all ? META_FINAL_ONLY : META_SIGMA0);
+        // ragged non-finite samples: rare, finished with dynamic indices (combine.rs:21-26 first)
+        result = n ? s[0] : 0.0f;
+        if (n <= 1) return true;
+        meta = (unsigned)n << 8;
         return false;
     }
 }
@@ -353,13 +493,17 @@ __device__ __forceinline__ bool phase_a(float (&s)[P], int n, float sigma_low, f
 // Warp-autonomous kernels: no block-wide synchronisation at all.
 //
 // Every warp walks its own sequence of 32-pixel groups.  Lanes whose pixel needs phase B park the
-// sorted samples in a warp-private ring in shared memory (column = ring slot, conflict-free); as
-// soon as the ring holds >= 32 parked pixels the warp finishes 32 of them at once, one per lane,
-// so phase B always runs with full lanes and only every ~6th group.  While one warp is in its
-// (FP64 / XU heavy) phase B the other warps of the SM keep the ALU and FMA pipes busy with their
-// sorting networks: warps drift apart instead of marching in lock-step.
+// sorted samples in a warp-private stack in shared memory (column = slot, conflict-free).  At the
+// top of a group iteration -- where nothing but the loop state is live, so the register-resident
+// phase B can be inlined without spills -- a warp whose stack holds >= DRAIN_AT pixels finishes
+// all of them at once, one per lane.  Phase B therefore runs every ~4th group with mostly full
+// lanes; while one warp is in its (FP64 / XU heavy) phase B the other warps of the SM keep the ALU
+// and FMA pipes busy with their sorting networks: warps drift apart instead of marching in
+// lock-step.  A group whose parked pixels do not fit the remaining slots (rare: several times the
+// average park rate) first empties the stack through the out-of-line dynamic-index code.
 constexpr int WARPS_PER_BLOCK = 8;
-constexpr int WQ_CAP = 32;  // ring slots per warp; a group that does not fit drains first
+constexpr int WQ_CAP = 32;    // slots per warp
+constexpr int DRAIN_AT = 24;  // inline drain threshold (average group parks ~6 pixels)
 
 template <int P, int CAP = WQ_CAP>
 struct WarpQueue {
@@ -371,20 +515,37 @@ struct WarpQueue {
     unsigned pix[CAP];  // pixel index relative to the launch (npix < 2^32 per launch)
 };
 
-// finish `cnt` (<= 32) parked pixels starting at ring position head; lane i takes entry i
-template <int P, int CAP>
-__device__ __forceinline__ void drain_batch(WarpQueue<P, CAP> &q, unsigned head, unsigned cnt, int lane,
-                                            float sigma_low, float sigma_high, unsigned max_iter,
-                                            float *__restrict__ out, unsigned &local_rej) {
+// finish the `cnt` (<= 32) parked pixels; lane i takes slot i.  kStatic: register-resident
+// phase B for META_SIGMA0 pixels (inlined once per kernel); otherwise everything goes through the
+// shared out-of-line dynamic-index code.
+template <int P, bool kStatic>
+__device__ __forceinline__ void drain_impl(WarpQueue<P> &q, unsigned cnt, int lane, float sigma_low,
+                                           float sigma_high, unsigned max_iter,
+                                           float *__restrict__ out, unsigned &local_rej) {
     if ((unsigned)lane < cnt) {
-        const unsigned slot = (head + lane) & (CAP - 1);
+        const unsigned meta = q.meta[lane];
+        const float *col = &q.v[0][lane];
         unsigned rej = 0;
-        const float r = finish_parked(&q.v[0][slot], CAP, q.meta[slot], P, q.lastc[slot],
-                                      q.aux[slot], rej, sigma_low, sigma_high, max_iter);
-        __stcs(out + q.pix[slot], r);
+        float r;
+        if (kStatic && (meta & META_SIGMA0) && ((meta >> 8) & 0x1ffu) == (unsigned)P) {
+            r = finish_static<P>(col, WQ_CAP, q.lastc[lane], q.aux[lane], rej, sigma_low,
+                                 sigma_high, max_iter);
+        } else {  // non-finite samples (n < P), or only the f64 mean of everything is left
+            const int n = (int)((meta >> 8) & 0x1ffu);
+            const unsigned it0 = (meta & META_FINAL_ONLY) ? 0xffffffffu : 0u;  // skips the clip loop
+            r = finish_dynamic(col, WQ_CAP, n, 0, n, it0, q.lastc[lane], (meta & META_SIGMA0) != 0,
+                               q.aux[lane], rej, sigma_low, sigma_high, max_iter);
+        }
+        __stcs(out + q.pix[lane], r);
         local_rej += rej;
     }
     __syncwarp();
+}
+template <int P>
+__device__ __noinline__ void drain_dynamic(WarpQueue<P> &q, unsigned cnt, int lane, float sigma_low,
+                                           float sigma_high, unsigned max_iter,
+                                           float *__restrict__ out, unsigned &local_rej) {
+    drain_impl<P, false>(q, cnt, lane, sigma_low, sigma_high, max_iter, out, local_rej);
 }
 
 // Non-finite samples -> +inf (they sort last and are not counted in n).  probe is NaN iff any
@@ -404,49 +565,43 @@ __device__ __forceinline__ int drop_non_finite(float (&s)[P], float probe) {
     return n;
 }
 
-// Shared tail of both kernels: phase A on the registers, store or park, drain when 32 are parked.
+// Shared tail of both kernels: phase A on the registers, then store or park.  Every lane runs
+// phase A (inactive lanes of a ragged last group carry zeros); n_uni is found with two votes only
+// when some lane of the warp dropped samples.
 template <int P, int MN, int MD>
-__device__ __forceinline__ void process_group(float (&s)[P], int n, bool active, size_t p, int lane,
-                                              WarpQueue<P> &q, unsigned &head, unsigned &count,
-                                              unsigned &local_rej, float sigma_low, float sigma_high,
-                                              unsigned max_iter, const CeConst &k,
-                                              float *__restrict__ out) {
+__device__ __forceinline__ void process_group(float (&s)[P], int n, bool active, unsigned p, int lane,
+                                              WarpQueue<P> &q, unsigned &count, unsigned &local_rej,
+                                              float sigma_low, float sigma_high, unsigned max_iter,
+                                              const CeConst &k, float *__restrict__ out) {
+    int n_uni = P;
+    if (__any_sync(0xffffffffu, n != P)) {
+        const int n0 = __shfl_sync(0xffffffffu, n, 0);
+        n_uni = __all_sync(0xffffffffu, n == n0) ? n0 : -1;
+    }
     float result, aux;
     unsigned meta;
-    bool park = false;
-    if (active) {
-        if (phase_a<P, MN, MD>(s, n, sigma_low, sigma_high, max_iter, k, result, aux, meta))
-            __stcs(out + p, result);
-        else
-            park = true;
-    }
+    const bool done =
+        phase_a<P, MN, MD>(s, n, n_uni, sigma_low, sigma_high, max_iter, k, result, aux, meta);
+    if (active && done) __stcs(out + p, result);
+    const bool park = active && !done;
     const unsigned pmask = __ballot_sync(0xffffffffu, park);
     if (pmask) {
         const unsigned c = __popc(pmask);
-        if (count + c > (unsigned)WQ_CAP) {  // make room: finish what is parked (< 32 lanes)
-            drain_batch<P, WQ_CAP>(q, head, count, lane, sigma_low, sigma_high, max_iter, out,
-                                   local_rej);
-            head = (head + count) & (WQ_CAP - 1);
+        if (count + c > (unsigned)WQ_CAP) {  // rare: make room first
+            drain_dynamic<P>(q, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
             count = 0;
         }
         if (park) {
-            const unsigned slot =
-                (head + count + __popc(pmask & ((1u << lane) - 1u))) & (WQ_CAP - 1);
+            const unsigned slot = count + __popc(pmask & ((1u << lane) - 1u));
 #pragma unroll
             for (int f = 0; f < P; ++f) q.v[f][slot] = s[f];
             q.meta[slot] = meta;
             q.lastc[slot] = result;
             q.aux[slot] = aux;
-            q.pix[slot] = (unsigned)p;
+            q.pix[slot] = p;
         }
         count += c;
         __syncwarp();
-        if (count >= 32u) {
-            drain_batch<P, WQ_CAP>(q, head, 32u, lane, sigma_low, sigma_high, max_iter, out,
-                                   local_rej);
-            head = (head + 32u) & (WQ_CAP - 1);
-            count -= 32u;
-        }
     }
 }
 
@@ -462,31 +617,32 @@ stack_warp_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigm
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     WarpQueue<P> &q = queues[warp];
-    unsigned head = 0, count = 0;  // warp-uniform ring state
+    unsigned count = 0;  // parked pixels (warp-uniform)
     unsigned local_rej = 0;
 
-    const size_t n_groups = (npix + 31) / 32;
-    const size_t warp_global = (size_t)blockIdx.x * WARPS_PER_BLOCK + warp;
-    const size_t warp_stride = (size_t)gridDim.x * WARPS_PER_BLOCK;
-    for (size_t g = warp_global; g < n_groups; g += warp_stride) {
-        const size_t p = g * 32 + lane;
+    // npix < 2^32 per launch (checked by the launcher): 32-bit pixel indices
+    const unsigned n_groups = (unsigned)((npix + 31) / 32);
+    const unsigned warp_global = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const unsigned warp_stride = gridDim.x * WARPS_PER_BLOCK;
+    for (unsigned g = warp_global; g < n_groups; g += warp_stride) {
+        if (count >= (unsigned)DRAIN_AT) {
+            drain_impl<P, true>(q, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
+            count = 0;
+        }
+        const unsigned p = g * 32 + lane;
         const bool active = p < npix;
         float s[P];
-        int n = P;
-        if (active) {
-            float probe = 0.0f;
+        float probe = 0.0f;
 #pragma unroll
-            for (int f = 0; f < P; ++f) {
-                s[f] = __ldcs(ft.p[f] + p);
-                probe = fmaf(s[f], 0.0f, probe);
-            }
-            n = drop_non_finite<P>(s, probe);
+        for (int f = 0; f < P; ++f) {
+            s[f] = active ? __ldcs(ft.p[f] + p) : 0.0f;
+            probe = fmaf(s[f], 0.0f, probe);
         }
-        process_group<P, MN, MD>(s, n, active, p, lane, q, head, count, local_rej, sigma_low,
-                                 sigma_high, max_iter, k, out);
+        const int n = drop_non_finite<P>(s, probe);
+        process_group<P, MN, MD>(s, n, active, p, lane, q, count, local_rej, sigma_low, sigma_high,
+                                 max_iter, k, out);
     }
-    if (count)
-        drain_batch<P, WQ_CAP>(q, head, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
+    if (count) drain_dynamic<P>(q, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
     const unsigned w = __reduce_add_sync(0xffffffffu, local_rej);
     if (lane == 0 && w) atomicAdd(rejected_total, (unsigned long long)w);
 }
@@ -563,7 +719,7 @@ struct WarpTmaSmem {
 template <int P, int MN, int MD, bool kTensorMap>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 3)
 stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__ TmapParam tmap,
-                  size_t n_groups, float sigma_low, float sigma_high, unsigned max_iter, CeConst k,
+                  unsigned n_groups, float sigma_low, float sigma_high, unsigned max_iter, CeConst k,
                   float *__restrict__ out, unsigned long long *__restrict__ rejected_total) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -579,26 +735,30 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
     }
     __syncwarp();
 
-    const size_t warp_global = (size_t)blockIdx.x * WARPS_PER_BLOCK + warp;
-    const size_t warp_stride = (size_t)gridDim.x * WARPS_PER_BLOCK;
+    const unsigned warp_global = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const unsigned warp_stride = gridDim.x * WARPS_PER_BLOCK;
 
-    auto issue = [&](size_t g) {  // lane 0 only
+    auto issue = [&](unsigned g) {  // lane 0 only
         mbar_arrive_expect_tx(bar, GROUP_BYTES);
         if constexpr (kTensorMap) {
             tma_load_2d(stage_addr, &tmap, (int)(g * 32), 0, bar);
         } else {
 #pragma unroll 4
             for (int f = 0; f < P; ++f)
-                tma_load_1d(stage_addr + f * 128, ft.p[f] + g * 32, 128, bar);
+                tma_load_1d(stage_addr + f * 128, ft.p[f] + (size_t)g * 32, 128, bar);
         }
     };
     if (lane == 0 && warp_global < n_groups) issue(warp_global);
 
-    unsigned head = 0, count = 0;  // warp-uniform ring state
+    unsigned count = 0;  // parked pixels (warp-uniform)
     unsigned local_rej = 0;
     uint32_t parity = 0;
-    for (size_t g = warp_global; g < n_groups; g += warp_stride, parity ^= 1u) {
-        const size_t p = g * 32 + lane;
+    for (unsigned g = warp_global; g < n_groups; g += warp_stride, parity ^= 1u) {
+        if (count >= (unsigned)DRAIN_AT) {
+            drain_impl<P, true>(sm.q, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
+            count = 0;
+        }
+        const unsigned p = g * 32 + lane;
         mbar_wait(bar, parity);
         float s[P];
         float probe = 0.0f;
@@ -615,12 +775,10 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
             issue(g + warp_stride);
         }
         const int n = drop_non_finite<P>(s, probe);
-        process_group<P, MN, MD>(s, n, true, p, lane, sm.q, head, count, local_rej, sigma_low,
-                                 sigma_high, max_iter, k, out);
+        process_group<P, MN, MD>(s, n, true, p, lane, sm.q, count, local_rej, sigma_low, sigma_high,
+                                 max_iter, k, out);
     }
-    if (count)
-        drain_batch<P, WQ_CAP>(sm.q, head, count, lane, sigma_low, sigma_high, max_iter, out,
-                               local_rej);
+    if (count) drain_dynamic<P>(sm.q, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
     const unsigned w = __reduce_add_sync(0xffffffffu, local_rej);
     if (lane == 0 && w) atomicAdd(rejected_total, (unsigned long long)w);
 }
@@ -683,7 +841,7 @@ ab_status launch_mix(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, f
         size_t grid = (size_t)ctx->sm_count * per_sm;
         const size_t need = (groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
         if (grid > need) grid = need;
-        kern<<<(unsigned)grid, threads, smem, stream>>>(ft, tm, groups, sl, sh, max_iter,
+        kern<<<(unsigned)grid, threads, smem, stream>>>(ft, tm, (unsigned)groups, sl, sh, max_iter,
                                                         CeConst{1, -1}, d_out, d_rej);
         AB_LAUNCH_CHECK(ctx);
     }

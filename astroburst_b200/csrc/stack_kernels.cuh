@@ -300,40 +300,77 @@ static __device__ __noinline__ float finish_dynamic(const float *s, int stride, 
                                    sigma_low, sigma_high, max_iter);
 }
 
-// Phase B of a META_SIGMA0 pixel (all P samples finite, something rejected at iteration 0).
-// The sorted samples are re-read into registers with immediate offsets; the surviving run [a, b)
-// almost always keeps the "core" [E, P-E), so the passes of iterations >= 1 run over the core with
-// literal register indices (no loop, address or predicate instructions) and only the few edge
-// elements [a, E) and [P-E, b) are visited with dynamic indices in shared memory.  The core's exact
-// f32 difference sums (see sum_run_mem) do not depend on the iteration and are taken once.  A run
-// that loses core elements continues in the dynamic-index code at the same iteration.
+// Frame-uniform gaps (the NaN borders registration leaves: every pixel of a region misses the
+// same frames) make n warp-uniform; up to MAX_MISSING dropped samples are then handled by
+// register-resident code specialised on n instead of the dynamic-index code.
+constexpr int MAX_MISSING = 8;
 template <int P>
-__device__ __forceinline__ float finish_static(const float *col, int stride, float med, float sigma0,
+constexpr int static_missing() {
+    return P >= 24 ? MAX_MISSING : 0;  // dropped samples phase B still handles in registers
+}
+
+// Phase B of a META_SIGMA0 pixel (n >= P - static_missing<P>() finite samples, something rejected
+// at iteration 0).  The sorted samples are re-read into registers with 128-bit loads; the
+// surviving run [a, b) almost always keeps the "core" [E, n-E), so the passes of iterations >= 1
+// run over the core with literal register indices (no loop, address or predicate instructions)
+// and only the few edge elements are visited with dynamic indices in shared memory.  Zones of
+// the core, for every admissible n (median index n/2 in [ML, MH]):
+//   A = [E, ML)       below the median: differences <= 0
+//   M = [ML, MH]      around the median: differences split by sign
+//   B = (MH, P-M-E)   above the median: differences >= 0
+//   C = [P-M-E, P-E)  only when n == P (else a dynamic edge up to b)
+// The core's exact f32 difference sums (see sum_run_mem) do not depend on the iteration and are
+// taken once.  A run that loses core elements continues in the dynamic-index code at the same
+// iteration.  col = the slot's row in the WarpQueue (stride 1, 16-byte aligned).
+template <int P>
+__device__ __forceinline__ float finish_static(const float *col, int n, float med, float sigma0,
                                                unsigned &rej, float sigma_low, float sigma_high,
                                                unsigned max_iter) {
-    constexpr int H = P / 2;
+    constexpr int M = static_missing<P>();
     constexpr int E = P >= 24 ? 3 : (P >= 12 ? 2 : (P >= 6 ? 1 : 0));
-    constexpr int C0 = E, C1 = P - E;
+    constexpr int ML = (P - M) / 2, MH = P / 2;
+    constexpr int C0 = E, CB = P - M - E, CC = P - E;
+    static_assert(C0 <= ML && MH < CB && CB <= CC, "zone layout");
+    const bool full = n == P;
+    const int c1 = full ? CC : CB;  // the static core of this pixel is [C0, c1)
     float s[P];
 #pragma unroll
-    for (int j = 0; j < P; ++j) s[j] = col[j * stride];
+    for (int j = 0; j + 4 <= P; j += 4) {
+        const float4 v4 = *reinterpret_cast<const float4 *>(col + j);
+        s[j] = v4.x;
+        s[j + 1] = v4.y;
+        s[j + 2] = v4.z;
+        s[j + 3] = v4.w;
+    }
+#pragma unroll
+    for (int j = P & ~3; j < P; ++j) s[j] = col[j];
     float lo_acc[2] = {0.0f, 0.0f}, hi_acc[2] = {0.0f, 0.0f};
 #pragma unroll
-    for (int j = C0; j < H; ++j) lo_acc[j & 1] += s[j] - med;  // <= 0
+    for (int j = C0; j < ML; ++j) lo_acc[j & 1] += s[j] - med;  // <= 0
 #pragma unroll
-    for (int j = H + 1; j < C1; ++j) hi_acc[j & 1] += s[j] - med;  // >= 0
+    for (int j = ML; j <= MH; ++j) {
+        const float d = s[j] - med;
+        lo_acc[j & 1] += fminf(d, 0.0f);
+        hi_acc[j & 1] += fmaxf(d, 0.0f);
+    }
+#pragma unroll
+    for (int j = MH + 1; j < CB; ++j) hi_acc[j & 1] += s[j] - med;  // >= 0
+    if (full) {
+#pragma unroll
+        for (int j = CB; j < CC; ++j) hi_acc[j & 1] += s[j] - med;
+    }
     const float core_lo = lo_acc[0] + lo_acc[1], core_hi = hi_acc[0] + hi_acc[1];
 
-    int a = 0, b = P;
+    int a = 0, b = n;
     float center = med, sigma = sigma0;
     for (unsigned it = 0;;) {
         const float lo = -sigma_low * sigma;
         const float hi = sigma_high * sigma;
         int na = a, nb = b;
 #pragma unroll 1
-        while (na < nb && !(col[na * stride] - center >= lo)) ++na;
+        while (na < nb && !(col[na] - center >= lo)) ++na;
 #pragma unroll 1
-        while (nb > na && !(col[(nb - 1) * stride] - center <= hi)) --nb;
+        while (nb > na && !(col[nb - 1] - center <= hi)) --nb;
         const int removed = (b - a) - (nb - na);
         rej += (unsigned)removed;
         a = na;
@@ -344,42 +381,49 @@ __device__ __forceinline__ float finish_static(const float *col, int stride, flo
         if (removed == 0 && it > 0) return center;
         if (len == 0) return isfinite(center) ? center : 0.0f;  // combine.rs:85-88
         ++it;
-        if (a > C0 || b < C1)  // the run lost core elements: rare, dynamic indices from here on
-            return finish_dynamic(col, stride, P, a, b, removed ? it : 0xffffffffu, center, false,
-                                  0.0f, rej, sigma_low, sigma_high, max_iter);
+        if (a > C0 || b < c1)  // the run lost core elements: rare, dynamic indices from here on
+            return finish_dynamic(col, 1, n, a, b, removed ? it : 0xffffffffu, center, false, 0.0f,
+                                  rej, sigma_low, sigma_high, max_iter);
         // mean of the run: the next iteration's center (combine.rs:49-53) or, when the loop is
         // over, the result (combine.rs:90-91).  Exact sum = core sums + edge differences when
         // the f32 certificate holds, else the f64 accumulation.
         float d_lo = core_lo, d_hi = core_hi;
 #pragma unroll 1
-        for (int j = a; j < C0; ++j) d_lo += col[j * stride] - med;
+        for (int j = a; j < C0; ++j) d_lo += col[j] - med;
 #pragma unroll 1
-        for (int j = C1; j < b; ++j) d_hi += col[j * stride] - med;
-        const float sa = col[a * stride];
+        for (int j = c1; j < b; ++j) d_hi += col[j] - med;
+        const float sa = col[a];
         const float T = next_pow2_above(sa);
         double sum;
-        if (sa >= 1.17549435e-38f && col[(b - 1) * stride] <= 2.0f * sa && d_hi < T && -d_lo < T)
+        if (sa >= 1.17549435e-38f && col[b - 1] <= 2.0f * sa && d_hi < T && -d_lo < T)
             sum = (double)len * (double)med + (double)(d_hi + d_lo);
         else
-            sum = sum_run_mem(col, stride, a, b);
+            sum = sum_run_mem(col, 1, a, b);
         const double mean = div_small(sum, len);
         center = (float)mean;
         if (removed == 0 || it >= max_iter || len < 2) return center;
         // sample standard deviation of the run (combine.rs:54-60)
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int j = C0; j < C1; ++j) {
+        for (int j = C0; j < CB; ++j) {
             const double e = (double)s[j] - mean;
             acc[j & 3] += e * e;
         }
+        if (full) {
+#pragma unroll
+            for (int j = CB; j < CC; ++j) {
+                const double e = (double)s[j] - mean;
+                acc[j & 3] += e * e;
+            }
+        }
 #pragma unroll 1
         for (int j = a; j < C0; ++j) {
-            const double e = (double)col[j * stride] - mean;
+            const double e = (double)col[j] - mean;
             acc[0] += e * e;
         }
 #pragma unroll 1
-        for (int j = C1; j < b; ++j) {
-            const double e = (double)col[j * stride] - mean;
+        for (int j = c1; j < b; ++j) {
+            const double e = (double)col[j] - mean;
             acc[1] += e * e;
         }
         const double ss = (acc[0] + acc[1]) + (acc[2] + acc[3]);
@@ -440,10 +484,7 @@ __device__ __forceinline__ bool phase_a_tail(const float (&s)[P], float sigma_lo
     return false;
 }
 
-// Frame-uniform gaps (the NaN borders registration leaves: every pixel of a region misses the
-// same frames) make n warp-uniform; up to MAX_MISSING dropped samples are then handled by a
-// register-resident tail specialised on n instead of the dynamic-index code.
-constexpr int MAX_MISSING = 8;
+// Warp-uniform n < P: the tail specialised on n (see MAX_MISSING).
 template <int P, int K>
 __device__ __forceinline__ bool phase_a_uniform(const float (&s)[P], int n, float sigma_low,
                                                 float sigma_high, unsigned max_iter, float &result,
@@ -505,10 +546,14 @@ constexpr int WARPS_PER_BLOCK = 8;
 constexpr int WQ_CAP = 32;    // slots per warp
 constexpr int DRAIN_AT = 24;  // inline drain threshold (average group parks ~6 pixels)
 
+// One row of sorted samples per slot.  ROW = 4 x odd words: a lane's row is 16-byte aligned and the
+// rows of a quarter-warp start 4 banks apart, so parking and the register reload are conflict-free
+// 128-bit accesses (P/4 instructions instead of P).
 template <int P, int CAP = WQ_CAP>
 struct WarpQueue {
     static constexpr int kCap = CAP;
-    float v[P][CAP];
+    static constexpr int ROW = 4 * (2 * ((P + 7) / 8) + 1);
+    alignas(16) float v[CAP][ROW];
     float lastc[CAP];
     float aux[CAP];
     unsigned meta[CAP];
@@ -524,16 +569,16 @@ __device__ __forceinline__ void drain_impl(WarpQueue<P> &q, unsigned cnt, int la
                                            float *__restrict__ out, unsigned &local_rej) {
     if ((unsigned)lane < cnt) {
         const unsigned meta = q.meta[lane];
-        const float *col = &q.v[0][lane];
+        const float *col = &q.v[lane][0];
         unsigned rej = 0;
         float r;
-        if (kStatic && (meta & META_SIGMA0) && ((meta >> 8) & 0x1ffu) == (unsigned)P) {
-            r = finish_static<P>(col, WQ_CAP, q.lastc[lane], q.aux[lane], rej, sigma_low,
-                                 sigma_high, max_iter);
-        } else {  // non-finite samples (n < P), or only the f64 mean of everything is left
-            const int n = (int)((meta >> 8) & 0x1ffu);
+        const int n = (int)((meta >> 8) & 0x1ffu);
+        if (kStatic && (meta & META_SIGMA0) && n >= P - static_missing<P>()) {
+            r = finish_static<P>(col, n, q.lastc[lane], q.aux[lane], rej, sigma_low, sigma_high,
+                                 max_iter);
+        } else {  // ragged non-finite samples, or only the f64 mean of everything is left
             const unsigned it0 = (meta & META_FINAL_ONLY) ? 0xffffffffu : 0u;  // skips the clip loop
-            r = finish_dynamic(col, WQ_CAP, n, 0, n, it0, q.lastc[lane], (meta & META_SIGMA0) != 0,
+            r = finish_dynamic(col, 1, n, 0, n, it0, q.lastc[lane], (meta & META_SIGMA0) != 0,
                                q.aux[lane], rej, sigma_low, sigma_high, max_iter);
         }
         __stcs(out + q.pix[lane], r);
@@ -593,8 +638,12 @@ __device__ __forceinline__ void process_group(float (&s)[P], int n, bool active,
         }
         if (park) {
             const unsigned slot = count + __popc(pmask & ((1u << lane) - 1u));
+            float *row = &q.v[slot][0];
 #pragma unroll
-            for (int f = 0; f < P; ++f) q.v[f][slot] = s[f];
+            for (int f = 0; f + 4 <= P; f += 4)
+                *reinterpret_cast<float4 *>(row + f) = make_float4(s[f], s[f + 1], s[f + 2], s[f + 3]);
+#pragma unroll
+            for (int f = P & ~3; f < P; ++f) row[f] = s[f];
             q.meta[slot] = meta;
             q.lastc[slot] = result;
             q.aux[slot] = aux;
@@ -632,12 +681,13 @@ stack_warp_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigm
         const unsigned p = g * 32 + lane;
         const bool active = p < npix;
         float s[P];
-        float probe = 0.0f;
+        float pr[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // NaN iff a sample of the pixel is non-finite
 #pragma unroll
         for (int f = 0; f < P; ++f) {
             s[f] = active ? __ldcs(ft.p[f] + p) : 0.0f;
-            probe = fmaf(s[f], 0.0f, probe);
+            pr[f & 3] = fmaf(s[f], 0.0f, pr[f & 3]);
         }
+        const float probe = (pr[0] + pr[1]) + (pr[2] + pr[3]);
         const int n = drop_non_finite<P>(s, probe);
         process_group<P, MN, MD>(s, n, active, p, lane, q, count, local_rej, sigma_low, sigma_high,
                                  max_iter, k, out);
@@ -761,16 +811,18 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
         const unsigned p = g * 32 + lane;
         mbar_wait(bar, parity);
         float s[P];
-        float probe = 0.0f;
+        float pr[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // NaN iff a sample of the pixel is non-finite
 #pragma unroll
         for (int f = 0; f < P; ++f) {
             s[f] = sm.stage[f][lane];
-            probe = fmaf(s[f], 0.0f, probe);
+            pr[f & 3] = fmaf(s[f], 0.0f, pr[f & 3]);
         }
+        const float probe = (pr[0] + pr[1]) + (pr[2] + pr[3]);
         // every lane has consumed its column (probe depends on all P loads): refill the stage
         asm volatile("" ::"f"(probe) : "memory");
         __syncwarp();
         if (lane == 0 && g + warp_stride < n_groups) {
+            // order the generic-proxy reads of the stage before the async-proxy refill
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(g + warp_stride);
         }

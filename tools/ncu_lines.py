@@ -19,7 +19,7 @@ for r in rows:
         ie = hdr.index("Instructions Executed")
         ss = hdr.index("# Samples")
         continue
-    if hdr and len(r) > ie and r[0].isdigit():
+    if hdr and len(r) > ie and r[0].isdigit() and r[ie].isdigit():
         n = int(r[ie]) / (npix / 32)
         tot += n
         if n >= thr:

@@ -6,7 +6,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "lib", "libastroburst_cuda.so")
+# AB_LIBRARY: developer override (A/B-testing a differently built copy of the same library)
+_SO = os.environ.get("AB_LIBRARY") or os.path.join(_HERE, "lib", "libastroburst_cuda.so")
 
 AB_OK, AB_ERR_INVALID, AB_ERR_CUDA, AB_ERR_UNSUPPORTED, AB_ERR_NOMEM = range(5)
 AB_MAX_FRAMES = 256

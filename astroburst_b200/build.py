@@ -60,6 +60,35 @@ def _compile(src: str, force: bool) -> str:
     return obj
 
 
+def build_variant(name: str, defines) -> str:
+    """Developer A/B builds: the same sources with extra -D flags -> lib/variants/<name>.so
+    (select it with AB_LIBRARY=<path>)."""
+    vdir = os.path.join(LIBDIR, "variants")
+    odir = os.path.join(vdir, name + "_obj")
+    os.makedirs(odir, exist_ok=True)
+    flags = NVCC_FLAGS + [f"-D{d}" for d in defines]
+
+    def one(src):
+        obj = os.path.join(odir, os.path.basename(src)[:-3] + ".o")
+        r = subprocess.run([NVCC] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    srcs = _sources()
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(one, srcs))
+    so = os.path.join(vdir, name + ".so")
+    r = subprocess.run([NVCC, "-shared", "-o", so] + objs +
+                       ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++",
+                        "-lcudart_static"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    for o in objs:
+        os.remove(o)
+    return so
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     srcs = _sources()
@@ -77,4 +106,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":  # --variant NAME DEF[=VAL] ...
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        build(force="--force" in sys.argv, verbose=True)

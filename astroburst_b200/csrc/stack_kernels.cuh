@@ -41,6 +41,20 @@
 
 #include "ab_internal.h"
 
+// developer A/B knobs (python -m astroburst_b200.build --variant NAME KNOB=VALUE)
+#ifndef AB_DRAIN_AT
+#define AB_DRAIN_AT 24
+#endif
+#ifndef AB_STATIC_PEEL
+#define AB_STATIC_PEEL 1
+#endif
+#ifndef AB_LDG_BLOCKS
+#define AB_LDG_BLOCKS 3
+#endif
+#ifndef AB_PROXY_FENCE
+#define AB_PROXY_FENCE 0
+#endif
+
 namespace abk {
 
 constexpr double MAD_TO_SIGMA = 1.4826;  // types/constants.rs:7
@@ -366,11 +380,28 @@ __device__ __forceinline__ float finish_static(const float *col, int n, float me
     for (unsigned it = 0;;) {
         const float lo = -sigma_low * sigma;
         const float hi = sigma_high * sigma;
+        // dev = v - center is monotone over the ascending samples: the rejects are a prefix and a
+        // suffix of the run.  The first E candidates of either end are tested in registers
+        // (a <= E and, for n == P, b >= P - E here); the loops only continue past them.
         int na = a, nb = b;
+        if constexpr (E > 0 && AB_STATIC_PEEL) {
+            int kl = 0, kr = 0;
+#pragma unroll
+            for (int j = 0; j < E; ++j) kl += !(s[j] - center >= lo) ? 1 : 0;
+            na = max(a, kl);  // rejected prefix of [0, E) (monotone), never below a
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) kr += !(s[P - 1 - j] - center <= hi) ? 1 : 0;
+                nb = min(b, P - kr);
+            }
+        }
 #pragma unroll 1
-        while (na < nb && !(col[na] - center >= lo)) ++na;
+        while (na < nb && (!AB_STATIC_PEEL || na >= E) && !(col[na] - center >= lo)) ++na;
 #pragma unroll 1
-        while (nb > na && !(col[nb - 1] - center <= hi)) --nb;
+        while (nb > na && (!AB_STATIC_PEEL || !full || nb <= P - E) &&
+               !(col[nb - 1] - center <= hi))
+            --nb;
+        if (nb < na) nb = na;  // everything rejected from both ends
         const int removed = (b - a) - (nb - na);
         rej += (unsigned)removed;
         a = na;
@@ -388,10 +419,15 @@ __device__ __forceinline__ float finish_static(const float *col, int n, float me
         // over, the result (combine.rs:90-91).  Exact sum = core sums + edge differences when
         // the f32 certificate holds, else the f64 accumulation.
         float d_lo = core_lo, d_hi = core_hi;
+#pragma unroll
+        for (int j = 0; j < C0; ++j) d_lo += j >= a ? s[j] - med : 0.0f;
+        if (full) {
+#pragma unroll
+            for (int j = CC; j < P; ++j) d_hi += j < b ? s[j] - med : 0.0f;
+        } else {
 #pragma unroll 1
-        for (int j = a; j < C0; ++j) d_lo += col[j] - med;
-#pragma unroll 1
-        for (int j = c1; j < b; ++j) d_hi += col[j] - med;
+            for (int j = c1; j < b; ++j) d_hi += col[j] - med;
+        }
         const float sa = col[a];
         const float T = next_pow2_above(sa);
         double sum;
@@ -416,15 +452,23 @@ __device__ __forceinline__ float finish_static(const float *col, int n, float me
                 acc[j & 3] += e * e;
             }
         }
-#pragma unroll 1
-        for (int j = a; j < C0; ++j) {
-            const double e = (double)col[j] - mean;
-            acc[0] += e * e;
+#pragma unroll
+        for (int j = 0; j < C0; ++j) {
+            const double e = (double)s[j] - mean;
+            acc[j & 3] += j >= a ? e * e : 0.0;
         }
+        if (full) {
+#pragma unroll
+            for (int j = CC; j < P; ++j) {
+                const double e = (double)s[j] - mean;
+                acc[j & 3] += j < b ? e * e : 0.0;
+            }
+        } else {
 #pragma unroll 1
-        for (int j = c1; j < b; ++j) {
-            const double e = (double)col[j] - mean;
-            acc[1] += e * e;
+            for (int j = c1; j < b; ++j) {
+                const double e = (double)col[j] - mean;
+                acc[1] += e * e;
+            }
         }
         const double ss = (acc[0] + acc[1]) + (acc[2] + acc[3]);
         sigma = fmaxf((float)sqrt(div_small(ss, len > 2 ? len - 1 : 1)), 1e-10f);
@@ -544,7 +588,7 @@ __device__ __forceinline__ bool phase_a(float (&s)[P], int n, int n_uni, float s
 // average park rate) first empties the stack through the out-of-line dynamic-index code.
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr int WQ_CAP = 32;    // slots per warp
-constexpr int DRAIN_AT = 24;  // inline drain threshold (average group parks ~6 pixels)
+constexpr int DRAIN_AT = AB_DRAIN_AT;  // inline drain threshold (average group parks ~6 pixels)
 
 // One row of sorted samples per slot.  ROW = 4 x odd words: a lane's row is 16-byte aligned and the
 // rows of a quarter-warp start 4 banks apart, so parking and the register reload are conflict-free
@@ -657,7 +701,7 @@ __device__ __forceinline__ void process_group(float (&s)[P], int n, bool active,
 // Plain coalesced loads (one 128 B line per warp per frame plane): frames that are not 16-byte
 // aligned, and the ragged tail of the TMA kernel.
 template <int P, int MN, int MD>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 3)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AB_LDG_BLOCKS)
 stack_warp_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigma_low,
                   float sigma_high, unsigned max_iter, CeConst k, float *__restrict__ out,
                   unsigned long long *__restrict__ rejected_total) {
@@ -821,9 +865,12 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
         // every lane has consumed its column (probe depends on all P loads): refill the stage
         asm volatile("" ::"f"(probe) : "memory");
         __syncwarp();
+        // (write-after-read: the loads above have returned their data -- probe depends on all of
+        // them -- so the refill needs no proxy fence, only the warp-level ordering)
         if (lane == 0 && g + warp_stride < n_groups) {
-            // order the generic-proxy reads of the stage before the async-proxy refill
+#if AB_PROXY_FENCE
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
             issue(g + warp_stride);
         }
         const int n = drop_non_finite<P>(s, probe);
@@ -908,11 +955,11 @@ ab_status launch_mix(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, f
 }
 
 // Default mix per frame count (tuned on B200 at P = 32).
-constexpr int DEFAULT_MN = 1, DEFAULT_MD = 2;
+constexpr int DEFAULT_MN = 2, DEFAULT_MD = 3;
 
 // P = 32 also carries alternative mixes (AB_STACK_MIX=1..7) for A/B measurements; they are
 // instantiated in stack_inst_mix*.cu.
-#define AB_MIX_LIST(X) X(1, 0, 1) X(2, 1, 3) X(3, 2, 5) X(4, 3, 5) X(5, 2, 3) X(6, 3, 4) X(7, 1, 1)
+#define AB_MIX_LIST(X) X(1, 0, 1) X(2, 1, 3) X(3, 2, 5) X(4, 3, 5) X(5, 1, 2) X(6, 3, 4) X(7, 1, 1)
 #define AB_MIX_EXTERN(idx, mn, md)                                                               \
     extern template ab_status launch_mix<32, mn, md>(ab_ctx *, const FrameTable &, size_t, float, \
                                                      float, unsigned, float *,                   \

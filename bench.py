@@ -43,7 +43,8 @@ def _measured_peak():
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons of one GPU during the timed region (NVML in a thread,
+    1 ms period; falls back to `nvidia-smi -lms` when the NVML binding is missing)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -53,8 +54,45 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.sm = []
+        self.reasons = set()
+        self.mx = None
+        self.stop_flag = False
+        self.nvml = None
+
+    def _nvml_loop(self):
+        n, h = self.nvml, self.handle
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                "sw_power_cap": 0x4}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for nm, b in bits.items():
+                    if r & b:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        try:
+            import pynvml as n
+            n.nvmlInit()
+            # NVML indices follow PCI order; CUDA_VISIBLE_DEVICES may remap -> go through the UUID
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            try:
+                self.handle = n.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.handle = n.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+            self.nvml = n
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
@@ -70,6 +108,12 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                    "sm_max_mhz": self.mx, "samples": len(self.sm),
+                    "reasons": sorted(self.reasons), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -92,7 +136,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def cpu_sample_rate(frames_rows, threads=None):

@@ -83,6 +83,9 @@ ab_status ab_scratch_reserve(ab_ctx *ctx, int slot, size_t bytes);
 struct FrameTable {
     const float *p[AB_MAX_FRAMES];
 };
+ab_status ab_stack_launch_deep(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix,
+                               float sigma_low, float sigma_high, unsigned max_iter, float *d_out,
+                               unsigned long long *d_rejected, cudaStream_t stream);
 ab_status ab_stack_launch(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix,
                           float sigma_low, float sigma_high, unsigned max_iter, float *d_out,
                           unsigned long long *d_rejected, cudaStream_t stream);

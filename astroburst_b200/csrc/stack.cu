@@ -4,7 +4,7 @@
 // src-tauri/src/core/stacking/combine.rs:14-92,160-182 (align=false core loop).
 // The register-resident kernels (exact frame count P, see stack_kernels.cuh) are instantiated
 // in stack_inst_*.cu for P = 1..32, 36, 40, 48, 56, 64; every other count <= 256 runs the
-// deep-stack kernel below.
+// chunked deep-stack kernel (stack_deep.cu).
 #include <cfloat>
 #include <cmath>
 
@@ -55,90 +55,6 @@ AB_DECL(36) AB_DECL(40) AB_DECL(48) AB_DECL(56) AB_DECL(64)
 #undef AB_DECL
 }  // namespace abk
 
-namespace {
-
-// ---------------------------------------------------------------------------------------------
-// Deep-stack path (frame counts without a register kernel, up to 256): one thread per pixel,
-// samples in a shared-memory column smem[i * DEEP_THREADS + tid] (conflict-free), bitonic sort
-// with runtime loops, then the dynamic-index algorithm.  Correct for any n; a warp-cooperative
-// version is future work.
-constexpr int DEEP_THREADS = 64;
-
-__global__ void __launch_bounds__(DEEP_THREADS)
-stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, int n_pad, size_t npix,
-                  float sigma_low, float sigma_high, unsigned max_iter, float *__restrict__ out,
-                  unsigned long long *__restrict__ rejected_total) {
-    extern __shared__ float sm[];
-    float *col = sm + threadIdx.x;
-    const int stride = DEEP_THREADS;
-    unsigned long long local_rej = 0;
-    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < npix;
-         base += (size_t)gridDim.x * blockDim.x) {
-        const size_t p = base + threadIdx.x;
-        const bool active = p < npix;
-        int n = 0;
-        for (int f = 0; f < n_pad; ++f) {
-            float v = CUDART_INF_F;
-            if (active && f < n_frames) {
-                v = __ldcs(ft.p[f] + p);
-                const bool fin = fabsf(v) < CUDART_INF_F;
-                n += fin ? 1 : 0;
-                v = fin ? v : CUDART_INF_F;
-            }
-            col[f * stride] = v;
-        }
-        // bitonic sort, ascending, private column (no cross-thread hazards)
-        for (int k = 2; k <= n_pad; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = 0; i < n_pad; ++i) {
-                    const int l = i ^ j;
-                    if (l > i) {
-                        const float x = col[i * stride], y = col[l * stride];
-                        const bool up = (i & k) == 0;
-                        if (up ? (x > y) : (x < y)) {
-                            col[i * stride] = y;
-                            col[l * stride] = x;
-                        }
-                    }
-                }
-            }
-        }
-        if (active) {
-            unsigned rej = 0;
-            const float r = abk::clip_combine_sorted_mem(col, stride, n, 0, n, 0, nanf(""), false,
-                                                         0.0f, rej, sigma_low, sigma_high,
-                                                         max_iter);
-            __stcs(out + p, r);
-            local_rej += rej;
-        }
-    }
-    unsigned w = __reduce_add_sync(0xffffffffu, (unsigned)local_rej);
-    if ((threadIdx.x & 31) == 0 && w) atomicAdd(rejected_total, (unsigned long long)w);
-}
-
-ab_status launch_deep(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix, float sl,
-                      float sh, unsigned max_iter, float *d_out, unsigned long long *d_rej,
-                      cudaStream_t stream) {
-    int n_pad = 2;
-    while (n_pad < n_frames) n_pad <<= 1;
-    const size_t smem = (size_t)n_pad * DEEP_THREADS * sizeof(float);
-    AB_CUDA(ctx, cudaFuncSetAttribute(stack_deep_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    int per_sm = 0;
-    AB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stack_deep_kernel,
-                                                               DEEP_THREADS, smem));
-    if (per_sm < 1) per_sm = 1;
-    const size_t need = (npix + DEEP_THREADS - 1) / DEEP_THREADS;
-    size_t grid = (size_t)ctx->sm_count * per_sm * 4;
-    if (grid > need) grid = need;
-    stack_deep_kernel<<<(unsigned)grid, DEEP_THREADS, smem, stream>>>(
-        ft, n_frames, n_pad, npix, sl, sh, max_iter, d_out, d_rej);
-    AB_LAUNCH_CHECK(ctx);
-    return AB_OK;
-}
-
-}  // namespace
-
 ab_status ab_stack_launch(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix,
                           float sigma_low, float sigma_high, unsigned max_iter, float *d_out,
                           unsigned long long *d_rejected, cudaStream_t stream) {
@@ -162,6 +78,6 @@ ab_status ab_stack_launch(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_
             break;
     }
 #undef AB_CASE
-    return launch_deep(ctx, ft, n_frames, npix, sigma_low, sigma_high, max_iter, d_out,
-                       d_rejected, stream);
+    return ab_stack_launch_deep(ctx, ft, n_frames, npix, sigma_low, sigma_high, max_iter, d_out,
+                                d_rejected, stream);
 }

@@ -42,6 +42,16 @@ def _measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one stack launch, from the committed
+    `ncu --set full` capture of this command (profiles/stack_ncu_traffic.json), else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "stack_ncu_traffic.json")) as f:
+            return int(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples SM clocks / throttle reasons of one GPU during the timed region (NVML in a thread,
     1 ms period; falls back to `nvidia-smi -lms` when the NVML binding is missing)."""
@@ -314,13 +324,13 @@ def main():
                     "h2d_bytes_per_step": N_FRAMES * npix * 4, "d2h_bytes_per_step": npix * 4 + 8,
                     "steps": args.e2e_steps, "matches_device_path": e2e_same},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "stack_tile_kernel<32>", "kernel_ms": kern_ms,
-                         "algorithmic_bytes": ALGO_BYTES},
+                         "frac": achieved / peak, "traffic": _ncu_traffic(), "peak_source": peak_src,
+                         "kernel": "abk::stack_wtma_kernel<32, 2, 3, true> (one launch per step)",
+                         "kernel_ms": kern_ms, "algorithmic_bytes": ALGO_BYTES},
         }
         if not args.no_cpu_baseline and world == 1:
-            sample_rows = 1024
-            r0 = ROWS // 2
+            sample_rows = ROWS  # the whole stack: ~1 s on 16 host cores (~15 core-seconds)
+            r0 = 0
             band = [f[r0:r0 + sample_rows].cpu().numpy() for f in frames]
             rate, dt, cores, cpu_out, _ = cpu_sample_rate(band)
             same = bool(np.array_equal(cpu_out, out[r0:r0 + sample_rows].cpu().numpy()))

@@ -4,7 +4,7 @@ usage: tools/ncu_summary.py gpurun_out/prof_stack.ncu-rep [npix]"""
 import collections, csv, subprocess, sys
 
 rep = sys.argv[1]
-npix = int(sys.argv[2]) if len(sys.argv) > 2 else 4096 * 4096
+npix = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 4096 * 4096
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -29,6 +29,18 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
         "smsp__average_warp_latency_per_inst_issued.ratio"]
 print("== kernel:", vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "")
+if "--traffic-json" in sys.argv:  # per-launch DRAM traffic for bench.py's roofline.traffic
+    import json
+    def _bytes(name):
+        i = hdr.index(name)
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+        return float(vals[i].replace(",", "")) * mult
+    rd, wr = _bytes("dram__bytes_read.sum"), _bytes("dram__bytes_write.sum")
+    out = sys.argv[sys.argv.index("--traffic-json") + 1]
+    json.dump({"kernel": vals[hdr.index("Kernel Name")], "dram_bytes_read": int(rd),
+               "dram_bytes_write": int(wr), "dram_bytes_per_launch": int(rd + wr),
+               "source": "ncu --set full --clock-control none, one launch of bench.py's step"},
+              open(out, "w"), indent=1)
 for w in want:
     if w in hdr:
         i = hdr.index(w)

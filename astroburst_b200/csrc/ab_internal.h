@@ -32,6 +32,10 @@ struct ab_ctx {
     int stack_mix = 0;         // AB_STACK_MIX: 0 default compare-exchange mix, 1..7 A/B variants (P = 32)
     bool force_tma1d = false;  // AB_STACK_FORCE_TMA1D=1: per-frame bulk copies instead of the tensor map
     void *encode_tmap_fn = nullptr;  // cuTensorMapEncodeTiled, resolved lazily
+    // work-queue counters of the stack kernels (one per launch in flight, round-robin)
+    static constexpr unsigned WORK_COUNTERS = 256;
+    unsigned *d_work_counters = nullptr;
+    std::atomic<unsigned> work_seq{0};
     std::mutex mu;
     std::atomic<uint64_t> launches{0};
     std::string last_error;

@@ -60,6 +60,7 @@ ab_status ab_ctx_create(int device, ab_ctx **out) {
         ok = ok && cudaEventCreateWithFlags(&ctx->copy_events[i], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaMalloc(&ctx->d_small, ab_ctx::SMALL_BYTES) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_work_counters, ab_ctx::WORK_COUNTERS * sizeof(unsigned)) == cudaSuccess;
     ok = ok && cudaMallocHost(&ctx->h_small, ab_ctx::SMALL_BYTES) == cudaSuccess;
     if (!ok) {
         ab_ctx_destroy(ctx);
@@ -80,6 +81,7 @@ void ab_ctx_destroy(ab_ctx *ctx) {
             if (ctx->copy_streams[i]) cudaStreamDestroy(ctx->copy_streams[i]);
         }
         if (ctx->d_small) cudaFree(ctx->d_small);
+        if (ctx->d_work_counters) cudaFree(ctx->d_work_counters);
         if (ctx->h_small) cudaFreeHost(ctx->h_small);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
     }

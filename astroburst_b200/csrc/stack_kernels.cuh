@@ -814,7 +814,8 @@ template <int P, int MN, int MD, bool kTensorMap>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 3)
 stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__ TmapParam tmap,
                   unsigned n_groups, float sigma_low, float sigma_high, unsigned max_iter, CeConst k,
-                  float *__restrict__ out, unsigned long long *__restrict__ rejected_total) {
+                  unsigned *__restrict__ work_counter, float *__restrict__ out,
+                  unsigned long long *__restrict__ rejected_total) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -829,9 +830,6 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
     }
     __syncwarp();
 
-    const unsigned warp_global = blockIdx.x * WARPS_PER_BLOCK + warp;
-    const unsigned warp_stride = gridDim.x * WARPS_PER_BLOCK;
-
     auto issue = [&](unsigned g) {  // lane 0 only
         mbar_arrive_expect_tx(bar, GROUP_BYTES);
         if constexpr (kTensorMap) {
@@ -842,12 +840,37 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
                 tma_load_1d(stage_addr + f * 128, ft.p[f] + (size_t)g * 32, 128, bar);
         }
     };
-    if (lane == 0 && warp_global < n_groups) issue(warp_global);
+    // SMs do not run at exactly the same speed: a fully static split left ~6 % of the SM-cycles
+    // idle at the tail.  Every warp takes its first `static_rounds` groups strided (no traffic),
+    // the last ~1/8 of the groups are handed out through a global counter (one same-address
+    // atomic per group for ALL groups measured 2x slower: ~900 atomics/us on one L2 line).  Lane 0
+    // fetches the next index one iteration ahead, so the atomic's latency hides behind the sort
+    // and the next group's TMA is issued on time.
+    const unsigned n_warps = gridDim.x * WARPS_PER_BLOCK;
+    const unsigned static_rounds = (n_groups / n_warps) * 7 / 8;
+    const unsigned dyn_base = static_rounds * n_warps;
+    unsigned g = blockIdx.x * WARPS_PER_BLOCK + warp;
+    unsigned round = 1;  // rounds taken so far (lane 0's view of g_next)
+    auto fetch_next = [&](unsigned cur) -> unsigned {  // lane 0 only
+        if (round < static_rounds) {
+            ++round;
+            return cur + n_warps;
+        }
+        return dyn_base + atomicAdd(work_counter, 1u);
+    };
+    unsigned g_next = 0;
+    if (static_rounds == 0) g = 0xffffffffu;  // tiny launch: everything through the counter
+    if (lane == 0) {
+        if (static_rounds == 0) g = dyn_base + atomicAdd(work_counter, 1u);
+        if (g < n_groups) issue(g);
+        g_next = fetch_next(g);
+    }
+    g = __shfl_sync(0xffffffffu, g, 0);
 
     unsigned count = 0;  // parked pixels (warp-uniform)
     unsigned local_rej = 0;
     uint32_t parity = 0;
-    for (unsigned g = warp_global; g < n_groups; g += warp_stride, parity ^= 1u) {
+    for (; g < n_groups; parity ^= 1u) {
         if (count >= (unsigned)DRAIN_AT) {
             drain_impl<P, true>(sm.q, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
             count = 0;
@@ -867,15 +890,22 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
         __syncwarp();
         // (write-after-read: the loads above have returned their data -- probe depends on all of
         // them -- so the refill needs no proxy fence, only the warp-level ordering)
-        if (lane == 0 && g + warp_stride < n_groups) {
+        const unsigned g_cur_next = __shfl_sync(0xffffffffu, g_next, 0);
+        if (lane == 0) {
+            if (g_cur_next < n_groups) {
 #if AB_PROXY_FENCE
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
-            issue(g + warp_stride);
+                issue(g_cur_next);
+                g_next = fetch_next(g_cur_next);  // consumed one iteration later
+            } else {
+                g_next = 0xffffffffu;
+            }
         }
         const int n = drop_non_finite<P>(s, probe);
         process_group<P, MN, MD>(s, n, true, p, lane, sm.q, count, local_rej, sigma_low, sigma_high,
                                  max_iter, k, out);
+        g = g_cur_next;
     }
     if (count) drain_dynamic<P>(sm.q, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
     const unsigned w = __reduce_add_sync(0xffffffffu, local_rej);
@@ -940,8 +970,11 @@ ab_status launch_mix(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, f
         size_t grid = (size_t)ctx->sm_count * per_sm;
         const size_t need = (groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
         if (grid > need) grid = need;
+        unsigned *counter =
+            ctx->d_work_counters + (ctx->work_seq.fetch_add(1) % ab_ctx::WORK_COUNTERS);
+        AB_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
         kern<<<(unsigned)grid, threads, smem, stream>>>(ft, tm, (unsigned)groups, sl, sh, max_iter,
-                                                        CeConst{1, -1}, d_out, d_rej);
+                                                        CeConst{1, -1}, counter, d_out, d_rej);
         AB_LAUNCH_CHECK(ctx);
     }
     const size_t done = groups * 32;

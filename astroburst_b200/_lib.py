@@ -27,6 +27,12 @@ class StackConfigC(C.Structure):
                 ("max_iterations", C.c_uint32), ("align", C.c_uint32)]
 
 
+class CalibrationConfigC(C.Structure):
+    _fields_ = [("master_bias", C.c_void_p), ("master_dark", C.c_void_p),
+                ("master_flat", C.c_void_p), ("dark_exposure_ratio", C.c_float),
+                ("clamp_negative", C.c_uint32)]
+
+
 class ImageStatsC(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("min", "max", "median", "mad", "sigma", "mean")] + [
         ("valid_count", C.c_uint64)]
@@ -105,6 +111,13 @@ SIGNATURES = {
                                           C.POINTER(StackConfigC), _vp, _vp, _vp]),
     "ab_sigma_clip_combine": (C.c_int, [_vp, _vp, _sz, C.c_float, C.c_float, C.c_uint32,
                                         C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    # calibration
+    "ab_median_combine": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz, _sz, _vp, _vp, C.c_float, _vp]),
+    "ab_median_combine_dev": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz, _vp, _vp, C.c_float, _vp, _vp]),
+    "ab_normalize_flat": (C.c_int, [_vp, _vp, _sz]),
+    "ab_normalize_flat_dev": (C.c_int, [_vp, _vp, _sz, _vp]),
+    "ab_calibrate_image": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
+    "ab_calibrate_image_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp]),
     # pointwise
     "ab_apply_stf_u8": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "ab_apply_stf_u8_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp, _vp]),

@@ -87,9 +87,17 @@ ab_status ab_scratch_reserve(ab_ctx *ctx, int slot, size_t bytes);
 struct FrameTable {
     const float *p[AB_MAX_FRAMES];
 };
+// per-sample preprocessing / mode of the chunked deep kernel (stack_deep.cu)
+struct DeepPre {
+    const float *bias = nullptr;  // v -= bias[p]
+    const float *dark = nullptr;  // v -= dark[p] * dark_ratio
+    float dark_ratio = 1.0f;
+    int median_only = 0;          // 1: upper median of the finite samples (calibration masters)
+};
 ab_status ab_stack_launch_deep(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix,
-                               float sigma_low, float sigma_high, unsigned max_iter, float *d_out,
-                               unsigned long long *d_rejected, cudaStream_t stream);
+                               float sigma_low, float sigma_high, unsigned max_iter,
+                               const DeepPre &pre, float *d_out, unsigned long long *d_rejected,
+                               cudaStream_t stream);
 ab_status ab_stack_launch(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix,
                           float sigma_low, float sigma_high, unsigned max_iter, float *d_out,
                           unsigned long long *d_rejected, cudaStream_t stream);

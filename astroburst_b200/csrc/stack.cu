@@ -78,6 +78,6 @@ ab_status ab_stack_launch(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_
             break;
     }
 #undef AB_CASE
-    return ab_stack_launch_deep(ctx, ft, n_frames, npix, sigma_low, sigma_high, max_iter, d_out,
-                                d_rejected, stream);
+    return ab_stack_launch_deep(ctx, ft, n_frames, npix, sigma_low, sigma_high, max_iter, DeepPre{},
+                                d_out, d_rejected, stream);
 }

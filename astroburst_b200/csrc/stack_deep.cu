@@ -235,7 +235,8 @@ template <int K>
 __global__ void __launch_bounds__(DEEP_WARPS * 32)
 stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t npix,
                   float sigma_low, float sigma_high, unsigned max_iter, CeConst kc,
-                  float *__restrict__ out, unsigned long long *__restrict__ rejected_total) {
+                  const __grid_constant__ DeepPre pre, float *__restrict__ out,
+                  unsigned long long *__restrict__ rejected_total) {
     extern __shared__ __align__(16) float deep_smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -256,10 +257,19 @@ stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t np
         double cd = 0.0, S1 = 0.0, S2 = 0.0;
         float pivot_acc = 0.0f, spread_acc = 0.0f;
         int pivot_cnt = 0;
+        // calibration.rs:160-162,199-206: frame - bias, then - dark * ratio (median-combine callers)
+        const float pre_b = (active && pre.bias) ? pre.bias[p] : 0.0f;
+        const float pre_d = (active && pre.dark) ? pre.dark[p] * pre.dark_ratio : 0.0f;
+        auto fetch = [&](int f) -> float {
+            if (!(active && f < n_frames)) return CUDART_INF_F;
+            float v = __ldcs(ft.p[f] + p);
+            if (pre.bias) v -= pre_b;
+            if (pre.dark) v -= pre_d;
+            return v;
+        };
         float nxt[CH];
 #pragma unroll
-        for (int j = 0; j < CH; ++j)
-            nxt[j] = (active && j < n_frames) ? __ldcs(ft.p[j] + p) : CUDART_INF_F;
+        for (int j = 0; j < CH; ++j) nxt[j] = fetch(j);
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
             float s[CH];
@@ -272,10 +282,7 @@ stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t np
             }
             if (k + 1 < K) {  // next chunk's loads fly while this one is sorted
 #pragma unroll
-                for (int j = 0; j < CH; ++j) {
-                    const int f = (k + 1) * CH + j;
-                    nxt[j] = (active && f < n_frames) ? __ldcs(ft.p[f] + p) : CUDART_INF_F;
-                }
+                for (int j = 0; j < CH; ++j) nxt[j] = fetch((k + 1) * CH + j);
             }
             abk::sort_network<CH, abk::DEFAULT_MN, abk::DEFAULT_MD>(s, kc);
             float *dst = col + (size_t)k * CH * 32;
@@ -293,12 +300,14 @@ stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t np
                     cd = (double)mk;
                 }
             }
+            if (!pre.median_only) {
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                if (j < nk) {
-                    const double d = (double)s[j] - cd;
-                    S1 += d;
-                    S2 += d * d;
+                for (int j = 0; j < CH; ++j) {
+                    if (j < nk) {
+                        const double d = (double)s[j] - cd;
+                        S1 += d;
+                        S2 += d * d;
+                    }
                 }
             }
         }
@@ -309,7 +318,10 @@ stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t np
 
         float result = 0.0f;
         unsigned rejected = 0;
-        if (n_tot == 1) {  // combine.rs:24-26
+        if (pre.median_only) {  // median_combine_row_major, calibration.rs:108-116
+            if (n_tot > 0)
+                result = select_rank<K>(col, n, n_tot, n_tot >> 1, pivot_acc / (float)pivot_cnt);
+        } else if (n_tot == 1) {  // combine.rs:24-26
 #pragma unroll
             for (int k = 0; k < K; ++k)
                 if (n[k]) result = at(col, k, 0);
@@ -394,8 +406,8 @@ stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t np
 
 template <int K>
 static ab_status launch_deep_k(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix, float sl,
-                               float sh, unsigned max_iter, float *d_out, unsigned long long *d_rej,
-                               cudaStream_t stream) {
+                               float sh, unsigned max_iter, const DeepPre &pre, float *d_out,
+                               unsigned long long *d_rej, cudaStream_t stream) {
     const size_t smem = (size_t)DEEP_WARPS * K * CH * 32 * sizeof(float);
     auto kern = stack_deep_kernel<K>;
     AB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -407,18 +419,18 @@ static ab_status launch_deep_k(ab_ctx *ctx, const FrameTable &ft, int n_frames, 
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, DEEP_WARPS * 32, smem, stream>>>(ft, n_frames, npix, sl, sh, max_iter,
-                                                           CeConst{1, -1}, d_out, d_rej);
+                                                           CeConst{1, -1}, pre, d_out, d_rej);
     AB_LAUNCH_CHECK(ctx);
     return AB_OK;
 }
 
 ab_status ab_stack_launch_deep(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix,
-                               float sl, float sh, unsigned max_iter, float *d_out,
-                               unsigned long long *d_rej, cudaStream_t stream) {
+                               float sl, float sh, unsigned max_iter, const DeepPre &pre,
+                               float *d_out, unsigned long long *d_rej, cudaStream_t stream) {
     const int K = (n_frames + CH - 1) / CH;
 #define AB_DEEP_CASE(k)                                                                         \
     case k:                                                                                     \
-        return launch_deep_k<k>(ctx, ft, n_frames, npix, sl, sh, max_iter, d_out, d_rej, stream);
+        return launch_deep_k<k>(ctx, ft, n_frames, npix, sl, sh, max_iter, pre, d_out, d_rej, stream);
     switch (K) {
         AB_DEEP_CASE(1) AB_DEEP_CASE(2) AB_DEEP_CASE(3) AB_DEEP_CASE(4) AB_DEEP_CASE(5)
         AB_DEEP_CASE(6) AB_DEEP_CASE(7) AB_DEEP_CASE(8)

@@ -159,6 +159,41 @@ ab_status ab_sigma_clip_combine(ab_ctx *ctx, const float *values, size_t n, floa
                                 float sigma_high, uint32_t max_iter, float *mean_out,
                                 uint32_t *rejected_out);
 
+/* ---------------------------------------------------------------- calibration
+ * core/stacking/calibration.rs.  FITS loading stays with the caller (load_fits_image).
+ *
+ * ab_median_combine: median_combine_row_major (:85-123) -- per pixel the upper median
+ * vals[len/2] of the finite samples, 0 when none -- fused with the per-frame preprocessing of
+ * create_master_dark (:160-186, frame - bias) and create_master_flat (:199-229, frame - bias, then
+ * - dark * 1.0): bias / dark may be NULL, dark_ratio multiplies the dark.  n_frames == 0 ->
+ * AB_ERR_INVALID ("No ... frames provided", :126-128).  n_frames <= AB_MAX_FRAMES. */
+ab_status ab_median_combine(ab_ctx *ctx, const float *const *frames, size_t n_frames, size_t rows,
+                            size_t cols, const float *bias, const float *dark, float dark_ratio,
+                            float *out);
+/* d_frames: HOST array of DEVICE pointers; npix = any row band (the multi-GPU sharding unit). */
+ab_status ab_median_combine_dev(ab_ctx *ctx, const float *const *d_frames, size_t n_frames,
+                                size_t npix, const float *d_bias, const float *d_dark,
+                                float dark_ratio, float *d_out, void *stream);
+/* master-flat normalisation, create_master_flat :231-252, in place: finite positive pixels are
+ * divided by their mean (f64 sum, f32 reciprocal), every other pixel becomes 1.0; untouched when
+ * no pixel is finite and positive. */
+ab_status ab_normalize_flat(ab_ctx *ctx, float *data, size_t len);
+ab_status ab_normalize_flat_dev(ab_ctx *ctx, float *d_data, size_t len, void *stream);
+/* CalibrationConfig (:8-13); masters may be NULL.  clamp_negative = 1: calibrate_image (:47-83,
+ * `if v < 0.0 { 0.0 }`); 0: the unclamped subtract_bias / subtract_dark / divide_flat (:15-45). */
+typedef struct ab_calibration_config {
+    const float *master_bias;
+    const float *master_dark;
+    const float *master_flat;
+    float dark_exposure_ratio;
+    uint32_t clamp_negative;
+} ab_calibration_config;
+ab_status ab_calibrate_image(ab_ctx *ctx, const float *raw, size_t len,
+                             const ab_calibration_config *cfg, float *out);
+/* the masters in cfg are DEVICE pointers here */
+ab_status ab_calibrate_image_dev(ab_ctx *ctx, const float *d_raw, size_t len,
+                                 const ab_calibration_config *cfg, float *d_out, void *stream);
+
 /* ---------------------------------------------------------------- pointwise operators
  * Each op has a host-buffer form (synchronous, copies included) and a `_dev` form (device
  * pointers, enqueued on `stream`, no synchronisation).  `len` = rows*cols. */

@@ -73,6 +73,13 @@ float orc_exact_mad_mut(float *data, size_t n, float median);
 void orc_sigma_clipped_stats(float *values, size_t *n, float kappa, size_t iterations,
                              double *median, double *sigma);
 
+/* ---- calibration (core/stacking/calibration.rs) ---- */
+int orc_median_combine(const float *const *frames, size_t n_frames, size_t rows, size_t cols,
+                       const float *bias, const float *dark, float dark_ratio, float *out);
+void orc_normalize_flat(float *data, size_t len);
+void orc_calibrate_image(const float *raw, size_t len, const float *bias, const float *dark,
+                         const float *flat, float dark_ratio, int clamp_negative, float *out);
+
 /* ---- stats / histogram / STF params (core/imaging/stats.rs, stf.rs) ---- */
 void orc_compute_image_stats(const float *data, size_t len, orc_image_stats *out);
 void orc_compute_image_stats_exact(const float *data, size_t len, orc_image_stats *out);

@@ -132,6 +132,41 @@ def stack_images(frames, sigma_low=3.0, sigma_high=3.0, max_iterations=5):
     return out, int(rej.value)
 
 
+# ---------------------------------------------------------------- calibration
+def median_combine(frames, bias=None, dark=None, dark_ratio=1.0):
+    """median_combine_row_major with the masters' per-frame preprocessing (calibration.rs:85-229)."""
+    fr = [_f32(f) for f in frames]
+    if not fr:
+        raise ValueError("No frames provided")
+    rows, cols = fr[0].shape
+    ptrs = (C.c_void_p * len(fr))(*[f.ctypes.data for f in fr])
+    b = _f32(bias) if bias is not None else None
+    d = _f32(dark) if dark is not None else None
+    out = np.empty((rows, cols), np.float32)
+    lib().orc_median_combine(ptrs, C.c_size_t(len(fr)), C.c_size_t(rows), C.c_size_t(cols),
+                             _p(b) if b is not None else None, _p(d) if d is not None else None,
+                             C.c_float(dark_ratio), _p(out))
+    return out
+
+
+def normalize_flat(data):
+    out = _f32(data).copy()
+    lib().orc_normalize_flat(_p(out), C.c_size_t(out.size))
+    return out
+
+
+def calibrate_image(raw, bias=None, dark=None, flat=None, dark_ratio=1.0, clamp_negative=True):
+    r = _f32(raw)
+    b = _f32(bias) if bias is not None else None
+    d = _f32(dark) if dark is not None else None
+    f = _f32(flat) if flat is not None else None
+    out = np.empty_like(r)
+    lib().orc_calibrate_image(_p(r), C.c_size_t(r.size), _p(b) if b is not None else None,
+                              _p(d) if d is not None else None, _p(f) if f is not None else None,
+                              C.c_float(dark_ratio), C.c_int(1 if clamp_negative else 0), _p(out))
+    return out
+
+
 def exact_median_mut(data):
     v = _f32(data).copy()
     return lib().orc_exact_median_mut(_p(v), C.c_size_t(v.size))

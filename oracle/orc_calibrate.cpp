@@ -1,0 +1,93 @@
+// orc_calibrate.cpp -- CPU oracle (TEST INFRASTRUCTURE, see oracle.h) for the calibration
+// masters and frame calibration.
+//
+// Restates src-tauri/src/core/stacking/calibration.rs:
+//   :15-45   subtract_bias, subtract_dark, divide_flat (calibrate without the final clamp)
+//   :47-83   calibrate_image
+//   :85-123  median_combine_row_major (upper median vals[len/2] of the finite samples; empty -> 0)
+//   :160-186 create_master_dark's preprocessing (frame - bias)
+//   :199-229 create_master_flat's preprocessing (frame - bias, then - dark * 1.0)
+//   :231-252 master-flat normalisation (sequential f64 sum of the finite positive pixels)
+// FITS loading (load_fits_image) is outside the path: frames arrive as arrays.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "oracle.h"
+
+namespace {
+// math/median.rs:4-13 -- total order with NaN last (only finite values reach it here)
+inline bool f32_less(float a, float b) {
+    const bool an = std::isnan(a), bn = std::isnan(b);
+    if (an || bn) return !an && bn;
+    return a < b;
+}
+}  // namespace
+
+extern "C" {
+
+int orc_median_combine(const float *const *frames, size_t n_frames, size_t rows, size_t cols,
+                       const float *bias, const float *dark, float dark_ratio, float *out) {
+    if (n_frames == 0) return 1;  // "No ... frames provided", calibration.rs:126-128
+#pragma omp parallel for schedule(dynamic)
+    for (long long y = 0; y < (long long)rows; ++y) {
+        std::vector<float> vals;
+        vals.reserve(n_frames);
+        const size_t base = (size_t)y * cols;
+        for (size_t x = 0; x < cols; ++x) {
+            vals.clear();
+            const size_t idx = base + x;
+            for (size_t f = 0; f < n_frames; ++f) {
+                float v = frames[f][idx];
+                if (bias) v = v - bias[idx];               // subtract_bias, :15-17
+                if (dark) v = v - dark[idx] * dark_ratio;  // subtract_dark, :19-25
+                if (std::isfinite(v)) vals.push_back(v);
+            }
+            if (vals.empty()) {
+                out[idx] = 0.0f;
+            } else {
+                const size_t mid = vals.size() / 2;
+                std::nth_element(vals.begin(), vals.begin() + mid, vals.end(), f32_less);
+                out[idx] = vals[mid];
+            }
+        }
+    }
+    return 0;
+}
+
+void orc_normalize_flat(float *data, size_t len) {
+    double sum = 0.0;
+    size_t count = 0;
+    for (size_t i = 0; i < len; ++i) {
+        const float v = data[i];
+        if (std::isfinite(v) && v > 0.0f) {
+            sum += (double)v;
+            ++count;
+        }
+    }
+    if (count == 0) return;
+    const double mean = sum / (double)count;
+    const float inv_mean = std::fabs(mean) > 1e-10 ? 1.0f / (float)mean : 1.0f;
+    for (size_t i = 0; i < len; ++i) {
+        float &v = data[i];
+        if (std::isfinite(v) && v > 0.0f) v *= inv_mean;
+        else v = 1.0f;
+    }
+}
+
+void orc_calibrate_image(const float *raw, size_t len, const float *bias, const float *dark,
+                         const float *flat, float dark_ratio, int clamp_negative, float *out) {
+#pragma omp parallel for
+    for (long long i = 0; i < (long long)len; ++i) {
+        float v = raw[i];
+        if (bias) v -= bias[i];
+        if (dark) v -= dark[i] * dark_ratio;
+        if (flat) {
+            const float fv = flat[i];
+            if (std::isfinite(fv) && std::fabs(fv) > 1e-4f) v /= fv;
+        }
+        out[i] = (clamp_negative && v < 0.0f) ? 0.0f : v;
+    }
+}
+
+}  // extern "C"

@@ -275,3 +275,36 @@ def test_stats_hist_path_close_to_exact(orc):
     assert h.valid_count == e.valid_count and h.min == e.min and h.max == e.max
     assert abs(h.median - e.median) < 1e-3 and abs(h.mad - e.mad) < 1e-3
     assert abs(h.mean - e.mean) < 1e-9 * abs(e.mean)
+
+
+# ---- core/stacking/calibration.rs:344-410 -------------------------------------------
+def test_calibration_reference_unit_tests(orc):
+    img = np.array([[110, 120], [130, 140]], np.float32)
+    r = orc.calibrate_image(img, bias=np.full((2, 2), 10, np.float32), clamp_negative=False)
+    assert abs(r[0, 0] - 100.0) < 1e-6 and abs(r[1, 1] - 130.0) < 1e-6      # test_subtract_bias
+    r = orc.calibrate_image(np.full((2, 2), 200, np.float32), dark=np.full((2, 2), 20, np.float32),
+                            dark_ratio=2.0, clamp_negative=False)
+    assert abs(r[0, 0] - 160.0) < 1e-6                                      # test_subtract_dark_with_ratio
+    img = np.array([[100, 200], [300, 400]], np.float32)
+    r = orc.calibrate_image(img, flat=np.array([[0.5, 1.0], [1.5, 2.0]], np.float32), clamp_negative=False)
+    assert np.all(np.abs(r - 200.0) < 1e-4)                                 # test_divide_flat
+    r = orc.calibrate_image(img, flat=np.array([[0.0, 1.0], [np.nan, 2.0]], np.float32), clamp_negative=False)
+    assert abs(r[0, 0] - 100.0) < 1e-4 and np.isfinite(r[0, 1]) and abs(r[1, 0] - 300.0) < 1e-4
+    raw = np.arange(110, 200, 10, dtype=np.float32).reshape(3, 3)           # test_full_calibration_pipeline
+    r = orc.calibrate_image(raw, np.full((3, 3), 10, np.float32), np.full((3, 3), 5, np.float32),
+                            np.ones((3, 3), np.float32), 1.0, True)
+    assert abs(r[0, 0] - 95.0) < 1e-4 and abs(r[2, 2] - 175.0) < 1e-4
+
+
+def test_median_combine_semantics(orc):
+    """upper median of the finite samples, 0 when none (calibration.rs:108-116)."""
+    fr = [np.full((1, 4), v, np.float32) for v in (5.0, 1.0, 3.0, 9.0)]
+    fr[0][0, 1] = np.nan
+    for f in fr:
+        f[0, 2] = np.inf
+    out = orc.median_combine(fr)
+    assert out[0, 0] == 5.0          # sorted 1 3 5 9 -> index 2
+    assert out[0, 1] == 3.0          # sorted 1 3 9   -> index 1
+    assert out[0, 2] == 0.0          # nothing finite
+    flat = orc.normalize_flat(np.array([[2.0, 4.0, -1.0, np.nan]], np.float32))
+    assert np.allclose(flat, [[2 / 3, 4 / 3, 1.0, 1.0]])

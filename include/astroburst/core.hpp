@@ -94,6 +94,53 @@ inline StackResult stack_images(const Context &ctx, const std::vector<Image> &im
                                   res.image.data.data(), &res.rejected_pixels));
     return res;
 }
+
+// core/stacking/calibration.rs (frames arrive loaded; FITS I/O stays with the caller)
+namespace calibration {
+struct CalibrationConfig {  // :8-13
+    const Image *master_bias = nullptr, *master_dark = nullptr, *master_flat = nullptr;
+    float dark_exposure_ratio = 1.0f;
+};
+// median_combine_row_major :85-123 of (frame - bias - dark * dark_ratio)
+inline Image median_combine(const Context &ctx, const std::vector<Image> &frames,
+                            const Image *bias = nullptr, const Image *dark = nullptr,
+                            float dark_ratio = 1.0f) {
+    if (frames.empty()) throw Error(AB_ERR_INVALID, "No frames provided");
+    const size_t rows = frames[0].rows, cols = frames[0].cols;
+    std::vector<const float *> ptrs;
+    for (const Image &f : frames) {
+        if (f.rows != rows || f.cols != cols) throw Error(AB_ERR_INVALID, "Dimension mismatch");  // :140-145
+        ptrs.push_back(f.data.data());
+    }
+    Image out(rows, cols);
+    ctx.check(ab_median_combine(ctx.get(), ptrs.data(), ptrs.size(), rows, cols,
+                                bias ? bias->data.data() : nullptr, dark ? dark->data.data() : nullptr,
+                                dark_ratio, out.data.data()));
+    return out;
+}
+inline Image create_master_bias(const Context &ctx, const std::vector<Image> &bias) {  // :125-152
+    return median_combine(ctx, bias);
+}
+inline Image create_master_dark(const Context &ctx, const std::vector<Image> &dark,
+                                const Image *master_bias) {  // :154-190
+    return median_combine(ctx, dark, master_bias);
+}
+inline Image create_master_flat(const Context &ctx, const std::vector<Image> &flat,
+                                const Image *master_bias, const Image *master_dark) {  // :192-256
+    Image m = median_combine(ctx, flat, master_bias, master_dark, 1.0f);
+    ctx.check(ab_normalize_flat(ctx.get(), m.data.data(), m.data.size()));
+    return m;
+}
+inline Image calibrate_image(const Context &ctx, const Image &raw, const CalibrationConfig &c) {  // :47-83
+    const ab_calibration_config cfg{c.master_bias ? c.master_bias->data.data() : nullptr,
+                                    c.master_dark ? c.master_dark->data.data() : nullptr,
+                                    c.master_flat ? c.master_flat->data.data() : nullptr,
+                                    c.dark_exposure_ratio, 1u};
+    Image out(raw.rows, raw.cols);
+    ctx.check(ab_calibrate_image(ctx.get(), raw.data.data(), raw.data.size(), &cfg, out.data.data()));
+    return out;
+}
+}  // namespace calibration
 }  // namespace stacking
 
 namespace imaging {

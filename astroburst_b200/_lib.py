@@ -27,6 +27,10 @@ class StackConfigC(C.Structure):
                 ("max_iterations", C.c_uint32), ("align", C.c_uint32)]
 
 
+class PhaseResultC(C.Structure):
+    _fields_ = [("dx", C.c_double), ("dy", C.c_double), ("confidence", C.c_double)]
+
+
 class CalibrationConfigC(C.Structure):
     _fields_ = [("master_bias", C.c_void_p), ("master_dark", C.c_void_p),
                 ("master_flat", C.c_void_p), ("dark_exposure_ratio", C.c_float),
@@ -111,6 +115,13 @@ SIGNATURES = {
                                           C.POINTER(StackConfigC), _vp, _vp, _vp]),
     "ab_sigma_clip_combine": (C.c_int, [_vp, _vp, _sz, C.c_float, C.c_float, C.c_uint32,
                                         C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    # phase correlation / aligned stack
+    "ab_phase_correlate": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp]),
+    "ab_phase_correlate_dev": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp]),
+    "ab_area_downsample": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, _vp]),
+    "ab_area_downsample_dev": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _vp]),
+    "ab_stack_images": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz, _sz, C.POINTER(StackConfigC), _vp,
+                                  _u64p, _vp]),
     # calibration
     "ab_median_combine": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz, _sz, _vp, _vp, C.c_float, _vp]),
     "ab_median_combine_dev": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz, _vp, _vp, C.c_float, _vp, _vp]),

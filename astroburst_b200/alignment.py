@@ -98,3 +98,39 @@ def ransac_affine(matches, method: str = "affine", n_threads: int = 8):
     if st:
         raise AstroBurstError(st, "ab_ransac_affine")
     return out if found.value else None
+
+
+# ---------------------------------------------------------------- phase correlation
+@dataclass
+class PhaseCorrelationResult:
+    """core/alignment/phase_correlation.rs:15-20."""
+    dx: float
+    dy: float
+    confidence: float
+
+
+def phase_correlate(reference: np.ndarray, target: np.ndarray, ctx=None) -> PhaseCorrelationResult:
+    """phase_correlation.rs:22-99 (both images are cropped to the common minimum size)."""
+    from ._lib import PhaseResultC
+    ctx = ctx or default_context()
+    r = np.ascontiguousarray(reference, dtype=np.float32)
+    t = np.ascontiguousarray(target, dtype=np.float32)
+    res = PhaseResultC()
+    ctx.check(lib().ab_phase_correlate(ctx.handle, r.ctypes.data, r.shape[0], r.shape[1],
+                                       t.ctypes.data, t.shape[0], t.shape[1], C.byref(res)))
+    return PhaseCorrelationResult(res.dx, res.dy, res.confidence)
+
+
+def is_low_confidence(confidence: float) -> bool:
+    """phase_correlation.rs:163-165."""
+    return confidence < 2.0
+
+
+def area_downsample(img: np.ndarray, out_rows: int, out_cols: int, ctx=None) -> np.ndarray:
+    """core/alignment/downsample.rs:6-46."""
+    ctx = ctx or default_context()
+    a = np.ascontiguousarray(img, dtype=np.float32)
+    out = np.empty((out_rows, out_cols), np.float32)
+    ctx.check(lib().ab_area_downsample(ctx.handle, a.ctypes.data, a.shape[0], a.shape[1],
+                                       out_rows, out_cols, out.ctypes.data))
+    return out

@@ -81,7 +81,7 @@ def build_variant(name: str, defines) -> str:
     so = os.path.join(vdir, name + ".so")
     r = subprocess.run([NVCC, "-shared", "-o", so] + objs +
                        ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++",
-                        "-lcudart_static"], capture_output=True, text=True)
+                        "-lcudart_static", "-lcufft"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     for o in objs:
@@ -96,7 +96,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs = list(ex.map(lambda s: _compile(s, force), srcs))
     if force or _stale(SO, objs):
         cmd = [NVCC, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                     "-ccbin", "/usr/bin/g++", "-lcudart_static"]
+                                                     "-ccbin", "/usr/bin/g++", "-lcudart_static", "-lcufft"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

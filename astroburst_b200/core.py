@@ -54,7 +54,8 @@ def stack_images(images: Sequence[np.ndarray], config: StackConfig,
     """combine.rs:94-193.  Host arrays in, host result out (pinned arrays run at PCIe speed).
 
     Frames are cropped to the common minimum size like combine.rs:104-113.  `align=True`
-    (phase-correlation pre-alignment) is rejected with AB_ERR_UNSUPPORTED.
+    phase-correlates every frame against frame 0 and shifts it with the bicubic sampler first
+    (combine.rs:118-147); `offsets` are the rounded (dy, dx) of each frame.
     """
     ctx = ctx or default_context()
     if len(images) == 0:
@@ -71,9 +72,10 @@ def stack_images(images: Sequence[np.ndarray], config: StackConfig,
     ptrs = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
     cfg = config.to_c()
     rej = C.c_uint64(0)
-    ctx.check(lib().ab_stack_sigma_clip(ctx.handle, ptrs, len(frames), min_rows, min_cols,
-                                        C.byref(cfg), out.ctypes.data, C.byref(rej)))
-    return StackResult(out, len(frames), int(rej.value), [(0, 0)] * len(frames))
+    offs = np.zeros((len(frames), 2), np.int32)
+    ctx.check(lib().ab_stack_images(ctx.handle, ptrs, len(frames), min_rows, min_cols,
+                                    C.byref(cfg), out.ctypes.data, C.byref(rej), offs.ctypes.data))
+    return StackResult(out, len(frames), int(rej.value), [(int(a), int(b)) for a, b in offs])
 
 
 def stack_images_device(frame_ptrs: Sequence[int], npix: int, config: StackConfig, out_ptr: int,

@@ -83,6 +83,11 @@ struct DeviceGuard {
 
 ab_status ab_scratch_reserve(ab_ctx *ctx, int slot, size_t bytes);
 
+// ---- phasecorr.cu
+void ab_phasecorr_release(ab_ctx *ctx);
+ab_status ab_phase_correlate_on(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t rows,
+                                size_t cols, cudaStream_t s, ab_phase_result *out);
+
 // ---- stack.cu
 struct FrameTable {
     const float *p[AB_MAX_FRAMES];

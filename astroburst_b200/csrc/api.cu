@@ -6,6 +6,9 @@
 #include <new>
 #include <vector>
 
+#include <climits>
+#include <cmath>
+
 #include "ab_internal.h"
 
 ab_status ab_scratch_reserve(ab_ctx *ctx, int slot, size_t bytes) {
@@ -80,6 +83,7 @@ void ab_ctx_destroy(ab_ctx *ctx) {
             if (ctx->copy_events[i]) cudaEventDestroy(ctx->copy_events[i]);
             if (ctx->copy_streams[i]) cudaStreamDestroy(ctx->copy_streams[i]);
         }
+        ab_phasecorr_release(ctx);
         if (ctx->d_small) cudaFree(ctx->d_small);
         if (ctx->d_work_counters) cudaFree(ctx->d_work_counters);
         if (ctx->h_small) cudaFreeHost(ctx->h_small);
@@ -139,13 +143,15 @@ ab_status ab_memcpy_d2h(ab_ctx *ctx, void *dst, const void *src, size_t bytes) {
 
 // ------------------------------------------------------------------------------- stacking
 static ab_status check_stack_args(ab_ctx *ctx, const void *frames, size_t n_frames,
-                                  const ab_stack_config *cfg, const void *out) {
+                                  const ab_stack_config *cfg, const void *out,
+                                  bool align_ok = false) {
     if (!ctx) return AB_ERR_INVALID;
     if (n_frames == 0) return ab_fail(ctx, AB_ERR_INVALID, "No images to stack");
     if (!frames || !cfg || !out) return ab_fail(ctx, AB_ERR_INVALID, "null argument");
-    if (cfg->align)
+    if (cfg->align && !align_ok)
         return ab_fail(ctx, AB_ERR_UNSUPPORTED,
-                       "align=true (phase-correlation pre-alignment) is not implemented");
+                       "align=true needs whole frames: use ab_stack_images (device bands cannot "
+                       "be phase-correlated)");
     if (n_frames > AB_MAX_FRAMES)
         return ab_fail(ctx, AB_ERR_UNSUPPORTED, "n_frames %zu > AB_MAX_FRAMES %d", n_frames,
                        AB_MAX_FRAMES);
@@ -177,10 +183,12 @@ ab_status ab_stack_sigma_clip_dev(ab_ctx *ctx, const float *const *d_frames, siz
 ab_status ab_stack_sigma_clip(ab_ctx *ctx, const float *const *frames, size_t n_frames,
                               size_t rows, size_t cols, const ab_stack_config *cfg, float *out,
                               uint64_t *rejected_pixels) {
-    ab_status st = check_stack_args(ctx, frames, n_frames, cfg, out);
+    ab_status st = check_stack_args(ctx, frames, n_frames, cfg, out, true);
     if (st != AB_OK) return st;
     for (size_t f = 0; f < n_frames; ++f)
         if (!frames[f]) return ab_fail(ctx, AB_ERR_INVALID, "null frame pointer %zu", f);
+    if (cfg->align)
+        return ab_stack_images(ctx, frames, n_frames, rows, cols, cfg, out, rejected_pixels, nullptr);
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
     if (rejected_pixels) *rejected_pixels = 0;
@@ -234,6 +242,71 @@ ab_status ab_stack_sigma_clip(ab_ctx *ctx, const float *const *frames, size_t n_
     uint64_t total = 0;
     for (size_t b = 0; b < n_bands; ++b) total += h_rej[b];
     if (rejected_pixels) *rejected_pixels = total;
+    return AB_OK;
+}
+
+// stack_images with config.align honoured (combine.rs:118-147): frame 0 is the reference, every
+// other frame is phase-correlated against it (align.rs:84-97) and shifted with the bicubic
+// sampler (align.rs:36-57); offsets[i] = (round(dy), round(dx)) like combine.rs:139-141.  All
+// frames stay resident in HBM (n_frames + 1 planes), so this path is for stacks that fit the GPU.
+ab_status ab_stack_images(ab_ctx *ctx, const float *const *frames, size_t n_frames, size_t rows,
+                          size_t cols, const ab_stack_config *cfg, float *out,
+                          uint64_t *rejected_pixels, int32_t *offsets) {
+    ab_status st = check_stack_args(ctx, frames, n_frames, cfg, out, true);
+    if (st != AB_OK) return st;
+    for (size_t f = 0; f < n_frames; ++f)
+        if (!frames[f]) return ab_fail(ctx, AB_ERR_INVALID, "null frame pointer %zu", f);
+    if (offsets)
+        for (size_t f = 0; f < 2 * n_frames; ++f) offsets[f] = 0;
+    if (!cfg->align) {
+        ab_stack_config c = *cfg;
+        return ab_stack_sigma_clip(ctx, frames, n_frames, rows, cols, &c, out, rejected_pixels);
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    if (rejected_pixels) *rejected_pixels = 0;
+    const size_t npix = rows * cols;
+    if (npix == 0) return AB_OK;
+    const size_t plane_bytes = ((npix * sizeof(float) + 255) / 256) * 256;
+    // slot 1: aligned planes + output; slot 0: the raw frame being aligned (the phase correlation
+    // of the host-buffer entry point is not used here, so slot 0 is free)
+    if ((st = ab_scratch_reserve(ctx, 1, plane_bytes * (n_frames + 1))) != AB_OK) return st;
+    if ((st = ab_scratch_reserve(ctx, 0, plane_bytes)) != AB_OK) return st;
+    char *base = static_cast<char *>(ctx->d_scratch[1]);
+    float *d_raw = static_cast<float *>(ctx->d_scratch[0]);
+    cudaStream_t s = ctx->stream;
+    FrameTable ft;
+    for (size_t f = 0; f < AB_MAX_FRAMES; ++f)
+        ft.p[f] = f < n_frames ? reinterpret_cast<float *>(base + f * plane_bytes) : nullptr;
+    float *d_ref = reinterpret_cast<float *>(base);
+    AB_CUDA(ctx, cudaMemcpyAsync(d_ref, frames[0], npix * sizeof(float), cudaMemcpyHostToDevice, s));
+    for (size_t f = 1; f < n_frames; ++f) {
+        AB_CUDA(ctx, cudaMemcpyAsync(d_raw, frames[f], npix * sizeof(float), cudaMemcpyHostToDevice, s));
+        ab_phase_result pc;
+        if ((st = ab_phase_correlate_on(ctx, d_ref, d_raw, rows, cols, s, &pc)) != AB_OK) return st;
+        float *d_al = reinterpret_cast<float *>(base + f * plane_bytes);
+        if ((st = ab_shift_bicubic_dev(ctx, d_raw, rows, cols, pc.dy, pc.dx, d_al, s)) != AB_OK)
+            return st;
+        if (offsets) {  // `.round() as i32`: half away from zero, saturating, NaN -> 0
+            auto r32 = [](double v) -> int32_t {
+                const double r = std::round(v);
+                if (!(r == r)) return 0;
+                return r >= 2147483647.0 ? INT32_MAX : (r <= -2147483648.0 ? INT32_MIN : (int32_t)r);
+            };
+            offsets[2 * f] = r32(pc.dy);
+            offsets[2 * f + 1] = r32(pc.dx);
+        }
+    }
+    float *d_out = reinterpret_cast<float *>(base + n_frames * plane_bytes);
+    unsigned long long *d_rej = reinterpret_cast<unsigned long long *>(ctx->d_small);
+    unsigned long long *h_rej = reinterpret_cast<unsigned long long *>(ctx->h_small);
+    st = ab_stack_launch(ctx, ft, (int)n_frames, npix, cfg->sigma_low, cfg->sigma_high,
+                         cfg->max_iterations, d_out, d_rej, s);
+    if (st != AB_OK) return st;
+    AB_CUDA(ctx, cudaMemcpyAsync(out, d_out, npix * sizeof(float), cudaMemcpyDeviceToHost, s));
+    AB_CUDA(ctx, cudaMemcpyAsync(h_rej, d_rej, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    AB_CUDA(ctx, cudaStreamSynchronize(s));
+    if (rejected_pixels) *rejected_pixels = *h_rej;
     return AB_OK;
 }
 

@@ -53,7 +53,7 @@ typedef struct {
     float sigma_low;
     float sigma_high;
     uint32_t max_iterations;
-    uint32_t align; /* must be 0: phase-correlation pre-alignment is SURVEY 8(f) N1 */
+    uint32_t align; /* 1: phase-correlate + shift every frame onto frame 0 first (host-buffer calls) */
 } ab_stack_config;
 
 /* mirrors ImageStats, types/image.rs:2-10 */
@@ -153,11 +153,44 @@ ab_status ab_stack_sigma_clip(ab_ctx *ctx, const float *const *frames, size_t n_
 ab_status ab_stack_sigma_clip_dev(ab_ctx *ctx, const float *const *d_frames, size_t n_frames,
                                   size_t npix, const ab_stack_config *cfg, float *d_out,
                                   uint64_t *d_rejected, void *stream);
+/* stack_images with config.align honoured (combine.rs:118-147): every frame i >= 1 is
+ * phase-correlated against frame 0 (core/stacking/align.rs:84-97) and shifted with the bicubic
+ * sampler (align.rs:36-57) before the combine.  offsets: NULL or 2*n_frames int32 =
+ * StackResult.offsets as (dy, dx) pairs = (round(dy), round(dx)), (0,0) for frame 0.
+ * ab_stack_sigma_clip with cfg->align != 0 forwards here (offsets dropped). */
+ab_status ab_stack_images(ab_ctx *ctx, const float *const *frames, size_t n_frames, size_t rows,
+                          size_t cols, const ab_stack_config *cfg, float *out,
+                          uint64_t *rejected_pixels, int32_t *offsets);
 /* One pixel's sample list through the same device code path (combine.rs:14-92); n <= 256.
  * Used by the parity tests for the reference's sigma_clip_combine unit tests. */
 ab_status ab_sigma_clip_combine(ab_ctx *ctx, const float *values, size_t n, float sigma_low,
                                 float sigma_high, uint32_t max_iter, float *mean_out,
                                 uint32_t *rejected_out);
+
+/* ---------------------------------------------------------------- phase correlation
+ * PhaseCorrelationResult, core/alignment/phase_correlation.rs:15-20: shift_image_subpixel(target,
+ * dy, dx) registers the target on the reference. */
+typedef struct ab_phase_result {
+    double dx, dy, confidence;
+} ab_phase_result;
+/* phase_correlate, phase_correlation.rs:22-99: both images cropped to the common minimum size;
+ * constant / nearly empty inputs -> zeros; <= 512 x 512 one correlation, else a 512 x 512 area
+ * downsample for the coarse shift and a 512 x 512 centre crop for the refinement.  Hann window,
+ * power-of-two f64 FFT (cuFFT Z2Z for the reference's rustfft), normalised cross-power spectrum,
+ * peak + SNR confidence + 3-point sub-pixel refinement.  Parity with the reference is to f64 FFT
+ * rounding (shifts ~1e-12 px), not bit-exact. */
+ab_status ab_phase_correlate(ab_ctx *ctx, const float *ref, size_t ref_rows, size_t ref_cols,
+                             const float *tgt, size_t tgt_rows, size_t tgt_cols,
+                             ab_phase_result *out);
+/* same-size contiguous device planes; synchronizes `stream` (the result is a host struct) */
+ab_status ab_phase_correlate_dev(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t rows,
+                                 size_t cols, ab_phase_result *out, void *stream);
+/* area_downsample, core/alignment/downsample.rs:6-46: mean of the finite pixels of each box
+ * (f64 sum in the reference's order -> bit-exact), 0 for an empty box */
+ab_status ab_area_downsample(ab_ctx *ctx, const float *src, size_t in_rows, size_t in_cols,
+                             size_t out_rows, size_t out_cols, float *out);
+ab_status ab_area_downsample_dev(ab_ctx *ctx, const float *d_src, size_t in_rows, size_t in_cols,
+                                 size_t out_rows, size_t out_cols, float *d_out, void *stream);
 
 /* ---------------------------------------------------------------- calibration
  * core/stacking/calibration.rs.  FITS loading stays with the caller (load_fits_image).

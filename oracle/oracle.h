@@ -73,6 +73,12 @@ float orc_exact_mad_mut(float *data, size_t n, float median);
 void orc_sigma_clipped_stats(float *values, size_t *n, float kappa, size_t iterations,
                              double *median, double *sigma);
 
+/* ---- phase correlation (core/alignment/phase_correlation.rs, downsample.rs, math) ---- */
+void orc_area_downsample(const float *src, size_t in_rows, size_t in_cols, size_t out_rows,
+                         size_t out_cols, float *out);
+void orc_phase_correlate(const float *ref, size_t ref_rows, size_t ref_cols, const float *tgt,
+                         size_t tgt_rows, size_t tgt_cols, double *dx, double *dy, double *conf);
+
 /* ---- calibration (core/stacking/calibration.rs) ---- */
 int orc_median_combine(const float *const *frames, size_t n_frames, size_t rows, size_t cols,
                        const float *bias, const float *dark, float dark_ratio, float *out);

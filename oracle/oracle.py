@@ -132,6 +132,41 @@ def stack_images(frames, sigma_low=3.0, sigma_high=3.0, max_iterations=5):
     return out, int(rej.value)
 
 
+# ---------------------------------------------------------------- phase correlation
+def area_downsample(img, out_rows, out_cols):
+    a = _f32(img)
+    out = np.empty((out_rows, out_cols), np.float32)
+    lib().orc_area_downsample(_p(a), C.c_size_t(a.shape[0]), C.c_size_t(a.shape[1]),
+                              C.c_size_t(out_rows), C.c_size_t(out_cols), _p(out))
+    return out
+
+
+def phase_correlate(reference, target):
+    """-> (dx, dy, confidence), phase_correlation.rs:22-99."""
+    r, t = _f32(reference), _f32(target)
+    dx, dy, conf = C.c_double(0), C.c_double(0), C.c_double(0)
+    lib().orc_phase_correlate(_p(r), C.c_size_t(r.shape[0]), C.c_size_t(r.shape[1]), _p(t),
+                              C.c_size_t(t.shape[0]), C.c_size_t(t.shape[1]), C.byref(dx),
+                              C.byref(dy), C.byref(conf))
+    return dx.value, dy.value, conf.value
+
+
+def stack_images_aligned(frames, sigma_low=3.0, sigma_high=3.0, max_iterations=5):
+    """stack_images with config.align = true (combine.rs:118-147): -> (image, rejected, offsets)."""
+    fr = [_f32(f) for f in frames]
+    rows = min(f.shape[0] for f in fr)
+    cols = min(f.shape[1] for f in fr)
+    fr = [np.ascontiguousarray(f[:rows, :cols]) for f in fr]
+    aligned, offsets = [fr[0]], [(0, 0)]
+    for f in fr[1:]:
+        dx, dy, _ = phase_correlate(fr[0], f)
+        aligned.append(shift_image_subpixel(f, dy, dx))
+        rnd = lambda v: int(np.sign(v) * np.floor(abs(v) + 0.5))  # f64::round: half away from zero
+        offsets.append((rnd(dy), rnd(dx)))
+    img, rej = stack_images(aligned, sigma_low, sigma_high, max_iterations)
+    return img, rej, offsets
+
+
 # ---------------------------------------------------------------- calibration
 def median_combine(frames, bias=None, dark=None, dark_ratio=1.0):
     """median_combine_row_major with the masters' per-frame preprocessing (calibration.rs:85-229)."""

@@ -308,3 +308,41 @@ def test_median_combine_semantics(orc):
     assert out[0, 2] == 0.0          # nothing finite
     flat = orc.normalize_flat(np.array([[2.0, 4.0, -1.0, np.nan]], np.float32))
     assert np.allclose(flat, [[2 / 3, 4 / 3, 1.0, 1.0]])
+
+
+# ---- phase correlation: oracle self-checks ------------------------------------------
+def test_area_downsample_reference_unit_tests(orc):
+    img = (np.arange(64 * 64, dtype=np.float32)).reshape(64, 64)          # downsample.rs:52-58
+    assert np.array_equal(orc.area_downsample(img, 64, 64), img)
+    ramp = np.arange(16, dtype=np.float32).reshape(4, 4)                  # downsample.rs:60-67
+    assert abs(orc.area_downsample(ramp, 2, 2)[0, 0] - (0 + 1 + 4 + 5) / 4) < 1e-4
+
+
+def test_phase_correlate_oracle_self_consistency(orc):
+    """The oracle's own radix-2 DFT against numpy's FFT on the same pipeline, and the reference's
+    edge-case tests (phase_correlation.rs:197-240)."""
+    rng = np.random.default_rng(0)
+    img = rng.normal(1000, 10, (128, 96)).astype(np.float32)
+    for _ in range(60):
+        y, x = rng.integers(3, 125), rng.integers(3, 93)
+        img[y - 1:y + 2, x - 1:x + 2] += rng.uniform(500, 5000)
+    tgt = np.zeros_like(img)
+    tgt[6:, :-3] = img[:-6, 3:]
+    dx, dy, conf = orc.phase_correlate(img, tgt)
+    wy = 0.5 * (1 - np.cos(2 * np.pi * np.arange(128) / 128))
+    wx = 0.5 * (1 - np.cos(2 * np.pi * np.arange(96) / 96))
+    pad = lambda a: np.pad(a.astype(np.float64) * np.outer(wy, wx), ((0, 0), (0, 32)))
+    A, B = np.fft.fft2(pad(img)), np.fft.fft2(pad(tgt))
+    P = A * np.conj(B)
+    mag = np.abs(P)
+    P = np.where(mag > 1e-15, P / np.where(mag > 0, mag, 1), 0)
+    c = np.fft.ifft2(P).real
+    py, px = np.unravel_index(np.argmax(c), c.shape)
+    assert round(dy) == (py - 128 if py > 64 else py) and round(dx) == (px - 128 if px > 64 else px)
+    assert abs(dy + 6) < 0.5 and abs(dx - 3) < 0.5 and conf > 2.0
+    assert orc.phase_correlate(img, img)[:2] == (0.0, 0.0)                     # test_identical_images
+    const = np.full((64, 64), 100.0, np.float32)
+    assert orc.phase_correlate(const, const) == (0.0, 0.0, 0.0)               # test_constant_image
+    bad = img.copy()
+    bad[10, 10], bad[20, 30], bad[5, 5] = np.nan, np.inf, -np.inf
+    assert all(np.isfinite(orc.phase_correlate(bad, bad)))                    # test_nan_no_panic

@@ -60,8 +60,17 @@ def test_stack_identical_and_outlier(ab):
 def test_error_behaviour(ab):
     with pytest.raises(ab.AstroBurstError):  # bail!("No images to stack")
         ab.stack_images([], ab.StackConfig(align=False))
-    with pytest.raises(ab.AstroBurstError):  # align=true needs phase correlation (not built)
-        ab.stack_images([np.zeros((4, 4), np.float32)], ab.StackConfig())
+    # align=true on device row bands cannot be phase-correlated: the _dev entry point refuses it
+    import ctypes as C
+    from astroburst_b200._lib import lib
+    ctx = ab.default_context(0)
+    cfg = ab.StackConfig().to_c()  # align defaults to true (types/stacking.rs:13-20)
+    ptrs = (C.c_void_p * 1)(1)
+    assert lib().ab_stack_sigma_clip_dev(ctx.handle, ptrs, 1, 16, C.byref(cfg), 1, 1, None) != 0
+    # a single frame with align=true is just that frame (combine.rs:118-121)
+    one = np.arange(16, dtype=np.float32).reshape(4, 4)
+    res = ab.stack_images([one], ab.StackConfig())
+    assert np.array_equal(res.image, one) and res.offsets == [(0, 0)]
 
 
 # ---- random single-pixel vectors, every length class (register 8/16/32/64 and deep path)

@@ -768,12 +768,23 @@ bool sane(const ab_align_result &r, size_t rows, size_t cols) {
     const double sx = std::sqrt(t.a * t.a + t.c * t.c), sy = std::sqrt(t.b * t.b + t.d * t.d);
     return !(sx < MIN_SCALE || sx > MAX_SCALE || sy < MIN_SCALE || sy > MAX_SCALE);
 }
-void fallback(ab_align_result *out) {  // affine.rs:243-270; phase correlation is SURVEY N1
+// fallback_phase_correlation, affine.rs:243-270 (on the original, un-normalised planes)
+ab_status fallback(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t rows, size_t cols,
+                   cudaStream_t s, ab_align_result *out) {
     out->transform = aff_identity();
     out->matched_stars = 0;
     out->inliers = 0;
     out->residual_px = 0.0;
     out->method = 3;
+    ab_phase_result pc;
+    ab_status st = ab_phase_correlate_on(ctx, d_ref, d_tgt, rows, cols, s, &pc);
+    if (st != AB_OK) return st;
+    const double max_tx = (double)cols * MAX_OFFSET_FRACTION, max_ty = (double)rows * MAX_OFFSET_FRACTION;
+    if (std::fabs(pc.dx) > max_tx || std::fabs(pc.dy) > max_ty || pc.confidence < 1.5) return AB_OK;
+    out->transform.tx = pc.dx;  // AffineTransform::translation(pc.dx, pc.dy)
+    out->transform.ty = pc.dy;
+    out->method = 2;
+    return AB_OK;
 }
 
 // match_triangles (affine.rs:320-384): votes on the GPU, greedy 1-1 assignment on the host.
@@ -861,17 +872,12 @@ ab_status align_on_device(ab_ctx *ctx, const float *d_ref, const float *d_tgt, s
     std::vector<Pt> rs, ts;
     for (size_t i = 0; i < std::min(rst.size(), (size_t)MAX_STARS); ++i) rs.push_back({rst[i].x, rst[i].y});
     for (size_t i = 0; i < std::min(tst.size(), (size_t)MAX_STARS); ++i) ts.push_back({tst[i].x, tst[i].y});
-    if (rs.size() < MIN_MATCHES_RIGID || ts.size() < MIN_MATCHES_RIGID) {
-        fallback(out);
-        return AB_OK;
-    }
+    if (rs.size() < MIN_MATCHES_RIGID || ts.size() < MIN_MATCHES_RIGID)
+        return fallback(ctx, d_ref, d_tgt, rows, cols, s, out);
     std::vector<Match> matches;
     st = match_stars(ctx, rs, ts, s, matches);
     if (st != AB_OK) return st;
-    if (matches.size() < MIN_MATCHES_RIGID) {
-        fallback(out);
-        return AB_OK;
-    }
+    if (matches.size() < MIN_MATCHES_RIGID) return fallback(ctx, d_ref, d_tgt, rows, cols, s, out);
     ab_align_result r;
     if (matches.size() >= MIN_MATCHES_AFFINE && ransac(matches, 0, n_threads, &r) && sane(r, rows, cols)) {
         *out = r;
@@ -881,8 +887,7 @@ ab_status align_on_device(ab_ctx *ctx, const float *d_ref, const float *d_tgt, s
         *out = r;
         return AB_OK;
     }
-    fallback(out);
-    return AB_OK;
+    return fallback(ctx, d_ref, d_tgt, rows, cols, s, out);
 }
 
 ab_status upload(ab_ctx *ctx, int slot, const float *h, size_t len, float **d) {

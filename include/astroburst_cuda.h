@@ -358,8 +358,9 @@ ab_status ab_estimate_background(ab_ctx *ctx, const float *img, size_t rows, siz
 /* normalize_for_detection, core/alignment/affine.rs:24-53 */
 ab_status ab_normalize_for_detection(ab_ctx *ctx, const float *img, size_t len, float *out);
 /* align_channel_affine, affine.rs:129-212.  n_threads stands for rayon::current_num_threads(),
- * which seeds the reference's RANSAC streams (affine.rs:410-416).  The phase-correlation fallback
- * (affine.rs:243-270, rustfft) is not built: method = 3 (identity) where the reference would try it. */
+ * which seeds the reference's RANSAC streams (affine.rs:410-416).  The fallback chain ends in
+ * fallback_phase_correlation (affine.rs:243-270): method = 2 with a pure translation when the
+ * phase correlation is confident (>= 1.5) and within 40 % of the frame, else method = 3 (identity). */
 ab_status ab_align_affine(ab_ctx *ctx, const float *ref, const float *tgt, size_t rows, size_t cols,
                           int n_threads, ab_align_result *out);
 ab_status ab_align_affine_dev(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t rows,

@@ -14,9 +14,8 @@
 //    orders equal-vote pairs by (ref index, tgt index) ascending.
 //  * the RANSAC stream depends on rayon::current_num_threads() (affine.rs:410);
 //    the oracle takes that thread count as a parameter.
-// The phase-correlation fallback (affine.rs:243-270) needs rustfft (un-vendored,
-// SURVEY 8c/N1); the oracle reports method=identity where the reference would
-// try phase correlation.
+// The phase-correlation fallback (affine.rs:243-270) goes through orc_phasecorr.cpp (own DFT in
+// place of the un-vendored rustfft).
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -343,12 +342,20 @@ bool sane(const orc_align_result &r, size_t rows, size_t cols) {
     return true;
 }
 
-void fallback(orc_align_result *out) {  // affine.rs:243-270 without rustfft -> identity
+// fallback_phase_correlation, affine.rs:243-270 (orc_phasecorr.cpp stands in for rustfft)
+void fallback(const float *ref, const float *tgt, size_t rows, size_t cols, orc_align_result *out) {
     out->transform = identity();
     out->matched_stars = 0;
     out->inliers = 0;
     out->residual_px = 0.0;
     out->method = 3;
+    double dx, dy, conf;
+    orc_phase_correlate(ref, rows, cols, tgt, rows, cols, &dx, &dy, &conf);
+    const double max_tx = (double)cols * MAX_OFFSET_FRACTION, max_ty = (double)rows * MAX_OFFSET_FRACTION;
+    if (std::fabs(dx) > max_tx || std::fabs(dy) > max_ty || conf < 1.5) return;
+    out->transform.tx = dx;
+    out->transform.ty = dy;
+    out->method = 2;
 }
 
 }  // namespace
@@ -430,15 +437,15 @@ void orc_align_channel_affine(const float *ref, const float *tgt, size_t rows, s
         std::min(orc_detect_stars(rn.data(), rows, cols, DETECTION_SIGMA, rstars.data(), MAX_STARS, &bm, &bs), MAX_STARS);
     const size_t nt =
         std::min(orc_detect_stars(tn.data(), rows, cols, DETECTION_SIGMA, tstars.data(), MAX_STARS, &bm, &bs), MAX_STARS);
-    if (nr < MIN_MATCHES_RIGID || nt < MIN_MATCHES_RIGID) return fallback(out);
+    if (nr < MIN_MATCHES_RIGID || nt < MIN_MATCHES_RIGID) return fallback(ref, tgt, rows, cols, out);
 
     std::vector<Pt> rs(nr), ts(nt);
     for (size_t i = 0; i < nr; ++i) rs[i] = {rstars[i].x, rstars[i].y};
     for (size_t i = 0; i < nt; ++i) ts[i] = {tstars[i].x, tstars[i].y};
     const auto rt = build_triangles(rs), tt = build_triangles(ts);
-    if (rt.empty() || tt.empty()) return fallback(out);
+    if (rt.empty() || tt.empty()) return fallback(ref, tgt, rows, cols, out);
     const auto matches = match_triangles(rs, ts, rt, tt);
-    if (matches.size() < MIN_MATCHES_RIGID) return fallback(out);
+    if (matches.size() < MIN_MATCHES_RIGID) return fallback(ref, tgt, rows, cols, out);
 
     orc_align_result r;
     if (matches.size() >= MIN_MATCHES_AFFINE && ransac(matches, 0, n_threads, &r) &&
@@ -451,7 +458,7 @@ void orc_align_channel_affine(const float *ref, const float *tgt, size_t rows, s
         *out = r;
         return;
     }
-    fallback(out);
+    fallback(ref, tgt, rows, cols, out);
 }
 
 }  // extern "C"

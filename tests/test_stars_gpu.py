@@ -139,3 +139,20 @@ def test_align_recovers_known_transform(al, orc):
     flat = np.full((256, 256), 10.0, np.float32)                   # no stars -> identity fallback
     r = al.align_channel_affine(flat, flat)
     assert r.method == 3 and (r.transform.a, r.transform.tx) == (1.0, 0.0)
+
+
+def test_align_falls_back_to_phase_correlation(al, orc):
+    """No detectable stars but a correlatable texture: affine.rs:243-270 -> method 2 (pure
+    translation from phase_correlate), identical decision and ~1e-6 px agreement with the oracle."""
+    rng = np.random.default_rng(5)
+    base = np.cumsum(np.cumsum(rng.normal(0, 1, (300, 340)), axis=0), axis=1).astype(np.float32)
+    base = (base - base.min()) / (base.max() - base.min()) * 100.0 + 50.0   # smooth, star-free
+    ref, tgt = base[10:266, 12:268].copy(), base[14:270, 7:263].copy()
+    r, o = al.align_channel_affine(ref, tgt, 8), orc.align_channel_affine(ref, tgt, 8)
+    assert r.method == o.method
+    got, want = (r.transform.a, r.transform.b, r.transform.tx, r.transform.c, r.transform.d, r.transform.ty), \
+        o.transform.as_tuple()
+    assert all(abs(g - w) < 1e-6 for g, w in zip(got, want)), (got, want)
+    if r.method == 2:
+        assert (r.transform.a, r.transform.b, r.transform.c, r.transform.d) == (1.0, 0.0, 0.0, 1.0)
+        assert r.matched_stars == 0 and r.inliers == 0

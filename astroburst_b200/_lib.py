@@ -122,6 +122,11 @@ SIGNATURES = {
     "ab_area_downsample_dev": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _vp]),
     "ab_stack_images": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz, _sz, C.POINTER(StackConfigC), _vp,
                                   _u64p, _vp]),
+    # FITS data unit
+    "ab_fits_decode": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_double, C.c_double, _vp]),
+    "ab_fits_decode_dev": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_double, C.c_double, _vp, _vp]),
+    "ab_fits_encode": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_double, C.c_double, _vp]),
+    "ab_fits_encode_dev": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_double, C.c_double, _vp, _vp]),
     # calibration
     "ab_median_combine": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz, _sz, _vp, _vp, C.c_float, _vp]),
     "ab_median_combine_dev": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz, _vp, _vp, C.c_float, _vp, _vp]),

@@ -167,6 +167,22 @@ ab_status ab_sigma_clip_combine(ab_ctx *ctx, const float *values, size_t n, floa
                                 float sigma_high, uint32_t max_iter, float *mean_out,
                                 uint32_t *rejected_out);
 
+/* ---------------------------------------------------------------- FITS data unit
+ * decode_pixels, infra/fits/reader.rs:37-101: big-endian BITPIX 8 / 16 / 32 / -32 / -64 -> f32,
+ * `(v as f64 * bscale + bzero) as f32` unless the scaling is identity (|bscale-1|, |bzero| < 1e-15).
+ * data: n_pixels * |bitpix|/8 bytes.  Any other BITPIX -> AB_ERR_UNSUPPORTED (the reference returns
+ * an empty Vec).  Header parsing and file I/O stay with the caller. */
+ab_status ab_fits_decode(ab_ctx *ctx, const uint8_t *data, size_t n_pixels, int bitpix, double bscale,
+                         double bzero, float *out);
+ab_status ab_fits_decode_dev(ab_ctx *ctx, const uint8_t *d_data, size_t n_pixels, int bitpix,
+                             double bscale, double bzero, float *d_out, void *stream);
+/* write_f32 / i16 / f64_slice_as_be, infra/fits/writer.rs:82-136: f32 -> big-endian BITPIX -32, 16
+ * (`((val - bzero) / bscale).clamp(i16).round() as i16`) or -64. */
+ab_status ab_fits_encode(ab_ctx *ctx, const float *data, size_t n_pixels, int bitpix, double bzero,
+                         double bscale, uint8_t *out);
+ab_status ab_fits_encode_dev(ab_ctx *ctx, const float *d_data, size_t n_pixels, int bitpix,
+                             double bzero, double bscale, uint8_t *d_out, void *stream);
+
 /* ---------------------------------------------------------------- phase correlation
  * PhaseCorrelationResult, core/alignment/phase_correlation.rs:15-20: shift_image_subpixel(target,
  * dy, dx) registers the target on the reference. */

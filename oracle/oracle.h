@@ -79,6 +79,10 @@ void orc_area_downsample(const float *src, size_t in_rows, size_t in_cols, size_
 void orc_phase_correlate(const float *ref, size_t ref_rows, size_t ref_cols, const float *tgt,
                          size_t tgt_rows, size_t tgt_cols, double *dx, double *dy, double *conf);
 
+/* ---- FITS data-unit codec (infra/fits/reader.rs:37-101, writer.rs:82-136) ---- */
+int orc_fits_decode(const uint8_t *data, size_t n_pixels, int bitpix, double bscale, double bzero, float *out);
+int orc_fits_encode(const float *data, size_t n_pixels, int bitpix, double bzero, double bscale, uint8_t *out);
+
 /* ---- calibration (core/stacking/calibration.rs) ---- */
 int orc_median_combine(const float *const *frames, size_t n_frames, size_t rows, size_t cols,
                        const float *bias, const float *dark, float dark_ratio, float *out);

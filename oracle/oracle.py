@@ -167,6 +167,25 @@ def stack_images_aligned(frames, sigma_low=3.0, sigma_high=3.0, max_iterations=5
     return img, rej, offsets
 
 
+# ---------------------------------------------------------------- FITS data-unit codec
+_BPP = {8: 1, 16: 2, 32: 4, -32: 4, -64: 8}
+
+
+def fits_decode(data: bytes, bitpix: int, bscale=1.0, bzero=0.0):
+    raw = np.frombuffer(data, dtype=np.uint8)
+    n = raw.size // _BPP[bitpix]
+    out = np.empty(n, np.float32)
+    lib().orc_fits_decode(_p(raw), C.c_size_t(n), C.c_int(bitpix), C.c_double(bscale), C.c_double(bzero), _p(out))
+    return out
+
+
+def fits_encode(data, bitpix: int, bzero=0.0, bscale=1.0) -> bytes:
+    a = _f32(data).ravel()
+    out = np.empty(a.size * _BPP[bitpix], np.uint8)
+    lib().orc_fits_encode(_p(a), C.c_size_t(a.size), C.c_int(bitpix), C.c_double(bzero), C.c_double(bscale), _p(out))
+    return out.tobytes()
+
+
 # ---------------------------------------------------------------- calibration
 def median_combine(frames, bias=None, dark=None, dark_ratio=1.0):
     """median_combine_row_major with the masters' per-frame preprocessing (calibration.rs:85-229)."""

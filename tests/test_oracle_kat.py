@@ -346,3 +346,17 @@ def test_phase_correlate_oracle_self_consistency(orc):
     bad = img.copy()
     bad[10, 10], bad[20, 30], bad[5, 5] = np.nan, np.inf, -np.inf
     assert all(np.isfinite(orc.phase_correlate(bad, bad)))                    # test_nan_no_panic
+
+
+# ---- FITS data-unit codec: infra/fits/reader.rs:570-616 ------------------------------
+def test_fits_decode_reference_unit_tests(orc):
+    p = orc.fits_decode(bytes([0x01, 0x00, 0xFF, 0xFF]), 16)
+    assert p.size == 2 and abs(p[0] - 256.0) < 1e-6 and abs(p[1] + 1.0) < 1e-6
+    assert abs(orc.fits_decode(bytes([0x3F, 0x80, 0x00, 0x00]), -32)[0] - 1.0) < 1e-6
+    assert abs(orc.fits_decode(bytes([100]), 8, 2.0, 10.0)[0] - 210.0) < 1e-6
+    pi = np.float32(np.pi)
+    assert orc.fits_decode(np.array([pi]).astype(">f4").tobytes(), -32)[0] == pi
+    a = np.array([1.5, -2.25, 3e4, np.nan], np.float32)
+    assert np.array_equal(orc.fits_decode(orc.fits_encode(a, -32), -32), a, equal_nan=True)
+    assert orc.fits_encode(np.array([40000.0, -1.0, 100.4], np.float32), 16, 32768.0, 1.0) == \
+        np.array([7232, -32768, -32668], ">i2").tobytes()

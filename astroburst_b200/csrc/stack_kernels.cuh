@@ -42,11 +42,17 @@
 #include "ab_internal.h"
 
 // developer A/B knobs (python -m astroburst_b200.build --variant NAME KNOB=VALUE)
+#ifndef AB_WQ_CAP
+#define AB_WQ_CAP 44
+#endif
 #ifndef AB_DRAIN_AT
-#define AB_DRAIN_AT 24
+#define AB_DRAIN_AT 32
 #endif
 #ifndef AB_STATIC_PEEL
 #define AB_STATIC_PEEL 1
+#endif
+#ifndef AB_TMA_WARPS
+#define AB_TMA_WARPS 20
 #endif
 #ifndef AB_LDG_BLOCKS
 #define AB_LDG_BLOCKS 3
@@ -516,10 +522,19 @@ __device__ __forceinline__ bool phase_a_tail(const float (&s)[P], float sigma_lo
     const bool keep_all = max_iter == 0 || (d_first >= lo && d_last <= hi);
     const float d_lo = lo_acc[0] + lo_acc[1], d_hi = hi_acc[0] + hi_acc[1];
     const float T = next_pow2_above(s[0]);
-    const bool exact = s[0] >= 1.17549435e-38f && s[N - 1] <= 2.0f * s[0] && d_hi < T && -d_lo < T;
+    // (power-of-two N takes an all-f32 mean below: D / N must not underflow, hence the 1e-30 floor;
+    // smaller samples go to phase B's f64 mean)
+    constexpr float kMinS0 = (N & (N - 1)) == 0 ? 1e-30f : 1.17549435e-38f;
+    const bool exact = s[0] >= kMinS0 && s[N - 1] <= 2.0f * s[0] && d_hi < T && -d_lo < T;
     if (keep_all && exact) {
-        const double sum = (double)N * (double)med + (double)(d_hi + d_lo);
-        result = (float)div_small(sum, N);
+        if constexpr ((N & (N - 1)) == 0) {
+            // N = 2^k: (N med + D) / N = med + D / N with D / N exact in f32, so one f32 addition
+            // rounds exactly like the f64 route's final cast -- no F2F / f64 instructions at all
+            result = med + (d_hi + d_lo) * (1.0f / (float)N);
+        } else {
+            const double sum = (double)N * (double)med + (double)(d_hi + d_lo);
+            result = (float)div_small(sum, N);
+        }
         return true;
     }
     result = med;  // last_center carried into phase B
@@ -580,15 +595,16 @@ __device__ __forceinline__ bool phase_a(float (&s)[P], int n, int n_uni, float s
 // Every warp walks its own sequence of 32-pixel groups.  Lanes whose pixel needs phase B park the
 // sorted samples in a warp-private stack in shared memory (column = slot, conflict-free).  At the
 // top of a group iteration -- where nothing but the loop state is live, so the register-resident
-// phase B can be inlined without spills -- a warp whose stack holds >= DRAIN_AT pixels finishes
-// all of them at once, one per lane.  Phase B therefore runs every ~4th group with mostly full
-// lanes; while one warp is in its (FP64 / XU heavy) phase B the other warps of the SM keep the ALU
-// and FMA pipes busy with their sorting networks: warps drift apart instead of marching in
-// lock-step.  A group whose parked pixels do not fit the remaining slots (rare: several times the
-// average park rate) first empties the stack through the out-of-line dynamic-index code.
-constexpr int WARPS_PER_BLOCK = 8;
-constexpr int WQ_CAP = 32;    // slots per warp
-constexpr int DRAIN_AT = AB_DRAIN_AT;  // inline drain threshold (average group parks ~6 pixels)
+// phase B can be inlined without spills -- a warp whose stack holds >= DRAIN_AT (32) pixels
+// finishes the top 32 of them at once, one per lane.  Phase B therefore runs every ~6th group with
+// full lanes; while one warp is in its (FP64 / XU heavy) phase B the other warps of the SM keep
+// the ALU and FMA pipes busy with their sorting networks: warps drift apart instead of marching in
+// lock-step.  A group whose parked pixels do not fit the WQ_CAP - 31 or more free slots (rare:
+// twice the average park rate) first empties the stack through the out-of-line dynamic code.
+constexpr int WARPS_PER_BLOCK = 8;      // LDG kernel: 8 warps x AB_LDG_BLOCKS blocks per SM
+constexpr int WQ_CAP = AB_WQ_CAP;       // slots per warp
+constexpr int DRAIN_AT = AB_DRAIN_AT;   // inline drain threshold: a full warp of parked pixels
+static_assert(DRAIN_AT <= 32 && DRAIN_AT <= WQ_CAP, "one parked pixel per lane");
 
 // One row of sorted samples per slot.  ROW = 4 x odd words: a lane's row is 16-byte aligned and the
 // rows of a quarter-warp start 4 banks apart, so parking and the register reload are conflict-free
@@ -598,34 +614,35 @@ struct WarpQueue {
     static constexpr int kCap = CAP;
     static constexpr int ROW = 4 * (2 * ((P + 7) / 8) + 1);
     alignas(16) float v[CAP][ROW];
-    float lastc[CAP];
-    float aux[CAP];
-    unsigned meta[CAP];
-    unsigned pix[CAP];  // pixel index relative to the launch (npix < 2^32 per launch)
+    // per slot: {last center, iteration-0 sigma, meta word, pixel index relative to the launch
+    // (npix < 2^32 per launch)} as one 16-byte record: one STS.128 / LDS.128
+    alignas(16) uint4 info[CAP];
 };
 
-// finish the `cnt` (<= 32) parked pixels; lane i takes slot i.  kStatic: register-resident
+// finish the `cnt` (<= 32) parked pixels of slots [first, first + cnt); lane i takes slot first + i.  kStatic: register-resident
 // phase B for META_SIGMA0 pixels (inlined once per kernel); otherwise everything goes through the
 // shared out-of-line dynamic-index code.
 template <int P, bool kStatic>
-__device__ __forceinline__ void drain_impl(WarpQueue<P> &q, unsigned cnt, int lane, float sigma_low,
-                                           float sigma_high, unsigned max_iter,
+__device__ __forceinline__ void drain_impl(WarpQueue<P> &q, unsigned first, unsigned cnt, int lane,
+                                           float sigma_low, float sigma_high, unsigned max_iter,
                                            float *__restrict__ out, unsigned &local_rej) {
     if ((unsigned)lane < cnt) {
-        const unsigned meta = q.meta[lane];
-        const float *col = &q.v[lane][0];
+        const unsigned slot = first + lane;
+        const uint4 info = q.info[slot];
+        const float lastc = __uint_as_float(info.x), aux = __uint_as_float(info.y);
+        const unsigned meta = info.z;
+        const float *col = &q.v[slot][0];
         unsigned rej = 0;
         float r;
         const int n = (int)((meta >> 8) & 0x1ffu);
         if (kStatic && (meta & META_SIGMA0) && n >= P - static_missing<P>()) {
-            r = finish_static<P>(col, n, q.lastc[lane], q.aux[lane], rej, sigma_low, sigma_high,
-                                 max_iter);
+            r = finish_static<P>(col, n, lastc, aux, rej, sigma_low, sigma_high, max_iter);
         } else {  // ragged non-finite samples, or only the f64 mean of everything is left
             const unsigned it0 = (meta & META_FINAL_ONLY) ? 0xffffffffu : 0u;  // skips the clip loop
-            r = finish_dynamic(col, 1, n, 0, n, it0, q.lastc[lane], (meta & META_SIGMA0) != 0,
-                               q.aux[lane], rej, sigma_low, sigma_high, max_iter);
+            r = finish_dynamic(col, 1, n, 0, n, it0, lastc, (meta & META_SIGMA0) != 0, aux, rej,
+                               sigma_low, sigma_high, max_iter);
         }
-        __stcs(out + q.pix[lane], r);
+        __stcs(out + info.w, r);
         local_rej += rej;
     }
     __syncwarp();
@@ -634,7 +651,9 @@ template <int P>
 __device__ __noinline__ void drain_dynamic(WarpQueue<P> &q, unsigned cnt, int lane, float sigma_low,
                                            float sigma_high, unsigned max_iter,
                                            float *__restrict__ out, unsigned &local_rej) {
-    drain_impl<P, false>(q, cnt, lane, sigma_low, sigma_high, max_iter, out, local_rej);
+    for (unsigned first = 0; first < cnt; first += 32u)  // (cnt <= WQ_CAP: at most two rounds)
+        drain_impl<P, false>(q, first, cnt - first < 32u ? cnt - first : 32u, lane, sigma_low,
+                             sigma_high, max_iter, out, local_rej);
 }
 
 // Non-finite samples -> +inf (they sort last and are not counted in n).  probe is NaN iff any
@@ -688,10 +707,7 @@ __device__ __forceinline__ void process_group(float (&s)[P], int n, bool active,
                 *reinterpret_cast<float4 *>(row + f) = make_float4(s[f], s[f + 1], s[f + 2], s[f + 3]);
 #pragma unroll
             for (int f = P & ~3; f < P; ++f) row[f] = s[f];
-            q.meta[slot] = meta;
-            q.lastc[slot] = result;
-            q.aux[slot] = aux;
-            q.pix[slot] = p;
+            q.info[slot] = make_uint4(__float_as_uint(result), __float_as_uint(aux), meta, p);
         }
         count += c;
         __syncwarp();
@@ -718,9 +734,10 @@ stack_warp_kernel(const __grid_constant__ FrameTable ft, size_t npix, float sigm
     const unsigned warp_global = blockIdx.x * WARPS_PER_BLOCK + warp;
     const unsigned warp_stride = gridDim.x * WARPS_PER_BLOCK;
     for (unsigned g = warp_global; g < n_groups; g += warp_stride) {
-        if (count >= (unsigned)DRAIN_AT) {
-            drain_impl<P, true>(q, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
-            count = 0;
+        if (count >= (unsigned)DRAIN_AT) {  // the top min(count, 32) slots, one per lane
+            const unsigned m = count < 32u ? count : 32u;
+            drain_impl<P, true>(q, count - m, m, lane, sigma_low, sigma_high, max_iter, out, local_rej);
+            count -= m;
         }
         const unsigned p = g * 32 + lane;
         const bool active = p < npix;
@@ -809,14 +826,25 @@ struct WarpTmaSmem {
     alignas(8) unsigned long long full;
     unsigned pad[30];
 };
+// ONE block per SM: measured on B200 at P = 32 (r1), 20 warps at 94 registers beat 24 warps at 80
+// (3 x 8, 0.590 ms -> 0.531 ms): the compiler stops rematerialising addresses in the hot loop, and
+// the warps of an SM walk adjacent groups.  Frame counts whose per-warp shared memory does not
+// allow 20 warps in 227 KiB run as many as fit.
+template <int P>
+constexpr int tma_warps() {
+    constexpr size_t per_warp = sizeof(WarpTmaSmem<P>);
+    constexpr size_t fit = (227 * 1024) / per_warp;
+    return fit >= AB_TMA_WARPS ? AB_TMA_WARPS : (fit < 1 ? 1 : (int)fit);
+}
 
 template <int P, int MN, int MD, bool kTensorMap>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 3)
+__global__ void __launch_bounds__(tma_warps<P>() * 32, 1)
 stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__ TmapParam tmap,
                   unsigned n_groups, float sigma_low, float sigma_high, unsigned max_iter, CeConst k,
                   unsigned *__restrict__ work_counter, float *__restrict__ out,
                   unsigned long long *__restrict__ rejected_total) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr unsigned TW = tma_warps<P>();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     WarpTmaSmem<P> &sm = reinterpret_cast<WarpTmaSmem<P> *>(smem_raw)[warp];
@@ -846,10 +874,10 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
     // atomic per group for ALL groups measured 2x slower: ~900 atomics/us on one L2 line).  Lane 0
     // fetches the next index one iteration ahead, so the atomic's latency hides behind the sort
     // and the next group's TMA is issued on time.
-    const unsigned n_warps = gridDim.x * WARPS_PER_BLOCK;
+    const unsigned n_warps = gridDim.x * TW;
     const unsigned static_rounds = (n_groups / n_warps) * 7 / 8;
     const unsigned dyn_base = static_rounds * n_warps;
-    unsigned g = blockIdx.x * WARPS_PER_BLOCK + warp;
+    unsigned g = blockIdx.x * TW + warp;
     unsigned round = 1;  // rounds taken so far (lane 0's view of g_next)
     auto fetch_next = [&](unsigned cur) -> unsigned {  // lane 0 only
         if (round < static_rounds) {
@@ -871,9 +899,11 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
     unsigned local_rej = 0;
     uint32_t parity = 0;
     for (; g < n_groups; parity ^= 1u) {
-        if (count >= (unsigned)DRAIN_AT) {
-            drain_impl<P, true>(sm.q, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
-            count = 0;
+        if (count >= (unsigned)DRAIN_AT) {  // the top min(count, 32) slots, one per lane
+            const unsigned m = count < 32u ? count : 32u;
+            drain_impl<P, true>(sm.q, count - m, m, lane, sigma_low, sigma_high, max_iter, out,
+                                local_rej);
+            count -= m;
         }
         const unsigned p = g * 32 + lane;
         mbar_wait(bar, parity);
@@ -959,8 +989,9 @@ ab_status launch_mix(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, f
         // coalesced loads (0.92 ms) -> only the tensor-map form is used unless forced
         if (!cube && !ctx->force_tma1d)
             return launch_ldg<P, MN, MD>(ctx, ft, npix, sl, sh, max_iter, d_out, d_rej, stream);
-        const size_t smem = sizeof(WarpTmaSmem<P>) * WARPS_PER_BLOCK;
-        constexpr int threads = WARPS_PER_BLOCK * 32;
+        constexpr int TW = tma_warps<P>();
+        const size_t smem = sizeof(WarpTmaSmem<P>) * TW;
+        constexpr int threads = TW * 32;
         auto kern = cube ? stack_wtma_kernel<P, MN, MD, true> : stack_wtma_kernel<P, MN, MD, false>;
         AB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
@@ -968,7 +999,7 @@ ab_status launch_mix(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, f
         AB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
         if (per_sm < 1) per_sm = 1;
         size_t grid = (size_t)ctx->sm_count * per_sm;
-        const size_t need = (groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+        const size_t need = (groups + TW - 1) / TW;
         if (grid > need) grid = need;
         unsigned *counter =
             ctx->d_work_counters + (ctx->work_seq.fetch_add(1) % ab_ctx::WORK_COUNTERS);

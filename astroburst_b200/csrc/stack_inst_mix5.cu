@@ -1,8 +1,8 @@
-// Explicit instantiation of the P = 32 stack kernels with 1/2 of the compare-exchanges in the
+// Explicit instantiation of the P = 32 stack kernels with 2/3 of the compare-exchanges in the
 // IMAD form (AB_STACK_MIX=5; A/B measurement only, see stack_kernels.cuh).
 #include "stack_kernels.cuh"
 
 namespace abk {
-template ab_status launch_mix<32, 1, 2>(ab_ctx *, const FrameTable &, size_t, float, float, unsigned,
+template ab_status launch_mix<32, 2, 3>(ab_ctx *, const FrameTable &, size_t, float, float, unsigned,
                                         float *, unsigned long long *, cudaStream_t);
 }  // namespace abk

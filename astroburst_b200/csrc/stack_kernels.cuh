@@ -1019,11 +1019,11 @@ ab_status launch_mix(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, f
 }
 
 // Default mix per frame count (tuned on B200 at P = 32).
-constexpr int DEFAULT_MN = 2, DEFAULT_MD = 3;
+constexpr int DEFAULT_MN = 1, DEFAULT_MD = 2;
 
 // P = 32 also carries alternative mixes (AB_STACK_MIX=1..7) for A/B measurements; they are
 // instantiated in stack_inst_mix*.cu.
-#define AB_MIX_LIST(X) X(1, 0, 1) X(2, 1, 3) X(3, 2, 5) X(4, 3, 5) X(5, 1, 2) X(6, 3, 4) X(7, 1, 1)
+#define AB_MIX_LIST(X) X(1, 0, 1) X(2, 1, 3) X(3, 2, 5) X(4, 3, 5) X(5, 2, 3) X(6, 3, 4) X(7, 1, 1)
 #define AB_MIX_EXTERN(idx, mn, md)                                                               \
     extern template ab_status launch_mix<32, mn, md>(ab_ctx *, const FrameTable &, size_t, float, \
                                                      float, unsigned, float *,                   \

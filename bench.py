@@ -325,7 +325,7 @@ def main():
                     "steps": args.e2e_steps, "matches_device_path": e2e_same},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": _ncu_traffic(), "peak_source": peak_src,
-                         "kernel": "abk::stack_wtma_kernel<32, 2, 3, true> (one launch per step)",
+                         "kernel": "abk::stack_wtma_kernel<32, 1, 2, true> (one launch per step)",
                          "kernel_ms": kern_ms, "algorithmic_bytes": ALGO_BYTES},
         }
         if not args.no_cpu_baseline and world == 1:

@@ -51,6 +51,10 @@
 #ifndef AB_STATIC_PEEL
 #define AB_STATIC_PEEL 1
 #endif
+#ifndef AB_STATIC_NUM
+#define AB_STATIC_NUM 7
+#define AB_STATIC_DEN 8
+#endif
 #ifndef AB_TMA_WARPS
 #define AB_TMA_WARPS 20
 #endif
@@ -875,7 +879,7 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
     // fetches the next index one iteration ahead, so the atomic's latency hides behind the sort
     // and the next group's TMA is issued on time.
     const unsigned n_warps = gridDim.x * TW;
-    const unsigned static_rounds = (n_groups / n_warps) * 7 / 8;
+    const unsigned static_rounds = (n_groups / n_warps) * AB_STATIC_NUM / AB_STATIC_DEN;
     const unsigned dyn_base = static_rounds * n_warps;
     unsigned g = blockIdx.x * TW + warp;
     unsigned round = 1;  // rounds taken so far (lane 0's view of g_next)

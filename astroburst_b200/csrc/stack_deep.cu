@@ -31,6 +31,7 @@ using abk::CeConst;
 
 constexpr int CH = 32;           // samples per chunk
 constexpr int MAX_CHUNKS = AB_MAX_FRAMES / CH;
+constexpr int DEEP_MN = 2, DEEP_MD = 3;  // IMAD share of the compare-exchanges (tuned at r1: 4.05 ms)
 constexpr int DEEP_WARPS = 2;    // warps per block (32 KiB of columns per warp at 256 frames)
 
 // 8 small integers (0..255) packed in one 64-bit register: per-list counters without local memory
@@ -231,7 +232,8 @@ __device__ __forceinline__ float select_mad(const float *col, const int (&n)[K],
     }
 }
 
-template <int K>
+// PRE = false is the plain stack (no calibration terms, no median-only mode compiled in).
+template <int K, bool PRE>
 __global__ void __launch_bounds__(DEEP_WARPS * 32)
 stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t npix,
                   float sigma_low, float sigma_high, unsigned max_iter, CeConst kc,
@@ -242,6 +244,9 @@ stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t np
     const int warp = threadIdx.x >> 5;
     float *col = deep_smem + warp * (K * CH * 32) + lane;
     unsigned local_rej = 0;
+    const bool has_bias = PRE && pre.bias != nullptr;
+    const bool has_dark = PRE && pre.dark != nullptr;
+    const bool median_only = PRE && pre.median_only != 0;
 
     const size_t n_groups = (npix + 31) / 32;
     const size_t warp_global = (size_t)blockIdx.x * DEEP_WARPS + warp;
@@ -258,13 +263,13 @@ stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t np
         float pivot_acc = 0.0f, spread_acc = 0.0f;
         int pivot_cnt = 0;
         // calibration.rs:160-162,199-206: frame - bias, then - dark * ratio (median-combine callers)
-        const float pre_b = (active && pre.bias) ? pre.bias[p] : 0.0f;
-        const float pre_d = (active && pre.dark) ? pre.dark[p] * pre.dark_ratio : 0.0f;
+        const float pre_b = (active && has_bias) ? pre.bias[p] : 0.0f;
+        const float pre_d = (active && has_dark) ? pre.dark[p] * pre.dark_ratio : 0.0f;
         auto fetch = [&](int f) -> float {
             if (!(active && f < n_frames)) return CUDART_INF_F;
             float v = __ldcs(ft.p[f] + p);
-            if (pre.bias) v -= pre_b;
-            if (pre.dark) v -= pre_d;
+            if (has_bias) v -= pre_b;
+            if (has_dark) v -= pre_d;
             return v;
         };
         float nxt[CH];
@@ -284,7 +289,7 @@ stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t np
 #pragma unroll
                 for (int j = 0; j < CH; ++j) nxt[j] = fetch((k + 1) * CH + j);
             }
-            abk::sort_network<CH, abk::DEFAULT_MN, abk::DEFAULT_MD>(s, kc);
+            abk::sort_network<CH, DEEP_MN, DEEP_MD>(s, kc);
             float *dst = col + (size_t)k * CH * 32;
 #pragma unroll
             for (int j = 0; j < CH; ++j) dst[j * 32] = s[j];
@@ -300,7 +305,7 @@ stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t np
                     cd = (double)mk;
                 }
             }
-            if (!pre.median_only) {
+            if (!median_only) {
 #pragma unroll
                 for (int j = 0; j < CH; ++j) {
                     if (j < nk) {
@@ -318,7 +323,7 @@ stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t np
 
         float result = 0.0f;
         unsigned rejected = 0;
-        if (pre.median_only) {  // median_combine_row_major, calibration.rs:108-116
+        if (median_only) {  // median_combine_row_major, calibration.rs:108-116
             if (n_tot > 0)
                 result = select_rank<K>(col, n, n_tot, n_tot >> 1, pivot_acc / (float)pivot_cnt);
         } else if (n_tot == 1) {  // combine.rs:24-26
@@ -404,12 +409,12 @@ stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t np
 
 }  // namespace
 
-template <int K>
+template <int K, bool PRE>
 static ab_status launch_deep_k(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix, float sl,
                                float sh, unsigned max_iter, const DeepPre &pre, float *d_out,
                                unsigned long long *d_rej, cudaStream_t stream) {
     const size_t smem = (size_t)DEEP_WARPS * K * CH * 32 * sizeof(float);
-    auto kern = stack_deep_kernel<K>;
+    auto kern = stack_deep_kernel<K, PRE>;
     AB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     AB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEEP_WARPS * 32, smem));
@@ -428,9 +433,13 @@ ab_status ab_stack_launch_deep(ab_ctx *ctx, const FrameTable &ft, int n_frames, 
                                float sl, float sh, unsigned max_iter, const DeepPre &pre,
                                float *d_out, unsigned long long *d_rej, cudaStream_t stream) {
     const int K = (n_frames + CH - 1) / CH;
+    const bool use_pre = pre.bias || pre.dark || pre.median_only;
 #define AB_DEEP_CASE(k)                                                                         \
     case k:                                                                                     \
-        return launch_deep_k<k>(ctx, ft, n_frames, npix, sl, sh, max_iter, pre, d_out, d_rej, stream);
+        return use_pre ? launch_deep_k<k, true>(ctx, ft, n_frames, npix, sl, sh, max_iter, pre,     \
+                                                d_out, d_rej, stream)                           \
+                       : launch_deep_k<k, false>(ctx, ft, n_frames, npix, sl, sh, max_iter, pre,    \
+                                                 d_out, d_rej, stream);
     switch (K) {
         AB_DEEP_CASE(1) AB_DEEP_CASE(2) AB_DEEP_CASE(3) AB_DEEP_CASE(4) AB_DEEP_CASE(5)
         AB_DEEP_CASE(6) AB_DEEP_CASE(7) AB_DEEP_CASE(8)

@@ -12,10 +12,10 @@
 //
 // GPU mapping.  Every pass is one HBM sweep (float4 loads).  Bin indices use the reference's f64
 // expression `((v as f64 - lo) * inv) as usize` evaluated on the FP64 pipe, so integer bin counts
-// are bit-exact.  65,536-bin histograms: each block keeps a 16,384-bin window (64 KiB of shared
-// memory, u32) positioned where its first pixels fall -- astronomical images are sharply peaked at
-// the sky level, so nearly all increments are shared-memory atomics -- and spills the rest to the
-// global u32 histogram (L2-resident, 256 KiB).  The small rank/percentile walks over the
+// are bit-exact.  65,536-bin histograms: one 1,024-thread block per SM keeps the WHOLE histogram
+// in shared memory as packed u16 counters (128 KiB), so every increment is a shared-memory atomic
+// regardless of where the block's pixels fall; a counter reaching 0x8000 hands 0x8000 counts to
+// the global u32 bin (L2-resident, 256 KiB).  The small rank/percentile walks over the
 // histograms are host scalar code, as in the reference.  Exact medians (<= 4 M px) use an MSB-first
 // radix select on the float bit patterns (valid pixels are positive, so bits are monotone).
 // The f64 pixel sum is reduced block-partial by block-partial in a fixed order (deterministic;
@@ -37,7 +37,8 @@ constexpr float PADDING_THRESHOLD = 1e-7f;  // types/constants.rs:6
 constexpr double MAD_TO_SIGMA = 1.4826;     // types/constants.rs:7
 constexpr unsigned HIST_BINS = 65536;       // stats.rs:8
 constexpr int ST_THREADS = 512;
-constexpr unsigned WIN = 16384;             // shared-memory window bins
+constexpr int HT_THREADS = 1024;            // histogram passes: one block per SM
+constexpr unsigned HALF_FLUSH = 0x8000u;    // packed u16 counter -> global u32 bin hand-over
 
 __device__ __forceinline__ bool valid_px(float v) {
     return (fabsf(v) < CUDART_INF_F) && v > PADDING_THRESHOLD;
@@ -67,11 +68,18 @@ scan_kernel(const float *__restrict__ data, size_t len, ScanPartial *__restrict_
             ++cnt;
         }
     };
-    for (size_t i = tid; i < n4; i += stride) {
-        const float4 v = __ldcs(reinterpret_cast<const float4 *>(data) + i);
-        acc(v.x); acc(v.y); acc(v.z); acc(v.w);
+    auto four = [&](const float4 &v) { acc(v.x); acc(v.y); acc(v.z); acc(v.w); };
+    const float4 *d4 = reinterpret_cast<const float4 *>(data);
+    size_t i = tid;
+    for (; i + 3 * stride < n4; i += 4 * stride) {  // four 16-byte loads in flight per thread
+        const float4 v0 = __ldcs(d4 + i);
+        const float4 v1 = __ldcs(d4 + i + stride);
+        const float4 v2 = __ldcs(d4 + i + 2 * stride);
+        const float4 v3 = __ldcs(d4 + i + 3 * stride);
+        four(v0); four(v1); four(v2); four(v3);
     }
-    for (size_t i = n4 * 4 + tid; i < len; i += stride) acc(data[i]);
+    for (; i < n4; i += stride) four(__ldcs(d4 + i));
+    for (size_t j = n4 * 4 + tid; j < len; j += stride) acc(data[j]);
 
     __shared__ ScanPartial sh[ST_THREADS / 32];
     for (int o = 16; o > 0; o >>= 1) {
@@ -105,48 +113,21 @@ struct HistPartial {
 };
 
 template <typename F>
-__global__ void __launch_bounds__(ST_THREADS)
+__global__ void __launch_bounds__(HT_THREADS, 1)
 hist_kernel(const float *__restrict__ data, size_t len, F f, unsigned *__restrict__ histA,
             unsigned *__restrict__ histB, HistPartial *__restrict__ partials) {
-    extern __shared__ unsigned win[];
-    __shared__ unsigned s_base;
-    __shared__ unsigned s_min;
-    for (unsigned i = threadIdx.x; i < WIN; i += blockDim.x) win[i] = 0;
-    if (threadIdx.x == 0) s_min = 0xffffffffu;
+    // histogram A lives whole in shared memory as 65,536 packed u16 counters (128 KiB, one block
+    // per SM): every increment is a shared-memory atomic wherever the block's pixels fall.  A
+    // counter that reaches 0x8000 moves 0x8000 counts to the global u32 bin; at most
+    // HT_THREADS - 1 further increments can land before the subtraction, so a half never wraps.
+    extern __shared__ unsigned packed[];
+    for (unsigned i = threadIdx.x; i < HIST_BINS / 2; i += HT_THREADS) packed[i] = 0;
     __syncthreads();
 
     const bool vec_ok = (reinterpret_cast<uintptr_t>(data) & 15) == 0;
     const size_t n4 = vec_ok ? len / 4 : 0;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-
-    // position the window from the block's first pixels
-    {
-        unsigned my = 0xffffffffu;
-        if (tid < n4) {
-            const float4 v = reinterpret_cast<const float4 *>(data)[tid];
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                unsigned a = 0, b = 0;
-                if (f(vv[q], a, b) & 1u) my = min(my, a);
-            }
-        } else if (n4 == 0 && tid < len) {
-            unsigned a = 0, b = 0;
-            if (f(data[tid], a, b) & 1u) my = a;
-        }
-        my = __reduce_min_sync(0xffffffffu, my);
-        if ((threadIdx.x & 31) == 0 && my != 0xffffffffu) atomicMin(&s_min, my);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned m = s_min == 0xffffffffu ? 0u : s_min;
-            unsigned base = m > WIN / 8 ? m - WIN / 8 : 0u;
-            if (base + WIN > HIST_BINS) base = HIST_BINS - WIN;
-            s_base = base;
-        }
-        __syncthreads();
-    }
-    const unsigned base = s_base;
+    const size_t stride = (size_t)gridDim.x * HT_THREADS;
+    const size_t tid = (size_t)blockIdx.x * HT_THREADS + threadIdx.x;
     double sum = 0.0;
     unsigned long long cnt = 0, below = 0;
 
@@ -158,25 +139,36 @@ hist_kernel(const float *__restrict__ data, size_t len, F f, unsigned *__restric
             ++cnt;
         }
         if (code & 1u) {
-            const unsigned rel = a - base;
-            if (rel < WIN) atomicAdd(&win[rel], 1u);
-            else atomicAdd(&histA[a], 1u);
+            const unsigned sh = (a & 1u) << 4;
+            const unsigned old = atomicAdd(&packed[a >> 1], 1u << sh);
+            if (((old >> sh) & 0xffffu) == HALF_FLUSH - 1u) {
+                atomicAdd(&histA[a], HALF_FLUSH);
+                atomicSub(&packed[a >> 1], HALF_FLUSH << sh);
+            }
         }
         if (code & 2u) atomicAdd(&histB[b], 1u);
         if (code & 4u) ++below;
     };
-    for (size_t i = tid; i < n4; i += stride) {
-        const float4 v = __ldcs(reinterpret_cast<const float4 *>(data) + i);
-        one(v.x); one(v.y); one(v.z); one(v.w);
+    auto four = [&](const float4 &v) { one(v.x); one(v.y); one(v.z); one(v.w); };
+    const float4 *d4 = reinterpret_cast<const float4 *>(data);
+    size_t i = tid;
+    for (; i + 3 * stride < n4; i += 4 * stride) {  // four 16-byte loads in flight per thread
+        const float4 v0 = __ldcs(d4 + i);
+        const float4 v1 = __ldcs(d4 + i + stride);
+        const float4 v2 = __ldcs(d4 + i + 2 * stride);
+        const float4 v3 = __ldcs(d4 + i + 3 * stride);
+        four(v0); four(v1); four(v2); four(v3);
     }
-    for (size_t i = n4 * 4 + tid; i < len; i += stride) one(data[i]);
+    for (; i < n4; i += stride) four(__ldcs(d4 + i));
+    for (size_t j = n4 * 4 + tid; j < len; j += stride) one(data[j]);
     __syncthreads();
-    for (unsigned i = threadIdx.x; i < WIN; i += blockDim.x) {
-        const unsigned c = win[i];
-        if (c) atomicAdd(&histA[base + i], c);
+    for (unsigned w = threadIdx.x; w < HIST_BINS / 2; w += HT_THREADS) {
+        const unsigned c = packed[w];
+        if (c & 0xffffu) atomicAdd(&histA[2 * w], c & 0xffffu);
+        if (c >> 16) atomicAdd(&histA[2 * w + 1], c >> 16);
     }
     // deterministic per-block partial of the f64 sum
-    __shared__ HistPartial sh[ST_THREADS / 32];
+    __shared__ HistPartial sh[HT_THREADS / 32];
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_down_sync(0xffffffffu, sum, o);
         cnt += __shfl_down_sync(0xffffffffu, cnt, o);
@@ -187,7 +179,7 @@ hist_kernel(const float *__restrict__ data, size_t len, F f, unsigned *__restric
     __syncthreads();
     if (threadIdx.x == 0) {
         HistPartial r = sh[0];
-        for (int w = 1; w < ST_THREADS / 32; ++w) {
+        for (int w = 1; w < HT_THREADS / 32; ++w) {
             r.sum += sh[w].sum;
             r.count += sh[w].count;
             r.below += sh[w].below;
@@ -372,13 +364,13 @@ ab_status run_hist(ab_ctx *ctx, const float *d, size_t len, F f, bool wantA, boo
                    cudaStream_t s, double *sum, unsigned long long *count,
                    unsigned long long *below) {
     Small sm(ctx);
-    const unsigned grid = grid_for(ctx, len, 16);
+    size_t blocks = (len / 16 + HT_THREADS - 1) / HT_THREADS + 1;
+    if (blocks > (size_t)ctx->sm_count) blocks = (size_t)ctx->sm_count;
+    const unsigned grid = (unsigned)blocks;
+    constexpr int smem = (int)(HIST_BINS / 2 * sizeof(unsigned));
     AB_CUDA(ctx, cudaMemsetAsync(sm.dA, 0, 2 * HIST_BINS * sizeof(unsigned), s));
-    static bool attr = false;
-    AB_CUDA(ctx, cudaFuncSetAttribute(hist_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(WIN * sizeof(unsigned))));
-    (void)attr;
-    hist_kernel<F><<<grid, ST_THREADS, WIN * sizeof(unsigned), s>>>(
+    AB_CUDA(ctx, cudaFuncSetAttribute(hist_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    hist_kernel<F><<<grid, HT_THREADS, smem, s>>>(
         d, len, f, sm.dA, sm.dB, reinterpret_cast<HistPartial *>(sm.d));
     AB_LAUNCH_CHECK(ctx);
     AB_CUDA(ctx, cudaMemcpyAsync(sm.h, sm.d, grid * sizeof(HistPartial), cudaMemcpyDeviceToHost, s));

@@ -16,6 +16,6 @@ from .core import (  # noqa: F401
     stack_images_device,
 )
 
-from . import alignment, calibration, fits, imaging  # noqa: F401,E402
+from . import alignment, calibration, fits, imaging, preview  # noqa: F401,E402
 
 __version__ = "0.1.0"

@@ -83,6 +83,29 @@ class AlignResultC(C.Structure):
                 ("residual_px", C.c_double), ("method", C.c_int32)]
 
 
+class StarMaskConfigC(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("growth_factor", "softness", "detection_sigma", "min_fwhm",
+                                          "max_fwhm")] + [("luminance_protect", C.c_int32),
+                                                          ("luminance_ceiling", C.c_double)]
+
+
+class StarMaskInfoC(C.Structure):
+    _fields_ = [("stars_masked", C.c_uint64), ("coverage_fraction", C.c_double)]
+
+
+class MaskedStretchConfigC(C.Structure):
+    _fields_ = [("iterations", C.c_uint64), ("target_background", C.c_double),
+                ("mask_growth", C.c_double), ("mask_softness", C.c_double),
+                ("luminance_protect", C.c_int32), ("luminance_ceiling", C.c_double),
+                ("protection_amount", C.c_double), ("convergence_threshold", C.c_double)]
+
+
+class MaskedStretchInfoC(C.Structure):
+    _fields_ = [("iterations_run", C.c_uint64), ("final_background", C.c_double),
+                ("stars_masked", C.c_uint64), ("mask_coverage", C.c_double),
+                ("converged", C.c_int32)]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int)
 
 
@@ -181,6 +204,27 @@ SIGNATURES = {
     "ab_align_affine_dev": (C.c_int, [_vp, _vp, _vp, _sz, _sz, C.c_int, _vp, _vp]),
     "ab_match_stars": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, C.POINTER(C.c_size_t)]),
     "ab_ransac_affine": (C.c_int, [_vp, _sz, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),
+    # preview / export tail, LRGB, star mask, masked stretch
+    "ab_preview_size": (C.c_int, [_sz, _sz, _sz, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "ab_render_rgb_u8": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp]),
+    "ab_render_rgb_u8_dev": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp]),
+    "ab_render_rgb_stf_u8": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _sz, _vp, _vp, _sz, _vp]),
+    "ab_render_rgb_stf_u8_dev": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _sz, _vp, _vp, _sz, _vp, _vp]),
+    "ab_render_rgb_u16be": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "ab_render_rgb_u16be_dev": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "ab_apply_lrgb": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, C.c_float, C.c_float]),
+    "ab_apply_lrgb_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, C.c_float, C.c_float, _vp]),
+    "ab_luminance": (C.c_int, [_vp, _vp, _vp, _vp, _sz, C.c_int, _vp]),
+    "ab_luminance_dev": (C.c_int, [_vp, _vp, _vp, _vp, _sz, C.c_int, _vp, _vp]),
+    "ab_star_mask_from_stars": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz, _vp, _vp, _vp]),
+    "ab_star_mask_from_stars_dev": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "ab_generate_star_mask": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _vp, _vp]),
+    "ab_generate_star_mask_dev": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp]),
+    "ab_masked_median_dev": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(C.c_double), _vp]),
+    "ab_masked_stretch_with_mask": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "ab_masked_stretch_with_mask_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "ab_masked_stretch": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _vp, _vp]),
+    "ab_masked_stretch_dev": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

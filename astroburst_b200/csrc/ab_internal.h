@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "astroburst_cuda.h"
 
@@ -82,6 +83,13 @@ struct DeviceGuard {
 };
 
 ab_status ab_scratch_reserve(ab_ctx *ctx, int slot, size_t bytes);
+
+// ---- stats.cu / stars.cu pieces used by preview.cu (no locking: the caller holds ctx->mu)
+ab_status ab_scan_on(ab_ctx *ctx, const float *d, size_t len, cudaStream_t s, double *mn, double *mx,
+                     double *sum, unsigned long long *count);
+ab_status ab_detect_stars_on(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols,
+                             double sigma_threshold, cudaStream_t s, std::vector<ab_star> &stars,
+                             double *bg_median, double *bg_sigma);
 
 // ---- phasecorr.cu
 void ab_phasecorr_release(ab_ctx *ctx);

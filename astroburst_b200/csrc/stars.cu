@@ -910,6 +910,13 @@ void fill_info(ab_detection_info *info, double bm, double bs, double thr, size_t
 
 }  // namespace
 
+ab_status ab_detect_stars_on(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols,
+                             double sigma_threshold, cudaStream_t s, std::vector<ab_star> &stars,
+                             double *bg_median, double *bg_sigma) {
+    Norm nm{0, 0.0, 1.0};
+    return detect_on_device(ctx, d_img, rows, cols, nm, sigma_threshold, s, stars, bg_median, bg_sigma);
+}
+
 extern "C" {
 
 ab_status ab_detect_stars_dev(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols,

@@ -640,6 +640,12 @@ ab_status upload_plane(ab_ctx *ctx, const float *h, size_t len, float **d) {
 
 }  // namespace
 
+// min / max / sum / count over the valid pixels (stats.rs:212-257); min = DBL_MAX when count == 0
+ab_status ab_scan_on(ab_ctx *ctx, const float *d, size_t len, cudaStream_t s, double *mn, double *mx,
+                     double *sum, unsigned long long *count) {
+    return run_scan(ctx, d, len, s, mn, mx, sum, count);
+}
+
 extern "C" {
 
 ab_status ab_image_stats_dev(ab_ctx *ctx, const float *d_data, size_t len, int mode,

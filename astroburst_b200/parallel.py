@@ -87,3 +87,78 @@ def allreduce_rejected(rejected_tensor, group=None):
 
     dist.all_reduce(rejected_tensor, group=group)
     return rejected_tensor
+
+
+def frame_owner(f: int, n_frames: int, world: int) -> int:
+    """Rank holding frame `f` of a frame-sharded stack (contiguous blocks, like the plan above)."""
+    return f * world // n_frames if n_frames >= world else f % world
+
+
+def reshard_frames_to_bands(local_frames, n_frames: int, rows: int, cols: int, out=None, group=None):
+    """Frame-sharded -> row-band sharded input: the exchange step a
+    frame-sharded deep stack needs before the exact per-pixel median/MAD.
+
+    `local_frames`: [n_local, rows, cols] tensor holding this rank's frames in global frame order
+    (frame f lives on frame_owner(f)).  Returns `out` = [n_frames, band_rows, cols]: this rank's row
+    band of EVERY frame.  Zero-copy on both sides: each (frame, band) block is a contiguous slice of
+    the source and of the destination cube, sent with one batched isend/irecv group (NCCL: one
+    ncclGroup of ncclSend/ncclRecv over NVLink; gloo on CPU for the tests)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = [f for f in range(n_frames) if frame_owner(f, n_frames, world) == rank]
+    if local_frames.shape[0] != len(mine) or tuple(local_frames.shape[1:]) != (rows, cols):
+        raise ValueError(f"rank {rank} must hold {len(mine)} frames of {rows}x{cols}, "
+                         f"got {tuple(local_frames.shape)}")
+    if not local_frames.is_contiguous():
+        raise ValueError("local_frames must be contiguous")
+    r0, r1 = row_band(rows, rank, world)
+    if out is None:
+        out = torch.empty((n_frames, r1 - r0, cols), dtype=local_frames.dtype,
+                          device=local_frames.device)
+    ops = []
+    local_index = {f: i for i, f in enumerate(mine)}
+    for f in range(n_frames):
+        src = frame_owner(f, n_frames, world)
+        if src == rank:
+            for dst in range(world):
+                d0, d1 = row_band(rows, dst, world)
+                if d1 == d0:
+                    continue
+                blk = local_frames[local_index[f], d0:d1]
+                if dst == rank:
+                    out[f].copy_(blk)
+                else:
+                    ops.append(dist.P2POp(dist.isend, blk, dst, group))
+        elif r1 > r0:
+            ops.append(dist.P2POp(dist.irecv, out[f], src, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out
+
+
+def stack_frame_sharded(local_frames, n_frames: int, rows: int, cols: int, config, stream: int = 0,
+                        ctx: Context | None = None, group=None):
+    """Config 5: sigma-clip stack of a stack whose FRAMES are sharded over the ranks.  Re-shards to
+    row bands (one all-to-all over NVLink), runs the exact local kernel on the band, all-reduces
+    StackResult.rejected_pixels.  Returns (band [band_rows, cols] device tensor, rejected int64
+    tensor, (r0, r1)); bit-identical to the single-GPU stack of all frames."""
+    import torch
+    import torch.distributed as dist
+
+    from .core import stack_images_device
+
+    ctx = ctx or default_context()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    cube = reshard_frames_to_bands(local_frames, n_frames, rows, cols, group=group)
+    r0, r1 = row_band(rows, rank, world)
+    out = torch.empty((r1 - r0, cols), dtype=torch.float32, device=cube.device)
+    rej = torch.zeros(1, dtype=torch.int64, device=cube.device)
+    if r1 > r0:
+        stack_images_device([cube[f].data_ptr() for f in range(n_frames)], out.numel(), config,
+                            out.data_ptr(), rej.data_ptr(), stream, ctx)
+    allreduce_rejected(rej, group)
+    return out, rej, (r0, r1)

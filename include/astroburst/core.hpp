@@ -188,5 +188,53 @@ inline ab_align_result align_channel_affine(const Context &ctx, const Image &ref
 }
 }  // namespace alignment
 
+namespace preview {
+// cmd/helpers.rs:204-262 / infra/render/rgb.rs:7-47 without the PNG encoder: interleaved RGB8
+inline std::vector<uint8_t> render_rgb_preview(const Context &ctx, const Image &r, const Image &g,
+                                               const Image &b, size_t max_dim, size_t *pw = nullptr,
+                                               size_t *ph = nullptr) {
+    size_t w = 0, h = 0;
+    ab_preview_size(r.rows, r.cols, max_dim, &w, &h);
+    std::vector<uint8_t> out(w * h * 3);
+    ctx.check(ab_render_rgb_u8(ctx.get(), r.data.data(), g.data.data(), b.data.data(), r.rows, r.cols,
+                               max_dim, out.data()));
+    if (pw) *pw = w;
+    if (ph) *ph = h;
+    return out;
+}
+// core/compose/lrgb.rs:4-46
+inline void apply_lrgb(const Context &ctx, const Image &l, Image &r, Image &g, Image &b,
+                       float lightness_weight, float chrominance_weight) {
+    if (l.rows != r.rows || l.cols != r.cols || g.data.size() != r.data.size() ||
+        b.data.size() != r.data.size())
+        throw Error(AB_ERR_INVALID, "L dimensions do not match RGB");
+    ctx.check(ab_apply_lrgb(ctx.get(), l.data.data(), r.data.data(), g.data.data(), b.data.data(),
+                            r.data.size(), lightness_weight, chrominance_weight));
+}
+// core/imaging/masked_stretch.rs:7-57
+struct MaskedStretchConfig {
+    size_t iterations = 10;
+    double target_background = 0.25, mask_growth = 2.5, mask_softness = 4.0;
+    bool luminance_protect = true;
+    double luminance_ceiling = 0.85, protection_amount = 0.85, convergence_threshold = 1e-5;
+};
+struct MaskedStretchResult {
+    Image image;
+    ab_masked_stretch_info info{};
+};
+inline MaskedStretchResult masked_stretch(const Context &ctx, const Image &img,
+                                          const MaskedStretchConfig &c = MaskedStretchConfig()) {
+    const ab_masked_stretch_config cfg{c.iterations, c.target_background, c.mask_growth,
+                                       c.mask_softness, c.luminance_protect ? 1 : 0,
+                                       c.luminance_ceiling, c.protection_amount,
+                                       c.convergence_threshold};
+    MaskedStretchResult out;
+    out.image = Image(img.rows, img.cols);
+    ctx.check(ab_masked_stretch(ctx.get(), img.data.data(), img.rows, img.cols, &cfg,
+                                out.image.data.data(), &out.info));
+    return out;
+}
+}  // namespace preview
+
 }  // namespace core
 }  // namespace astroburst

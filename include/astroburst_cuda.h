@@ -118,6 +118,37 @@ typedef struct {
     int32_t method;
 } ab_align_result;
 
+/* mirrors StarMaskConfig, core/imaging/star_mask.rs:7-29 (defaults 2.5, 4.0, 5.0, 1.5, 30.0, false, 0.85) */
+typedef struct {
+    double growth_factor, softness, detection_sigma, min_fwhm, max_fwhm;
+    int32_t luminance_protect;
+    double luminance_ceiling;
+} ab_star_mask_config;
+
+/* mirrors StarMaskResult (minus the mask), star_mask.rs:31-36 */
+typedef struct {
+    uint64_t stars_masked;
+    double coverage_fraction;
+} ab_star_mask_info;
+
+/* mirrors MaskedStretchConfig, core/imaging/masked_stretch.rs:7-32
+ * (defaults 10, 0.25, 2.5, 4.0, true, 0.85, 0.85, 1e-5) */
+typedef struct {
+    uint64_t iterations;
+    double target_background, mask_growth, mask_softness;
+    int32_t luminance_protect;
+    double luminance_ceiling, protection_amount, convergence_threshold;
+} ab_masked_stretch_config;
+
+/* mirrors MaskedStretchResult (minus the image), masked_stretch.rs:34-42 */
+typedef struct {
+    uint64_t iterations_run;
+    double final_background;
+    uint64_t stars_masked;
+    double mask_coverage;
+    int32_t converged;
+} ab_masked_stretch_info;
+
 /* ---------------------------------------------------------------- context / memory */
 int ab_abi_version(void);
 /* device < 0 selects the current CUDA device */
@@ -388,6 +419,82 @@ ab_status ab_match_stars(ab_ctx *ctx, const double *ref_xy, size_t n_ref, const 
 /* ransac_affine, affine.rs:400-517 (host scalar code); *found = 0 where the reference returns None */
 ab_status ab_ransac_affine(const double *matches, size_t n, int method, int n_threads,
                            ab_align_result *out, int *found);
+
+/* ---------------------------------------------------------------- preview / export tail
+ * Preview size of render_rgb_preview(_with_stf), cmd/helpers.rs:222-227: planes that fit max_dim
+ * (or max_dim == 0) keep their size, else round(dim * max_dim / max(rows, cols)).max(1). */
+ab_status ab_preview_size(size_t rows, size_t cols, size_t max_dim, size_t *pw, size_t *ph);
+/* render_rgb, infra/render/rgb.rs:7-47 + render_rgb_preview, cmd/helpers.rs:204-262: interleaved
+ * RGB8, `(v.clamp(0,1) * 255) as u8` (truncating), nearest-neighbour decimation when the planes
+ * exceed max_dim.  out = ph * pw * 3 bytes (ab_preview_size).  PNG encoding stays on the host. */
+ab_status ab_render_rgb_u8(ab_ctx *ctx, const float *r, const float *g, const float *b, size_t rows,
+                           size_t cols, size_t max_dim, uint8_t *out);
+ab_status ab_render_rgb_u8_dev(ab_ctx *ctx, const float *d_r, const float *d_g, const float *d_b,
+                               size_t rows, size_t cols, size_t max_dim, uint8_t *d_out,
+                               void *stream);
+/* render_rgb_preview_with_stf, cmd/helpers.rs:264-322 with make_stf_u8_fn closures
+ * (core/imaging/stf.rs:122-145): stf3 / stats3 = (r, g, b) parameters */
+ab_status ab_render_rgb_stf_u8(ab_ctx *ctx, const float *r, const float *g, const float *b,
+                               size_t rows, size_t cols, const ab_stf_params *stf3,
+                               const ab_image_stats *stats3, size_t max_dim, uint8_t *out);
+ab_status ab_render_rgb_stf_u8_dev(ab_ctx *ctx, const float *d_r, const float *d_g,
+                                   const float *d_b, size_t rows, size_t cols,
+                                   const ab_stf_params *stf3, const ab_image_stats *stats3,
+                                   size_t max_dim, uint8_t *d_out, void *stream);
+/* render_rgb_16bit, rgb.rs:49-98: `(v.clamp(0,1) * 65535) as u16` as big-endian bytes, interleaved;
+ * out = len * 6 bytes */
+ab_status ab_render_rgb_u16be(ab_ctx *ctx, const float *r, const float *g, const float *b,
+                              size_t len, uint8_t *out);
+ab_status ab_render_rgb_u16be_dev(ab_ctx *ctx, const float *d_r, const float *d_g,
+                                  const float *d_b, size_t len, uint8_t *d_out, void *stream);
+/* apply_lrgb, core/compose/lrgb.rs:4-46 (in place on r, g, b; the caller checks equal dims, :14-19) */
+ab_status ab_apply_lrgb(ab_ctx *ctx, const float *l, float *r, float *g, float *b, size_t len,
+                        float lightness_weight, float chrominance_weight);
+ab_status ab_apply_lrgb_dev(ab_ctx *ctx, const float *d_l, float *d_r, float *d_g, float *d_b,
+                            size_t len, float lightness_weight, float chrominance_weight,
+                            void *stream);
+/* finite_only = 0: synthesize_luminance, lrgb.rs:48-62; 1: compute_luminance,
+ * core/imaging/masked_stretch.rs:134-159 (non-finite samples count as 0) */
+ab_status ab_luminance(ab_ctx *ctx, const float *r, const float *g, const float *b, size_t len,
+                       int finite_only, float *out);
+ab_status ab_luminance_dev(ab_ctx *ctx, const float *d_r, const float *d_g, const float *d_b,
+                           size_t len, int finite_only, float *d_out, void *stream);
+/* generate_star_mask_from_detection, core/imaging/star_mask.rs:46-138 (stars: a detect_stars
+ * result; only x, y, fwhm are read); the call synchronizes (coverage is a host scalar) */
+ab_status ab_star_mask_from_stars(ab_ctx *ctx, const float *img, size_t rows, size_t cols,
+                                  const ab_star *stars, size_t n_stars,
+                                  const ab_star_mask_config *cfg, float *mask,
+                                  ab_star_mask_info *info);
+ab_status ab_star_mask_from_stars_dev(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols,
+                                      const ab_star *stars, size_t n_stars,
+                                      const ab_star_mask_config *cfg, float *d_mask,
+                                      ab_star_mask_info *info, void *stream);
+/* generate_star_mask, star_mask.rs:38-44: detect_stars(cfg->detection_sigma) then the mask */
+ab_status ab_generate_star_mask(ab_ctx *ctx, const float *img, size_t rows, size_t cols,
+                                const ab_star_mask_config *cfg, float *mask,
+                                ab_star_mask_info *info);
+ab_status ab_generate_star_mask_dev(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols,
+                                    const ab_star_mask_config *cfg, float *d_mask,
+                                    ab_star_mask_info *info, void *stream);
+/* compute_masked_median, masked_stretch.rs:211-228 (synchronizes) */
+ab_status ab_masked_median_dev(ab_ctx *ctx, const float *d_img, const float *d_mask, size_t len,
+                               double *out, void *stream);
+/* masked_stretch_with_mask, masked_stretch.rs:59-117; info->stars_masked / mask_coverage are the
+ * caller's (they come from the StarMaskResult).  Synchronizes (the loop control is host scalar code). */
+ab_status ab_masked_stretch_with_mask(ab_ctx *ctx, const float *img, size_t len, const float *mask,
+                                      const ab_masked_stretch_config *cfg, float *out,
+                                      ab_masked_stretch_info *info);
+ab_status ab_masked_stretch_with_mask_dev(ab_ctx *ctx, const float *d_img, size_t len,
+                                          const float *d_mask, const ab_masked_stretch_config *cfg,
+                                          float *d_out, ab_masked_stretch_info *info, void *stream);
+/* masked_stretch, masked_stretch.rs:45-57 (detect at sigma 5 -> mask -> stretch); the _dev form
+ * also returns the mask in d_mask */
+ab_status ab_masked_stretch(ab_ctx *ctx, const float *img, size_t rows, size_t cols,
+                            const ab_masked_stretch_config *cfg, float *out,
+                            ab_masked_stretch_info *info);
+ab_status ab_masked_stretch_dev(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols,
+                                const ab_masked_stretch_config *cfg, float *d_mask, float *d_out,
+                                ab_masked_stretch_info *info, void *stream);
 
 #ifdef __cplusplus
 }

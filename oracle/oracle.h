@@ -160,6 +160,28 @@ int orc_ransac(const double *matches, size_t n, int method, int n_threads, orc_a
 int orc_fit_affine(const double *matches, size_t n, orc_affine *out);
 int orc_fit_rigid(const double *matches, size_t n, orc_affine *out);
 
+/* ---- preview/export tail, LRGB, star mask, masked stretch ---- */
+void orc_preview_size(size_t rows, size_t cols, size_t max_dim, size_t *pw, size_t *ph);
+void orc_render_rgb_u8(const float *r, const float *g, const float *b, size_t rows, size_t cols,
+                       size_t max_dim, uint8_t *out);
+void orc_render_rgb_u16be(const float *r, const float *g, const float *b, size_t len, uint8_t *out);
+void orc_render_rgb_stf_u8(const float *r, const float *g, const float *b, size_t rows, size_t cols,
+                           const orc_stf_params *stf3, const orc_image_stats *st3, size_t max_dim,
+                           uint8_t *out);
+void orc_apply_lrgb(const float *l, float *r, float *g, float *b, size_t len, float lightness_weight,
+                    float chrominance_weight);
+void orc_luminance(const float *r, const float *g, const float *b, size_t len, int finite_only,
+                   float *out);
+size_t orc_star_mask(const float *img, size_t h, size_t w, const orc_star *stars, size_t n_stars,
+                     double growth_factor, double softness, double min_fwhm, double max_fwhm,
+                     int luminance_protect, double luminance_ceiling, float *mask,
+                     double *coverage_fraction);
+double orc_masked_median(const float *img, const float *mask, size_t len);
+size_t orc_masked_stretch_with_mask(const float *img, size_t len, const float *mask,
+                                    size_t iterations, double target_bg, double protection_amount,
+                                    double convergence_threshold, float *out,
+                                    double *final_background, int *converged);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,9 @@ def lib():
         _lib.orc_bilinear_sample.restype = C.c_float
         _lib.orc_detect_stars.restype = C.c_size_t
         _lib.orc_match_stars.restype = C.c_size_t
+        _lib.orc_star_mask.restype = C.c_size_t
+        _lib.orc_masked_median.restype = C.c_double
+        _lib.orc_masked_stretch_with_mask.restype = C.c_size_t
     return _lib
 
 
@@ -509,3 +512,112 @@ def fit_rigid(matches):
     out = Affine()
     ok = lib().orc_fit_rigid(_p(m), C.c_size_t(m.shape[0]), C.byref(out))
     return out if ok else None
+
+
+# ---------------------------------------------------------------- preview tail / LRGB / masks (N4)
+def preview_size(rows, cols, max_dim):
+    pw, ph = C.c_size_t(), C.c_size_t()
+    lib().orc_preview_size(C.c_size_t(rows), C.c_size_t(cols), C.c_size_t(max_dim), C.byref(pw),
+                           C.byref(ph))
+    return pw.value, ph.value
+
+
+def render_rgb_u8(r, g, b, max_dim=0):
+    """render_rgb / render_rgb_preview -> uint8 [ph, pw, 3]."""
+    r, g, b = _f32(r), _f32(g), _f32(b)
+    pw, ph = preview_size(r.shape[0], r.shape[1], max_dim)
+    out = np.empty((ph, pw, 3), np.uint8)
+    lib().orc_render_rgb_u8(_p(r), _p(g), _p(b), C.c_size_t(r.shape[0]), C.c_size_t(r.shape[1]),
+                            C.c_size_t(max_dim), _p(out))
+    return out
+
+
+def render_rgb_u16be(r, g, b):
+    """render_rgb_16bit's byte stream -> uint8 [rows, cols, 6]."""
+    r, g, b = _f32(r), _f32(g), _f32(b)
+    out = np.empty(r.shape + (6,), np.uint8)
+    lib().orc_render_rgb_u16be(_p(r), _p(g), _p(b), C.c_size_t(r.size), _p(out))
+    return out
+
+
+def render_rgb_stf_u8(r, g, b, stf3, stats3, max_dim=0):
+    r, g, b = _f32(r), _f32(g), _f32(b)
+    pw, ph = preview_size(r.shape[0], r.shape[1], max_dim)
+    out = np.empty((ph, pw, 3), np.uint8)
+    sp = (StfParams * 3)(*stf3)
+    st = (ImageStats * 3)(*stats3)
+    lib().orc_render_rgb_stf_u8(_p(r), _p(g), _p(b), C.c_size_t(r.shape[0]), C.c_size_t(r.shape[1]),
+                                sp, st, C.c_size_t(max_dim), _p(out))
+    return out
+
+
+def apply_lrgb(l, r, g, b, lightness_weight=1.0, chrominance_weight=1.0):
+    """lrgb.rs:4-46: in place on r, g, b (float32 C-contiguous); raises on a shape mismatch."""
+    if not (l.shape == r.shape == g.shape == b.shape):
+        raise ValueError("L dimensions do not match RGB")
+    lib().orc_apply_lrgb(_p(_f32(l)), _p(r), _p(g), _p(b), C.c_size_t(r.size),
+                         C.c_float(lightness_weight), C.c_float(chrominance_weight))
+
+
+def synthesize_luminance(r, g, b, finite_only=False):
+    r, g, b = _f32(r), _f32(g), _f32(b)
+    out = np.empty(r.shape, np.float32)
+    lib().orc_luminance(_p(r), _p(g), _p(b), C.c_size_t(r.size), C.c_int(1 if finite_only else 0),
+                        _p(out))
+    return out
+
+
+def star_mask_from_stars(img, stars, growth_factor=2.5, softness=4.0, min_fwhm=1.5, max_fwhm=30.0,
+                         luminance_protect=False, luminance_ceiling=0.85):
+    """generate_star_mask_from_detection -> (mask, stars_masked, coverage_fraction).
+    stars: list of dicts with x, y, fwhm (detect_stars().stars)."""
+    d = _f32(img)
+    buf = (Star * max(len(stars), 1))()
+    for i, s in enumerate(stars):
+        buf[i].x, buf[i].y, buf[i].fwhm = s["x"], s["y"], s["fwhm"]
+    mask = np.empty(d.shape, np.float32)
+    cov = C.c_double()
+    n = lib().orc_star_mask(_p(d), C.c_size_t(d.shape[0]), C.c_size_t(d.shape[1]), buf,
+                            C.c_size_t(len(stars)), C.c_double(growth_factor), C.c_double(softness),
+                            C.c_double(min_fwhm), C.c_double(max_fwhm),
+                            C.c_int(1 if luminance_protect else 0), C.c_double(luminance_ceiling),
+                            _p(mask), C.byref(cov))
+    return mask, int(n), cov.value
+
+
+def generate_star_mask(img, growth_factor=2.5, softness=4.0, detection_sigma=5.0, min_fwhm=1.5,
+                       max_fwhm=30.0, luminance_protect=False, luminance_ceiling=0.85):
+    det = detect_stars(img, detection_sigma)
+    return star_mask_from_stars(img, det.stars, growth_factor, softness, min_fwhm, max_fwhm,
+                                luminance_protect, luminance_ceiling)
+
+
+def masked_median(img, mask):
+    d, m = _f32(img), _f32(mask)
+    return lib().orc_masked_median(_p(d), _p(m), C.c_size_t(d.size))
+
+
+def masked_stretch_with_mask(img, mask, iterations=10, target_background=0.25,
+                             protection_amount=0.85, convergence_threshold=1e-5):
+    """-> (image, iterations_run, final_background, converged)."""
+    d, m = _f32(img), _f32(mask)
+    out = np.empty(d.shape, np.float32)
+    fb, conv = C.c_double(), C.c_int()
+    n = lib().orc_masked_stretch_with_mask(_p(d), C.c_size_t(d.size), _p(m), C.c_size_t(iterations),
+                                           C.c_double(target_background),
+                                           C.c_double(protection_amount),
+                                           C.c_double(convergence_threshold), _p(out),
+                                           C.byref(fb), C.byref(conv))
+    return out, int(n), fb.value, bool(conv.value)
+
+
+def masked_stretch(img, iterations=10, target_background=0.25, mask_growth=2.5, mask_softness=4.0,
+                   luminance_protect=True, luminance_ceiling=0.85, protection_amount=0.85,
+                   convergence_threshold=1e-5):
+    """masked_stretch.rs:45-57 -> (image, iterations_run, final_background, converged,
+    stars_masked, mask_coverage)."""
+    mask, n, cov = generate_star_mask(img, mask_growth, mask_softness, 5.0, 1.5, 30.0,
+                                      luminance_protect, luminance_ceiling)
+    out, it, fb, conv = masked_stretch_with_mask(img, mask, iterations, target_background,
+                                                 protection_amount, convergence_threshold)
+    return out, it, fb, conv, n, cov

@@ -360,3 +360,80 @@ def test_fits_decode_reference_unit_tests(orc):
     assert np.array_equal(orc.fits_decode(orc.fits_encode(a, -32), -32), a, equal_nan=True)
     assert orc.fits_encode(np.array([40000.0, -1.0, 100.4], np.float32), 16, 32768.0, 1.0) == \
         np.array([7232, -32768, -32668], ">i2").tobytes()
+
+
+# ---- preview tail / LRGB / star mask / masked stretch ---------------------------------
+# The reference holds unit tests only for lrgb.rs (ported below); star_mask.rs, masked_stretch.rs and
+# the render helpers have none, so those restatements are "parity unpinned" beyond the definitional
+# checks here (numpy restatements of the closed-form parts).
+def test_lrgb_reference_unit_tests(orc):
+    full = lambda v, s=(10, 10): np.full(s, v, np.float32)
+    l, r, g, b = full(0.5), full(0.5), full(0.5), full(0.5)                    # test_lrgb_preserves_gray
+    orc.apply_lrgb(l, r, g, b, 1.0, 1.0)
+    assert all(np.all(np.abs(x - 0.5) < 0.01) for x in (r, g, b))
+    l, r, g, b = full(0.8), full(0.3), full(0.1), full(0.05)                   # test_lrgb_boosts_luminance
+    orc.apply_lrgb(l, r, g, b, 1.0, 1.0)
+    assert r[5, 5] > 0.3 and g[5, 5] > 0.1
+    with pytest.raises(ValueError):                                            # test_lrgb_dimension_mismatch
+        orc.apply_lrgb(full(0.5), full(0.5, (10, 20)), full(0.5, (10, 20)), full(0.5, (10, 20)))
+    lum = orc.synthesize_luminance(full(1.0), full(1.0), full(1.0))            # test_synthesize_luminance
+    assert abs(lum[5, 5] - 1.0) < 0.001
+    l, r, g, b = full(1.0), full(0.9), full(0.1), full(0.1)                    # test_output_clamped
+    orc.apply_lrgb(l, r, g, b, 1.0, 1.0)
+    assert all(np.all((x >= 0.0) & (x <= 1.0)) for x in (r, g, b))
+
+
+def test_render_rgb_definitions(orc):
+    rng = np.random.default_rng(0)
+    r, g, b = (rng.uniform(-0.2, 1.2, (37, 53)).astype(np.float32) for _ in range(3))
+    r[0, 0] = np.nan
+    want = np.stack([(np.nan_to_num(np.clip(c, 0, 1), nan=0.0) * np.float32(255.0)).astype(np.uint8)
+                     for c in (r, g, b)], axis=-1)
+    assert np.array_equal(orc.render_rgb_u8(r, g, b), want)
+    # decimated preview: nearest source pixel at floor(d * ratio) (cmd/helpers.rs:241-245)
+    pw, ph = orc.preview_size(37, 53, 20)
+    assert (pw, ph) == (20, 14)
+    small = orc.render_rgb_u8(r, g, b, 20)
+    sy = np.minimum(np.arange(ph) * (37 / ph), 36).astype(int)
+    sx = np.minimum(np.arange(pw) * (53 / pw), 52).astype(int)
+    assert np.array_equal(small, want[np.ix_(sy, sx)])
+    be = orc.render_rgb_u16be(r, g, b)
+    v16 = (np.nan_to_num(np.clip(g, 0, 1), nan=0.0) * np.float32(65535.0)).astype(np.uint16)
+    assert np.array_equal(be[..., 2].astype(np.uint16) * 256 + be[..., 3], v16)
+    # with STF closures: same bytes as apply_stf per channel (stf.rs:89-102 vs :122-145)
+    chans = [rng.normal(500 + 100 * k, 10, (37, 53)).astype(np.float32) for k in range(3)]
+    st = [orc.compute_image_stats(c) for c in chans]
+    sp = [orc.auto_stf(s) for s in st]
+    got = orc.render_rgb_stf_u8(*chans, sp, st)
+    for k in range(3):
+        assert np.array_equal(got[..., k], orc.apply_stf(chans[k], sp[k], st[k]))
+
+
+def test_star_mask_and_masked_stretch_definitions(orc):
+    img = np.full((64, 64), 0.1, np.float32)
+    stars = [dict(x=32.0, y=32.0, fwhm=4.0), dict(x=5.0, y=5.0, fwhm=1.0)]  # 2nd below min_fwhm
+    mask, n, cov = orc.star_mask_from_stars(img, stars)
+    assert n == 1
+    yy, xx = np.mgrid[0:64, 0:64]
+    d2 = (xx - 32.0) ** 2 + (yy - 32.0) ** 2
+    assert np.all(mask[d2 <= 100.0] == 1.0) and np.all(mask[d2 > 196.0] == 0.0)  # radius 10, soft 14
+    ring = (d2 > 100.0) & (d2 <= 196.0)
+    t = ((d2 - 100.0) / 96.0).astype(np.float32)
+    assert np.array_equal(mask[ring], (np.float32(1) - t * t * (np.float32(3) - np.float32(2) * t))[ring])
+    assert cov == np.count_nonzero(mask > 0.01) / mask.size
+    # luminance protection lifts bright pixels only
+    img[10, 10] = 0.95
+    m2, _, _ = orc.star_mask_from_stars(img, stars, luminance_protect=True, luminance_ceiling=0.85)
+    e = np.float32((np.float32(0.95) - np.float32(0.85)) * (np.float32(1) / (np.float32(1) - np.float32(0.85))))
+    assert m2[10, 10] == e * e * (np.float32(3) - np.float32(2) * e) and m2[20, 50] == 0.0
+    # masked median: upper median of the unmasked positive finite pixels
+    v = np.array([[0.3, 0.1, np.nan, 0.2], [0.0, 0.9, 0.4, -1.0]], np.float32)
+    mk = np.array([[0, 0, 0, 0], [0, 1, 0.49, 0]], np.float32)
+    assert orc.masked_median(v, mk) == np.float32(0.3)   # {0.1, 0.2, 0.3, 0.4}[2]
+    assert orc.masked_median(v, np.ones_like(v)) == 0.0
+    # masked stretch drives the unmasked background to the target
+    rng = np.random.default_rng(1)
+    sky = np.clip(rng.normal(0.02, 0.002, (128, 128)), 1e-4, 1).astype(np.float32)
+    sky[0, 0], sky[0, 1] = 0.0, 1.0
+    out, it, fb, conv = orc.masked_stretch_with_mask(sky, np.zeros_like(sky))
+    assert conv and it >= 2 and abs(fb - 0.25) < 1e-4 and out.min() >= 0.0 and out.max() <= 1.0

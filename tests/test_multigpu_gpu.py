@@ -49,6 +49,15 @@ def _worker(rank, world, port, q):
     torch.cuda.synchronize()
     res["stack_band"] = out.cpu().numpy()
     res["rej"] = int(rej)
+    # --- frame-sharded input (config 5 shape): all-to-all re-shard to row bands, then the exact kernel
+    for key, nf in (("fs16", 16), ("fs40", 40)):          # register path and deep (> 32 frames) path
+        fr = synth.stack_frames(nf, 64, 512, seed=11, nan_border=3)
+        mine = [f for f in range(nf) if parallel.frame_owner(f, nf, world) == rank]
+        local = torch.from_numpy(np.ascontiguousarray(fr[mine])).to(dev)
+        band, rj, (b0, b1) = parallel.stack_frame_sharded(local, nf, 64, 512,
+                                                          ab.StackConfig(3.0, 3.0, 5, False), s, ctx)
+        torch.cuda.synchronize()
+        res[key] = (band.cpu().numpy(), int(rj), b0, b1)
     q.put((rank, res))
     dist.destroy_process_group()
 
@@ -90,3 +99,10 @@ def test_sharded_equals_single_gpu(orc):
     got_img = np.concatenate([out[0]["stack_band"], out[1]["stack_band"]])
     assert np.array_equal(got_img, want_img)
     assert out[0]["rej"] == out[1]["rej"] == want_rej
+    for key, nf in (("fs16", 16), ("fs40", 40)):
+        fr = synth.stack_frames(nf, 64, 512, seed=11, nan_border=3)
+        want_img, want_rej = orc.stack_images(list(fr), 3.0, 3.0, 5)
+        got = np.concatenate([out[0][key][0], out[1][key][0]])
+        assert (out[0][key][2], out[0][key][3], out[1][key][2], out[1][key][3]) == (0, 32, 32, 64)
+        assert np.array_equal(got, want_img)
+        assert out[0][key][1] == out[1][key][1] == want_rej

@@ -97,40 +97,44 @@ def test_allreduce_callback_gloo_world2():
         assert out[r]["rej"] == 201
 
 
-def _reshard_worker(rank, world, port, q, n_frames, rows, cols):
+RESHARD_CASES = [(8, 10, 6), (5, 7, 3), (1, 4, 4), (6, 1, 5)]
+
+
+def _reshard_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from astroburst_b200.parallel import frame_owner, reshard_frames_to_bands, row_band
 
-    full = torch.arange(n_frames * rows * cols, dtype=torch.float32).reshape(n_frames, rows, cols)
-    mine = [f for f in range(n_frames) if frame_owner(f, n_frames, world) == rank]
-    local = full[mine].contiguous()
-    cube = reshard_frames_to_bands(local, n_frames, rows, cols)
-    r0, r1 = row_band(rows, rank, world)
-    ok = bool(torch.equal(cube, full[:, r0:r1]))
-    bad = False
-    try:
-        reshard_frames_to_bands(local[:-1], n_frames, rows, cols)
-    except ValueError:
-        bad = True
-    q.put((rank, ok and bad))
+    ok = []
+    for n_frames, rows, cols in RESHARD_CASES:
+        full = torch.arange(n_frames * rows * cols, dtype=torch.float32).reshape(n_frames, rows, cols)
+        mine = [f for f in range(n_frames) if frame_owner(f, n_frames, world) == rank]
+        local = full[mine].contiguous()
+        cube = reshard_frames_to_bands(local, n_frames, rows, cols)
+        r0, r1 = row_band(rows, rank, world)
+        good = bool(torch.equal(cube, full[:, r0:r1]))
+        try:  # a shape that contradicts (rows, cols) is refused on every rank before any traffic
+            reshard_frames_to_bands(local, n_frames, rows + 1, cols)
+            good = False
+        except ValueError:
+            pass
+        ok.append(good)
+    q.put((rank, ok))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_frames,rows,cols", [(8, 10, 6), (5, 7, 3), (1, 4, 4), (6, 1, 5)])
-def test_reshard_frames_to_bands_gloo_world2(n_frames, rows, cols):
+def test_reshard_frames_to_bands_gloo_world2():
     """Frame-sharded -> row-band sharded exchange (config 5): every rank ends with its row band of
-    every frame, ragged frame counts / band sizes and empty bands included."""
+    every frame; ragged frame counts / band sizes, a rank without frames and an empty band included."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + (os.getpid() % 2000) + n_frames
-    procs = [ctx.Process(target=_reshard_worker, args=(r, 2, port, q, n_frames, rows, cols))
-             for r in range(2)]
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_reshard_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     out = dict(q.get(timeout=120) for _ in procs)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert out[0] and out[1]
+    assert all(out[0]) and all(out[1]), out

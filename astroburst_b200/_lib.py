@@ -83,6 +83,11 @@ class AlignResultC(C.Structure):
                 ("residual_px", C.c_double), ("method", C.c_int32)]
 
 
+class ToneChainC(C.Structure):
+    _fields_ = [("stf", StfParamsC * 3), ("stats", ImageStatsC * 3), ("levels", LevelsParamsC * 3),
+                ("lut", C.c_void_p * 3), ("apply_scnr", C.c_int32), ("scnr", ScnrConfigC)]
+
+
 class StarMaskConfigC(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("growth_factor", "softness", "detection_sigma", "min_fwhm",
                                           "max_fwhm")] + [("luminance_protect", C.c_int32),
@@ -176,6 +181,8 @@ SIGNATURES = {
     "ab_blend_channels_dev": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp]),
     "ab_apply_scnr": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "ab_apply_scnr_dev": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "ab_tone_composite": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "ab_tone_composite_dev": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     # stats
     "ab_compute_image_stats": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_double, C.c_double, _vp]),
     "ab_image_stats_dev": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_double, C.c_double, _vp, _vp]),

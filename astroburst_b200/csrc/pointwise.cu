@@ -286,6 +286,57 @@ scnr_kernel(float *__restrict__ r, float *__restrict__ g, float *__restrict__ b,
     }
 }
 
+// ---- fused tone chain (apply_tone_composite_cmd, cmd/processing/curves.rs:111-151): per channel
+// apply_stf_f32 -> apply_levels (unless identity) -> apply_curve (when curves are applied), then
+// apply_scnr_inplace across the channels; one read and one write of the three planes instead of
+// four sweeps.  Every stage is the same device function the standalone operators use.
+struct ToneChain {
+    StfTx stf[3];
+    Levels lv[3];
+    bool lv_on[3];
+    const float *lut[3];
+    bool curves, scnr, preserve;
+    int method;
+    float amount;
+};
+__device__ __forceinline__ float tone_px(const ToneChain &c, int ch, float v) {
+    v = StfF32{c.stf[ch]}(v);
+    if (c.lv_on[ch]) v = c.lv[ch](v);
+    if (c.curves) v = CurveLut{c.lut[ch]}(v);
+    return v;
+}
+__global__ void __launch_bounds__(PW_THREADS)
+tone_chain_kernel(const float *r, const float *g, const float *b, size_t len,
+                  const __grid_constant__ ToneChain c, float *out_r, float *out_g, float *out_b,
+                  bool vec_ok) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n4 = vec_ok ? len / 4 : 0;
+    for (size_t i = tid; i < n4; i += stride) {
+        float4 rv = __ldcs(reinterpret_cast<const float4 *>(r) + i);
+        float4 gv = __ldcs(reinterpret_cast<const float4 *>(g) + i);
+        float4 bv = __ldcs(reinterpret_cast<const float4 *>(b) + i);
+        float *rr = &rv.x, *gg = &gv.x, *bb = &bv.x;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            rr[q] = tone_px(c, 0, rr[q]);
+            gg[q] = tone_px(c, 1, gg[q]);
+            bb[q] = tone_px(c, 2, bb[q]);
+            if (c.scnr) scnr_px(rr[q], gg[q], bb[q], c.method, c.amount, c.preserve);
+        }
+        __stcs(reinterpret_cast<float4 *>(out_r) + i, rv);
+        __stcs(reinterpret_cast<float4 *>(out_g) + i, gv);
+        __stcs(reinterpret_cast<float4 *>(out_b) + i, bv);
+    }
+    for (size_t i = n4 * 4 + tid; i < len; i += stride) {
+        float rv = tone_px(c, 0, r[i]), gv = tone_px(c, 1, g[i]), bv = tone_px(c, 2, b[i]);
+        if (c.scnr) scnr_px(rv, gv, bv, c.method, c.amount, c.preserve);
+        out_r[i] = rv;
+        out_g[i] = gv;
+        out_b[i] = bv;
+    }
+}
+
 unsigned sweep_blocks(ab_ctx *ctx, size_t len) {
     size_t blocks = (len / 4 + PW_THREADS - 1) / PW_THREADS + 1;
     const size_t cap = (size_t)ctx->sm_count * 8;
@@ -702,6 +753,69 @@ ab_status ab_apply_scnr(ab_ctx *ctx, float *r, float *g, float *b, size_t len,
             AB_CUDA(ctx, cudaMemcpyAsync(o[i], d[i], ib[i], cudaMemcpyDeviceToHost, ctx->stream));
     AB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return AB_OK;
+}
+
+// ------------------------------------------------------------------------------------ tone chain
+static bool tone_setup(const ab_tone_chain *t, const float *const *d_lut, ToneChain *c) {
+    for (int ch = 0; ch < 3; ++ch) {
+        c->stf[ch] = make_tx(&t->stf[ch], &t->stats[ch]);
+        c->lv_on[ch] = !levels_identity(&t->levels[ch]);
+        c->lv[ch] = levels_make(&t->levels[ch]);
+        c->lut[ch] = d_lut ? d_lut[ch] : nullptr;
+    }
+    c->curves = d_lut != nullptr;
+    float amount = t->scnr.amount;
+    amount = amount < 0.0f ? 0.0f : (amount > 1.0f ? 1.0f : amount);
+    // curves.rs:143-148: applied when cfg.amount > 1e-7 (scnr.rs:28-31 clamps, then re-checks)
+    c->scnr = t->apply_scnr != 0 && t->scnr.amount > 1e-7f && !(amount < 1e-7f);
+    c->amount = amount;
+    c->method = t->scnr.method;
+    c->preserve = t->scnr.preserve_luminance != 0;
+    return true;
+}
+ab_status ab_tone_composite_dev(ab_ctx *ctx, const float *d_r, const float *d_g, const float *d_b,
+                                size_t len, const ab_tone_chain *chain, float *d_out_r,
+                                float *d_out_g, float *d_out_b, void *stream) {
+    if (!ctx || !chain || (len && (!d_r || !d_g || !d_b || !d_out_r || !d_out_g || !d_out_b)))
+        return AB_ERR_INVALID;
+    const bool any_lut = chain->lut[0] || chain->lut[1] || chain->lut[2];
+    if (any_lut && !(chain->lut[0] && chain->lut[1] && chain->lut[2]))
+        return ab_fail(ctx, AB_ERR_INVALID, "tone chain: give all three curve LUTs or none");
+    if (len == 0) return AB_OK;
+    DeviceGuard g(ctx->device);
+    ToneChain c;
+    tone_setup(chain, any_lut ? chain->lut : nullptr, &c);
+    uintptr_t al = 0;
+    for (const void *q : {(const void *)d_r, (const void *)d_g, (const void *)d_b,
+                          (const void *)d_out_r, (const void *)d_out_g, (const void *)d_out_b})
+        al |= reinterpret_cast<uintptr_t>(q);
+    tone_chain_kernel<<<sweep_blocks(ctx, len), PW_THREADS, 0, (cudaStream_t)stream>>>(
+        d_r, d_g, d_b, len, c, d_out_r, d_out_g, d_out_b, (al & 15) == 0);
+    AB_LAUNCH_CHECK(ctx);
+    return AB_OK;
+}
+ab_status ab_tone_composite(ab_ctx *ctx, const float *r, const float *g, const float *b, size_t len,
+                            const ab_tone_chain *chain, float *out_r, float *out_g, float *out_b) {
+    if (!ctx || !chain || (len && (!r || !g || !b || !out_r || !out_g || !out_b)))
+        return AB_ERR_INVALID;
+    const bool any_lut = chain->lut[0] || chain->lut[1] || chain->lut[2];
+    if (any_lut && !(chain->lut[0] && chain->lut[1] && chain->lut[2]))
+        return ab_fail(ctx, AB_ERR_INVALID, "tone chain: give all three curve LUTs or none");
+    if (len == 0) return AB_OK;
+    const size_t lb = any_lut ? AB_CURVE_LUT_SIZE * 4 : 0;
+    const void *in[6] = {r, g, b, chain->lut[0], chain->lut[1], chain->lut[2]};
+    void *o[3] = {out_r, out_g, out_b};
+    const size_t ib[6] = {len * 4, len * 4, len * 4, lb, lb, lb}, ob[3] = {len * 4, len * 4, len * 4};
+    return with_host_planes(ctx, in, ib, 6, o, ob, 3, [&](void **di, void **dout, cudaStream_t s) {
+        ToneChain c;
+        const float *luts[3] = {(const float *)di[3], (const float *)di[4], (const float *)di[5]};
+        tone_setup(chain, any_lut ? luts : nullptr, &c);
+        tone_chain_kernel<<<sweep_blocks(ctx, len), PW_THREADS, 0, s>>>(
+            (const float *)di[0], (const float *)di[1], (const float *)di[2], len, c,
+            (float *)dout[0], (float *)dout[1], (float *)dout[2], true);
+        AB_LAUNCH_CHECK(ctx);
+        return AB_OK;
+    });
 }
 
 }  // extern "C"

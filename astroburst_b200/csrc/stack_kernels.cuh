@@ -61,6 +61,9 @@
 #ifndef AB_LDG_BLOCKS
 #define AB_LDG_BLOCKS 3
 #endif
+#ifndef AB_PROBE2
+#define AB_PROBE2 1
+#endif
 #ifndef AB_PROXY_FENCE
 #define AB_PROXY_FENCE 0
 #endif
@@ -912,6 +915,23 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
         const unsigned p = g * 32 + lane;
         mbar_wait(bar, parity);
         float s[P];
+#if AB_PROBE2
+        // probe with packed f32x2 FMAs: one FFMA2 per sample pair
+        unsigned long long pr2[2] = {0ull, 0ull};
+#pragma unroll
+        for (int f = 0; f < P; ++f) s[f] = sm.stage[f][lane];
+#pragma unroll
+        for (int f = 0; f + 1 < P; f += 2) {
+            unsigned long long pair;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(pair) : "f"(s[f]), "f"(s[f + 1]));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(pr2[(f >> 1) & 1]) : "l"(pair), "l"(0ull));
+        }
+        float q0, q1, q2, q3;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(pr2[0]));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(q2), "=f"(q3) : "l"(pr2[1]));
+        float probe = (q0 + q1) + (q2 + q3);
+        if (P & 1) probe = fmaf(s[P - 1], 0.0f, probe);
+#else
         float pr[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // NaN iff a sample of the pixel is non-finite
 #pragma unroll
         for (int f = 0; f < P; ++f) {
@@ -919,6 +939,7 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
             pr[f & 3] = fmaf(s[f], 0.0f, pr[f & 3]);
         }
         const float probe = (pr[0] + pr[1]) + (pr[2] + pr[3]);
+#endif
         // every lane has consumed its column (probe depends on all P loads): refill the stage
         asm volatile("" ::"f"(probe) : "memory");
         __syncwarp();

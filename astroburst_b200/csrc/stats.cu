@@ -103,9 +103,9 @@ scan_kernel(const float *__restrict__ data, size_t len, ScanPartial *__restrict_
     }
 }
 
-// ---- generic 65,536-bin histogram pass.  F::operator()(v, idxA, idxB) classifies one pixel:
-// bit 0 of the return value -> count idxA in histogram A (windowed), bit 1 -> count idxB in
-// histogram B (global atomics only: used for the sparse refine histograms), bit 2 -> ++below.
+// ---- generic 65,536-bin histogram pass over the valid pixels.  The classifier F says at compile
+// time what a pass collects: kSum (f64 sum + count), kA (bin_a -> histogram A, shared memory),
+// kB (bin_b -> sparse refine histogram B, global atomics), kBelow (is_below -> counter).
 struct HistPartial {
     double sum;
     unsigned long long count;
@@ -129,16 +129,19 @@ hist_kernel(const float *__restrict__ data, size_t len, F f, unsigned *__restric
     const size_t stride = (size_t)gridDim.x * HT_THREADS;
     const size_t tid = (size_t)blockIdx.x * HT_THREADS + threadIdx.x;
     double sum = 0.0;
-    unsigned long long cnt = 0, below = 0;
+    unsigned cnt = 0, below = 0;  // per thread < 2^32 (len < 2^32)
 
+    // one early-out for invalid pixels, then straight-line code selected at compile time by the
+    // classifier's flags (kSum / kA / kB / kBelow): no per-pixel flag tests
     auto one = [&](float v) {
-        unsigned a = 0, b = 0;
-        const unsigned code = f(v, a, b);
-        if (code & 8u) {
-            sum += (double)v;
+        if (!valid_px(v)) return;
+        const double dv = (double)v;
+        if constexpr (F::kSum) {
+            sum += dv;
             ++cnt;
         }
-        if (code & 1u) {
+        if constexpr (F::kA) {
+            const unsigned a = f.bin_a(v, dv);
             const unsigned sh = (a & 1u) << 4;
             const unsigned old = atomicAdd(&packed[a >> 1], 1u << sh);
             if (((old >> sh) & 0xffffu) == HALF_FLUSH - 1u) {
@@ -146,8 +149,11 @@ hist_kernel(const float *__restrict__ data, size_t len, F f, unsigned *__restric
                 atomicSub(&packed[a >> 1], HALF_FLUSH << sh);
             }
         }
-        if (code & 2u) atomicAdd(&histB[b], 1u);
-        if (code & 4u) ++below;
+        if constexpr (F::kB) {
+            unsigned b;
+            if (f.bin_b(v, dv, b)) atomicAdd(&histB[b], 1u);
+        }
+        if constexpr (F::kBelow) below += f.is_below(v) ? 1u : 0u;
     };
     auto four = [&](const float4 &v) { one(v.x); one(v.y); one(v.z); one(v.w); };
     const float4 *d4 = reinterpret_cast<const float4 *>(data);
@@ -169,13 +175,14 @@ hist_kernel(const float *__restrict__ data, size_t len, F f, unsigned *__restric
     }
     // deterministic per-block partial of the f64 sum
     __shared__ HistPartial sh[HT_THREADS / 32];
+    unsigned long long cnt64 = cnt, below64 = below;
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_down_sync(0xffffffffu, sum, o);
-        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-        below += __shfl_down_sync(0xffffffffu, below, o);
+        cnt64 += __shfl_down_sync(0xffffffffu, cnt64, o);
+        below64 += __shfl_down_sync(0xffffffffu, below64, o);
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) sh[warp] = {sum, cnt, below};
+    if (lane == 0) sh[warp] = {sum, cnt64, below64};
     __syncthreads();
     if (threadIdx.x == 0) {
         HistPartial r = sh[0];
@@ -188,49 +195,46 @@ hist_kernel(const float *__restrict__ data, size_t len, F f, unsigned *__restric
     }
 }
 
-// `((x) as usize).min(last)` for x = f64
+// `((x) as usize).min(last)` for x = f64.  The f64 -> u32 conversion saturates like Rust's `as`
+// (negative and NaN -> 0, >= 2^32 -> u32::MAX), so the clamp to the last bin is exact for every x.
 __device__ __forceinline__ unsigned bin_of(double x) {
-    const unsigned long long u = (unsigned long long)x;  // saturating, NaN -> 0, like Rust `as`
-    return u > (unsigned long long)(HIST_BINS - 1) ? HIST_BINS - 1 : (unsigned)u;
+    return min(__double2uint_rz(x), HIST_BINS - 1);
 }
 
 struct ValueHistF {  // stats.rs:259-297 scan_sum_and_hist; also build_histogram :393-400
+    static constexpr bool kSum = true, kA = true, kB = false, kBelow = false;
     double lo, inv;
-    __device__ unsigned operator()(float v, unsigned &a, unsigned &) const {
-        if (!valid_px(v)) return 0;
-        a = bin_of(((double)v - lo) * inv);
-        return 1u | 8u;
-    }
+    __device__ unsigned bin_a(float, double dv) const { return bin_of((dv - lo) * inv); }
+    __device__ bool bin_b(float, double, unsigned &) const { return false; }
+    __device__ bool is_below(float) const { return false; }
 };
 struct RefineDevF {  // stats.rs:119-146
+    static constexpr bool kSum = false, kA = true, kB = true, kBelow = false;
     double bin_lo, bin_hi, refine_inv, dev_inv;
     float coarse_med;
-    __device__ unsigned operator()(float v, unsigned &a, unsigned &b) const {
-        if (!valid_px(v)) return 0;
-        unsigned code = 1u;
-        const double vf = (double)v;
-        if (vf >= bin_lo && vf < bin_hi) {
-            b = bin_of((vf - bin_lo) * refine_inv);
-            code |= 2u;
-        }
+    __device__ unsigned bin_a(float v, double) const {
         const float d = fabsf(v - coarse_med);  // f32 subtraction
-        a = bin_of((double)d * dev_inv);
-        return code;
+        return bin_of((double)d * dev_inv);
     }
+    __device__ bool bin_b(float, double vf, unsigned &b) const {
+        if (!(vf >= bin_lo && vf < bin_hi)) return false;
+        b = bin_of((vf - bin_lo) * refine_inv);
+        return true;
+    }
+    __device__ bool is_below(float) const { return false; }
 };
 struct MadRefineF {  // stats.rs:164-193
+    static constexpr bool kSum = false, kA = false, kB = true, kBelow = true;
     double region_lo, refine_inv;
     float med, lo_f32, hi_f32;
-    __device__ unsigned operator()(float v, unsigned &, unsigned &b) const {
-        if (!valid_px(v)) return 0;
+    __device__ unsigned bin_a(float, double) const { return 0; }
+    __device__ bool bin_b(float v, double, unsigned &b) const {
         const float dev = fabsf(v - med);
-        if (dev < lo_f32) return 4u;
-        if (dev < hi_f32) {
-            b = bin_of(((double)dev - region_lo) * refine_inv);
-            return 2u;
-        }
-        return 0;
+        if (!(dev >= lo_f32 && dev < hi_f32)) return false;
+        b = bin_of(((double)dev - region_lo) * refine_inv);
+        return true;
     }
+    __device__ bool is_below(float v) const { return fabsf(v - med) < lo_f32; }
 };
 
 // ---- radix select on float bit patterns (exact path)

@@ -210,6 +210,36 @@ def apply_curve(data, lut, ctx=None):
     return out
 
 
+def apply_tone_composite(r, g, b, stf3, stats3, levels3=None, curves3=None, scnr=None, ctx=None):
+    """The pixel chain of apply_tone_composite_cmd (cmd/processing/curves.rs:111-151) in one sweep:
+    STF -> levels -> curves -> SCNR.  stf3 / stats3: per-channel StfParams / ImageStats;
+    levels3: three (black, gamma, white) or None; curves3: three 4096-entry LUTs (spline_lut) or
+    None; scnr: (method, amount, preserve_luminance) or None.  -> (r, g, b) float32 arrays."""
+    ctx = ctx or default_context()
+    r, g, b = _f32(r), _f32(g), _f32(b)
+    if not (r.shape == g.shape == b.shape):
+        raise ValueError("channel dimension mismatch")
+    ch = _lib.ToneChainC()
+    luts = []
+    for k in range(3):
+        ch.stf[k], ch.stats[k] = stf3[k], stats3[k]
+        ch.levels[k] = LevelsParamsC(*(levels3[k] if levels3 is not None else (0.0, 1.0, 1.0)))
+        if curves3 is not None:
+            l = _f32(curves3[k])
+            assert l.size == 4096
+            luts.append(l)
+            ch.lut[k] = l.ctypes.data
+    if scnr is not None:
+        method, amount, preserve = scnr
+        ch.apply_scnr = 1
+        ch.scnr = ScnrConfigC(0 if method == "average" else 1, amount, 1 if preserve else 0)
+    outs = [np.empty(r.shape, np.float32) for _ in range(3)]
+    ctx.check(lib().ab_tone_composite(ctx.handle, r.ctypes.data, g.ctypes.data, b.ctypes.data, r.size,
+                                      C.addressof(ch), outs[0].ctypes.data, outs[1].ctypes.data,
+                                      outs[2].ctypes.data))
+    return tuple(outs)
+
+
 # ------------------------------------------------------------------ bicubic gathers
 def warp_image(image, transform, out_rows: int, out_cols: int, ctx=None):
     """affine.rs:663-690; transform = (a, b, tx, c, d, ty) mapping OUTPUT -> SOURCE."""

@@ -329,6 +329,26 @@ ab_status ab_apply_scnr(ab_ctx *ctx, float *r, float *g, float *b, size_t len,
 ab_status ab_apply_scnr_dev(ab_ctx *ctx, float *d_r, float *d_g, float *d_b, size_t len,
                             const ab_scnr_config *cfg, void *stream);
 
+/* The pixel chain of apply_tone_composite_cmd, cmd/processing/curves.rs:111-151, as ONE sweep:
+ * apply_stf_f32 (stf.rs:104-120) per channel -> apply_levels (curves.rs:31-50; identity params are
+ * skipped like :32-34) -> apply_curve (curves.rs:186-198) when the three LUTs are given (the
+ * caller passes identity LUTs for channels without a curve, as curves.rs:132-136 does) ->
+ * apply_scnr_inplace (scnr.rs:18-53) when apply_scnr != 0 and amount > 1e-7.  Results equal the
+ * four separate calls bit for bit; outputs may alias the inputs. */
+typedef struct {
+    ab_stf_params stf[3];     /* r, g, b */
+    ab_image_stats stats[3];  /* the stats each STF normalises with (combined stats when linked) */
+    ab_levels_params levels[3];
+    const float *lut[3];      /* AB_CURVE_LUT_SIZE f32 each (device pointers for _dev), or all NULL */
+    int32_t apply_scnr;
+    ab_scnr_config scnr;
+} ab_tone_chain;
+ab_status ab_tone_composite(ab_ctx *ctx, const float *r, const float *g, const float *b, size_t len,
+                            const ab_tone_chain *chain, float *out_r, float *out_g, float *out_b);
+ab_status ab_tone_composite_dev(ab_ctx *ctx, const float *d_r, const float *d_g, const float *d_b,
+                                size_t len, const ab_tone_chain *chain, float *d_out_r,
+                                float *d_out_g, float *d_out_b, void *stream);
+
 /* ---------------------------------------------------------------- statistics / histogram / STF
  * mode: 0 compute_image_stats (core/imaging/stats.rs:15-23: exact select <= 4,000,000 px,
  *         65,536-bin 3-pass histogram algorithm above), 1 exact path (stats.rs:43-73),

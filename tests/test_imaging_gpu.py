@@ -198,6 +198,53 @@ def test_scale_levels_curves(im, orc):
         assert np.array_equal(im.apply_curve(u, lut), orc.apply_curve(u, olut))
 
 
+def test_tone_composite_fused_equals_separate_steps(im, orc):
+    """apply_tone_composite_cmd's chain (curves.rs:111-151) in one sweep == the oracle's four
+    separate operators, per-channel and linked STF, with and without levels / curves / SCNR."""
+    chans = [sky(257, 301, seed=20 + k) * np.float32(1.0 + 0.1 * k) for k in range(3)]
+    ost = [orc.compute_image_stats(c) for c in chans]
+    gst = [im.compute_image_stats(c) for c in chans]
+    pts = [(0.0, 0.0), (0.25, 0.15), (0.5, 0.5), (0.75, 0.85), (1.0, 1.0)]
+    ident = [(0.0, 0.0), (1.0, 1.0)]
+    cases = [
+        dict(linked=False, levels=None, curves=None, scnr=None),
+        dict(linked=True, levels=None, curves=[pts, ident, pts], scnr=("average", 0.5, False)),
+        dict(linked=False, levels=[(0.02, 1.4, 0.95), (0.0, 1.0, 1.0), (0.1, 0.7, 1.0)], curves=None,
+             scnr=("maximum", 1.0, True)),
+        dict(linked=True, levels=[(0.05, 2.0, 0.9)] * 3, curves=[pts] * 3, scnr=("average", 1e-9, True)),
+    ]
+    for c in cases:
+        if c["linked"]:
+            ocomb = orc.linked_stats(*ost)
+            ostf, onorm = [orc.auto_stf(ocomb)] * 3, [ocomb] * 3
+            gcomb = im.linked_stats(*gst)
+            gstf, gnorm = [im.auto_stf(gcomb)] * 3, [gcomb] * 3
+        else:
+            ostf, onorm = [orc.auto_stf(s_) for s_ in ost], ost
+            gstf, gnorm = [im.auto_stf(s_) for s_ in gst], gst
+        want = [orc.apply_stf_f32(ch, p, n) for ch, p, n in zip(chans, ostf, onorm)]
+        if c["levels"]:
+            want = [orc.apply_levels(w, *lv) for w, lv in zip(want, c["levels"])]
+        luts = None
+        if c["curves"]:
+            luts = [im.spline_lut(p) for p in c["curves"]]
+            want = [orc.apply_curve(w, orc.spline_lut(p)) for w, p in zip(want, c["curves"])]
+        if c["scnr"] and c["scnr"][1] > 1e-7:
+            want = [np.ascontiguousarray(w) for w in want]
+            orc.apply_scnr_inplace(*want, *c["scnr"])
+        got = im.apply_tone_composite(*chans, gstf, gnorm, c["levels"], luts, c["scnr"])
+        for x, y in zip(got, want):
+            if c["levels"] and c["curves"]:
+                # an ulp of f64 pow (libm vs CUDA) can move a pixel across one LUT index
+                d = np.abs(x.astype(np.float64) - y)
+                off = d > 2e-6 * np.abs(y)
+                assert off.mean() < 1e-3 and (not off.any() or d[off].max() < 2e-3)
+            elif c["levels"]:
+                assert close(x, y, 2e-6)       # f64 pow: within the libm/CUDA ulp difference
+            else:
+                assert np.array_equal(x, y)
+
+
 # ------------------------------------------------------------------ bicubic gathers
 def test_warp_shift_resample_bit_exact(im, orc):
     img = sky(301, 407, seed=12, pad=False)

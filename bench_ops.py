@@ -184,7 +184,62 @@ def main():
     ms = timed(lambda: ctx.check(lib().ab_arcsinh_stretch_dev(h, gg.data_ptr(), npix, 1.0, 3000.0, 50.0, 1.0,
                                                               out.data_ptr(), stream)))
     emit("arcsinh_stretch (factor 50)", cfg4, ms, 2 * npix * 4, npix)
-    del chans, r, gg, b, out, u8
+    # fused tone chain: linked STF -> curves -> SCNR in one sweep (3 planes in, 3 planes out)
+    tc = _lib.ToneChainC()
+    for k in range(3):
+        tc.stf[k], tc.stats[k] = stf, st
+        tc.levels[k] = _lib.LevelsParamsC(0.0, 1.0, 1.0)
+        tc.lut[k] = lut.data_ptr()
+    tc.apply_scnr, tc.scnr = 1, _lib.ScnrConfigC(0, 0.5, 0)
+    o3 = [torch.empty_like(gg) for _ in range(3)]
+    src3 = [chans[0], gg, chans[2]]
+    ms = timed(lambda: ctx.check(lib().ab_tone_composite_dev(h, src3[0].data_ptr(), src3[1].data_ptr(), src3[2].data_ptr(),
+                                                             npix, C.addressof(tc), o3[0].data_ptr(), o3[1].data_ptr(),
+                                                             o3[2].data_ptr(), stream)))
+    hb3 = [c[band].cpu().numpy() for c in src3]
+    w3 = [oracle.apply_curve(oracle.apply_stf_f32(x, osf, ost), lut.cpu().numpy()) for x in hb3]
+    oracle.apply_scnr_inplace(*w3, "average", 0.5, False)
+    par = all(np.array_equal(o[band].cpu().numpy(), w) for o, w in zip(o3, w3))
+    emit("tone chain fused (STF + curve + SCNR, one sweep)", cfg4, ms, 6 * npix * 4, npix, None, par,
+         "the four separate operators move 20 planes; the fused sweep moves 6")
+    # RGB8 interleave: full size and the 2048-px preview (cmd/helpers.rs MAX_PREVIEW_DIM)
+    rgb8 = torch.empty((rows, cols, 3), dtype=torch.uint8, device=dev)
+    ms = timed(lambda: ctx.check(lib().ab_render_rgb_u8_dev(h, o3[0].data_ptr(), o3[1].data_ptr(), o3[2].data_ptr(),
+                                                            rows, cols, 0, rgb8.data_ptr(), stream)))
+    par = bool(np.array_equal(rgb8[band].cpu().numpy(),
+                              oracle.render_rgb_u8(*[o[band].cpu().numpy() for o in o3])))
+    emit("render_rgb (RGB8 interleave, full size)", cfg4, ms, npix * 15, npix, None, par)
+    ms = timed(lambda: ctx.check(lib().ab_render_rgb_u8_dev(h, o3[0].data_ptr(), o3[1].data_ptr(), o3[2].data_ptr(),
+                                                            rows, cols, 2048, rgb8.data_ptr(), stream)))
+    pw, ph = ab.preview.preview_size(rows, cols, 2048)
+    emit("render_rgb_preview (nearest decimation to 2048 px)", cfg4, ms, pw * ph * 15, pw * ph, None, None,
+         "gather: one sector per sampled pixel")
+    del chans, r, gg, b, out, u8, o3, rgb8, src3
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ masked stretch (N4) on a 4096^2 star field
+    Rm = 4096 if not args.small else 2048
+    fm = synth.stack_frames_torch(1, Rm, Rm, dev, seed=9, nan_border=0, cosmic_fraction=0.0)[0]
+    fm = ((fm - 900.0).clamp_(min=0.0) / 20000.0).contiguous()
+    msk = torch.empty_like(fm)
+    mo = torch.empty_like(fm)
+    mcfg = _lib.MaskedStretchConfigC(10, 0.25, 2.5, 4.0, 1, 0.85, 0.85, 1e-5)
+    minfo = _lib.MaskedStretchInfoC()
+    ms = wall(lambda: ctx.check(lib().ab_masked_stretch_dev(h, fm.data_ptr(), Rm, Rm, C.addressof(mcfg), msk.data_ptr(),
+                                                            mo.data_ptr(), C.addressof(minfo), stream)))
+    subm = fm[:1024, :1024].contiguous()
+    o_img, o_it, o_fb, o_conv, o_n, o_cov = oracle.masked_stretch(subm.cpu().numpy())
+    mi2 = _lib.MaskedStretchInfoC()
+    so, sk = torch.empty_like(subm), torch.empty_like(subm)
+    ctx.check(lib().ab_masked_stretch_dev(h, subm.data_ptr(), 1024, 1024, C.addressof(mcfg), sk.data_ptr(), so.data_ptr(),
+                                          C.addressof(mi2), stream))
+    par = bool(np.array_equal(so.cpu().numpy(), o_img)) and (int(mi2.iterations_run), int(mi2.stars_masked)) == (o_it, o_n)
+    cr = cpu_rate(lambda: oracle.masked_stretch(subm.cpu().numpy()), subm.numel())
+    itn = int(minfo.iterations_run)
+    emit(f"masked_stretch (detect + mask + {itn} iterations, {int(minfo.stars_masked)} stars)", f"{Rm}x{Rm} f32", ms,
+         Rm * Rm * 4 * (4 + itn * (4 * 2 + 3) + 4 * 2 + 2), Rm * Rm, (cr[0], cr[1], "1024x1024 crop"), par,
+         "wall clock: detection + mask + per iteration 4 radix sweeps (pixel + mask) and one fused MTF/blend sweep")
+    del fm, msk, mo
     torch.cuda.empty_cache()
 
     # ------------------------------------------------------------------ config 3: detect + align + warp

@@ -344,11 +344,19 @@ void flood_fill_stars(const SparseImage &sp, double bg_median, double bg_sigma,
     std::vector<ab_star> stars;
     std::deque<long long> queue;
     std::vector<long long> comp;
-    static const int DR[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
-    static const int DC[8] = {0, 0, -1, 1, -1, 1, -1, 1};
-    auto row_of = [&](long long idx) {
-        return (size_t)(std::upper_bound(sp.row_off.begin(), sp.row_off.end(),
-                                         (unsigned long long)idx) - sp.row_off.begin() - 1);
+    // row of every sparse pixel, so neither the fill nor the moment loops search for it
+    std::vector<unsigned> row_idx(sp.col.size());
+    for (size_t r = 0; r < rows; ++r)
+        for (unsigned long long p = sp.row_off[r]; p < sp.row_off[r + 1]; ++p) row_idx[p] = (unsigned)r;
+    auto row_of = [&](long long idx) { return (size_t)row_idx[idx]; };
+    // the up-to-three list entries of row `r` in columns c-1, c, c+1 (-1 where absent): one search
+    auto three = [&](long long r, size_t c, long long out3[3]) {
+        out3[0] = out3[1] = out3[2] = -1;
+        if (r < 0 || r >= (long long)rows) return;
+        const unsigned *b = sp.col.data() + sp.row_off[r], *e = sp.col.data() + sp.row_off[r + 1];
+        const unsigned lo = c ? (unsigned)(c - 1) : 0u;
+        for (const unsigned *it = std::lower_bound(b, e, lo); it != e && *it <= c + 1; ++it)
+            out3[*it + 1 - c] = (long long)(it - sp.col.data());
     };
     for (size_t r = 1; r + 1 < rows; ++r) {
         for (unsigned long long p = sp.row_off[r]; p < sp.row_off[r + 1]; ++p) {
@@ -363,10 +371,15 @@ void flood_fill_stars(const SparseImage &sp, double bg_median, double bg_sigma,
                 queue.pop_front();
                 comp.push_back(cur);
                 const size_t cr = row_of(cur), cc = sp.col[cur];
+                long long up[3], dn[3];
+                three((long long)cr - 1, cc, up);
+                three((long long)cr + 1, cc, dn);
+                const long long left = ((unsigned long long)cur > sp.row_off[cr] && sp.col[cur - 1] + 1 == cc) ? cur - 1 : -1;
+                const long long right = ((unsigned long long)cur + 1 < sp.row_off[cr + 1] && sp.col[cur + 1] == cc + 1) ? cur + 1 : -1;
+                // the reference's neighbour order (star_detection.rs:123-138): N, S, W, E, NW, NE, SW, SE
+                const long long nb[8] = {up[1], dn[1], left, right, up[0], up[2], dn[0], dn[2]};
                 for (int k = 0; k < 8; ++k) {
-                    const long long nr = (long long)cr + DR[k], nc = (long long)cc + DC[k];
-                    if (nr < 0 || nc < 0 || nr >= (long long)rows || nc >= (long long)cols) continue;
-                    const long long q = sp.find((size_t)nr, (size_t)nc);
+                    const long long q = nb[k];
                     if (q < 0 || visited[q]) continue;
                     visited[q] = 1;
                     queue.push_back(q);

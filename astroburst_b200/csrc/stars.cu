@@ -27,7 +27,9 @@
 #include <cstdint>
 #include <cstring>
 #include <deque>
+#include <cstdlib>
 #include <map>
+#include <thread>
 #include <vector>
 
 #include <math_constants.h>
@@ -337,94 +339,177 @@ inline size_t f2us(double x) {  // Rust `f64 as usize`
 }
 
 // star_detection.rs:105-248 on the sparse list: identical visiting order, identical f64 sums.
-void flood_fill_stars(const SparseImage &sp, double bg_median, double bg_sigma,
-                      std::vector<ab_star> &out) {
-    const size_t rows = sp.rows, cols = sp.cols;
-    std::vector<char> visited(sp.col.size(), 0);
-    std::vector<ab_star> stars;
-    std::deque<long long> queue;
-    std::vector<long long> comp;
-    // row of every sparse pixel, so neither the fill nor the moment loops search for it
-    std::vector<unsigned> row_idx(sp.col.size());
-    for (size_t r = 0; r < rows; ++r)
-        for (unsigned long long p = sp.row_off[r]; p < sp.row_off[r + 1]; ++p) row_idx[p] = (unsigned)r;
-    auto row_of = [&](long long idx) { return (size_t)row_idx[idx]; };
+//
+// The reference's raster scan + BFS is sequential, but connected components are disjoint: the
+// BFS of a component (from its first interior pixel in raster order) does not depend on any other
+// component.  So the list is cut into row bands of equal pixel count, one host thread per band
+// grows the components that lie entirely inside its band (it never touches a pixel of another
+// band), components that cross a band edge are grown afterwards by the sequential algorithm, and
+// the stars are put back into discovery order by their seed index.
+struct Filler {
+    const SparseImage &sp;
+    double bg_median, bg_sigma;
+    std::vector<unsigned> row_idx;  // row of every sparse pixel
+    std::vector<char> visited;      // 0 free, 1 taken, 2 part of a band-crossing component
+    struct Found {
+        unsigned long long seed;
+        ab_star star;
+    };
+
+    Filler(const SparseImage &s, double med, double sig)
+        : sp(s), bg_median(med), bg_sigma(sig), row_idx(s.col.size()), visited(s.col.size(), 0) {
+        for (size_t r = 0; r < sp.rows; ++r)
+            for (unsigned long long p = sp.row_off[r]; p < sp.row_off[r + 1]; ++p) row_idx[p] = (unsigned)r;
+    }
     // the up-to-three list entries of row `r` in columns c-1, c, c+1 (-1 where absent): one search
-    auto three = [&](long long r, size_t c, long long out3[3]) {
+    void three(long long r, size_t c, long long out3[3]) const {
         out3[0] = out3[1] = out3[2] = -1;
-        if (r < 0 || r >= (long long)rows) return;
+        if (r < 0 || r >= (long long)sp.rows) return;
         const unsigned *b = sp.col.data() + sp.row_off[r], *e = sp.col.data() + sp.row_off[r + 1];
         const unsigned lo = c ? (unsigned)(c - 1) : 0u;
         for (const unsigned *it = std::lower_bound(b, e, lo); it != e && *it <= c + 1; ++it)
             out3[*it + 1 - c] = (long long)(it - sp.col.data());
-    };
-    for (size_t r = 1; r + 1 < rows; ++r) {
-        for (unsigned long long p = sp.row_off[r]; p < sp.row_off[r + 1]; ++p) {
-            const size_t c = sp.col[p];
-            if (c < 1 || c + 1 >= cols || visited[p]) continue;  // seeds are interior pixels
-            queue.clear();
-            comp.clear();
-            queue.push_back((long long)p);
-            visited[p] = 1;
-            while (!queue.empty()) {
-                const long long cur = queue.front();
-                queue.pop_front();
-                comp.push_back(cur);
-                const size_t cr = row_of(cur), cc = sp.col[cur];
-                long long up[3], dn[3];
-                three((long long)cr - 1, cc, up);
-                three((long long)cr + 1, cc, dn);
-                const long long left = ((unsigned long long)cur > sp.row_off[cr] && sp.col[cur - 1] + 1 == cc) ? cur - 1 : -1;
-                const long long right = ((unsigned long long)cur + 1 < sp.row_off[cr + 1] && sp.col[cur + 1] == cc + 1) ? cur + 1 : -1;
-                // the reference's neighbour order (star_detection.rs:123-138): N, S, W, E, NW, NE, SW, SE
-                const long long nb[8] = {up[1], dn[1], left, right, up[0], up[2], dn[0], dn[2]};
-                for (int k = 0; k < 8; ++k) {
-                    const long long q = nb[k];
-                    if (q < 0 || visited[q]) continue;
-                    visited[q] = 1;
-                    queue.push_back(q);
+    }
+    // BFS from `seed` in the reference's neighbour order.  With a band [r0, r1) given, pixels of
+    // other rows are not touched; returns false when the component reaches outside the band.
+    bool grow(long long seed, size_t r0, size_t r1, std::deque<long long> &queue,
+              std::vector<long long> &comp) {
+        bool inside = true;
+        queue.clear();
+        comp.clear();
+        queue.push_back(seed);
+        visited[seed] = 1;
+        while (!queue.empty()) {
+            const long long cur = queue.front();
+            queue.pop_front();
+            comp.push_back(cur);
+            const size_t cr = row_idx[cur], cc = sp.col[cur];
+            long long up[3], dn[3];
+            three((long long)cr - 1, cc, up);
+            three((long long)cr + 1, cc, dn);
+            const long long left =
+                ((unsigned long long)cur > sp.row_off[cr] && sp.col[cur - 1] + 1 == cc) ? cur - 1 : -1;
+            const long long right =
+                ((unsigned long long)cur + 1 < sp.row_off[cr + 1] && sp.col[cur + 1] == cc + 1) ? cur + 1 : -1;
+            // star_detection.rs:123: N, S, W, E, NW, NE, SW, SE
+            const long long nb[8] = {up[1], dn[1], left, right, up[0], up[2], dn[0], dn[2]};
+            for (int k = 0; k < 8; ++k) {
+                const long long q = nb[k];
+                if (q < 0) continue;
+                const size_t qr = row_idx[q];
+                if (qr < r0 || qr >= r1) {
+                    inside = false;
+                    continue;
                 }
+                if (visited[q]) continue;
+                visited[q] = 1;
+                queue.push_back(q);
             }
-            const size_t npix = comp.size();
-            if (npix < 3 || npix > 5000) continue;
-            double sum_flux = 0.0, sum_x = 0.0, sum_y = 0.0, peak_val = 0.0;
-            for (long long q : comp) {
-                const double w = std::fmax((double)sp.val[q] - bg_median, 0.0);
-                sum_flux += w;
-                sum_x += (double)sp.col[q] * w;
-                sum_y += (double)row_of(q) * w;
-                peak_val = std::fmax(peak_val, w);
+        }
+        return inside;
+    }
+    // star_detection.rs:142-214: moments of one component in BFS order
+    bool measure(const std::vector<long long> &comp, ab_star *out) const {
+        const size_t npix = comp.size();
+        if (npix < 3 || npix > 5000) return false;
+        double sum_flux = 0.0, sum_x = 0.0, sum_y = 0.0, peak_val = 0.0;
+        for (long long q : comp) {
+            const double w = std::fmax((double)sp.val[q] - bg_median, 0.0);
+            sum_flux += w;
+            sum_x += (double)sp.col[q] * w;
+            sum_y += (double)row_idx[q] * w;
+            peak_val = std::fmax(peak_val, w);
+        }
+        if (sum_flux <= 0.0) return false;
+        const double cx = sum_x / sum_flux, cy = sum_y / sum_flux;
+        double sum_r2 = 0.0, sum_xx = 0.0, sum_yy = 0.0, sum_xy = 0.0;
+        for (long long q : comp) {
+            const double w = std::fmax((double)sp.val[q] - bg_median, 0.0);
+            const double dx = (double)sp.col[q] - cx;
+            const double dy = (double)row_idx[q] - cy;
+            sum_r2 += (dx * dx + dy * dy) * w;
+            sum_xx += dx * dx * w;
+            sum_yy += dy * dy * w;
+            sum_xy += dx * dy * w;
+        }
+        const double sigma_star = std::sqrt(sum_r2 / (2.0 * sum_flux));
+        const double fwhm = sigma_star * 2.3548200450309493;
+        if (fwhm < 0.5 || fwhm > 30.0) return false;
+        const double ixx = sum_xx / sum_flux, iyy = sum_yy / sum_flux, ixy = sum_xy / sum_flux;
+        const double trace = ixx + iyy;
+        const double det = std::fmax(ixx * iyy - ixy * ixy, 0.0);
+        const double disc = std::sqrt(std::fmax((trace * trace / 4.0) - det, 0.0));
+        const double lambda1 = trace / 2.0 + disc;
+        const double lambda2 = std::fmax(trace / 2.0 - disc, 0.0);
+        double ecc = 0.0;
+        if (lambda1 > 1e-15) {
+            ecc = std::sqrt(1.0 - lambda2 / lambda1);
+            ecc = ecc < 0.0 ? 0.0 : (ecc > 1.0 ? 1.0 : ecc);
+        }
+        const double snr = bg_sigma <= DBL_EPSILON ? 0.0 : peak_val / bg_sigma;  // confidence.rs:3-8
+        *out = {cx, cy, sum_flux, fwhm, ecc, peak_val, (uint64_t)npix, snr};
+        return true;
+    }
+    // seeds of rows [r0, r1) in raster order; banded = stay inside the band
+    void scan(size_t r0, size_t r1, bool banded, std::vector<Found> &found) {
+        std::deque<long long> queue;
+        std::vector<long long> comp;
+        const size_t rows = sp.rows, cols = sp.cols;
+        for (size_t r = std::max(r0, (size_t)1); r < r1 && r + 1 < rows; ++r) {
+            for (unsigned long long p = sp.row_off[r]; p < sp.row_off[r + 1]; ++p) {
+                const size_t c = sp.col[p];
+                if (c < 1 || c + 1 >= cols || visited[p]) continue;  // seeds are interior pixels
+                const bool inside = banded ? grow((long long)p, r0, r1, queue, comp)
+                                           : grow((long long)p, 0, rows, queue, comp);
+                if (!inside) {  // leave it to the sequential pass
+                    for (long long q : comp) visited[q] = 2;
+                    continue;
+                }
+                ab_star st;
+                if (measure(comp, &st)) found.push_back({p, st});
             }
-            if (sum_flux <= 0.0) continue;
-            const double cx = sum_x / sum_flux, cy = sum_y / sum_flux;
-            double sum_r2 = 0.0, sum_xx = 0.0, sum_yy = 0.0, sum_xy = 0.0;
-            for (long long q : comp) {
-                const double w = std::fmax((double)sp.val[q] - bg_median, 0.0);
-                const double dx = (double)sp.col[q] - cx;
-                const double dy = (double)row_of(q) - cy;
-                sum_r2 += (dx * dx + dy * dy) * w;
-                sum_xx += dx * dx * w;
-                sum_yy += dy * dy * w;
-                sum_xy += dx * dy * w;
-            }
-            const double sigma_star = std::sqrt(sum_r2 / (2.0 * sum_flux));
-            const double fwhm = sigma_star * 2.3548200450309493;
-            if (fwhm < 0.5 || fwhm > 30.0) continue;
-            const double ixx = sum_xx / sum_flux, iyy = sum_yy / sum_flux, ixy = sum_xy / sum_flux;
-            const double trace = ixx + iyy;
-            const double det = std::fmax(ixx * iyy - ixy * ixy, 0.0);
-            const double disc = std::sqrt(std::fmax((trace * trace / 4.0) - det, 0.0));
-            const double lambda1 = trace / 2.0 + disc;
-            const double lambda2 = std::fmax(trace / 2.0 - disc, 0.0);
-            double ecc = 0.0;
-            if (lambda1 > 1e-15) {
-                ecc = std::sqrt(1.0 - lambda2 / lambda1);
-                ecc = ecc < 0.0 ? 0.0 : (ecc > 1.0 ? 1.0 : ecc);
-            }
-            const double snr = bg_sigma <= DBL_EPSILON ? 0.0 : peak_val / bg_sigma;  // confidence.rs:3-8
-            stars.push_back({cx, cy, sum_flux, fwhm, ecc, peak_val, (uint64_t)npix, snr});
         }
     }
+};
+
+void flood_fill_stars(const SparseImage &sp, double bg_median, double bg_sigma,
+                      std::vector<ab_star> &out) {
+    Filler fl(sp, bg_median, bg_sigma);
+    const size_t rows = sp.rows, nfg = sp.col.size();
+    std::vector<Filler::Found> found;
+    unsigned n_thr = std::thread::hardware_concurrency();
+    n_thr = n_thr > 16 ? 16 : n_thr;
+    bool forced = false;  // AB_FILL_THREADS=n: exactly n bands whatever the image size (tests)
+    if (const char *e = std::getenv("AB_FILL_THREADS")) {
+        n_thr = (unsigned)std::min(64, std::max(1, std::atoi(e)));
+        forced = true;
+    }
+    if (n_thr > 1 && (forced ? rows >= 2 * (size_t)n_thr : (nfg >= 20000 && rows >= 64 * (size_t)n_thr))) {
+        // band edges at equal shares of the sparse pixels
+        std::vector<size_t> edge(n_thr + 1, rows);
+        edge[0] = 0;
+        for (unsigned t = 1; t < n_thr; ++t) {
+            const unsigned long long want = (unsigned long long)nfg * t / n_thr;
+            edge[t] = (size_t)(std::lower_bound(sp.row_off.begin(), sp.row_off.end(), want) -
+                               sp.row_off.begin());
+            if (edge[t] > rows) edge[t] = rows;
+            if (edge[t] < edge[t - 1]) edge[t] = edge[t - 1];
+        }
+        std::vector<std::vector<Filler::Found>> part(n_thr);
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < n_thr; ++t)
+            pool.emplace_back([&, t] { fl.scan(edge[t], edge[t + 1], true, part[t]); });
+        for (auto &th : pool) th.join();
+        for (auto &v : part) found.insert(found.end(), v.begin(), v.end());
+        for (auto &v : fl.visited)
+            if (v == 2) v = 0;
+    }
+    fl.scan(0, rows, false, found);  // everything (sequential mode) or the band-crossing components
+    std::sort(found.begin(), found.end(),
+              [](const Filler::Found &a, const Filler::Found &b) { return a.seed < b.seed; });
+    std::vector<ab_star> stars;
+    stars.reserve(found.size());
+    for (const auto &f : found) stars.push_back(f.star);
     std::stable_sort(stars.begin(), stars.end(),
                      [](const ab_star &a, const ab_star &b) { return a.flux > b.flux; });
     const double dedup_r2 = 9.0, cell = 3.0;

@@ -156,3 +156,16 @@ def test_align_falls_back_to_phase_correlation(al, orc):
     if r.method == 2:
         assert (r.transform.a, r.transform.b, r.transform.c, r.transform.d) == (1.0, 0.0, 0.0, 1.0)
         assert r.matched_stars == 0 and r.inliers == 0
+
+
+def test_detect_stars_band_parallel_fill_is_order_exact(al, orc, monkeypatch):
+    """The host flood fill runs row bands on several threads and re-grows band-crossing components
+    sequentially; star lists must equal the oracle's (order, f64 parameters) for any band count --
+    including bands thinner than the stars, where most components cross an edge."""
+    img = star_field(600, 700, 150, seed=21)
+    img[100:140, 200:260] += 500.0  # one big blob crossing many bands
+    want = orc.detect_stars(img, 3.5)
+    assert len(want.stars) > 50
+    for n in ("1", "3", "16", "64"):
+        monkeypatch.setenv("AB_FILL_THREADS", n)
+        same_detection(al.detect_stars(img, 3.5), want)

@@ -13,6 +13,7 @@
 // of neighbouring lanes overlap and are served by L1/L2 (a source row band of an output tile is
 // read from HBM once).  Coordinates and weights are f64 exactly as in the reference
 // (-fmad=false keeps a*x + b*y + tx as two rounded products and two rounded sums).
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -74,9 +75,13 @@ __global__ void __launch_bounds__(256)
 gather_kernel(const float *__restrict__ src, size_t src_rows, size_t src_cols,
               float *__restrict__ out, size_t out_rows, size_t out_cols, GatherParams gp) {
     const size_t x = (size_t)blockIdx.x * 32 + threadIdx.x;
-    const size_t y0 = (size_t)blockIdx.y * 8 + threadIdx.y;
     if (x >= out_cols) return;
-    for (size_t y = y0; y < out_rows; y += (size_t)gridDim.y * 8) {
+    // each block walks a contiguous band of output rows, 8 rows per step: consecutive steps reuse
+    // the overlapping source rows from L1, and block start-up is paid once per band
+    const size_t band = (((out_rows + gridDim.y - 1) / gridDim.y) + 7) / 8 * 8;
+    const size_t y_begin = (size_t)blockIdx.y * band;
+    const size_t y_end = y_begin + band < out_rows ? y_begin + band : out_rows;
+    for (size_t y = y_begin + threadIdx.y; y < y_end; y += 8) {
         float r = 0.0f;
         if (MODE == MODE_WARP) {
             const double sx = gp.a * (double)x + gp.b * (double)y + gp.tx;
@@ -103,9 +108,12 @@ ab_status launch_gather(ab_ctx *ctx, const float *src, size_t sr, size_t sc, flo
                         size_t ocols, const GatherParams &gp, cudaStream_t s) {
     if (orows == 0 || ocols == 0) return AB_OK;
     dim3 block(32, 8);
+    const size_t gx = (ocols + 31) / 32;
     size_t gy = (orows + 7) / 8;
+    const size_t cap = std::max<size_t>(1, (size_t)ctx->sm_count * 32 / gx);  // ~8 waves of 4 blocks per SM
+    if (gy > cap) gy = cap;
     if (gy > 65535) gy = 65535;
-    dim3 grid((unsigned)((ocols + 31) / 32), (unsigned)gy);
+    dim3 grid((unsigned)gx, (unsigned)gy);
     gather_kernel<MODE><<<grid, block, 0, s>>>(src, sr, sc, out, orows, ocols, gp);
     AB_LAUNCH_CHECK(ctx);
     return AB_OK;

@@ -23,12 +23,11 @@
 // reference (affine.rs:410), so the thread count is a parameter.
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
-#include <deque>
 #include <cstdlib>
-#include <map>
 #include <thread>
 #include <vector>
 
@@ -101,10 +100,18 @@ __device__ unsigned tile_select(const TileCtx &t, Sel &s, int mode, double media
     for (int shift = 24; shift >= 0; shift -= 8) {
         if (threadIdx.x < 256) s.hist[threadIdx.x] = 0;
         __syncthreads();
-        for (unsigned i = threadIdx.x; i < t.th * t.tw; i += blockDim.x) {
-            unsigned key;
-            if (tile_key(t, i, mode, median, L, H, key) && (key & mask) == prefix)
-                atomicAdd(&s.hist[(key >> shift) & 255u], 1u);
+        // sky-dominated tiles put almost every key into one bin of the leading digits: lanes of a
+        // warp that hit the same bin are counted with ONE shared-memory atomic (match_any), not 32
+        // serialised ones.  The trip count is warp-uniform so every lane joins the match.
+        const unsigned n_px = (unsigned)(t.th * t.tw);
+        for (unsigned i0 = 0; i0 < n_px; i0 += blockDim.x) {
+            const unsigned i = i0 + threadIdx.x;
+            unsigned key = 0;
+            const bool in = i < n_px && tile_key(t, i, mode, median, L, H, key) && (key & mask) == prefix;
+            const unsigned b = in ? ((key >> shift) & 255u) : 256u;
+            const unsigned peers = __match_any_sync(0xffffffffu, b);
+            if (in && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1))
+                atomicAdd(&s.hist[b], (unsigned)__popc(peers));
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -372,17 +379,13 @@ struct Filler {
     }
     // BFS from `seed` in the reference's neighbour order.  With a band [r0, r1) given, pixels of
     // other rows are not touched; returns false when the component reaches outside the band.
-    bool grow(long long seed, size_t r0, size_t r1, std::deque<long long> &queue,
-              std::vector<long long> &comp) {
+    bool grow(long long seed, size_t r0, size_t r1, std::vector<long long> &comp) {
         bool inside = true;
-        queue.clear();
         comp.clear();
-        queue.push_back(seed);
+        comp.push_back(seed);  // `comp` is the BFS queue and, when done, the visiting order
         visited[seed] = 1;
-        while (!queue.empty()) {
-            const long long cur = queue.front();
-            queue.pop_front();
-            comp.push_back(cur);
+        for (size_t head = 0; head < comp.size(); ++head) {
+            const long long cur = comp[head];
             const size_t cr = row_idx[cur], cc = sp.col[cur];
             long long up[3], dn[3];
             three((long long)cr - 1, cc, up);
@@ -403,7 +406,7 @@ struct Filler {
                 }
                 if (visited[q]) continue;
                 visited[q] = 1;
-                queue.push_back(q);
+                comp.push_back(q);
             }
         }
         return inside;
@@ -452,15 +455,13 @@ struct Filler {
     }
     // seeds of rows [r0, r1) in raster order; banded = stay inside the band
     void scan(size_t r0, size_t r1, bool banded, std::vector<Found> &found) {
-        std::deque<long long> queue;
         std::vector<long long> comp;
         const size_t rows = sp.rows, cols = sp.cols;
         for (size_t r = std::max(r0, (size_t)1); r < r1 && r + 1 < rows; ++r) {
             for (unsigned long long p = sp.row_off[r]; p < sp.row_off[r + 1]; ++p) {
                 const size_t c = sp.col[p];
                 if (c < 1 || c + 1 >= cols || visited[p]) continue;  // seeds are interior pixels
-                const bool inside = banded ? grow((long long)p, r0, r1, queue, comp)
-                                           : grow((long long)p, 0, rows, queue, comp);
+                const bool inside = banded ? grow((long long)p, r0, r1, comp) : grow((long long)p, 0, rows, comp);
                 if (!inside) {  // leave it to the sequential pass
                     for (long long q : comp) visited[q] = 2;
                     continue;
@@ -512,8 +513,15 @@ void flood_fill_stars(const SparseImage &sp, double bg_median, double bg_sigma,
     for (const auto &f : found) stars.push_back(f.star);
     std::stable_sort(stars.begin(), stars.end(),
                      [](const ab_star &a, const ab_star &b) { return a.flux > b.flux; });
+    // greedy dedup on a 3-px grid (star_detection.rs:219-248); the grid is a flat hash of cell ->
+    // chain of kept stars (same decisions as the reference's HashMap<(usize, usize), Vec<usize>>)
     const double dedup_r2 = 9.0, cell = 3.0;
-    std::map<std::pair<size_t, size_t>, std::vector<size_t>> grid;
+    size_t cap = 16;
+    while (cap < stars.size() * 2) cap <<= 1;
+    std::vector<long long> head(cap, -1), next(stars.size(), -1);
+    std::vector<unsigned long long> cell_of(stars.size());
+    auto key_of = [](size_t gy, size_t gx) { return ((unsigned long long)gy << 32) ^ (unsigned long long)gx; };
+    auto slot_of = [&](unsigned long long k) { return (size_t)((k * 0x9E3779B97F4A7C15ull) >> 20) & (cap - 1); };
     out.clear();
     for (size_t i = 0; i < stars.size(); ++i) {
         const ab_star &s = stars[i];
@@ -521,9 +529,9 @@ void flood_fill_stars(const SparseImage &sp, double bg_median, double bg_sigma,
         bool too_close = false;
         for (size_t ny = (gy ? gy - 1 : 0); ny <= gy + 1 && !too_close; ++ny)
             for (size_t nx = (gx ? gx - 1 : 0); nx <= gx + 1 && !too_close; ++nx) {
-                auto it = grid.find({ny, nx});
-                if (it == grid.end()) continue;
-                for (size_t j : it->second) {
+                const unsigned long long k = key_of(ny, nx);
+                for (long long j = head[slot_of(k)]; j >= 0; j = next[j]) {
+                    if (cell_of[j] != k) continue;  // another cell sharing the slot
                     const double dx = s.x - stars[j].x, dy = s.y - stars[j].y;
                     if (dx * dx + dy * dy < dedup_r2) {
                         too_close = true;
@@ -532,7 +540,11 @@ void flood_fill_stars(const SparseImage &sp, double bg_median, double bg_sigma,
                 }
             }
         if (!too_close) {
-            grid[{gy, gx}].push_back(i);
+            const unsigned long long k = key_of(gy, gx);
+            const size_t sl = slot_of(k);
+            cell_of[i] = k;
+            next[i] = head[sl];
+            head[sl] = (long long)i;
             out.push_back(s);
         }
     }
@@ -568,6 +580,13 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
     unsigned *d_rc = reinterpret_cast<unsigned *>(base + off_rc);
     unsigned long long *d_ro = reinterpret_cast<unsigned long long *>(base + off_ro);
 
+    // AB_TRACE=1: per-stage wall clock on stderr (tiles / count / compact + D2H / host fill)
+    const bool trace = std::getenv("AB_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(now() - t0).count();
+    };
+    const auto t_start = now();
     bg_tiles_kernel<<<(unsigned)n_tiles, BG_THREADS, 0, s>>>(d_img, rows, cols, step, tiles_x, nm,
                                                             d_med, d_sig, d_ok);
     AB_LAUNCH_CHECK(ctx);
@@ -593,6 +612,8 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
     *bg_median_out = bg_median;
     *bg_sigma_out = bg_sigma;
     const double threshold = bg_median + sigma_threshold * bg_sigma;
+    const double t_bg = ms_since(t_start);
+    const auto t1 = now();
 
     row_count_kernel<<<(unsigned)rows, 256, 0, s>>>(d_img, rows, cols, nm, threshold, d_rc);
     AB_LAUNCH_CHECK(ctx);
@@ -606,6 +627,8 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
     sp.row_off[0] = 0;
     for (size_t r = 0; r < rows; ++r) sp.row_off[r + 1] = sp.row_off[r] + h_rc[r];
     const size_t nfg = (size_t)sp.row_off[rows];
+    const double t_count = ms_since(t1);
+    const auto t2 = now();
     if (nfg) {
         AB_CUDA(ctx, cudaMemcpyAsync(d_ro, sp.row_off.data(), (rows + 1) * 8, cudaMemcpyHostToDevice, s));
         const size_t lists = (nfg * 4 + 255) / 256 * 256;
@@ -622,7 +645,13 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
         AB_CUDA(ctx, cudaMemcpyAsync(sp.val.data(), d_val, nfg * 4, cudaMemcpyDeviceToHost, s));
         AB_CUDA(ctx, cudaStreamSynchronize(s));
     }
+    const double t_compact = ms_since(t2);
+    const auto t3 = now();
     flood_fill_stars(sp, bg_median, bg_sigma, stars);
+    if (trace)
+        fprintf(stderr, "[ab] detect %zux%zu: tiles %.2f ms, count %.2f ms, compact+D2H %.2f ms (%zu px), "
+                        "host fill %.2f ms (%zu stars)\n",
+                rows, cols, t_bg, t_count, t_compact, nfg, ms_since(t3), stars.size());
     return AB_OK;
 }
 

@@ -326,21 +326,12 @@ masked_radix_kernel(const float *__restrict__ img, const float *__restrict__ mas
     __shared__ unsigned sh[256];
     sh[threadIdx.x] = 0;  // PV_THREADS == 256
     __syncthreads();
-    // lanes hitting the same bin share one atomic (the background is one narrow peak)
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i0 = (size_t)blockIdx.x * blockDim.x; i0 < len; i0 += stride) {
-        const size_t i = i0 + threadIdx.x;
-        bool in = i < len;
-        unsigned key = 0;
-        if (in) {
-            const float v = img[i];
-            in = mask[i] < 0.5f && finite_f(v) && v > 0.0f;
-            key = __float_as_uint(v);
-        }
-        in = in && (key & prefix_mask) == prefix;
-        const unsigned b = in ? ((key >> shift) & 255u) : 256u;
-        const unsigned peers = __match_any_sync(0xffffffffu, b);
-        if (in && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[b], (unsigned)__popc(peers));
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const float v = img[i];
+        if (!(mask[i] < 0.5f && finite_f(v) && v > 0.0f)) continue;
+        const unsigned key = __float_as_uint(v);
+        if ((key & prefix_mask) == prefix) atomicAdd(&sh[(key >> shift) & 255u], 1u);
     }
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(&hist256[threadIdx.x], sh[threadIdx.x]);

@@ -100,18 +100,10 @@ __device__ unsigned tile_select(const TileCtx &t, Sel &s, int mode, double media
     for (int shift = 24; shift >= 0; shift -= 8) {
         if (threadIdx.x < 256) s.hist[threadIdx.x] = 0;
         __syncthreads();
-        // sky-dominated tiles put almost every key into one bin of the leading digits: lanes of a
-        // warp that hit the same bin are counted with ONE shared-memory atomic (match_any), not 32
-        // serialised ones.  The trip count is warp-uniform so every lane joins the match.
-        const unsigned n_px = (unsigned)(t.th * t.tw);
-        for (unsigned i0 = 0; i0 < n_px; i0 += blockDim.x) {
-            const unsigned i = i0 + threadIdx.x;
-            unsigned key = 0;
-            const bool in = i < n_px && tile_key(t, i, mode, median, L, H, key) && (key & mask) == prefix;
-            const unsigned b = in ? ((key >> shift) & 255u) : 256u;
-            const unsigned peers = __match_any_sync(0xffffffffu, b);
-            if (in && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1))
-                atomicAdd(&s.hist[b], (unsigned)__popc(peers));
+        for (unsigned i = threadIdx.x; i < t.th * t.tw; i += blockDim.x) {
+            unsigned key;
+            if (tile_key(t, i, mode, median, L, H, key) && (key & mask) == prefix)
+                atomicAdd(&s.hist[(key >> shift) & 255u], 1u);  // (match_any aggregation measured slower)
         }
         __syncthreads();
         if (threadIdx.x == 0) {

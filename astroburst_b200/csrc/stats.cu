@@ -245,22 +245,12 @@ radix_hist_kernel(const float *__restrict__ data, size_t len, int mode, float ce
     __shared__ unsigned sh[256];
     if (threadIdx.x < 256) sh[threadIdx.x] = 0;
     __syncthreads();
-    // lanes that hit the same bin (sky-dominated data: nearly all of them in the leading digits)
-    // are counted with one shared-memory atomic; the trip count is block-uniform for the match
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i0 = (size_t)blockIdx.x * blockDim.x; i0 < len; i0 += stride) {
-        const size_t i = i0 + threadIdx.x;
-        bool in = i < len;
-        unsigned key = 0;
-        if (in) {
-            const float v = data[i];
-            in = valid_px(v);
-            key = __float_as_uint(mode ? fabsf(v - center) : v);
-        }
-        in = in && (key & prefix_mask) == prefix;
-        const unsigned b = in ? ((key >> shift) & 255u) : 256u;
-        const unsigned peers = __match_any_sync(0xffffffffu, b);
-        if (in && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[b], (unsigned)__popc(peers));
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const float v = data[i];
+        if (!valid_px(v)) continue;
+        const unsigned key = __float_as_uint(mode ? fabsf(v - center) : v);
+        if ((key & prefix_mask) == prefix) atomicAdd(&sh[(key >> shift) & 255u], 1u);
     }
     __syncthreads();
     if (threadIdx.x < 256 && sh[threadIdx.x]) atomicAdd(&hist256[threadIdx.x], sh[threadIdx.x]);

@@ -53,11 +53,64 @@ __device__ __forceinline__ float norm_px(const Norm &nm, float v) {
 }
 
 // ------------------------------------------------------------------------- background tiles
+// One block per tile runs sigma_clipped_stats (sigma_clip.rs:4-34) as a sequence of exact
+// selections (MSB-first radix select on the float bit patterns).  The ~30 passes of a tile read
+// its pixels from a pixel source: `OnChip` holds the whole tile (<= 65,536 px, every tile the
+// detector makes) in the SM -- 48 values per thread in shared memory plus 16 in registers at
+// 1,024 threads -- so HBM/L2 is read once per tile; `FromGlobal` re-reads global memory and serves
+// caller-chosen tile sizes beyond that (ab_estimate_background).
 struct TileCtx {
     const float *img;
     size_t cols;
     size_t r0, c0, th, tw;
+    int tw_shift;  // log2(tw) when the tile width is a power of two (the usual 256), else -1
     Norm nm;
+};
+__device__ __forceinline__ float tile_load(const TileCtx &t, unsigned i) {
+    unsigned ir, ic;  // no integer division on the common power-of-two tile width
+    if (t.tw_shift >= 0) {
+        ir = i >> t.tw_shift;
+        ic = i & ((1u << t.tw_shift) - 1u);
+    } else {
+        ir = i / (unsigned)t.tw;
+        ic = i - ir * (unsigned)t.tw;
+    }
+    return norm_px(t.nm, __ldg(t.img + (t.r0 + ir) * t.cols + (t.c0 + ic)));
+}
+struct FromGlobal {
+    TileCtx t;
+    template <typename Fn>
+    __device__ __forceinline__ void for_each(Fn fn) const {
+        const unsigned n_px = (unsigned)(t.th * t.tw);
+        for (unsigned i = threadIdx.x; i < n_px; i += blockDim.x) fn(tile_load(t, i));
+    }
+};
+constexpr int OC_THREADS = 1024, OC_REG = 16, OC_SMEM = 48;  // 64 slots per thread = 65,536 px
+struct OnChip {
+    float rv[OC_REG];
+    const float *sm;  // [OC_SMEM][OC_THREADS], slot-major: conflict-free
+    int n_slots;      // ceil(n_px / OC_THREADS); empty positions hold NaN (never valid)
+    __device__ __forceinline__ void fill(const TileCtx &t, float *smw) {
+        const unsigned n_px = (unsigned)(t.th * t.tw);
+        n_slots = (int)((n_px + OC_THREADS - 1) / OC_THREADS);
+        sm = smw;
+#pragma unroll
+        for (int j = 0; j < OC_REG; ++j) {
+            const unsigned i = (unsigned)j * OC_THREADS + threadIdx.x;
+            rv[j] = i < n_px ? tile_load(t, i) : CUDART_NAN_F;
+        }
+        for (int j = OC_REG; j < n_slots; ++j) {
+            const unsigned i = (unsigned)j * OC_THREADS + threadIdx.x;
+            smw[(j - OC_REG) * OC_THREADS + threadIdx.x] = i < n_px ? tile_load(t, i) : CUDART_NAN_F;
+        }
+    }
+    template <typename Fn>
+    __device__ __forceinline__ void for_each(Fn fn) const {
+#pragma unroll
+        for (int j = 0; j < OC_REG; ++j)
+            if (j < n_slots) fn(rv[j]);
+        for (int j = OC_REG; j < n_slots; ++j) fn(sm[(j - OC_REG) * OC_THREADS + threadIdx.x]);
+    }
 };
 struct Sel {  // shared scratch of one block
     unsigned hist[256];
@@ -68,22 +121,23 @@ struct Sel {  // shared scratch of one block
 
 // key of one pixel for the current selection, or false when the pixel is not in the set.
 // mode 0: value; mode 1: |v - median| as f32 via f64 (sigma_clip.rs:15)
-__device__ __forceinline__ bool tile_key(const TileCtx &t, unsigned i, int mode, double median,
-                                         float L, float H, unsigned &key) {
-    const size_t r = t.r0 + i / t.tw, c = t.c0 + i % t.tw;
-    const float v = norm_px(t.nm, __ldg(t.img + r * t.cols + c));
+__device__ __forceinline__ bool px_key(float v, int mode, double median, float L, float H,
+                                       unsigned &key) {
     if (!((fabsf(v) < CUDART_INF_F) && v > 1e-7f)) return false;
     if (!(v >= L && v <= H)) return false;
     key = __float_as_uint(mode ? (float)fabs((double)v - median) : v);
     return true;
 }
 
-__device__ unsigned long long tile_count(const TileCtx &t, Sel &s, float L, float H) {
+template <typename Src>
+__device__ __forceinline__ unsigned long long tile_count(const Src &src, Sel &s, float L, float H) {
     if (threadIdx.x == 0) s.total = 0;
     __syncthreads();
-    unsigned c = 0, key;
-    for (unsigned i = threadIdx.x; i < t.th * t.tw; i += blockDim.x)
-        c += tile_key(t, i, 0, 0.0, L, H, key) ? 1u : 0u;
+    unsigned c = 0;
+    src.for_each([&](float v) {
+        unsigned key;
+        c += px_key(v, 0, 0.0, L, H, key) ? 1u : 0u;
+    });
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s.total, (unsigned long long)c);
     __syncthreads();
@@ -93,18 +147,21 @@ __device__ unsigned long long tile_count(const TileCtx &t, Sel &s, float L, floa
 }
 
 // k-th smallest key (0-based); *less = number of keys strictly smaller than the result
-__device__ unsigned tile_select(const TileCtx &t, Sel &s, int mode, double median, float L, float H,
-                                unsigned long long k, unsigned long long *less) {
+template <typename Src>
+__device__ __forceinline__ unsigned tile_select(const Src &src, Sel &s, int mode, double median,
+                                                float L, float H, unsigned long long k,
+                                                unsigned long long *less) {
     unsigned prefix = 0, mask = 0;
     unsigned long long below = 0;
+#pragma unroll 1
     for (int shift = 24; shift >= 0; shift -= 8) {
         if (threadIdx.x < 256) s.hist[threadIdx.x] = 0;
         __syncthreads();
-        for (unsigned i = threadIdx.x; i < t.th * t.tw; i += blockDim.x) {
+        src.for_each([&](float v) {
             unsigned key;
-            if (tile_key(t, i, mode, median, L, H, key) && (key & mask) == prefix)
+            if (px_key(v, mode, median, L, H, key) && (key & mask) == prefix)
                 atomicAdd(&s.hist[(key >> shift) & 255u], 1u);  // (match_any aggregation measured slower)
-        }
+        });
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned long long cum = 0;
@@ -128,15 +185,16 @@ __device__ unsigned tile_select(const TileCtx &t, Sel &s, int mode, double media
 }
 
 // largest key strictly below `bound` (exists by construction when called)
-__device__ unsigned tile_max_below(const TileCtx &t, Sel &s, int mode, double median, float L,
-                                   float H, unsigned bound) {
+template <typename Src>
+__device__ __forceinline__ unsigned tile_max_below(const Src &src, Sel &s, int mode, double median,
+                                                   float L, float H, unsigned bound) {
     if (threadIdx.x == 0) s.maxkey = 0;
     __syncthreads();
     unsigned m = 0;
-    for (unsigned i = threadIdx.x; i < t.th * t.tw; i += blockDim.x) {
+    src.for_each([&](float v) {
         unsigned key;
-        if (tile_key(t, i, mode, median, L, H, key) && key < bound) m = max(m, key);
-    }
+        if (px_key(v, mode, median, L, H, key) && key < bound) m = max(m, key);
+    });
     m = __reduce_max_sync(0xffffffffu, m);
     if ((threadIdx.x & 31) == 0) atomicMax(&s.maxkey, m);
     __syncthreads();
@@ -146,36 +204,67 @@ __device__ unsigned tile_max_below(const TileCtx &t, Sel &s, int mode, double me
 }
 
 // (left, right) = the (n/2 - 1)-th and (n/2)-th order statistics (left == right for odd n)
-__device__ void tile_median_pair(const TileCtx &t, Sel &s, int mode, double median, float L,
-                                 float H, unsigned long long n, float *left, float *right) {
+template <typename Src>
+__device__ __forceinline__ void tile_median_pair(const Src &src, Sel &s, int mode, double median,
+                                                 float L, float H, unsigned long long n, float *left,
+                                                 float *right) {
     const unsigned long long mid = n / 2;
     unsigned long long less;
-    const unsigned rk = tile_select(t, s, mode, median, L, H, mid, &less);
+    const unsigned rk = tile_select(src, s, mode, median, L, H, mid, &less);
     unsigned lk = rk;
-    if (n % 2 == 0 && less == mid) lk = tile_max_below(t, s, mode, median, L, H, rk);
+    if (n % 2 == 0 && less == mid) lk = tile_max_below(src, s, mode, median, L, H, rk);
     *left = __uint_as_float(lk);
     *right = __uint_as_float(rk);
 }
 
-// exact_median_mut (median.rs:27-44) and the MAD sigma of sigma_clip.rs:14-17
-__device__ double tile_median(const TileCtx &t, Sel &s, float L, float H, unsigned long long n) {
+// mode 0: exact_median_mut (median.rs:27-44); mode 1: the f32 MAD of sigma_clip.rs:14-17
+template <typename Src>
+__device__ __noinline__ double tile_stat(const Src &src, Sel &s, int mode, double median, float L,
+                                         float H, unsigned long long n) {
     float l, r;
-    tile_median_pair(t, s, 0, 0.0, L, H, n, &l, &r);
-    return (n % 2 == 0) ? ((double)l + (double)r) / 2.0 : (double)r;
-}
-__device__ double tile_mad(const TileCtx &t, Sel &s, double median, float L, float H,
-                           unsigned long long n) {
-    float l, r;
-    tile_median_pair(t, s, 1, median, L, H, n, &l, &r);
+    tile_median_pair(src, s, mode, median, L, H, n, &l, &r);
+    if (mode == 0) return (n % 2 == 0) ? ((double)l + (double)r) / 2.0 : (double)r;
     const float m = (n % 2 == 0) ? (l + r) / 2.0f : r;  // median_f32_mut
     return (double)m;
 }
 
-__global__ void __launch_bounds__(BG_THREADS)
-bg_tiles_kernel(const float *__restrict__ img, size_t rows, size_t cols, size_t step,
-                size_t tiles_x, Norm nm, double *__restrict__ med_out,
-                double *__restrict__ sig_out, int *__restrict__ ok_out) {
-    __shared__ Sel s;
+// sigma_clipped_stats(&mut vals, 3.0, 2) of one tile + the n >= 8 gate of star_detection.rs:61-66
+template <typename Src>
+__device__ __forceinline__ void tile_background(const Src &src, Sel &s, double *__restrict__ med_out,
+                                                double *__restrict__ sig_out, int *__restrict__ ok_out) {
+    float L = -CUDART_INF_F, H = CUDART_INF_F;
+    unsigned long long n = tile_count(src, s, L, H);
+    if (n < 8) {
+        if (threadIdx.x == 0) ok_out[blockIdx.x] = 0;
+        return;
+    }
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+        if (n < 3) break;
+        const double median = tile_stat(src, s, 0, 0.0, L, H, n);
+        const double mad = tile_stat(src, s, 1, median, L, H, n);
+        const double sig = fmax(mad * MAD_TO_SIGMA, 1e-30);
+        const float lo = (float)(median - 3.0 * sig);
+        const float hi = (float)(median + 3.0 * sig);
+        // retain(v >= lo && v <= hi) on the already retained set
+        if (!(lo <= L)) L = lo;  // NaN-safe max
+        if (!(hi >= H)) H = hi;
+        n = tile_count(src, s, L, H);
+    }
+    double median = 0.0, sigma = 1.0;  // sigma_clip.rs:24-26
+    if (n > 0) {
+        median = tile_stat(src, s, 0, 0.0, L, H, n);
+        sigma = fmax(tile_stat(src, s, 1, median, L, H, n) * MAD_TO_SIGMA, 1e-30);
+    }
+    if (threadIdx.x == 0) {
+        med_out[blockIdx.x] = median;
+        sig_out[blockIdx.x] = sigma;
+        ok_out[blockIdx.x] = 1;
+    }
+}
+
+__device__ __forceinline__ TileCtx tile_of_block(const float *img, size_t rows, size_t cols,
+                                                 size_t step, size_t tiles_x, const Norm &nm) {
     const size_t ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
     TileCtx t;
     t.img = img;
@@ -184,35 +273,50 @@ bg_tiles_kernel(const float *__restrict__ img, size_t rows, size_t cols, size_t 
     t.c0 = tx * step;
     t.th = min(step, rows - t.r0);
     t.tw = min(step, cols - t.c0);
+    t.tw_shift = (t.tw & (t.tw - 1)) == 0 ? __ffsll((long long)t.tw) - 1 : -1;
     t.nm = nm;
-    float L = -CUDART_INF_F, H = CUDART_INF_F;
-    unsigned long long n = tile_count(t, s, L, H);
-    if (n < 8) {  // star_detection.rs:61-66
-        if (threadIdx.x == 0) ok_out[blockIdx.x] = 0;
-        return;
+    return t;
+}
+
+__global__ void __launch_bounds__(BG_THREADS)
+bg_tiles_kernel(const float *__restrict__ img, size_t rows, size_t cols, size_t step,
+                size_t tiles_x, Norm nm, double *__restrict__ med_out,
+                double *__restrict__ sig_out, int *__restrict__ ok_out) {
+    __shared__ Sel s;
+    FromGlobal src{tile_of_block(img, rows, cols, step, tiles_x, nm)};
+    tile_background(src, s, med_out, sig_out, ok_out);
+}
+
+__global__ void __launch_bounds__(OC_THREADS, 1)
+bg_tiles_onchip_kernel(const float *__restrict__ img, size_t rows, size_t cols, size_t step,
+                       size_t tiles_x, Norm nm, double *__restrict__ med_out,
+                       double *__restrict__ sig_out, int *__restrict__ ok_out) {
+    extern __shared__ float oc_smem[];
+    __shared__ Sel s;
+    const TileCtx t = tile_of_block(img, rows, cols, step, tiles_x, nm);
+    OnChip src;
+    src.fill(t, oc_smem);
+    __syncthreads();
+    tile_background(src, s, med_out, sig_out, ok_out);
+}
+
+// step x step tiles of at most 65,536 px run from the on-chip copy
+ab_status launch_bg_tiles(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols, size_t step,
+                          size_t tiles_x, size_t n_tiles, const Norm &nm, double *d_med,
+                          double *d_sig, int *d_ok, cudaStream_t s) {
+    if (step * step <= (size_t)OC_THREADS * (OC_REG + OC_SMEM)) {
+        const size_t slots = (std::min(step, rows) * std::min(step, cols) + OC_THREADS - 1) / OC_THREADS;
+        const size_t smem = slots > OC_REG ? (slots - OC_REG) * OC_THREADS * sizeof(float) : 0;
+        AB_CUDA(ctx, cudaFuncSetAttribute(bg_tiles_onchip_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bg_tiles_onchip_kernel<<<(unsigned)n_tiles, OC_THREADS, smem, s>>>(d_img, rows, cols, step, tiles_x,
+                                                                          nm, d_med, d_sig, d_ok);
+    } else {
+        bg_tiles_kernel<<<(unsigned)n_tiles, BG_THREADS, 0, s>>>(d_img, rows, cols, step, tiles_x, nm,
+                                                                d_med, d_sig, d_ok);
     }
-    for (int it = 0; it < 2; ++it) {  // sigma_clipped_stats(&mut vals, 3.0, 2)
-        if (n < 3) break;
-        const double median = tile_median(t, s, L, H, n);
-        const double mad = tile_mad(t, s, median, L, H, n);
-        const double sig = fmax(mad * MAD_TO_SIGMA, 1e-30);
-        const float lo = (float)(median - 3.0 * sig);
-        const float hi = (float)(median + 3.0 * sig);
-        // retain(v >= lo && v <= hi) on the already retained set
-        if (!(lo <= L)) L = lo;  // NaN-safe max
-        if (!(hi >= H)) H = hi;
-        n = tile_count(t, s, L, H);
-    }
-    double median = 0.0, sigma = 1.0;  // sigma_clip.rs:24-26
-    if (n > 0) {
-        median = tile_median(t, s, L, H, n);
-        sigma = fmax(tile_mad(t, s, median, L, H, n) * MAD_TO_SIGMA, 1e-30);
-    }
-    if (threadIdx.x == 0) {
-        med_out[blockIdx.x] = median;
-        sig_out[blockIdx.x] = sigma;
-        ok_out[blockIdx.x] = 1;
-    }
+    AB_LAUNCH_CHECK(ctx);
+    return AB_OK;
 }
 
 // ------------------------------------------------------------------------- threshold + compaction
@@ -579,9 +683,8 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
         return std::chrono::duration<double, std::milli>(now() - t0).count();
     };
     const auto t_start = now();
-    bg_tiles_kernel<<<(unsigned)n_tiles, BG_THREADS, 0, s>>>(d_img, rows, cols, step, tiles_x, nm,
-                                                            d_med, d_sig, d_ok);
-    AB_LAUNCH_CHECK(ctx);
+    st = launch_bg_tiles(ctx, d_img, rows, cols, step, tiles_x, n_tiles, nm, d_med, d_sig, d_ok, s);
+    if (st != AB_OK) return st;
     std::vector<double> h_med(n_tiles), h_sig(n_tiles);
     std::vector<int> h_ok(n_tiles);
     AB_CUDA(ctx, cudaMemcpyAsync(h_med.data(), d_med, n_tiles * 8, cudaMemcpyDeviceToHost, s));
@@ -1097,9 +1200,8 @@ ab_status ab_estimate_background(ab_ctx *ctx, const float *img, size_t rows, siz
     double *d_med = reinterpret_cast<double *>(base), *d_sig = reinterpret_cast<double *>(base + n_tiles * 8);
     int *d_ok = reinterpret_cast<int *>(base + n_tiles * 16);
     Norm nm{0, 0.0, 1.0};
-    bg_tiles_kernel<<<(unsigned)n_tiles, BG_THREADS, 0, ctx->stream>>>(d, rows, cols, step, tiles_x,
-                                                                      nm, d_med, d_sig, d_ok);
-    AB_LAUNCH_CHECK(ctx);
+    st = launch_bg_tiles(ctx, d, rows, cols, step, tiles_x, n_tiles, nm, d_med, d_sig, d_ok, ctx->stream);
+    if (st != AB_OK) return st;
     std::vector<double> h_med(n_tiles), h_sig(n_tiles);
     std::vector<int> h_ok(n_tiles);
     AB_CUDA(ctx, cudaMemcpyAsync(h_med.data(), d_med, n_tiles * 8, cudaMemcpyDeviceToHost, ctx->stream));

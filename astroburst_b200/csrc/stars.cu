@@ -772,9 +772,12 @@ ab_status normalize_params(ab_ctx *ctx, const float *d_img, size_t len, cudaStre
         if (std::isfinite(samples[i])) samples[w++] = samples[i];
     samples.resize(w);
     if (samples.size() < 100) return AB_OK;
-    std::stable_sort(samples.begin(), samples.end());
-    const double lo = (double)samples[samples.size() / 100];
-    const double hi = (double)samples[samples.size() * 999 / 1000];
+    // affine.rs:36-41 sorts the samples and reads two ranks; two selections give the same values
+    const size_t k_lo = samples.size() / 100, k_hi = samples.size() * 999 / 1000;
+    std::nth_element(samples.begin(), samples.begin() + k_hi, samples.end());
+    std::nth_element(samples.begin(), samples.begin() + k_lo, samples.begin() + k_hi);
+    const double lo = (double)samples[k_lo];
+    const double hi = (double)samples[k_hi];
     const double range = hi - lo;
     if (range < 1e-15) return AB_OK;
     nm->on = 1;

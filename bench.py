@@ -243,10 +243,32 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     npix = ROWS * COLS
 
+    # The path's only exchange is StackResult.rejected_pixels: one 8-byte all-reduce
+    # per stack.  It is issued asynchronously on a ring of counters, so the reduction of stack k
+    # overlaps the kernel of stack k+1 (a pipeline of stacks); every reduction is complete before
+    # the closing synchronisation of the timed region.
+    rej_ring = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(4)]
+    pending = [None] * 4
+    step_no = [0]
+
     def step():
-        ab.stack_images_device(ptrs, npix, cfg, out.data_ptr(), rej.data_ptr(), stream, ctx)
-        if world > 1:  # the path's only exchange: StackResult.rejected_pixels
-            dist.all_reduce(rej)
+        k = step_no[0] % 4
+        step_no[0] += 1
+        if pending[k] is not None:
+            pending[k].wait()
+            pending[k] = None
+        r = rej_ring[k] if world > 1 else rej
+        ab.stack_images_device(ptrs, npix, cfg, out.data_ptr(), r.data_ptr(), stream, ctx)
+        if world > 1:
+            pending[k] = dist.all_reduce(r, async_op=True)
+
+    def drain():
+        for k in range(4):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
+        if world > 1:
+            rej.copy_(rej_ring[(step_no[0] - 1) % 4])
 
     def sync_all():
         torch.cuda.synchronize()
@@ -256,6 +278,7 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    drain()
     sync_all()
 
     sampler = ClockSampler(local)
@@ -274,6 +297,7 @@ def main():
         ev[k][0].record()
         step()
         ev[k][1].record()
+    drain()
     t_end.record()
     sync_all()
     torch.cuda.cudart().cudaProfilerStop()

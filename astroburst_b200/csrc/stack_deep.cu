@@ -32,7 +32,13 @@ using abk::CeConst;
 constexpr int CH = 32;           // samples per chunk
 constexpr int MAX_CHUNKS = AB_MAX_FRAMES / CH;
 constexpr int DEEP_MN = 2, DEEP_MD = 3;  // IMAD share of the compare-exchanges (tuned at r1: 4.05 ms)
-constexpr int DEEP_WARPS = 2;    // warps per block (32 KiB of columns per warp at 256 frames)
+// warps per block.  At K = 8 (225..256 frames) a warp's columns take 32 KiB: three 2-warp blocks fit
+// an SM (each block also reserves 1 KiB), ONE 7-warp block fits seven warps -- occupancy is what
+// bounds this kernel, so that layout is used there.
+template <int K>
+constexpr int deep_warps() {
+    return K == 8 ? 7 : 2;
+}
 
 // 8 small integers (0..255) packed in one 64-bit register: per-list counters without local memory
 struct Pack8 {
@@ -234,7 +240,7 @@ __device__ __forceinline__ float select_mad(const float *col, const int (&n)[K],
 
 // PRE = false is the plain stack (no calibration terms, no median-only mode compiled in).
 template <int K, bool PRE>
-__global__ void __launch_bounds__(DEEP_WARPS * 32)
+__global__ void __launch_bounds__(deep_warps<K>() * 32)
 stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t npix,
                   float sigma_low, float sigma_high, unsigned max_iter, CeConst kc,
                   const __grid_constant__ DeepPre pre, float *__restrict__ out,
@@ -249,6 +255,7 @@ stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t np
     const bool median_only = PRE && pre.median_only != 0;
 
     const size_t n_groups = (npix + 31) / 32;
+    constexpr int DEEP_WARPS = deep_warps<K>();
     const size_t warp_global = (size_t)blockIdx.x * DEEP_WARPS + warp;
     const size_t warp_stride = (size_t)gridDim.x * DEEP_WARPS;
     for (size_t g = warp_global; g < n_groups; g += warp_stride) {
@@ -413,6 +420,7 @@ template <int K, bool PRE>
 static ab_status launch_deep_k(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix, float sl,
                                float sh, unsigned max_iter, const DeepPre &pre, float *d_out,
                                unsigned long long *d_rej, cudaStream_t stream) {
+    constexpr int DEEP_WARPS = deep_warps<K>();
     const size_t smem = (size_t)DEEP_WARPS * K * CH * 32 * sizeof(float);
     auto kern = stack_deep_kernel<K, PRE>;
     AB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

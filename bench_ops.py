@@ -202,6 +202,15 @@ def main():
     par = all(np.array_equal(o[band].cpu().numpy(), w) for o, w in zip(o3, w3))
     emit("tone chain fused (STF + curve + SCNR, one sweep)", cfg4, ms, 6 * npix * 4, npix, None, par,
          "the four separate operators move 20 planes; the fused sweep moves 6")
+    # config-4 chain of SURVEY 8(d) from the measured stages: blend + 3 plane stats + WB (3 scales)
+    # + SCNR + G re-stat + fused tone = 20.56 GB algorithmic on one GPU
+    def stage(prefix):
+        return next(x["ms"] for x in results if x["op"].startswith(prefix))
+
+    chain_ms = (stage("blend_channels") + 4 * stage("compute_image_stats") + 3 * stage("white-balance scale")
+                + stage("apply_scnr_inplace (average") + stage("tone chain fused"))
+    emit("config-4 colour chain (sum of the measured stages: blend, 3+1 stats, WB, SCNR, fused tone)", cfg4,
+         chain_ms, int(20.56e9), npix, None, None, "SURVEY 8(d): 20.56 GB algorithmic, ideal 3.14 ms at the measured peak")
     # RGB8 interleave: full size and the 2048-px preview (cmd/helpers.rs MAX_PREVIEW_DIM)
     rgb8 = torch.empty((rows, cols, 3), dtype=torch.uint8, device=dev)
     ms = timed(lambda: ctx.check(lib().ab_render_rgb_u8_dev(h, o3[0].data_ptr(), o3[1].data_ptr(), o3[2].data_ptr(),

@@ -131,6 +131,7 @@ SIGNATURES = {
     "ab_ctx_device": (C.c_int, [_vp]),
     "ab_ctx_launch_count": (C.c_uint64, [_vp]),
     "ab_ctx_synchronize": (C.c_int, [_vp]),
+    "ab_ctx_enable_peer_access": (C.c_int, [_vp, C.c_int]),
     "ab_host_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
     "ab_host_free": (C.c_int, [_vp]),
     "ab_dev_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),

@@ -105,6 +105,26 @@ ab_status ab_ctx_synchronize(ab_ctx *ctx) {
     return AB_OK;
 }
 
+// Peer-memory loads (frame-sharded deep stacks): lets kernels launched on this
+// context's device dereference pointers into `peer_device`'s HBM (NVLink P2P).
+ab_status ab_ctx_enable_peer_access(ab_ctx *ctx, int peer_device) {
+    if (!ctx) return AB_ERR_INVALID;
+    if (peer_device == ctx->device) return AB_OK;
+    DeviceGuard g(ctx->device);
+    int can = 0;
+    AB_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can)
+        return ab_fail(ctx, AB_ERR_UNSUPPORTED, "device %d cannot access device %d memory", ctx->device,
+                       peer_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        (void)cudaGetLastError();
+        return AB_OK;
+    }
+    AB_CUDA(ctx, e);
+    return AB_OK;
+}
+
 ab_status ab_host_alloc(size_t bytes, void **out) {
     if (!out) return AB_ERR_INVALID;
     return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? AB_OK : AB_ERR_NOMEM;

@@ -105,8 +105,8 @@ ab_status ab_ctx_synchronize(ab_ctx *ctx) {
     return AB_OK;
 }
 
-// Peer-memory loads (frame-sharded deep stacks): lets kernels launched on this
-// context's device dereference pointers into `peer_device`'s HBM (NVLink P2P).
+// cudaDeviceEnablePeerAccess for this context's device (groundwork for peer-memory loads in the
+// frame-sharded deep stack; nothing in the library depends on it yet).
 ab_status ab_ctx_enable_peer_access(ab_ctx *ctx, int peer_device) {
     if (!ctx) return AB_ERR_INVALID;
     if (peer_device == ctx->device) return AB_OK;

@@ -162,73 +162,3 @@ def stack_frame_sharded(local_frames, n_frames: int, rows: int, cols: int, confi
                             out.data_ptr(), rej.data_ptr(), stream, ctx)
     allreduce_rejected(rej, group)
     return out, rej, (r0, r1)
-
-
-def map_peer_frames(local_frames, ctx: Context | None = None, group=None):
-    """Map every rank's frame cube into this process (CUDA IPC) and enable peer access to it.
-
-    Returns a list indexed by rank of tensors aliasing that rank's `local_frames` (this rank's own
-    entry is `local_frames` itself).  Their `data_ptr()`s are valid in kernels launched on this
-    rank's device: loads go to the owner's HBM over NVLink.  Keep the list alive while kernels use
-    it, and do not free or rewrite `local_frames` before a barrier."""
-    import torch
-    import torch.distributed as dist
-    from torch.multiprocessing.reductions import reduce_tensor
-
-    ctx = ctx or default_context(local_frames.device.index)
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    if not local_frames.is_contiguous():
-        raise ValueError("local_frames must be contiguous")
-    torch.cuda.synchronize(local_frames.device)  # the frames are complete before anyone maps them
-    gathered = [None] * world
-    dist.all_gather_object(gathered, reduce_tensor(local_frames), group=group)
-    peers = []
-    for r in range(world):
-        if r == rank:
-            peers.append(local_frames)
-            continue
-        rebuild, args = gathered[r]
-        t = rebuild(*args)  # lives on the owner's device, mapped into this process (cudaIpcOpenMemHandle)
-        ctx.check(lib().ab_ctx_enable_peer_access(ctx.handle, t.device.index))
-        peers.append(t)
-    dist.barrier(group)
-    return peers
-
-
-def peer_band_pointers(peers, n_frames: int, rows: int, cols: int, rank: int, world: int):
-    """Device pointers of this rank's row band of every frame, inside the owners' cubes."""
-    r0, r1 = row_band(rows, rank, world)
-    counts = [0] * world
-    ptrs = []
-    for f in range(n_frames):
-        o = frame_owner(f, n_frames, world)
-        t = peers[o]
-        ptrs.append(t.data_ptr() + ((counts[o] * rows + r0) * cols) * t.element_size())
-        counts[o] += 1
-    return ptrs, (r0, r1)
-
-
-def stack_frame_sharded_p2p(peers, n_frames: int, rows: int, cols: int, config, stream: int = 0,
-                            ctx: Context | None = None, group=None, out=None, rej=None):
-    """Config 5 without the staging copy: the stack kernel of each rank reads its row band of every
-    frame straight from the owners' HBM (peer-memory loads over NVLink), so the exchange overlaps
-    the per-pixel work load by load -- one kernel instead of all-to-all + kernel.  `peers` comes
-    from map_peer_frames.  Same results as stack_frame_sharded (the kernel and its inputs are the
-    same, only the addresses differ)."""
-    import torch
-    import torch.distributed as dist
-
-    from .core import stack_images_device
-
-    ctx = ctx or default_context()
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    ptrs, (r0, r1) = peer_band_pointers(peers, n_frames, rows, cols, rank, world)
-    dev = peers[rank].device
-    if out is None:
-        out = torch.empty((r1 - r0, cols), dtype=torch.float32, device=dev)
-    if rej is None:
-        rej = torch.zeros(1, dtype=torch.int64, device=dev)
-    if r1 > r0:
-        stack_images_device(ptrs, out.numel(), config, out.data_ptr(), rej.data_ptr(), stream, ctx)
-    allreduce_rejected(rej, group)
-    return out, rej, (r0, r1)

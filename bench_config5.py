@@ -33,8 +33,6 @@ def main():
     ap.add_argument("--cols", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--check-rows", type=int, default=4)
-    ap.add_argument("--p2p", action="store_true",
-                    help="no staging copy: the kernel loads its band from the owners' HBM over NVLink")
     args = ap.parse_args()
 
     import torch
@@ -73,16 +71,10 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     ptrs = [cube[f].data_ptr() for f in range(n)]
 
-    if args.p2p:
-        del cube
-        peers = parallel.map_peer_frames(local_frames)
-        ptrs, _ = parallel.peer_band_pointers(peers, n, rows, cols, rank, world)
-
     def step(ev=None):
         if ev:
             ev[0].record()
-        if not args.p2p:
-            parallel.reshard_frames_to_bands(local_frames, n, rows, cols, out=cube)
+        parallel.reshard_frames_to_bands(local_frames, n, rows, cols, out=cube)
         if ev:
             ev[1].record()
         ab.stack_images_device(ptrs, out.numel(), cfg, out.data_ptr(), rej.data_ptr(), stream, ctx)
@@ -122,18 +114,13 @@ def main():
         print(json.dumps({
             "metric": "Mpix/s sigma-clip deep stack, frames sharded (config 5)", "n_gpus": world,
             "config": {"workload": f"{n}-frame sigma-clip stack, {rows}x{cols} f32, {n // world} frames per GPU, "
-                                   + ("peer-memory loads in the stack kernel (no staging copy)" if args.p2p else
-                                      "re-shard to row bands + exact kernel") + " + rejected all-reduce"},
+                                   "re-shard to row bands + exact kernel + rejected all-reduce"},
             "ms_reshard": float(best[0]), "ms_stack": float(best[1]), "ms_total": float(best[2]),
             "value": npix / (best[2] * 1e-3) / 1e6, "unit": "Mpix/s",
-            "nvlink_gbs_per_gpu_per_direction": (sent / ((best[1] if args.p2p else best[0]) * 1e-3) / 1e9
-                                                 if world > 1 else None),
+            "nvlink_gbs_per_gpu_per_direction": sent / (best[0] * 1e-3) / 1e9 if world > 1 else None,
             "stack_gbs_per_gpu": (n + 1) * (r1 - r0) * cols * 4 / (best[1] * 1e-3) / 1e9,
             "rejected_pixels": int(rej.item()), "steps": args.steps,
             "matches_oracle_on_sample": ok, "timing": "CUDA events, max over ranks, best of steps"}))
-    if args.p2p:  # consumers release the mapped cubes before any producer exits
-        del peers
-    torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
 

@@ -159,10 +159,10 @@ int ab_ctx_device(ab_ctx *ctx);
 /* number of kernel launches issued through this context since creation */
 uint64_t ab_ctx_launch_count(ab_ctx *ctx);
 ab_status ab_ctx_synchronize(ab_ctx *ctx);
-/* Peer-memory loads: afterwards kernels of this context may read device pointers that live in
- * `peer_device`'s HBM (NVLink P2P) -- the frame-sharded deep stack reads its row band of every
- * frame from the owners' memory instead of re-sharding first.  AB_ERR_UNSUPPORTED when the two
- * GPUs are not P2P-capable. */
+/* cudaDeviceEnablePeerAccess from this context's device to `peer_device` (idempotent;
+ * AB_ERR_UNSUPPORTED when the two GPUs are not P2P-capable).  Groundwork for reading a
+ * frame-sharded stack's row bands straight from the owners' HBM instead of re-sharding first
+ * (not wired in yet -- the r1 attempt through CUDA-IPC-mapped cubes faulted). */
 ab_status ab_ctx_enable_peer_access(ab_ctx *ctx, int peer_device);
 
 /* pinned host memory, so host-buffer entry points overlap copies with kernels */

@@ -1,0 +1,77 @@
+"""GPU side of the real-data golden fixtures (tests/golden/): the CUDA path, through the C ABI, on the
+committed HST M16 crops against the committed vectors -- FITS decode, image statistics, auto-STF,
+STF u8 preview, star detection, and the linked-STF -> SCNR -> RGB8 compose tail.
+
+These fixtures were added after round 1's GPU budget was spent, so this file has not run on a B200
+yet: the tests are marked xfail(strict=False) until a GPU run confirms them (an unexpected pass is
+reported as XPASS and is the expected outcome -- every operator involved is already bit-exact
+against the oracle on synthetic inputs)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="new in r1 after the GPU budget ended: unconfirmed on B200")]
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+sys.path.insert(0, GOLD)
+
+
+@pytest.fixture(scope="module")
+def crops():
+    import astroburst_b200 as ab
+    import make_golden as mg
+
+    out = []
+    for name in mg.CHANNELS:
+        raw = np.frombuffer(open(os.path.join(GOLD, f"m16_{name}_crop{mg.N}.bef32"), "rb").read(), np.uint8)
+        out.append(ab.fits.decode_pixels(raw, -32).reshape(mg.N, mg.N))
+    return out
+
+
+def test_fits_decode_of_the_real_data_units(crops):
+    import make_golden as mg
+
+    for name, c in zip(mg.CHANNELS, crops):
+        raw = open(os.path.join(GOLD, f"m16_{name}_crop{mg.N}.bef32"), "rb").read()
+        assert np.array_equal(c, np.frombuffer(raw, ">f4").astype(np.float32).reshape(mg.N, mg.N))
+
+
+def test_stats_stf_and_stars_match_golden(crops):
+    import astroburst_b200 as ab
+    import make_golden as mg
+
+    gold = np.load(os.path.join(GOLD, "m16_golden.npz"))
+    im, al = ab.imaging, ab.alignment
+    for name, c in zip(mg.CHANNELS, crops):
+        st = im.compute_image_stats(c)
+        want = gold[f"stats_{name}"]
+        assert (st.min, st.max, st.median, st.mad, st.sigma, float(st.valid_count)) == tuple(want[[0, 1, 2, 3, 4, 6]])
+        assert abs(st.mean - want[5]) <= 1e-12 * abs(want[5])          # f64 sum order
+        stf = im.auto_stf(st)
+        assert np.allclose([stf.shadow, stf.midtone, stf.highlight], gold[f"stf_{name}"], rtol=1e-12, atol=0)
+        # the u8 preview with the GOLDEN parameters (so a mean-order ulp cannot leak into it)
+        gst = im.ImageStats(*want[:6], int(want[6]))
+        gstf = im.StfParams(*gold[f"stf_{name}"])
+        assert np.array_equal(im.apply_stf(c, gstf, gst), gold[f"u8_{name}"])
+        det = al.detect_stars(c, 5.0)
+        assert (det.background_median, det.background_sigma) == tuple(gold[f"bg_{name}"])
+        got = np.array([[s["x"], s["y"], s["flux"], s["fwhm"], s["eccentricity"], s["peak"], float(s["npix"]),
+                         s["snr"]] for s in det.stars], np.float64).reshape(-1, 8)
+        assert np.array_equal(got, gold[f"stars_{name}"])
+
+
+def test_compose_tail_matches_golden(crops):
+    import astroburst_b200 as ab
+
+    gold = np.load(os.path.join(GOLD, "m16_golden.npz"))
+    im, pv = ab.imaging, ab.preview
+    ls = gold["linked_stats"]
+    comb = im.ImageStats(*ls[:6], int(ls[6]))
+    lstf = im.StfParams(*gold["linked_stf"])
+    r, g, b = im.apply_tone_composite(crops[2], crops[1], crops[0], [lstf] * 3, [comb] * 3,
+                                      scnr=("average", 0.5, False))
+    rgb8 = pv.render_rgb(r, g, b)
+    diff = np.abs(rgb8.astype(np.int16) - gold["rgb8"].astype(np.int16))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3   # u8 truncation of an f32 ulp, if any

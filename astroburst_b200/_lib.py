@@ -132,6 +132,8 @@ SIGNATURES = {
     "ab_ctx_launch_count": (C.c_uint64, [_vp]),
     "ab_ctx_synchronize": (C.c_int, [_vp]),
     "ab_ctx_enable_peer_access": (C.c_int, [_vp, C.c_int]),
+    "ab_ipc_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "ab_ipc_close": (C.c_int, [_vp, _vp]),
     "ab_host_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
     "ab_host_free": (C.c_int, [_vp]),
     "ab_dev_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),

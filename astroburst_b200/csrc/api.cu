@@ -125,6 +125,28 @@ ab_status ab_ctx_enable_peer_access(ab_ctx *ctx, int peer_device) {
     return AB_OK;
 }
 
+// CUDA IPC import under THIS context's device: cudaIpcMemLazyEnablePeerAccess makes the runtime
+// set up peer access to the exporting GPU, so kernels of this context can load from the mapping.
+// (Opening the handle under the exporter's device -- what torch's tensor rebuild does -- and then
+// dereferencing it from another GPU faulted in r1)
+ab_status ab_ipc_open(ab_ctx *ctx, const void *handle64, void **dev_ptr) {
+    if (!ctx || !handle64 || !dev_ptr) return AB_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(&h, handle64, sizeof(h));
+    *dev_ptr = nullptr;
+    AB_CUDA(ctx, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return AB_OK;
+}
+ab_status ab_ipc_close(ab_ctx *ctx, void *dev_ptr) {
+    if (!ctx) return AB_ERR_INVALID;
+    if (!dev_ptr) return AB_OK;
+    DeviceGuard g(ctx->device);
+    AB_CUDA(ctx, cudaIpcCloseMemHandle(dev_ptr));
+    return AB_OK;
+}
+
 ab_status ab_host_alloc(size_t bytes, void **out) {
     if (!out) return AB_ERR_INVALID;
     return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? AB_OK : AB_ERR_NOMEM;

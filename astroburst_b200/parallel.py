@@ -162,3 +162,101 @@ def stack_frame_sharded(local_frames, n_frames: int, rows: int, cols: int, confi
                             out.data_ptr(), rej.data_ptr(), stream, ctx)
     allreduce_rejected(rej, group)
     return out, rej, (r0, r1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Peer-memory variant of the frame-sharded stack -- NOT CONFIRMED ON HARDWARE.
+# r1's first attempt mapped the peers' cubes with torch's tensor rebuild (which opens the IPC handle
+# under the OWNER's device) and faulted when another GPU dereferenced the mapping.  This version
+# opens the handles itself under the CONSUMER's device (ab_ipc_open, lazy peer access).  The
+# staged path above (reshard_frames_to_bands + stack) is the validated one.
+class PeerCubes:
+    """Base device pointers of every rank's frame cube, addressable from this rank's device."""
+
+    def __init__(self, local_frames, ctx: Context | None = None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.ctx = ctx or default_context(local_frames.device.index)
+        self.local = local_frames  # keeps the exported allocation alive
+        self.group = group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if not local_frames.is_contiguous():
+            raise ValueError("local_frames must be contiguous")
+        torch.cuda.synchronize(local_frames.device)  # the frames are complete before anyone maps them
+        shared = local_frames.untyped_storage()._share_cuda_()  # (device, handle, size, offset, ...)
+        handle, seg_offset = bytes(shared[1]), int(shared[3])
+        offset = seg_offset + local_frames.storage_offset() * local_frames.element_size()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (handle, offset), group=group)
+        self._opened = []
+        self.base = []
+        for r in range(world):
+            if r == rank:
+                self.base.append(local_frames.data_ptr())
+                continue
+            h, off = gathered[r]
+            # torch >= 2.5 prefixes the 64 handle bytes with (version, kind): kind 'c' = cudaMalloc block
+            if len(h) == 66 and h[1:2] == b"c":
+                h = h[2:]
+            if len(h) != 64:
+                raise RuntimeError(f"unsupported CUDA IPC handle ({len(h)} bytes, prefix {h[:2]!r}): "
+                                   "expandable segments are not mappable with cudaIpcOpenMemHandle")
+            p = C.c_void_p()
+            self.ctx.check(lib().ab_ipc_open(self.ctx.handle, h, C.byref(p)))
+            self._opened.append(p)
+            self.base.append(int(p.value) + off)
+        dist.barrier(group)
+
+    def band_pointers(self, n_frames: int, rows: int, cols: int, elem: int = 4):
+        """This rank's row band of every frame, inside the owners' cubes -> (pointers, (r0, r1))."""
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        return band_pointers_in_cubes(self.base, n_frames, rows, cols, rank, world, elem)
+
+    def close(self):
+        """Unmap the peers' cubes (every rank, before any owner frees its frames)."""
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize(self.local.device)
+        for p in self._opened:
+            self.ctx.check(lib().ab_ipc_close(self.ctx.handle, p))
+        self._opened = []
+        dist.barrier(self.group)
+
+
+def band_pointers_in_cubes(bases, n_frames: int, rows: int, cols: int, rank: int, world: int, elem: int = 4):
+    """Pointer arithmetic of the peer-memory stack: frame f's band of `rank` starts at its owner's
+    cube base + ((index of f among the owner's frames) * rows + r0) * cols elements."""
+    r0, r1 = row_band(rows, rank, world)
+    counts = [0] * world
+    ptrs = []
+    for f in range(n_frames):
+        o = frame_owner(f, n_frames, world)
+        ptrs.append(int(bases[o]) + ((counts[o] * rows + r0) * cols) * elem)
+        counts[o] += 1
+    return ptrs, (r0, r1)
+
+
+def stack_frame_sharded_p2p(cubes: PeerCubes, n_frames: int, rows: int, cols: int, config, stream: int = 0,
+                            group=None, out=None, rej=None):
+    """Config 5 without the staging copy (UNCONFIRMED, see above): each rank's stack kernel reads its
+    row band of every frame straight from the owners' HBM, so the NVLink transfer overlaps the
+    per-pixel work load by load -- one kernel instead of all-to-all + kernel.  Same kernel and same
+    samples as stack_frame_sharded, only the addresses differ."""
+    import torch
+
+    from .core import stack_images_device
+
+    ptrs, (r0, r1) = cubes.band_pointers(n_frames, rows, cols)
+    dev = cubes.local.device
+    if out is None:
+        out = torch.empty((r1 - r0, cols), dtype=torch.float32, device=dev)
+    if rej is None:
+        rej = torch.zeros(1, dtype=torch.int64, device=dev)
+    if r1 > r0:
+        stack_images_device(ptrs, out.numel(), config, out.data_ptr(), rej.data_ptr(), stream, cubes.ctx)
+    allreduce_rejected(rej, group)
+    return out, rej, (r0, r1)

@@ -33,6 +33,9 @@ def main():
     ap.add_argument("--cols", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--check-rows", type=int, default=4)
+    ap.add_argument("--p2p", action="store_true",
+                    help="UNCONFIRMED: no staging copy, the kernel loads its band from the owners' HBM "
+                         "(parallel.PeerCubes); the default staged path is the validated one")
     args = ap.parse_args()
 
     import torch
@@ -71,10 +74,16 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     ptrs = [cube[f].data_ptr() for f in range(n)]
 
+    cubes = None
+    if args.p2p:
+        cubes = parallel.PeerCubes(local_frames, ctx)
+        ptrs, _ = cubes.band_pointers(n, rows, cols)
+
     def step(ev=None):
         if ev:
             ev[0].record()
-        parallel.reshard_frames_to_bands(local_frames, n, rows, cols, out=cube)
+        if cubes is None:
+            parallel.reshard_frames_to_bands(local_frames, n, rows, cols, out=cube)
         if ev:
             ev[1].record()
         ab.stack_images_device(ptrs, out.numel(), cfg, out.data_ptr(), rej.data_ptr(), stream, ctx)
@@ -114,13 +123,16 @@ def main():
         print(json.dumps({
             "metric": "Mpix/s sigma-clip deep stack, frames sharded (config 5)", "n_gpus": world,
             "config": {"workload": f"{n}-frame sigma-clip stack, {rows}x{cols} f32, {n // world} frames per GPU, "
-                                   "re-shard to row bands + exact kernel + rejected all-reduce"},
+                                   + ("peer-memory loads in the stack kernel (no staging copy)" if args.p2p else
+                                      "re-shard to row bands + exact kernel") + " + rejected all-reduce"},
             "ms_reshard": float(best[0]), "ms_stack": float(best[1]), "ms_total": float(best[2]),
             "value": npix / (best[2] * 1e-3) / 1e6, "unit": "Mpix/s",
             "nvlink_gbs_per_gpu_per_direction": sent / (best[0] * 1e-3) / 1e9 if world > 1 else None,
             "stack_gbs_per_gpu": (n + 1) * (r1 - r0) * cols * 4 / (best[1] * 1e-3) / 1e9,
             "rejected_pixels": int(rej.item()), "steps": args.steps,
             "matches_oracle_on_sample": ok, "timing": "CUDA events, max over ranks, best of steps"}))
+    if cubes is not None:
+        cubes.close()
     dist.barrier()
     dist.destroy_process_group()
 

@@ -162,8 +162,14 @@ ab_status ab_ctx_synchronize(ab_ctx *ctx);
 /* cudaDeviceEnablePeerAccess from this context's device to `peer_device` (idempotent;
  * AB_ERR_UNSUPPORTED when the two GPUs are not P2P-capable).  Groundwork for reading a
  * frame-sharded stack's row bands straight from the owners' HBM instead of re-sharding first
- * (not wired in yet -- the r1 attempt through CUDA-IPC-mapped cubes faulted). */
+ * (used together with ab_ipc_open, unconfirmed on hardware). */
 ab_status ab_ctx_enable_peer_access(ab_ctx *ctx, int peer_device);
+/* CUDA IPC import of another process's allocation (64 handle bytes from cudaIpcGetMemHandle) under
+ * this context's device, with lazy peer access to the exporting GPU; ab_ipc_close unmaps it.
+ * Used by the peer-memory variant of the frame-sharded deep stack, which is
+ * NOT yet confirmed on hardware. */
+ab_status ab_ipc_open(ab_ctx *ctx, const void *handle64, void **dev_ptr);
+ab_status ab_ipc_close(ab_ctx *ctx, void *dev_ptr);
 
 /* pinned host memory, so host-buffer entry points overlap copies with kernels */
 ab_status ab_host_alloc(size_t bytes, void **out);

@@ -106,3 +106,63 @@ def test_sharded_equals_single_gpu(orc):
         assert (out[0][key][2], out[0][key][3], out[1][key][2], out[1][key][3]) == (0, 32, 32, 64)
         assert np.array_equal(got, want_img)
         assert out[0][key][1] == out[1][key][1] == want_rej
+
+
+def _p2p_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import astroburst_b200 as ab
+    from astroburst_b200 import parallel, synth
+
+    ctx = ab.default_context(rank)
+    s = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for key, nf in (("fs16", 16), ("fs40", 40)):
+        fr = synth.stack_frames(nf, 64, 512, seed=11, nan_border=3)
+        mine = [f for f in range(nf) if parallel.frame_owner(f, nf, world) == rank]
+        local = torch.from_numpy(np.ascontiguousarray(fr[mine])).to(dev)
+        cubes = parallel.PeerCubes(local, ctx)
+        band, rj, _ = parallel.stack_frame_sharded_p2p(cubes, nf, 64, 512, ab.StackConfig(3.0, 3.0, 5, False), s)
+        torch.cuda.synchronize()
+        res[key] = (band.cpu().numpy(), int(rj))
+        cubes.close()
+    q.put((rank, res))
+    dist.destroy_process_group()
+
+
+@pytest.mark.xfail(strict=False, reason="peer-memory stack: re-designed after r1's GPU budget ended, unconfirmed on B200")
+def test_frame_sharded_stack_with_peer_memory_loads(orc):
+    """The frame-sharded stack reading its row bands straight from the owners' HBM (no staging copy)
+    equals the oracle, register and deep paths."""
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from astroburst_b200 import synth
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_p2p_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        out = dict(q.get(timeout=90) for _ in procs)
+    finally:
+        for p in procs:
+            p.join(timeout=20)
+            if p.is_alive():
+                p.kill()
+    for key, nf in (("fs16", 16), ("fs40", 40)):
+        fr = synth.stack_frames(nf, 64, 512, seed=11, nan_border=3)
+        want_img, want_rej = orc.stack_images(list(fr), 3.0, 3.0, 5)
+        got = np.concatenate([out[0][key][0], out[1][key][0]])
+        assert np.array_equal(got, want_img)
+        assert out[0][key][1] == out[1][key][1] == want_rej

@@ -138,3 +138,22 @@ def test_reshard_frames_to_bands_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(out[0]) and all(out[1]), out
+
+
+def test_band_pointers_in_cubes():
+    """Pointer arithmetic of the peer-memory stack, checked on CPU tensors (data_ptr is plain)."""
+    from astroburst_b200.parallel import band_pointers_in_cubes, frame_owner, row_band
+
+    n_frames, rows, cols, world = 10, 7, 5, 3
+    owners = [frame_owner(f, n_frames, world) for f in range(n_frames)]
+    cubes = [torch.zeros((owners.count(r), rows, cols), dtype=torch.float32) for r in range(world)]
+    bases = [c.data_ptr() for c in cubes]
+    for rank in range(world):
+        ptrs, (r0, r1) = band_pointers_in_cubes(bases, n_frames, rows, cols, rank, world)
+        assert (r0, r1) == row_band(rows, rank, world) and len(ptrs) == n_frames
+        seen = [0] * world
+        for f, p in enumerate(ptrs):
+            o = owners[f]
+            if r1 > r0:
+                assert p == cubes[o][seen[o], r0].data_ptr()
+            seen[o] += 1

@@ -11,6 +11,11 @@
 //   core/imaging/masked_stretch.rs:59-258  masked_stretch_with_mask, compute_luminance,
 //                                      normalize_to_01, compute_masked_median, mtf_balance, apply_mtf
 //
+// PARITY PINNING: the reference holds unit tests for lrgb.rs only (ported in
+// tests/test_oracle_kat.py::test_lrgb_reference_unit_tests).  star_mask.rs, masked_stretch.rs and
+// the render helpers have no tests and no golden vectors: for those this restatement is checked
+// against numpy restatements of their closed-form parts and is otherwise "parity unpinned".
+//
 // Build with -ffp-contract=off (Rust never fuses mul+add).
 #include <algorithm>
 #include <cmath>

@@ -93,3 +93,112 @@ def test_oracle_stack_images_against_python_restatement(orc):
                 wrej += k
         got, grej = orc.stack_images(list(frames), 3.0, 3.0, 5)
         assert grej == wrej and np.array_equal(got, want), (n_frames, shape)
+
+
+# ---- image statistics, histogram path (core/imaging/stats.rs:75-210, helpers :212-353), restated with
+# numpy array operations (bincount / cumsum / searchsorted) instead of the oracle's scalar loops
+BINS = 65536
+
+
+def _as_usize(x):
+    """Rust `f64 as usize` for arrays: truncation toward zero, negatives and NaN -> 0."""
+    x = np.nan_to_num(x, nan=0.0)
+    return np.clip(x, 0.0, 1.8e19).astype(np.uint64)
+
+
+def _pct_bin(hist, total, pct):
+    target = np.uint64(math.ceil(total * pct))
+    cum = np.cumsum(hist, dtype=np.uint64)
+    i = int(np.searchsorted(cum, target, side="left"))               # first cum >= target
+    return (i if i < len(hist) else len(hist) - 1), cum, target
+
+
+def _interp(hist, total, pct, lo, width):
+    target = np.uint64(math.ceil(total * pct))
+    cum = np.cumsum(hist, dtype=np.uint64)
+    i = int(np.searchsorted(cum, target, side="left"))
+    if i >= len(hist):
+        return lo + len(hist) * width
+    over = int(cum[i] - target)
+    frac = 1.0 - over / float(hist[i]) if hist[i] > 0 else 0.5
+    return lo + (i + frac) * width
+
+
+def _rank(hist, rank, lo, width):
+    if rank == 0:
+        return lo
+    cum = np.cumsum(hist, dtype=np.uint64)
+    i = int(np.searchsorted(cum, np.uint64(rank), side="left"))
+    if i >= len(hist):
+        return lo + len(hist) * width
+    over = int(cum[i]) - int(rank)
+    frac = 1.0 - over / float(hist[i]) if hist[i] > 0 else 0.5
+    return lo + (i + frac) * width
+
+
+def np_stats_hist(data, known=None):
+    v = np.asarray(data, np.float32).reshape(-1)
+    v = v[np.isfinite(v) & (v > np.float32(1e-7))]
+    if v.size == 0:
+        return None
+    vf = v.astype(np.float64)
+    gmin, gmax = (float(vf.min()), float(vf.max())) if known is None else known
+    rng_ = max(gmax - gmin, 1e-30)
+    bw, inv = rng_ / BINS, BINS / rng_
+    hist = np.bincount(np.minimum(_as_usize((vf - gmin) * inv), BINS - 1).astype(np.int64), minlength=BINS)
+    total = int(v.size)
+    half = int(math.ceil(total * 0.5))
+    mbin, cum, _ = _pct_bin(hist, total, 0.5)
+    before = int(cum[mbin - 1]) if mbin > 0 else 0
+    mlo = gmin + mbin * bw
+    mhi = mlo + bw
+    coarse = _interp(hist, total, 0.5, gmin, bw)
+    rrange = max(mhi - mlo, 1e-30)
+    rinv = BINS / rrange
+    inbin = (vf >= mlo) & (vf < mhi)
+    refine = np.bincount(np.minimum(_as_usize((vf[inbin] - mlo) * rinv), BINS - 1).astype(np.int64), minlength=BINS)
+    d = np.abs(v - np.float32(coarse))                               # f32 subtraction
+    dev = np.bincount(np.minimum(_as_usize(d.astype(np.float64) * inv), BINS - 1).astype(np.int64), minlength=BINS)
+    median = _rank(refine, max(half - before, 0), mlo, rrange / BINS)
+    madbin, _, _ = _pct_bin(dev, total, 0.5)
+    elo, ehi = max(madbin - 1, 0), min(madbin + 2, BINS)
+    rlo, rhi = elo * bw, ehi * bw
+    mrange = max(rhi - rlo, 1e-30)
+    minv = BINS / mrange
+    dd = np.abs(v - np.float32(median))
+    below = int((dd < np.float32(rlo)).sum())
+    sel = (dd >= np.float32(rlo)) & (dd < np.float32(rhi))
+    mref = np.bincount(np.minimum(_as_usize((dd[sel].astype(np.float64) - rlo) * minv), BINS - 1).astype(np.int64),
+                       minlength=BINS)
+    mad = _rank(mref, max(half - below, 0), rlo, mrange / BINS)
+    return dict(min=gmin, max=gmax, median=median, mad=mad, sigma=max(mad * 1.4826, 1e-30), n=total,
+                mean=math.fsum(vf.tolist()) / total)
+
+
+def test_oracle_hist_stats_against_numpy_restatement(orc):
+    rng = np.random.default_rng(11)
+    cases = []
+    sky = rng.normal(1000.0, 12.0, (300, 400))
+    sky.reshape(-1)[rng.integers(0, sky.size, 300)] += rng.uniform(100, 40000, 300)
+    sky[:8] = 0.0
+    sky[20, 20] = np.nan
+    cases.append(sky.astype(np.float32))
+    cases.append(rng.uniform(1.0, 3000.0, (257, 129)).astype(np.float32))
+    cases.append(np.full((64, 64), 5.0, np.float32))                 # zero range
+    two = np.where(rng.random((100, 100)) < 0.5, 10.0, 20.0).astype(np.float32)
+    cases.append(two)                                                # two-valued: empty median bins
+    cases.append((rng.exponential(50.0, (200, 200)) + 1e-3).astype(np.float32))
+    for img in cases:
+        want = np_stats_hist(img)
+        got = orc.compute_image_stats_hist(img)
+        assert (got.min, got.max, got.valid_count) == (want["min"], want["max"], want["n"])
+        assert got.median == want["median"] and got.mad == want["mad"] and got.sigma == want["sigma"]
+        assert abs(got.mean - want["mean"]) <= 1e-12 * abs(want["mean"])
+        kr = (float(want["min"]) - 3.0, float(want["max"]) * 1.5)
+        w2 = np_stats_hist(img, known=kr)
+        g2 = orc.compute_image_stats_with_known_range(np.tile(img, (8, 8)), *kr) if img.size * 64 > 4000000 else None
+        if g2 is not None:                                           # the known-range form switches at 4 M px
+            t2 = np_stats_hist(np.tile(img, (8, 8)), known=kr)
+            assert (g2.median, g2.mad, g2.valid_count) == (t2["median"], t2["mad"], t2["n"])
+        assert w2 is not None
+    assert orc.compute_image_stats_hist(np.zeros((10, 10), np.float32)).valid_count == 0

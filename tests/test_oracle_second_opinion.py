@@ -202,3 +202,127 @@ def test_oracle_hist_stats_against_numpy_restatement(orc):
             assert (g2.median, g2.mad, g2.valid_count) == (t2["median"], t2["mad"], t2["n"])
         assert w2 is not None
     assert orc.compute_image_stats_hist(np.zeros((10, 10), np.float32)).valid_count == 0
+
+
+# ---- tile background and star detection (core/analysis/star_detection.rs:32-258, math/sigma_clip.rs,
+# math/median.rs) restated with numpy medians and scipy connected components.  Moment sums run in
+# raster order here and in BFS order in the reference/oracle, so star parameters are compared to
+# 1e-12 relative; counts, npix, ordering and the background are exact.
+def np_sigma_clipped_stats(vals, kappa=3.0, iterations=2):
+    v = np.asarray(vals, np.float32)
+
+    def med64(a):                                                    # exact_median_mut: even n -> f64 mean of the two middle f32
+        s = np.sort(a)
+        n = s.size
+        return float(s[n // 2]) if n % 2 else (float(s[n // 2 - 1]) + float(s[n // 2])) / 2.0
+
+    def mad32(a, median):                                            # devs cast to f32, median_f32_mut averages in f32
+        d = np.sort(np.abs(a.astype(np.float64) - median).astype(np.float32))
+        n = d.size
+        return float(d[n // 2]) if n % 2 else float(np.float32((d[n // 2 - 1] + d[n // 2]) / np.float32(2.0)))
+
+    for _ in range(iterations):
+        if v.size < 3:
+            break
+        median = med64(v)
+        sig = max(mad32(v, median) * 1.4826, 1e-30)
+        lo, hi = np.float32(median - kappa * sig), np.float32(median + kappa * sig)
+        v = v[(v >= lo) & (v <= hi)]
+    if v.size == 0:
+        return 0.0, 1.0
+    median = med64(v)
+    return median, max(mad32(v, median) * 1.4826, 1e-30)
+
+
+def np_estimate_background(img, tile):
+    rows, cols = img.shape
+    step = max(tile, 16)
+    meds, sigs = [], []
+    for y in range(0, rows, step):
+        for x in range(0, cols, step):
+            t = img[y:y + step, x:x + step].reshape(-1)
+            t = t[np.isfinite(t) & (t > np.float32(1e-7))]
+            if t.size >= 8:
+                m, s = np_sigma_clipped_stats(t)
+                meds.append(m)
+                sigs.append(s)
+    if not meds:
+        return 0.0, 1.0
+    meds.sort()
+    sigs.sort()
+    return meds[len(meds) // 2], max(sigs[len(sigs) // 2], 1e-10)
+
+
+def np_detect_stars(img, sigma_threshold):
+    from scipy import ndimage
+
+    rows, cols = img.shape
+    tile = min(max(min(rows, cols) // 8, 32), 256)
+    bg, sg = np_estimate_background(img, tile)
+    thr = bg + sigma_threshold * sg
+    fg = np.isfinite(img) & (img.astype(np.float64) > thr)
+    lab, n = ndimage.label(fg, structure=np.ones((3, 3), int))
+    stars = []
+    for k in range(1, n + 1):
+        rr, cc = np.nonzero(lab == k)                                # raster order
+        interior = (rr >= 1) & (rr < rows - 1) & (cc >= 1) & (cc < cols - 1)
+        if not interior.any():                                       # never seeded (seeds are interior pixels)
+            continue
+        seed = int(np.flatnonzero(interior)[0])
+        npix = rr.size
+        if npix < 3 or npix > 5000:
+            continue
+        w = np.maximum(img[rr, cc].astype(np.float64) - bg, 0.0)
+        flux = float(w.sum())
+        if flux <= 0.0:
+            continue
+        cx, cy = float((cc * w).sum() / flux), float((rr * w).sum() / flux)
+        dx, dy = cc - cx, rr - cy
+        fwhm = math.sqrt(float(((dx * dx + dy * dy) * w).sum()) / (2.0 * flux)) * 2.3548200450309493
+        if fwhm < 0.5 or fwhm > 30.0:
+            continue
+        ixx, iyy, ixy = float((dx * dx * w).sum() / flux), float((dy * dy * w).sum() / flux), float((dx * dy * w).sum() / flux)
+        tr = ixx + iyy
+        det = max(ixx * iyy - ixy * ixy, 0.0)
+        disc = math.sqrt(max(tr * tr / 4.0 - det, 0.0))
+        l1, l2 = tr / 2.0 + disc, max(tr / 2.0 - disc, 0.0)
+        ecc = min(max(math.sqrt(1.0 - l2 / l1), 0.0), 1.0) if l1 > 1e-15 else 0.0
+        peak = float(w.max())
+        order = (int(rr[seed]), int(cc[seed]))                       # discovery order = raster order of seeds
+        stars.append((order, dict(x=cx, y=cy, flux=flux, fwhm=fwhm, eccentricity=ecc, peak=peak, npix=int(npix),
+                                  snr=peak / sg if sg > 2.220446049250313e-16 else 0.0)))
+    stars.sort(key=lambda t: t[0])
+    stars = [s for _, s in stars]
+    stars.sort(key=lambda s: -s["flux"])                             # stable, like sort_by
+    kept = []
+    for s in stars:                                                  # greedy 3-px dedup (any kept star within 3 px)
+        if all((s["x"] - t["x"]) ** 2 + (s["y"] - t["y"]) ** 2 >= 9.0 for t in kept):
+            kept.append(s)
+    return kept, bg, sg
+
+
+def test_oracle_background_and_detection_against_numpy_scipy_restatement(orc):
+    rng = np.random.default_rng(3)
+    for shape, n_stars in (((200, 260), 40), ((333, 257), 90)):
+        img = rng.normal(100.0, 3.0, shape)
+        for _ in range(n_stars):
+            x, y = rng.uniform(-3, shape[1] + 3), rng.uniform(-3, shape[0] + 3)
+            f = 300.0 * (100.0 ** rng.uniform(0, 1))
+            yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+            img += f / (2 * np.pi * 1.6 ** 2) * np.exp(-((xx - x) ** 2 + (yy - y) ** 2) / (2 * 1.6 ** 2))
+        img = img.astype(np.float32)
+        img[:6, :] = 0.0                                             # padding, excluded from the background
+        img[50, 60] = np.nan
+        img[70:74, 80:86] += 4000.0                                  # a blob touching nothing
+        img[120:123, 0:2] += 4000.0                                  # a component on the image edge
+        for tile in (32, 64):
+            assert orc.estimate_background(img, tile) == np_estimate_background(img, tile)
+        want, bg, sg = np_detect_stars(img, 4.0)
+        got = orc.detect_stars(img, 4.0)
+        assert (got.background_median, got.background_sigma) == (bg, sg)
+        assert len(got.stars) == len(want) and len(want) > 10
+        for g, w in zip(got.stars, want):
+            assert g["npix"] == w["npix"]
+            for key in ("x", "y", "flux", "fwhm", "peak", "snr"):
+                assert abs(g[key] - w[key]) <= 1e-12 * max(abs(w[key]), 1.0), key
+            assert abs(g["eccentricity"] - w["eccentricity"]) <= 1e-9

@@ -326,3 +326,75 @@ def test_oracle_background_and_detection_against_numpy_scipy_restatement(orc):
             for key in ("x", "y", "flux", "fwhm", "peak", "snr"):
                 assert abs(g[key] - w[key]) <= 1e-12 * max(abs(w[key]), 1.0), key
             assert abs(g["eccentricity"] - w["eccentricity"]) <= 1e-9
+
+
+# ---- Catmull-Rom bicubic gathers (imaging/sampling.rs:4-13,51-80, boundary.rs:8-20) and their three
+# callers (alignment/affine.rs:663-690 warp_image, stacking/align.rs:36-57 shift_image_subpixel,
+# imaging/resample.rs:25-61 resample_image), restated as whole-array numpy f64 arithmetic in the
+# reference's evaluation order: bit-identical pixels expected.
+def _cr(t):
+    a = np.abs(t)
+    return np.where(a <= 1.0, a * a * (1.5 * a - 2.5) + 1.0,
+                    np.where(a <= 2.0, a * (a * (2.5 - 0.5 * a) - 4.0) + 2.0, 0.0))
+
+
+def np_bicubic(img, sy, sx):
+    rows, cols = img.shape
+    ix, iy = np.floor(sx), np.floor(sy)
+    fx, fy = sx - ix, sy - iy
+    ix, iy = ix.astype(np.int64), iy.astype(np.int64)
+    wx = [_cr(fx + 1.0), _cr(fx), _cr(fx - 1.0), _cr(fx - 2.0)]
+    val = np.zeros(sx.shape, np.float64)
+    for j in range(4):
+        r = np.clip(iy + j - 1, 0, rows - 1)
+        row_val = np.zeros(sx.shape, np.float64)
+        for i in range(4):
+            c = np.clip(ix + i - 1, 0, cols - 1)
+            row_val = row_val + img[r, c].astype(np.float64) * wx[i]
+        val = val + row_val * _cr(fy - float(j - 1))
+    return val.astype(np.float32)
+
+
+def np_warp(img, t, out_rows, out_cols):
+    a, b, tx, c, d, ty = t
+    y, x = np.mgrid[0:out_rows, 0:out_cols].astype(np.float64)
+    sx, sy = a * x + b * y + tx, c * x + d * y + ty
+    ok = (sx >= 0.0) & (sy >= 0.0) & (sx < img.shape[1] - 1) & (sy < img.shape[0] - 1)
+    out = np.zeros((out_rows, out_cols), np.float32)
+    out[ok] = np_bicubic(img, sy[ok], sx[ok])
+    return out
+
+
+def np_shift(img, dy, dx):
+    if abs(dy) < 1e-12 and abs(dx) < 1e-12:
+        return img.copy()
+    rows, cols = img.shape
+    y, x = np.mgrid[0:rows, 0:cols].astype(np.float64)
+    sy, sx = y + dy, x + dx
+    skip = (sy < -0.5) | (sy > rows - 0.5) | (sx < -0.5) | (sx > cols - 0.5)
+    out = np.zeros(img.shape, np.float32)
+    out[~skip] = np_bicubic(img, sy[~skip], sx[~skip])
+    return out
+
+
+def np_resample(img, tr, tc):
+    if (tr, tc) == img.shape:
+        return img.copy()
+    sy_, sx_ = img.shape[0] / tr, img.shape[1] / tc
+    ty, tx = np.mgrid[0:tr, 0:tc].astype(np.float64)
+    return np_bicubic(img, ty * sy_ + (sy_ - 1.0) * 0.5, tx * sx_ + (sx_ - 1.0) * 0.5)
+
+
+def test_oracle_bicubic_gathers_against_numpy_restatement(orc):
+    rng = np.random.default_rng(9)
+    img = rng.normal(500.0, 40.0, (97, 131)).astype(np.float32)
+    th = math.radians(2.3)
+    for t in ((1, 0, 0, 0, 1, 0), (1, 0, 4.5, 0, 1, -2.25),
+              (1.01 * math.cos(th), -math.sin(th), 7.3, math.sin(th), 0.99 * math.cos(th), -3.9),
+              (0.5, 0, 0.25, 0, 0.5, 0.75), (1, 0, 500.0, 0, 1, 500.0)):
+        for shape in ((97, 131), (60, 200)):
+            assert np.array_equal(orc.warp_image(img, t, *shape), np_warp(img, t, *shape)), (t, shape)
+    for dy, dx in ((0.0, 0.0), (0.5, -0.5), (3.25, 7.75), (-120.0, 2.0), (0.3, 130.6), (1e-13, 0.0)):
+        assert np.array_equal(orc.shift_image_subpixel(img, dy, dx), np_shift(img, dy, dx)), (dy, dx)
+    for tr, tc in ((97, 131), (48, 65), (194, 262), (33, 400), (1, 1)):
+        assert np.array_equal(orc.resample_image(img, tr, tc), np_resample(img, tr, tc)), (tr, tc)

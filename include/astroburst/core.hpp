@@ -166,6 +166,31 @@ inline std::vector<uint8_t> apply_stf(const Context &ctx, const Image &img, cons
     ctx.check(ab_apply_stf_u8(ctx.get(), img.data.data(), img.data.size(), &p, &st, out.data()));
     return out;
 }
+// The pixel chain of apply_tone_composite_cmd (cmd/processing/curves.rs:111-151) in one sweep:
+// STF -> levels -> curves (three 4096-entry LUTs or none) -> SCNR.  r, g, b are updated in place.
+struct ToneChain {
+    StfParams stf[3];
+    ImageStats stats[3];
+    ab_levels_params levels[3] = {{0.0, 1.0, 1.0}, {0.0, 1.0, 1.0}, {0.0, 1.0, 1.0}};
+    const std::vector<float> *lut[3] = {nullptr, nullptr, nullptr};
+    bool apply_scnr = false;
+    ab_scnr_config scnr{0, 1.0f, 0};
+};
+inline void apply_tone_composite(const Context &ctx, Image &r, Image &g, Image &b, const ToneChain &t) {
+    if (g.data.size() != r.data.size() || b.data.size() != r.data.size())
+        throw Error(AB_ERR_INVALID, "channel dimension mismatch");
+    ab_tone_chain c{};
+    for (int k = 0; k < 3; ++k) {
+        c.stf[k] = t.stf[k];
+        c.stats[k] = t.stats[k];
+        c.levels[k] = t.levels[k];
+        c.lut[k] = t.lut[k] ? t.lut[k]->data() : nullptr;
+    }
+    c.apply_scnr = t.apply_scnr ? 1 : 0;
+    c.scnr = t.scnr;
+    ctx.check(ab_tone_composite(ctx.get(), r.data.data(), g.data.data(), b.data.data(), r.data.size(), &c,
+                                r.data.data(), g.data.data(), b.data.data()));
+}
 }  // namespace imaging
 
 namespace alignment {

@@ -20,7 +20,9 @@ def test_headers_compile_and_link():
         cpp = os.path.join(td, "t.cpp")
         open(cpp, "w").write(
             '#include "astroburst/core.hpp"\n'
-            "int main(){ using namespace astroburst; try { Context c; } catch (const Error&) { return 0; }\n"
+            "int main(){ using namespace astroburst; try { Context c; Image r(2, 2), g(2, 2), b(2, 2);\n"
+            " core::imaging::ToneChain t; core::imaging::apply_tone_composite(c, r, g, b, t);\n"
+            " core::preview::masked_stretch(c, r); } catch (const Error&) { return 0; }\n"
             " return 0; }\n")
         subprocess.check_call(["g++", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), cpp, "-o",
                                os.path.join(td, "tcpp"), so, f"-Wl,-rpath,{os.path.dirname(so)}"])

@@ -398,3 +398,62 @@ def test_oracle_bicubic_gathers_against_numpy_restatement(orc):
         assert np.array_equal(orc.shift_image_subpixel(img, dy, dx), np_shift(img, dy, dx)), (dy, dx)
     for tr, tc in ((97, 131), (48, 65), (194, 262), (33, 400), (1, 1)):
         assert np.array_equal(orc.resample_image(img, tr, tc), np_resample(img, tr, tc)), (tr, tc)
+
+
+# ---- triangle matching (core/alignment/affine.rs:279-398) restated with numpy broadcasting.  The
+# reference sorts the vote pairs by votes only (HashMap order breaks ties); the oracle and the CUDA
+# path break ties by (ref, tgt) index -- the restatement does the same, so lists compare exactly.
+def np_match_stars(ref, tgt, tol=0.02, min_side=15.0, min_votes=1):
+    def tris(p):
+        p = np.asarray(p, np.float64)[:60]
+        n = len(p)
+        out = []
+        for i in range(n):
+            for j in range(i + 1, n):
+                for k in range(j + 1, n):
+                    d = lambda a, b: math.sqrt((a[0] - b[0]) ** 2 + (a[1] - b[1]) ** 2)  # affine.rs:659-661
+                    dij, djk, dik = d(p[i], p[j]), d(p[j], p[k]), d(p[i], p[k])
+                    s = sorted((dij, djk, dik))
+                    if s[0] < min_side:
+                        continue
+                    # vertices ordered by the length of the OPPOSITE side (stable)
+                    verts = sorted(((i, djk), (j, dik), (k, dij)), key=lambda t: t[1])
+                    out.append((s[1] / s[0], s[2] / s[0], [v[0] for v in verts]))
+        return out
+
+    rt, tt = tris(ref), tris(tgt)
+    if not rt or not tt:
+        return np.zeros((0, 4))
+    rm, rl = np.array([t[0] for t in rt]), np.array([t[1] for t in rt])
+    tm, tl = np.array([t[0] for t in tt]), np.array([t[1] for t in tt])
+    rv, tv = np.array([t[2] for t in rt]), np.array([t[2] for t in tt])
+    votes = np.zeros((len(ref), len(tgt)), np.int64)
+    for a in range(len(rt)):
+        hit = np.flatnonzero(~((np.abs(rm[a] - tm) > tol) | (np.abs(rl[a] - tl) > tol)))
+        for p in range(3):
+            np.add.at(votes, (rv[a, p], tv[hit, p]), 1)
+    pairs = [(int(votes[r, t]), r, t) for r in range(votes.shape[0]) for t in range(votes.shape[1]) if votes[r, t]]
+    pairs.sort(key=lambda x: (-x[0], x[1], x[2]))
+    used_r, used_t, out = set(), set(), []
+    for v, r, t in pairs:
+        if v < min_votes:
+            break
+        if r in used_r or t in used_t:
+            continue
+        used_r.add(r)
+        used_t.add(t)
+        out.append((ref[r][0], ref[r][1], tgt[t][0], tgt[t][1]))
+    return np.array(out, np.float64).reshape(-1, 4)
+
+
+def test_oracle_triangle_matching_against_numpy_restatement(orc):
+    rng = np.random.default_rng(17)
+    ref = rng.uniform(40, 960, (18, 2))
+    th = math.radians(3.0)
+    A = np.array([[1.02 * math.cos(th), -math.sin(th)], [math.sin(th), 0.98 * math.cos(th)]])
+    tgt = (ref @ A.T + np.array([15.0, -9.0]) + rng.normal(0, 0.05, ref.shape))[rng.permutation(18)][:15]
+    tgt = np.vstack([tgt, rng.uniform(40, 960, (3, 2))])             # strays
+    want = np_match_stars(ref, tgt)
+    got = orc.match_stars(ref, tgt, max_matches=256)
+    assert len(want) >= 10 and got.shape == want.shape and np.array_equal(got, want)
+    assert orc.match_stars(ref[:2], tgt).shape[0] == 0              # fewer than 3 stars: no triangles

@@ -457,3 +457,93 @@ def test_oracle_triangle_matching_against_numpy_restatement(orc):
     got = orc.match_stars(ref, tgt, max_matches=256)
     assert len(want) >= 10 and got.shape == want.shape and np.array_equal(got, want)
     assert orc.match_stars(ref[:2], tgt).shape[0] == 0              # fewer than 3 stars: no triangles
+
+
+# ---- the colour chain's pointwise operators as whole-array numpy arithmetic in the reference's
+# evaluation order and precision (f64 for STF, f32 for blend / SCNR): bit-identical results expected.
+def np_auto_stf(st, target_bg=0.25, shadow_k=-2.8):                  # stf.rs:13-47
+    if st.valid_count == 0:
+        return 0.0, 0.5, 1.0
+    rng_ = max(st.max - st.min, 1e-30)
+    med_n, sig_n = (st.median - st.min) / rng_, st.sigma / rng_
+    shadow = min(max(med_n + shadow_k * sig_n, 0.0), 0.98)
+    clip = max(1.0 - shadow, 1e-15)
+    m = min(max((med_n - shadow) / clip, 0.0), 1.0)
+    if m <= 0.0 or m >= 1.0:
+        mid = 0.5
+    else:
+        den = 2.0 * target_bg * m - target_bg - m
+        mid = 0.5 if abs(den) < 1e-15 else min(max(m * (target_bg - 1.0) / den, 0.0001), 0.9999)
+    return shadow, mid, 1.0
+
+
+def np_apply_stf(v, stf, st, as_u8):                                 # stf.rs:50-120
+    shadow, mid, hi = stf
+    valid = np.isfinite(v) & (v > np.float32(1e-7))
+    x = v.astype(np.float64)
+    norm = (x - st.min) * (1.0 / max(st.max - st.min, 1e-30))
+    c = np.clip((norm - shadow) * (1.0 / max(hi - shadow, 1e-15)), 0.0, 1.0)
+    with np.errstate(all="ignore"):
+        y = np.where(c <= 0.0, 0.0, np.where(c >= 1.0, 1.0, (mid - 1.0) * c / ((2.0 * mid - 1.0) * c - mid)))
+    if as_u8:
+        q = y * 255.0
+        q = np.clip(np.sign(q) * np.floor(np.abs(q) + 0.5), 0.0, 255.0)   # f64::round: half away from zero
+        return np.where(valid, np.nan_to_num(q), 0.0).astype(np.uint8)
+    return np.where(valid, y, 0.0).astype(np.float32)
+
+
+def np_scnr(r, g, b, method, amount, preserve):                      # scnr.rs:5-53
+    amount = np.float32(min(max(amount, 0.0), 1.0))
+    if amount < np.float32(1e-7):
+        return r, g, b
+    limit = (r + b) * np.float32(0.5) if method == "average" else np.maximum(r, b)
+    g_new = g + amount * (np.minimum(g, limit) - g)
+    delta = g - g_new
+    inv_rb = np.float32(1.0) / (np.float32(0.2126) + np.float32(0.0722))
+    boost = (np.float32(0.7152) * delta) * inv_rb
+    do = preserve & (delta > np.float32(1e-10)) & (r <= 1.0) & (b <= 1.0)
+    r2 = np.where(do, np.minimum(r + boost, np.float32(1.0)), r)
+    b2 = np.where(do, np.minimum(b + boost, np.float32(1.0)), b)
+    return r2.astype(np.float32), g_new.astype(np.float32), b2.astype(np.float32)
+
+
+def test_oracle_colour_chain_against_numpy_restatement(orc):
+    rng = np.random.default_rng(23)
+    chans = []
+    for k in range(3):
+        c = rng.normal(900.0 + 120 * k, 25.0, (120, 150))
+        c.reshape(-1)[rng.integers(0, c.size, 60)] += rng.uniform(200, 30000, 60)
+        c = c.astype(np.float32)
+        c[:4] = 0.0
+        c[10, 10], c[11, 11], c[12, 12] = np.nan, np.inf, -7.0
+        chans.append(c)
+    # blend: rv += v * w in weight order, f32, unfused (channel_blend.rs:45-63)
+    w = [(0, 0.8, 0.1, 0.0), (1, 0.2, 0.7, 0.15), (2, 0.0, 0.2, 0.85), (5, 1.0, 1.0, 1.0)]
+    want = [np.zeros((120, 150), np.float32) for _ in range(3)]
+    for ci, rw, gw, bw in w:
+        if ci >= len(chans):
+            continue
+        with np.errstate(invalid="ignore"):                      # inf * 0 weight -> NaN, as in the reference
+            for o, wt in zip(want, (rw, gw, bw)):
+                o += chans[ci] * np.float32(wt)
+    got = orc.blend_channels(chans, w, 120, 150)
+    for x, y in zip(got, want):
+        assert np.array_equal(x, y, equal_nan=True)
+    # stats -> auto-STF -> u8 and f32 stretch
+    for c in chans:
+        st = orc.compute_image_stats(c)
+        p = orc.auto_stf(st)
+        assert (p.shadow, p.midtone, p.highlight) == np_auto_stf(st)
+        stf = (p.shadow, p.midtone, p.highlight)
+        assert np.array_equal(orc.apply_stf(c, p, st), np_apply_stf(c, stf, st, True))
+        assert np.array_equal(orc.apply_stf_f32(c, p, st), np_apply_stf(c, stf, st, False))
+    # SCNR on stretched planes
+    st = [orc.compute_image_stats(c) for c in chans]
+    planes = [orc.apply_stf_f32(c, orc.auto_stf(s), s) for c, s in zip(chans, st)]
+    planes[0][5, 5] = 1.5                                             # r > 1 blocks the luminance boost
+    for method in ("average", "maximum"):
+        for amount, preserve in ((1.0, False), (0.5, True), (1e-9, True), (3.0, True)):
+            a = [p.copy() for p in planes]
+            orc.apply_scnr_inplace(*a, method, amount, preserve)
+            for x, y in zip(a, np_scnr(*planes, method, amount, preserve)):
+                assert np.array_equal(x, y), (method, amount, preserve)

@@ -547,3 +547,43 @@ def test_oracle_colour_chain_against_numpy_restatement(orc):
             orc.apply_scnr_inplace(*a, method, amount, preserve)
             for x, y in zip(a, np_scnr(*planes, method, amount, preserve)):
                 assert np.array_equal(x, y), (method, amount, preserve)
+
+
+# ---- exact statistics path (stats.rs:43-73, median.rs:27-73) and build/downsample_histogram
+# (stats.rs:378-444) with numpy sort / bincount / reduceat.
+def test_oracle_exact_stats_and_histogram_against_numpy_restatement(orc):
+    rng = np.random.default_rng(31)
+    for n in (1, 2, 7, 1000, 1001):
+        v = rng.normal(800.0, 30.0, n).astype(np.float32)
+        if n > 5:
+            v[:2] = [0.0, np.nan]
+        ok = v[np.isfinite(v) & (v > np.float32(1e-7))]
+        got = orc.compute_image_stats_exact(v)
+        if ok.size == 0:
+            assert got.valid_count == 0
+            continue
+        s = np.sort(ok)
+        m = s.size // 2
+        med = float(s[m]) if s.size % 2 else (float(s[m - 1]) + float(s[m])) / 2.0
+        d = np.sort(np.abs(ok - np.float32(med)))                    # f32 deviations about the f32 median
+        mad = float(d[m]) if d.size % 2 else float(np.float32((d[m - 1] + d[m]) / np.float32(2.0)))
+        assert (got.min, got.max, got.median, got.mad, got.valid_count) == (float(s[0]), float(s[-1]), med, mad, s.size)
+        assert got.sigma == max(mad * 1.4826, 1e-30)
+        assert abs(got.mean - math.fsum(ok.astype(np.float64).tolist()) / s.size) <= 1e-12 * abs(got.mean)
+    img = rng.normal(1000.0, 15.0, (200, 300)).astype(np.float32)
+    img[:3] = 0.0
+    img[9, 9] = np.inf
+    ok = img[np.isfinite(img) & (img > np.float32(1e-7))].astype(np.float64)
+    lo, hi = float(ok.min()), float(ok.max())
+    bins, edges = orc.build_histogram(img, 65536, lo, hi)
+    idx = np.minimum(((ok - lo) * (65536 / (hi - lo))).astype(np.int64), 65535)
+    assert np.array_equal(bins, np.bincount(idx, minlength=65536).astype(np.uint32))
+    assert np.array_equal(edges, lo + np.arange(65537, dtype=np.float64) * ((hi - lo) / 65536))
+    z, ez = orc.build_histogram(img, 65536, 5.0, 5.0)                # range < 1e-10: zeros, flat edges
+    assert not z.any() and np.all(ez == 5.0)
+    for target in (512, 100, 3):
+        ratio = 65536 / target
+        starts = (np.arange(target) * ratio).astype(np.int64)
+        ends = np.minimum(((np.arange(target) + 1) * ratio).astype(np.int64), 65536)
+        want = np.array([min(int(bins[a:b].astype(np.uint64).sum()), 2 ** 32 - 1) for a, b in zip(starts, ends)], np.uint32)
+        assert np.array_equal(orc.downsample_histogram(bins, target), want)

@@ -587,3 +587,80 @@ def test_oracle_exact_stats_and_histogram_against_numpy_restatement(orc):
         ends = np.minimum(((np.arange(target) + 1) * ratio).astype(np.int64), 65536)
         want = np.array([min(int(bins[a:b].astype(np.uint64).sum()), 2 ** 32 - 1) for a, b in zip(starts, ends)], np.uint32)
         assert np.array_equal(orc.downsample_histogram(bins, target), want)
+
+
+# ---- levels and the monotone-spline tone curve (core/imaging/curves.rs:17-208) in scalar Python
+def py_spline_lut(points):
+    pts = sorted(((float(x), float(y)) for x, y in points), key=lambda p: p[0])      # stable, like sort_by
+    ded = []
+    for p in pts:                                                    # dedup_by keeps the first of a run
+        if ded and abs(p[0] - ded[-1][0]) < 1e-9:
+            continue
+        ded.append(p)
+    pts = ded
+    if not pts or pts[0][0] > 1e-6:
+        pts.insert(0, (0.0, 0.0))
+    if pts[-1][0] < 1.0 - 1e-6:
+        pts.append((1.0, 1.0))
+    n = len(pts)
+    sgn = lambda v: math.copysign(1.0, v)                            # f64::signum: +0 -> 1, -0 -> -1
+    if n == 2:
+        m = [(pts[1][1] - pts[0][1]) / max(pts[1][0] - pts[0][0], 1e-15)] * 2
+    else:
+        dx = [max(pts[i + 1][0] - pts[i][0], 1e-15) for i in range(n - 1)]
+        sl = [(pts[i + 1][1] - pts[i][1]) / dx[i] for i in range(n - 1)]
+        m = [0.0] * n
+        m[0], m[-1] = sl[0], sl[-1]
+        for i in range(1, n - 1):
+            m[i] = 0.0 if sgn(sl[i - 1]) != sgn(sl[i]) else (sl[i - 1] + sl[i]) * 0.5
+        for i in range(n - 1):
+            if abs(sl[i]) < 1e-15:
+                m[i] = m[i + 1] = 0.0
+                continue
+            a, b = m[i] / sl[i], m[i + 1] / sl[i]
+            tau = a * a + b * b
+            if tau > 9.0:
+                s = 3.0 / math.sqrt(tau)
+                m[i], m[i + 1] = s * a * sl[i], s * b * sl[i]
+
+    def ev(x):
+        if x <= pts[0][0]:
+            return pts[0][1]
+        if x >= pts[-1][0]:
+            return pts[-1][1]
+        seg = 0
+        for i in range(1, n):
+            if x < pts[i][0]:
+                seg = i - 1
+                break
+        d = max(pts[seg + 1][0] - pts[seg][0], 1e-15)
+        t = (x - pts[seg][0]) / d
+        t2 = t * t
+        t3 = t2 * t
+        return ((2.0 * t3 - 3.0 * t2 + 1.0) * pts[seg][1] + (t3 - 2.0 * t2 + t) * d * m[seg]
+                + (-2.0 * t3 + 3.0 * t2) * pts[seg + 1][1] + (t3 - t2) * d * m[seg + 1])
+
+    return np.array([np.float32(min(max(ev(i / 4095.0), 0.0), 1.0)) for i in range(4096)], np.float32)
+
+
+def test_oracle_levels_and_curves_against_python_restatement(orc):
+    for pts in ([], [(0.0, 0.0), (1.0, 1.0)], [(0.0, 0.0), (0.25, 0.15), (0.5, 0.5), (0.75, 0.85), (1.0, 1.0)],
+                [(0.3, 0.1), (0.7, 0.9)], [(0.5, 0.5), (0.5, 0.6), (0.2, 0.9)], [(0.1, 0.9), (0.9, 0.1)],
+                [(0.0, 0.2), (0.4, 0.2), (0.6, 0.8), (1.0, 0.8)]):
+        assert np.array_equal(orc.spline_lut(pts), py_spline_lut(pts)), pts
+    rng = np.random.default_rng(41)
+    u = rng.uniform(-0.2, 1.4, (90, 110)).astype(np.float32)
+    u[0, 0], u[0, 1] = np.nan, np.inf
+    lut = orc.spline_lut([(0.0, 0.0), (0.25, 0.15), (0.5, 0.5), (0.75, 0.85), (1.0, 1.0)])
+    bad = ~np.isfinite(u) | (u < 0)
+    idx = np.minimum((np.clip(np.nan_to_num(u), 0.0, 1.0).astype(np.float32) * np.float32(4095.0)).astype(np.int64), 4095)
+    assert np.array_equal(orc.apply_curve(u, lut), np.where(bad, np.float32(0.0), lut[idx]))
+    for black, gamma, white in ((0.0, 1.0, 1.0), (0.2, 1.0, 1.0), (0.05, 2.0, 0.9), (0.1, 100.0, 0.1), (0.0, 0.001, 1.0)):
+        got = orc.apply_levels(u, black, gamma, white)
+        if abs(black) < 1e-7 and abs(gamma - 1.0) < 1e-7 and abs(white - 1.0) < 1e-7:
+            assert np.array_equal(got, u, equal_nan=True)            # identity short-circuit returns a clone
+            continue
+        inv_r, inv_g = 1.0 / max(white - black, 1e-15), 1.0 / min(max(gamma, 0.01), 10.0)
+        norm = np.clip((np.nan_to_num(u).astype(np.float64) - black) * inv_r, 0.0, 1.0)
+        want = np.where(bad, np.float32(0.0), np.array([math.pow(x, inv_g) for x in norm.reshape(-1)]).reshape(u.shape).astype(np.float32))
+        assert np.array_equal(got, want)

@@ -664,3 +664,135 @@ def test_oracle_levels_and_curves_against_python_restatement(orc):
         norm = np.clip((np.nan_to_num(u).astype(np.float64) - black) * inv_r, 0.0, 1.0)
         want = np.where(bad, np.float32(0.0), np.array([math.pow(x, inv_g) for x in norm.reshape(-1)]).reshape(u.shape).astype(np.float32))
         assert np.array_equal(got, want)
+
+
+# ---- RANSAC and the two fits (core/alignment/affine.rs:400-657) in scalar Python: xorshift64 streams
+# seeded per emulated rayon thread, least-squares affine via Cramer's rule, closed-form rigid fit.
+M64 = (1 << 64) - 1
+
+
+def py_fit_affine(ms):
+    if len(ms) < 3:
+        return None
+
+    def solve(which):
+        ata = [[0.0] * 3 for _ in range(3)]
+        atb = [0.0] * 3
+        for rx, ry, tx, ty in ms:
+            row, target = (rx, ry, 1.0), (tx if which == 0 else ty)
+            for i in range(3):
+                for j in range(3):
+                    ata[i][j] += row[i] * row[j]
+                atb[i] += row[i] * target
+        a = ata
+        det = (a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0])
+               + a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]))
+        if abs(det) < 1e-12:
+            return None
+        d = 1.0 / det
+        inv = [[(a[1][1] * a[2][2] - a[1][2] * a[2][1]) * d, (a[0][2] * a[2][1] - a[0][1] * a[2][2]) * d,
+                (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * d],
+               [(a[1][2] * a[2][0] - a[1][0] * a[2][2]) * d, (a[0][0] * a[2][2] - a[0][2] * a[2][0]) * d,
+                (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * d],
+               [(a[1][0] * a[2][1] - a[1][1] * a[2][0]) * d, (a[0][1] * a[2][0] - a[0][0] * a[2][1]) * d,
+                (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * d]]
+        return [inv[i][0] * atb[0] + inv[i][1] * atb[1] + inv[i][2] * atb[2] for i in range(3)]
+
+    x, y = solve(0), solve(1)
+    if x is None or y is None:
+        return None
+    return (x[0], x[1], x[2], y[0], y[1], y[2])
+
+
+def py_fit_rigid(ms):
+    n = len(ms)
+    if n < 2:
+        return None
+    rcx = rcy = tcx = tcy = 0.0
+    for rx, ry, tx, ty in ms:
+        rcx += rx
+        rcy += ry
+        tcx += tx
+        tcy += ty
+    rcx, rcy, tcx, tcy = rcx / n, rcy / n, tcx / n, tcy / n
+    num = den = 0.0
+    for rx, ry, tx, ty in ms:
+        drx, dry, dtx, dty = rx - rcx, ry - rcy, tx - tcx, ty - tcy
+        num += drx * dty - dry * dtx
+        den += drx * dtx + dry * dty
+    th = math.atan2(num, den)
+    c, s = math.cos(th), math.sin(th)
+    return (c, -s, tcx - c * rcx + s * rcy, s, c, tcy - s * rcx - c * rcy)
+
+
+def py_ransac(ms, method, n_threads):
+    n = len(ms)
+    k = 3 if method == "affine" else 2
+    if n < k:
+        return None
+    fit = py_fit_affine if method == "affine" else py_fit_rigid
+    chunk = (2000 + n_threads - 1) // n_threads
+    best = (0, (1.0, 0.0, 0.0, 0.0, 1.0, 0.0), [False] * n)
+    for tid in range(n_threads):
+        state = (0xDEADBEEFCAFEBABE + tid * 0x9E3779B97F4A7C15) & M64
+        lb, lt, lm = 0, best[1], [False] * n
+        for _ in range(chunk):
+            sample, attempts = [], 0
+            while len(sample) < k and attempts < 20:
+                state ^= (state << 13) & M64
+                state ^= state >> 7
+                state ^= (state << 17) & M64
+                idx = state % n
+                if idx not in sample:
+                    sample.append(idx)
+                attempts += 1
+            if len(sample) < k:
+                continue
+            t = fit([ms[i] for i in sample])
+            if t is None:
+                continue
+            mask = [math.sqrt((t[0] * rx + t[1] * ry + t[2] - tx) ** 2 + (t[3] * rx + t[4] * ry + t[5] - ty) ** 2) < 3.0
+                    for rx, ry, tx, ty in ms]
+            inl = sum(mask)
+            if inl > lb:
+                lb, lt, lm = inl, t, mask
+        if tid == 0 or lb > best[0]:                                 # reduce_with keeps the first maximum
+            best = (lb, lt, lm)
+    bi, bt, bm = best
+    if bi < 4 or bi / n < 0.20:
+        return None
+    inl = [m for m, keep in zip(ms, bm) if keep]
+    ref = fit(inl) or bt
+    res = 0.0                                                        # plain sequential f64 adds (Python >= 3.12's
+    for rx, ry, tx, ty in inl:                                       # sum() is compensated, the reference's is not)
+        res += math.sqrt((ref[0] * rx + ref[1] * ry + ref[2] - tx) ** 2 + (ref[3] * rx + ref[4] * ry + ref[5] - ty) ** 2)
+    res /= len(inl)
+    if res > 5.0:
+        return None
+    return ref, n, bi, res
+
+
+def test_oracle_ransac_and_fits_against_python_restatement(orc):
+    rng = np.random.default_rng(5)
+    ref = rng.uniform(50, 950, (40, 2))
+    th = math.radians(2.0)
+    A = np.array([[1.01 * math.cos(th), -math.sin(th)], [math.sin(th), 0.99 * math.cos(th)]])
+    tgt = ref @ A.T + np.array([20.0, -11.5]) + rng.normal(0, 0.1, ref.shape)
+    tgt[:9] = rng.uniform(50, 950, (9, 2))                           # outliers
+    m = np.hstack([ref, tgt])
+    ms = [tuple(float(v) for v in row) for row in m]
+    fa, fr = orc.fit_affine(m[10:]), orc.fit_rigid(m[10:])
+    assert fa.as_tuple() == py_fit_affine(ms[10:]) and fr.as_tuple() == py_fit_rigid(ms[10:])
+    for deg in (np.tile(m[:1], (5, 1)), np.array([[0, 0, 1, 1], [1, 1, 2, 2], [2, 2, 3, 3]], np.float64)):  # collinear
+        a, b = orc.fit_affine(deg), py_fit_affine([tuple(map(float, r)) for r in deg])
+        assert (a is None) == (b is None) and (a is None or a.as_tuple() == b)
+    assert orc.fit_affine(np.array([[0, 0, 1, 1], [1, 1, 2, 2], [2, 2, 3, 3]], np.float64)) is None   # det < 1e-12
+    for method in ("affine", "rigid"):
+        for threads in (1, 8):
+            got, want = orc.ransac(m, method, threads), py_ransac(ms, method, threads)
+            assert (got is None) == (want is None)
+            if got is not None:
+                assert got.transform.as_tuple() == want[0]
+                assert (got.matched_stars, got.inliers, got.residual_px) == want[1:]
+    junk = np.hstack([rng.uniform(0, 1000, (30, 2)), rng.uniform(0, 1000, (30, 2))])
+    assert (orc.ransac(junk, "affine", 8) is None) == (py_ransac([tuple(map(float, r)) for r in junk], "affine", 8) is None)

@@ -132,6 +132,7 @@ SIGNATURES = {
     "ab_ctx_launch_count": (C.c_uint64, [_vp]),
     "ab_ctx_synchronize": (C.c_int, [_vp]),
     "ab_ctx_enable_peer_access": (C.c_int, [_vp, C.c_int]),
+    "ab_ipc_export": (C.c_int, [_vp, _vp, _vp]),
     "ab_ipc_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "ab_ipc_close": (C.c_int, [_vp, _vp]),
     "ab_host_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
@@ -146,6 +147,13 @@ SIGNATURES = {
                                           C.POINTER(StackConfigC), _vp, _vp, _vp]),
     "ab_sigma_clip_combine": (C.c_int, [_vp, _vp, _sz, C.c_float, C.c_float, C.c_uint32,
                                         C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    # frame-sharded stacks over peer memory
+    "ab_row_band": (None, [_sz, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "ab_frame_owner": (C.c_int, [_sz, _sz, C.c_int]),
+    "ab_stack_frame_sharded_dev": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int, _sz, _sz, _sz,
+                                             C.POINTER(StackConfigC), _vp, C.POINTER(_vp), C.c_int, _vp]),
+    "ab_reshard_frames_to_bands_dev": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int, _sz, _sz, _sz,
+                                                 _vp, _vp]),
     # phase correlation / aligned stack
     "ab_phase_correlate": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp]),
     "ab_phase_correlate_dev": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp]),

@@ -37,10 +37,15 @@ struct ab_ctx {
     static constexpr unsigned WORK_COUNTERS = 256;
     unsigned *d_work_counters = nullptr;
     std::atomic<unsigned> work_seq{0};
-    std::mutex mu;
+    // Calls on one context serialize on `mu`.  Recursive: host-buffer entry points hold it while
+    // they call the _dev entry points, which take it themselves (they share d_small, the phase
+    // correlation state and the scratch slots with every other call on the context).
+    std::recursive_mutex mu;
+    std::mutex err_mu;  // last_error is also written by argument checks that run before `mu`
     std::atomic<uint64_t> launches{0};
     std::string last_error;
 };
+using CtxLock = std::lock_guard<std::recursive_mutex>;
 
 inline ab_status ab_fail(ab_ctx *ctx, ab_status st, const char *fmt, ...) {
     char buf[512];
@@ -48,7 +53,10 @@ inline ab_status ab_fail(ab_ctx *ctx, ab_status st, const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    if (ctx) ctx->last_error = buf;
+    if (ctx) {
+        std::lock_guard<std::mutex> lk(ctx->err_mu);
+        ctx->last_error = buf;
+    }
     return st;
 }
 

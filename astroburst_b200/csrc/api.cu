@@ -105,8 +105,8 @@ ab_status ab_ctx_synchronize(ab_ctx *ctx) {
     return AB_OK;
 }
 
-// cudaDeviceEnablePeerAccess for this context's device (groundwork for peer-memory loads in the
-// frame-sharded deep stack; nothing in the library depends on it yet).
+// cudaDeviceEnablePeerAccess for this context's device (several GPUs driven from one process;
+// across processes ab_ipc_open's lazy peer access does it).
 ab_status ab_ctx_enable_peer_access(ab_ctx *ctx, int peer_device) {
     if (!ctx) return AB_ERR_INVALID;
     if (peer_device == ctx->device) return AB_OK;
@@ -126,9 +126,8 @@ ab_status ab_ctx_enable_peer_access(ab_ctx *ctx, int peer_device) {
 }
 
 // CUDA IPC import under THIS context's device: cudaIpcMemLazyEnablePeerAccess makes the runtime
-// set up peer access to the exporting GPU, so kernels of this context can load from the mapping.
-// (Opening the handle under the exporter's device -- what torch's tensor rebuild does -- and then
-// dereferencing it from another GPU faulted in r1)
+// set up peer access to the exporting GPU, so kernels of this context can load from the mapping
+// (shard.cu: frame-sharded stacks read the owners' HBM over NVLink).
 ab_status ab_ipc_open(ab_ctx *ctx, const void *handle64, void **dev_ptr) {
     if (!ctx || !handle64 || !dev_ptr) return AB_ERR_INVALID;
     DeviceGuard g(ctx->device);
@@ -206,7 +205,7 @@ ab_status ab_stack_sigma_clip_dev(ab_ctx *ctx, const float *const *d_frames, siz
     ab_status st = check_stack_args(ctx, d_frames, n_frames, cfg, d_out);
     if (st != AB_OK) return st;
     if (!d_rejected) return ab_fail(ctx, AB_ERR_INVALID, "null d_rejected");
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     FrameTable ft;
     for (size_t f = 0; f < n_frames; ++f) {
@@ -231,7 +230,7 @@ ab_status ab_stack_sigma_clip(ab_ctx *ctx, const float *const *frames, size_t n_
         if (!frames[f]) return ab_fail(ctx, AB_ERR_INVALID, "null frame pointer %zu", f);
     if (cfg->align)
         return ab_stack_images(ctx, frames, n_frames, rows, cols, cfg, out, rejected_pixels, nullptr);
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     if (rejected_pixels) *rejected_pixels = 0;
     const size_t npix = rows * cols;
@@ -304,7 +303,7 @@ ab_status ab_stack_images(ab_ctx *ctx, const float *const *frames, size_t n_fram
         ab_stack_config c = *cfg;
         return ab_stack_sigma_clip(ctx, frames, n_frames, rows, cols, &c, out, rejected_pixels);
     }
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     if (rejected_pixels) *rejected_pixels = 0;
     const size_t npix = rows * cols;
@@ -362,7 +361,7 @@ ab_status ab_sigma_clip_combine(ab_ctx *ctx, const float *values, size_t n, floa
     *rejected_out = 0;
     if (n == 0) return AB_OK;  // combine.rs:21-23
     if (!values) return ab_fail(ctx, AB_ERR_INVALID, "null values");
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     // layout in d_small: [0,8) counter | [64, 64+4) out | [8192, ...) values
     char *d = static_cast<char *>(ctx->d_small);

@@ -136,6 +136,7 @@ ab_status ab_median_combine_dev(ab_ctx *ctx, const float *const *d_frames, size_
         return ab_fail(ctx, AB_ERR_UNSUPPORTED, "n_frames %zu > AB_MAX_FRAMES %d", n_frames,
                        AB_MAX_FRAMES);
     if (npix == 0) return AB_OK;
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     FrameTable ft;
     for (size_t f = 0; f < AB_MAX_FRAMES; ++f) ft.p[f] = f < n_frames ? d_frames[f] : nullptr;
@@ -164,7 +165,7 @@ ab_status ab_median_combine(ab_ctx *ctx, const float *const *frames, size_t n_fr
         if (!frames[f]) return ab_fail(ctx, AB_ERR_INVALID, "null frame pointer %zu", f);
     const size_t npix = rows * cols;
     if (npix == 0) return AB_OK;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     // row bands of ~96 MiB of input, copies of band b+1 overlap the kernel of band b
     const size_t planes = n_frames + 1 + (bias ? 1 : 0) + (dark ? 1 : 0);
@@ -215,6 +216,7 @@ ab_status ab_median_combine(ab_ctx *ctx, const float *const *frames, size_t n_fr
 ab_status ab_normalize_flat_dev(ab_ctx *ctx, float *d_data, size_t len, void *stream) {
     if (!ctx || (len && !d_data)) return AB_ERR_INVALID;
     if (len == 0) return AB_OK;
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     return normalize_flat_on(ctx, d_data, len, (cudaStream_t)stream);
 }
@@ -222,7 +224,7 @@ ab_status ab_normalize_flat_dev(ab_ctx *ctx, float *d_data, size_t len, void *st
 ab_status ab_normalize_flat(ab_ctx *ctx, float *data, size_t len) {
     if (!ctx || (len && !data)) return AB_ERR_INVALID;
     if (len == 0) return AB_OK;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     ab_status st = ab_scratch_reserve(ctx, 0, len * sizeof(float));
     if (st != AB_OK) return st;
@@ -239,6 +241,7 @@ ab_status ab_calibrate_image_dev(ab_ctx *ctx, const float *d_raw, size_t len,
                                  const ab_calibration_config *cfg, float *d_out, void *stream) {
     if (!ctx || !cfg || (len && (!d_raw || !d_out))) return AB_ERR_INVALID;
     if (len == 0) return AB_OK;
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     calibrate_kernel<<<cal_blocks(ctx, len), CAL_THREADS, 0, (cudaStream_t)stream>>>(
         d_raw, len, cfg->master_bias, cfg->master_dark, cfg->master_flat, cfg->dark_exposure_ratio,
@@ -251,7 +254,7 @@ ab_status ab_calibrate_image(ab_ctx *ctx, const float *raw, size_t len,
                              const ab_calibration_config *cfg, float *out) {
     if (!ctx || !cfg || (len && (!raw || !out))) return AB_ERR_INVALID;
     if (len == 0) return AB_OK;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     const size_t plane = (len * sizeof(float) + 255) / 256 * 256;
     ab_status st = ab_scratch_reserve(ctx, 0, plane * 5);

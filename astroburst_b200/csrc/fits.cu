@@ -127,6 +127,7 @@ ab_status ab_fits_decode_dev(ab_ctx *ctx, const uint8_t *d_data, size_t n_pixels
     if (!ctx || (n_pixels && (!d_data || !d_out))) return AB_ERR_INVALID;
     if (!bytes_per_pixel(bitpix)) return ab_fail(ctx, AB_ERR_UNSUPPORTED, "BITPIX %d", bitpix);
     if (n_pixels == 0) return AB_OK;
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     return decode_on(ctx, d_data, n_pixels, bitpix, bscale, bzero, d_out, (cudaStream_t)stream);
 }
@@ -137,7 +138,7 @@ ab_status ab_fits_decode(ab_ctx *ctx, const uint8_t *data, size_t n_pixels, int 
     const int bpp = bytes_per_pixel(bitpix);
     if (!bpp) return ab_fail(ctx, AB_ERR_UNSUPPORTED, "BITPIX %d", bitpix);
     if (n_pixels == 0) return AB_OK;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     const size_t in_b = (n_pixels * bpp + 255) / 256 * 256;
     ab_status st = ab_scratch_reserve(ctx, 0, in_b + n_pixels * sizeof(float));
@@ -156,6 +157,7 @@ ab_status ab_fits_encode_dev(ab_ctx *ctx, const float *d_data, size_t n_pixels, 
                              double bzero, double bscale, uint8_t *d_out, void *stream) {
     if (!ctx || (n_pixels && (!d_data || !d_out))) return AB_ERR_INVALID;
     if (n_pixels == 0) return AB_OK;
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     return encode_on(ctx, d_data, n_pixels, bitpix, bzero, bscale, d_out, (cudaStream_t)stream);
 }
@@ -167,7 +169,7 @@ ab_status ab_fits_encode(ab_ctx *ctx, const float *data, size_t n_pixels, int bi
         return ab_fail(ctx, AB_ERR_UNSUPPORTED, "BITPIX %d (writer: 16, -32, -64)", bitpix);
     if (n_pixels == 0) return AB_OK;
     const int bpp = bytes_per_pixel(bitpix);
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     const size_t in_b = (n_pixels * sizeof(float) + 255) / 256 * 256;
     ab_status st = ab_scratch_reserve(ctx, 0, in_b + n_pixels * bpp);

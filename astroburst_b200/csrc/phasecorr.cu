@@ -280,7 +280,7 @@ ab_status correlate_single(ab_ctx *ctx, PcState *st, const float *a, size_t pitc
             }
         sigma = std::sqrt(var_sum / (count > 1.0 ? count - 1.0 : 1.0));
     }
-    const double eps = 2.220446049250313e-16;  // f64::EPSILON
+    const double eps = 1e-15;  // FftFloat::epsilon_val() for f64 (math/fft.rs:57), NOT f64::EPSILON
     const double confidence = std::fabs(sigma) < eps ? 0.0 : (peak_val - mean) / sigma;
     // unwrap_and_refine, subpixel.rs:27-100
     auto unwrap = [](size_t peak, size_t size) {
@@ -418,6 +418,7 @@ extern "C" {
 ab_status ab_phase_correlate_dev(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t rows,
                                  size_t cols, ab_phase_result *out, void *stream) {
     if (!ctx || !out || ((rows * cols) && (!d_ref || !d_tgt))) return AB_ERR_INVALID;
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     return ab_phase_correlate_on(ctx, d_ref, d_tgt, rows, cols, (cudaStream_t)stream, out);
 }
@@ -429,7 +430,7 @@ ab_status ab_phase_correlate(ab_ctx *ctx, const float *ref, size_t ref_rows, siz
     const size_t rows = std::min(ref_rows, tgt_rows), cols = std::min(ref_cols, tgt_cols);  // :26-41
     out->dx = out->dy = out->confidence = 0.0;
     if (rows == 0 || cols == 0) return AB_OK;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     const size_t plane = (rows * cols * sizeof(float) + 255) / 256 * 256;
     ab_status st = ab_scratch_reserve(ctx, 0, plane * 2);
@@ -447,6 +448,7 @@ ab_status ab_area_downsample_dev(ab_ctx *ctx, const float *d_src, size_t in_rows
                                  size_t out_rows, size_t out_cols, float *d_out, void *stream) {
     if (!ctx || !d_src || !d_out || !in_rows || !in_cols || !out_rows || !out_cols)
         return AB_ERR_INVALID;
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     return downsample_on(ctx, d_src, in_rows, in_cols, out_rows, out_cols, d_out,
                          (cudaStream_t)stream);
@@ -455,7 +457,7 @@ ab_status ab_area_downsample_dev(ab_ctx *ctx, const float *d_src, size_t in_rows
 ab_status ab_area_downsample(ab_ctx *ctx, const float *src, size_t in_rows, size_t in_cols,
                              size_t out_rows, size_t out_cols, float *out) {
     if (!ctx || !src || !out || !in_rows || !in_cols || !out_rows || !out_cols) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     const size_t in_b = (in_rows * in_cols * sizeof(float) + 255) / 256 * 256;
     ab_status st = ab_scratch_reserve(ctx, 0, in_b + out_rows * out_cols * sizeof(float));

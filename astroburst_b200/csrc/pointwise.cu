@@ -348,7 +348,7 @@ unsigned sweep_blocks(ab_ctx *ctx, size_t len) {
 template <typename Body>
 ab_status with_host_planes(ab_ctx *ctx, const void *const *h_in, const size_t *in_bytes, int n_in,
                            void *const *h_out, const size_t *out_bytes, int n_out, Body body) {
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     size_t total = 0;
     std::vector<size_t> off;
@@ -733,7 +733,7 @@ ab_status ab_apply_scnr(ab_ctx *ctx, float *r, float *g, float *b, size_t len,
     void *o[3] = {r, g, b};
     const size_t ib[3] = {len * 4, len * 4, len * 4};
     // in place on the device copies: outputs alias inputs
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard gd(ctx->device);
     const size_t plane = (len * 4 + 255) / 256 * 256;
     ab_status st = ab_scratch_reserve(ctx, 0, plane * 3);

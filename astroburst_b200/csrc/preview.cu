@@ -633,7 +633,7 @@ static ab_status render_host(ab_ctx *ctx, const float *r, const float *g, const 
                              const ab_image_stats *st3, int mode16, uint8_t *out) {
     const size_t len = rows * cols;
     if (len == 0) return AB_OK;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard gd(ctx->device);
     size_t pw, ph;
     bool fits;
@@ -705,7 +705,7 @@ ab_status ab_apply_lrgb(ab_ctx *ctx, const float *l, float *r, float *g, float *
                         float lightness_weight, float chrominance_weight) {
     if (!ctx || (len && (!l || !r || !g || !b))) return AB_ERR_INVALID;
     if (len == 0) return AB_OK;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard gd(ctx->device);
     Planes p;
     ab_status st = planes_reserve(ctx, len, 4, &p);
@@ -741,7 +741,7 @@ ab_status ab_luminance(ab_ctx *ctx, const float *r, const float *g, const float 
                        int finite_only, float *out) {
     if (!ctx || (len && (!r || !g || !b || !out))) return AB_ERR_INVALID;
     if (len == 0) return AB_OK;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard gd(ctx->device);
     Planes p;
     ab_status st = planes_reserve(ctx, len, 4, &p);
@@ -767,7 +767,7 @@ ab_status ab_star_mask_from_stars_dev(ab_ctx *ctx, const float *d_img, size_t ro
                                       ab_star_mask_info *info, void *stream) {
     if (!ctx || !cfg || !info || (n_stars && !stars) || (rows * cols && (!d_img || !d_mask)))
         return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     return star_mask_on(ctx, d_img, rows, cols, stars, n_stars, cfg, d_mask, info, (cudaStream_t)stream);
 }
@@ -775,7 +775,7 @@ ab_status ab_generate_star_mask_dev(ab_ctx *ctx, const float *d_img, size_t rows
                                     const ab_star_mask_config *cfg, float *d_mask,
                                     ab_star_mask_info *info, void *stream) {
     if (!ctx || !cfg || !info || (rows * cols && (!d_img || !d_mask))) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     return generate_mask_on(ctx, d_img, rows, cols, cfg, d_mask, info, (cudaStream_t)stream);
 }
@@ -786,7 +786,7 @@ static ab_status mask_host(ab_ctx *ctx, const float *img, size_t rows, size_t co
     info->stars_masked = 0;
     info->coverage_fraction = 0.0;
     if (len == 0) return AB_OK;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard gd(ctx->device);
     Planes p;
     ab_status st = planes_reserve(ctx, len, 2, &p);
@@ -818,7 +818,7 @@ ab_status ab_generate_star_mask(ab_ctx *ctx, const float *img, size_t rows, size
 ab_status ab_masked_median_dev(ab_ctx *ctx, const float *d_img, const float *d_mask, size_t len,
                                double *out, void *stream) {
     if (!ctx || !out || (len && (!d_img || !d_mask))) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     return masked_median_on(ctx, d_img, d_mask, len, (cudaStream_t)stream, out);
 }
@@ -826,7 +826,7 @@ ab_status ab_masked_stretch_with_mask_dev(ab_ctx *ctx, const float *d_img, size_
                                           const float *d_mask, const ab_masked_stretch_config *cfg,
                                           float *d_out, ab_masked_stretch_info *info, void *stream) {
     if (!ctx || !cfg || !info || (len && (!d_img || !d_mask || !d_out))) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     info->stars_masked = 0;
     info->mask_coverage = 0.0;
@@ -836,7 +836,7 @@ ab_status ab_masked_stretch_with_mask(ab_ctx *ctx, const float *img, size_t len,
                                       const ab_masked_stretch_config *cfg, float *out,
                                       ab_masked_stretch_info *info) {
     if (!ctx || !cfg || !info || (len && (!img || !mask || !out))) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard gd(ctx->device);
     info->stars_masked = 0;
     info->mask_coverage = 0.0;
@@ -861,7 +861,7 @@ ab_status ab_masked_stretch_dev(ab_ctx *ctx, const float *d_img, size_t rows, si
                                 const ab_masked_stretch_config *cfg, float *d_mask, float *d_out,
                                 ab_masked_stretch_info *info, void *stream) {
     if (!ctx || !cfg || !info || (rows * cols && (!d_img || !d_mask || !d_out))) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     const ab_star_mask_config mc = mask_cfg_of(cfg);
     ab_star_mask_info mi;
@@ -876,7 +876,7 @@ ab_status ab_masked_stretch(ab_ctx *ctx, const float *img, size_t rows, size_t c
                             const ab_masked_stretch_config *cfg, float *out,
                             ab_masked_stretch_info *info) {
     if (!ctx || !cfg || !info || (rows * cols && (!img || !out))) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard gd(ctx->device);
     std::memset(info, 0, sizeof(*info));
     const size_t len = rows * cols;

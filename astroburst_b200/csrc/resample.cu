@@ -123,7 +123,7 @@ ab_status launch_gather(ab_ctx *ctx, const float *src, size_t sr, size_t sc, flo
 template <typename Body>
 ab_status with_src_out(ab_ctx *ctx, const float *src, size_t src_px, float *out, size_t out_px,
                        Body body) {
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     const size_t a = (src_px * 4 + 255) / 256 * 256, b = (out_px * 4 + 255) / 256 * 256;
     ab_status st = ab_scratch_reserve(ctx, 0, a + b);

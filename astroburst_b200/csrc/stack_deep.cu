@@ -1,438 +1,467 @@
 // stack_deep.cu -- sigma-clipped stack for frame counts without a register kernel (33..256 frames,
-// BASELINE config 5: 256 x 4096^2).
+// BASELINE config 5: 256 x 4096^2) and the per-pixel median combine of the calibration masters.
 //
 // Reference semantics: stack_images / sigma_clip_combine,
-// src-tauri/src/core/stacking/combine.rs:14-92,160-182 (align=false core loop).
+// src-tauri/src/core/stacking/combine.rs:14-92,160-182 (align=false core loop);
+// median_combine_row_major, src-tauri/src/core/stacking/calibration.rs:85-123.
 //
-// One thread = one output pixel; the N samples of a pixel are processed as K = ceil(N/32) chunks.
-//
-//  phase 1  per chunk, register-resident: 32 coalesced streaming loads (the next chunk's loads are
-//    in flight while this one is sorted), non-finite -> +inf, the 185-comparator sorting network of
-//    the register kernels (stack_kernels.cuh), then the sorted chunk is written to the thread's
-//    column in shared memory (element e of lane l at word e*32 + l: every dynamic access below is
-//    bank-conflict free) and the f64 sums S1 = sum (v - c), S2 = sum (v - c)^2 about a fixed centre
-//    c (the first chunk's median) are accumulated.
-//  phase 2  iteration 0 (combine.rs:37-48) on the K sorted lists: the upper median is the element
-//    of rank n/2 of their union -- lower-bound binary searches for a pivot near it (mean of the
-//    chunk medians), then a K-way merge walk over the few ranks in between; the upper-median MAD
-//    is the rank n/2 element of the 2K deviation sequences that fan out left and right of the
-//    median, found the same way.
-//  phase 3  the clip (combine.rs:65-82): dev = v - center is monotone in v, so every list loses a
-//    prefix and a suffix; removed samples are subtracted from S1, S2.  Iterations >= 1
-//    (combine.rs:49-61) need no pass over the data: mean = c + S1/len exactly (the f64 sum of the
-//    reference is exact for f32 samples of comparable magnitude), and the sample variance follows
-//    from S2 - 2 d S1 + len d^2 with d = mean - c, which agrees with the reference's sequential
-//    f64 accumulation to ~1e-15 relative before the cast to f32.
+// Layout of the work (R = samples per lane: 8/16/32/64 for <= 32/64/128/256 frames):
+//   * FOUR lanes cooperate on one pixel, a warp owns 8 pixels, a 4-warp block owns a 32-pixel tile
+//     (one 128-byte line of every frame).  The block streams tiles [4R frames x 32 px] into a
+//     double-buffered shared-memory stage with 16-byte cp.async (LDGSTS): every warp instruction
+//     fetches four whole 128-byte lines, so the same code runs at full efficiency on PEER pointers
+//     (frame-sharded stacks read the owners' HBM over NVLink, no staging copy); the fetch of tile
+//     i+1 overlaps all the arithmetic of tile i, one __syncthreads per tile.
+//   * each lane copies its R samples to registers (conflict-free LDS), non-finite -> +inf, and
+//     sorts them with the register network of stack_kernels.cuh; two bitonic merge levels across
+//     the lane quad (flip stage = 2 SHFL + 2 predicated FMNMX per register pair, then in-lane
+//     half-cleaners) leave the pixel's 4R samples fully sorted: rank g at lane g / R, register
+//     g % R.  The sorted run is also written to the warp's own (consumed) part of the stage for
+//     the few dynamically indexed reads below.
+//   * iteration 0 (combine.rs:37-48): upper median S[n/2]; the upper-median MAD is
+//     min_t max(med - S[t], S[t + n/2] - med) and, the first term falling and the second rising
+//     with t, the minimum sits at their crossing: a binary search instead of a scan.
+//   * the clip (combine.rs:65-82): dev = v - center is monotone in v, so the rejects are a prefix
+//     and a suffix of the surviving rank range [a, b); the quad probes four candidates per step.
+//   * iterations >= 1 (combine.rs:49-61): moments D1 = sum (v - c0), D2 = sum (v - c0)^2 about
+//     c0 = median, accumulated in f64 from the registers over the survivors of ITERATION 0 (so no
+//     far outlier ever enters them) and downdated by the few samples later iterations remove;
+//     mean = (len c0 + D1) / len exactly (the reference's f64 sum is exact for f32 samples of
+//     comparable magnitude), sum (v - mean)^2 = D2 - 2 d D1 + len d^2 with d = mean - c0.  A
+//     downdate that removes most of D2 (cancellation) triggers a fresh accumulation instead.
 #include "stack_kernels.cuh"
+
+#ifndef AB_DEEP_MN
+#define AB_DEEP_MN 2
+#define AB_DEEP_MD 3
+#endif
+#ifndef AB_DEEP_XIMAD  // cross-lane stages: upper lanes take a + b - min on the FMA pipe (predicated IMADs)
+#define AB_DEEP_XIMAD 0
+#endif
+#ifndef AB_DEEP_MAD4   // MAD crossing search: 1 = quad-cooperative 5-ary search, 0 = binary search
+#define AB_DEEP_MAD4 1
+#endif
 
 namespace {
 
 using abk::CeConst;
 
-constexpr int CH = 32;           // samples per chunk
-constexpr int MAX_CHUNKS = AB_MAX_FRAMES / CH;
-constexpr int DEEP_MN = 2, DEEP_MD = 3;  // IMAD share of the compare-exchanges (tuned at r1: 4.05 ms)
-// warps per block.  At K = 8 (225..256 frames) a warp's columns take 32 KiB: three 2-warp blocks fit
-// an SM (each block also reserves 1 KiB), ONE 7-warp block fits seven warps -- occupancy is what
-// bounds this kernel, so that layout is used there.
-template <int K>
-constexpr int deep_warps() {
-    return K == 8 ? 7 : 2;
-}
+constexpr int DL = 4;        // lanes per pixel
+constexpr int DPX = 32 / DL; // pixels per warp
+constexpr int DWARPS = 4;    // warps per block
+constexpr int DTHREADS = DWARPS * 32;
+constexpr int TILE_PX = DWARPS * DPX;  // 32 pixels = one 128-byte line per frame
+constexpr unsigned FULL = 0xffffffffu;
 
-// 8 small integers (0..255) packed in one 64-bit register: per-list counters without local memory
-struct Pack8 {
-    unsigned long long v;
-    __device__ __forceinline__ int get(int k) const { return (int)((v >> (8 * k)) & 0xffull); }
-    __device__ __forceinline__ void set(int k, int x) {
-        v = (v & ~(0xffull << (8 * k))) | ((unsigned long long)(x & 0xff) << (8 * k));
-    }
-    __device__ __forceinline__ void add(int k, int d) { v += (unsigned long long)(long long)d << (8 * k); }
+template <int R>
+struct Geom {
+    static constexpr int LOG2R = R == 64 ? 6 : (R == 32 ? 5 : (R == 16 ? 4 : 3));
+    static constexpr int FR = DL * R;             // frame rows of a tile (frame count padded)
+    static constexpr int LANE_PITCH = R + 4;      // sorted layout: words per lane block
+    static constexpr int PITCH = DL * R + 16;     // sorted layout: words per pixel
+    // words per warp region: the tile part [FR][8 px] (32 R words) overlaid by the sorted layout
+    // (8 PITCH = 32 R + 128 words); + 8 so the four regions start 8 banks apart (cp.async writes)
+    static constexpr int REGION = DPX * PITCH + 8;
+    static constexpr int STAGE = DWARPS * REGION;
+    static constexpr size_t SMEM = (size_t)2 * STAGE * sizeof(float) + AB_MAX_FRAMES * sizeof(float *);
 };
 
-// element i of list k in this lane's column
-__device__ __forceinline__ float at(const float *col, int k, int i) { return col[(k * CH + i) * 32]; }
+__device__ __forceinline__ void cp_async16(float *dst, const float *src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float *dst, const float *src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// Lock-step branchless searches: cnt[k] <- number of leading elements of list k's range that
-// satisfy the (monotone) predicate.  Six fixed steps; the K lists are independent, so their
-// shared-memory loads overlap.
-//   pred(k, idx) must be true for a prefix of [base[k], limit[k]) and false after it.
-template <int K, typename Pred>
-__device__ __forceinline__ void prefix_counts(const int (&base)[K], const int (&limit)[K],
-                                              int (&cnt)[K], Pred pred) {
+// Block-cooperative fetch of tile `tile` (pixels [32 tile, 32 tile + 32) of every frame) into
+// `stage`: frame f, 16-byte chunk k (pixels 4k..4k+3) -> region k/2, word f*8 + (k&1)*4.
+// Out of line (called when no sample registers are live): one copy of the address arithmetic.
+template <int R>
+static __device__ __noinline__ void fill_stage(float *stage, const float *const *ptrs, int n_frames,
+                                               size_t npix, size_t tile, bool aligned16) {
+    using G = Geom<R>;
+    const size_t px0 = tile * TILE_PX;
+    const int k = (int)threadIdx.x & 7;
+    const size_t px = px0 + 4 * k;
+    float *dst0 = stage + (k >> 1) * G::REGION + (k & 1) * 4;
+    const int f0 = (int)threadIdx.x >> 3;  // this thread's rows: f0, f0 + 16, ...
+    if (aligned16 && px0 + TILE_PX <= npix) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) cnt[k] = 0;
-#pragma unroll
-    for (int step = CH; step >= 1; step >>= 1) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int idx = base[k] + cnt[k] + step - 1;
-            if (idx < limit[k] && pred(k, idx)) cnt[k] += step;
+        for (int it = 0; it < (G::FR * 8) / DTHREADS; ++it) {
+            const int f = f0 + it * (DTHREADS / 8);
+            float *dst = dst0 + f * 8;
+            if (f < n_frames) cp_async16(dst, ptrs[f] + px);
+            else  // rows past the frame count: +inf sorts last and counts as "not finite"
+                *reinterpret_cast<float4 *>(dst) =
+                    make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
         }
+    } else {  // unaligned frames or the ragged last tile: 4-byte copies, pixels past the end untouched
+#pragma unroll 1
+        for (int it = 0; it < (G::FR * 8) / DTHREADS; ++it) {
+            const int f = f0 + it * (DTHREADS / 8);
+            float *dst = dst0 + f * 8;
+#pragma unroll 1
+            for (int e = 0; e < 4; ++e) {
+                if (f >= n_frames) dst[e] = CUDART_INF_F;
+                else if (px + e < npix) cp_async4(dst + e, ptrs[f] + px + e);
+            }
+        }
+    }
+    cp_async_commit();
+}
+
+// min(own, x) on the lower lane, max(own, x) on the upper lane.  Operands are finite or +inf.
+__device__ __forceinline__ float keep_side(float own, float x, bool upper, const CeConst &kc) {
+#if AB_DEEP_XIMAD
+    float m = fminf(own, x);
+    if (upper) {  // own + x - min on the integer bit patterns: exactly the other operand
+        const int t = __float_as_int(own) * kc.one + __float_as_int(x);
+        m = __int_as_float(__float_as_int(m) * kc.mone + t);
+    }
+    return m;
+#else
+    return upper ? fmaxf(own, x) : fminf(own, x);
+#endif
+}
+// One bitonic "flip" stage across lanes (lane ^ xm): register i meets the partner's register
+// R-1-i; the lower lane keeps the minima, the upper lane the maxima.
+template <int R>
+__device__ __forceinline__ void flip_stage(float (&s)[R], int xm, bool upper, const CeConst &kc) {
+#pragma unroll
+    for (int i = 0; i < R / 2; ++i) {
+        const float x = __shfl_xor_sync(FULL, s[i], xm);
+        const float y = __shfl_xor_sync(FULL, s[R - 1 - i], xm);
+        s[i] = keep_side(s[i], y, upper, kc);
+        s[R - 1 - i] = keep_side(s[R - 1 - i], x, upper, kc);
+    }
+}
+// Half-cleaner across lanes (stride = R elements): register i meets the partner's register i.
+template <int R>
+__device__ __forceinline__ void straight_stage(float (&s)[R], int xm, bool upper, const CeConst &kc) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const float x = __shfl_xor_sync(FULL, s[i], xm);
+        s[i] = keep_side(s[i], x, upper, kc);
+    }
+}
+// In-lane half-cleaners, strides R/2 .. 1: a bitonic run of R registers -> ascending.
+template <int R, int STRIDE, int... I>
+__device__ __forceinline__ void halfclean_stride(float (&s)[R], const CeConst &kc,
+                                                 std::integer_sequence<int, I...>) {
+    // pair I (0 .. R/2-1) of this stride: low index = (I / STRIDE) * 2 STRIDE + I % STRIDE
+    (abk::ce<abk::ce_is_imad<AB_DEEP_MN, AB_DEEP_MD>(I)>(
+         s[(I / STRIDE) * 2 * STRIDE + (I % STRIDE)],
+         s[(I / STRIDE) * 2 * STRIDE + (I % STRIDE) + STRIDE], kc),
+     ...);
+}
+template <int R, int STRIDE>
+__device__ __forceinline__ void halfclean(float (&s)[R], const CeConst &kc) {
+    if constexpr (STRIDE >= 1) {
+        halfclean_stride<R, STRIDE>(s, kc, std::make_integer_sequence<int, R / 2>{});
+        halfclean<R, STRIDE / 2>(s, kc);
     }
 }
 
-// Value of rank r (0-based) of the union of the K sorted lists (n[k] elements each): counts of
-// elements below a pivot near the target, then a K-way merge walk over the ranks in between.
-template <int K>
-__device__ __forceinline__ float select_rank(const float *col, const int (&n)[K], int n_tot, int r,
-                                             float pivot) {
-    int zero[K], c[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) zero[k] = 0;
-    auto below = [&](float p) {
-        prefix_counts<K>(zero, n, c, [&](int k, int idx) { return at(col, k, idx) < p; });
-        int t = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) t += c[k];
-        return t;
-    };
-    int c_less = below(pivot);
-    // one secant-like refinement: move the pivot to the element the count is off by, inside the
-    // list whose own count is largest (any value works as a pivot; only the walk length changes)
-    {
-        const int off = r - c_less;  // > 0: pivot too low
-        if (off > 2 || off < -2) {
-            int kb = 0;
-#pragma unroll
-            for (int k = 1; k < K; ++k)
-                if (n[k] > n[kb]) kb = k;
-            int ck = 0, nk = 0;
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                if (k == kb) {
-                    ck = c[k];
-                    nk = n[k];
-                }
-            // the list holds ~nk/n_tot of the samples: shift its index by the same share of `off`
-            int idx = ck + (off * nk + (off > 0 ? n_tot - 1 : -(n_tot - 1))) / n_tot;
-            idx = max(0, min(nk - 1, idx));
-            pivot = at(col, kb, idx);
-            c_less = below(pivot);
-        }
-    }
-    Pack8 pos{0};
-#pragma unroll
-    for (int k = 0; k < K; ++k) pos.set(k, c[k]);
-    if (c_less <= r) {  // walk forward over the elements >= pivot
-        int steps = r - c_less;
-#pragma unroll 1
-        for (;;) {
-            float best = CUDART_INF_F;
-            int arg = -1;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int i = pos.get(k);
-                const float v = i < n[k] ? at(col, k, i) : CUDART_INF_F;
-                if (i < n[k] && (arg < 0 || v < best)) {
-                    best = v;
-                    arg = k;
-                }
-            }
-            if (steps == 0 || arg < 0) return best;
-            pos.add(arg, 1);
-            --steps;
-        }
-    }
-    int steps = c_less - 1 - r;  // walk backward over the elements < pivot
-#pragma unroll 1
-    for (;;) {
-        float best = -CUDART_INF_F;
-        int arg = -1;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int i = pos.get(k);
-            const float v = i > 0 ? at(col, k, i - 1) : -CUDART_INF_F;
-            if (i > 0 && (arg < 0 || v > best)) {
-                best = v;
-                arg = k;
-            }
-        }
-        if (steps == 0 || arg < 0) return best;
-        pos.add(arg, -1);
-        --steps;
-    }
-}
-
-// Rank r2 element of the deviations |v - med| (f32, as combine.rs:41-44).  Per list the samples
-// >= med give an ascending deviation sequence to the right of q = lower_bound(med), the samples
-// < med one to the left; [lb, ub) is the window of samples whose deviation is < the pivot.
-template <int K>
-__device__ __forceinline__ float select_mad(const float *col, const int (&n)[K], float med, int r2,
-                                            float pivot) {
-    int zero[K], q[K], cr[K], cl[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) zero[k] = 0;
-    prefix_counts<K>(zero, n, q, [&](int k, int idx) { return at(col, k, idx) < med; });
-    auto inside = [&](float p) {
-        // right: leading samples of [q, n) with (v - med) < p; left: leading samples of [0, q)
-        // with (med - v) >= p (the deviation decreases with the index there)
-        prefix_counts<K>(q, n, cr, [&](int k, int idx) { return at(col, k, idx) - med < p; });
-        prefix_counts<K>(zero, q, cl, [&](int k, int idx) { return !(med - at(col, k, idx) < p); });
-        int t = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) t += cr[k] + (q[k] - cl[k]);
-        return t;
-    };
-    int cnt = inside(pivot);
-    if ((cnt - r2 > 3 || r2 - cnt > 3) && cnt > 0 && pivot > 0.0f) {
-        // deviations are roughly uniform near the MAD: rescale the pivot to the wanted count
-        pivot = pivot * ((float)r2 + 0.5f) / (float)cnt;
-        cnt = inside(pivot);
-    }
-    Pack8 lb{0}, ub{0};
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        lb.set(k, cl[k]);
-        ub.set(k, q[k] + cr[k]);
-    }
-    if (cnt <= r2) {  // grow the windows: pop the smallest outside deviation
-        int steps = r2 - cnt;
-#pragma unroll 1
-        for (;;) {
-            float best = CUDART_INF_F;
-            int arg = -1;  // k for a right head, k + 8 for a left head
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int u = ub.get(k), l = lb.get(k);
-                const float dr = u < n[k] ? at(col, k, u) - med : CUDART_INF_F;
-                if (u < n[k] && (arg < 0 || dr < best)) {
-                    best = dr;
-                    arg = k;
-                }
-                const float dl = l > 0 ? med - at(col, k, l - 1) : CUDART_INF_F;
-                if (l > 0 && (arg < 0 || dl < best)) {
-                    best = dl;
-                    arg = k + 8;
-                }
-            }
-            if (steps == 0 || arg < 0) return best;
-            if (arg < 8) ub.add(arg, 1);
-            else lb.add(arg - 8, -1);
-            --steps;
-        }
-    }
-    int steps = cnt - 1 - r2;  // shrink the windows: pop the largest inside deviation
-#pragma unroll 1
-    for (;;) {
-        float best = -CUDART_INF_F;
-        int arg = -1;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int u = ub.get(k), l = lb.get(k);
-            const float dr = u > q[k] ? at(col, k, u - 1) - med : -CUDART_INF_F;
-            if (u > q[k] && (arg < 0 || dr > best)) {
-                best = dr;
-                arg = k;
-            }
-            const float dl = l < q[k] ? med - at(col, k, l) : -CUDART_INF_F;
-            if (l < q[k] && (arg < 0 || dl > best)) {
-                best = dl;
-                arg = k + 8;
-            }
-        }
-        if (steps == 0 || arg < 0) return best;
-        if (arg < 8) ub.add(arg, -1);
-        else lb.add(arg - 8, 1);
-        --steps;
-    }
+__device__ __forceinline__ double quad_sum(double v) {
+    v += __shfl_xor_sync(FULL, v, 1);
+    v += __shfl_xor_sync(FULL, v, 2);
+    return v;
 }
 
 // PRE = false is the plain stack (no calibration terms, no median-only mode compiled in).
-template <int K, bool PRE>
-__global__ void __launch_bounds__(deep_warps<K>() * 32)
+template <int R, bool PRE>
+__global__ void __launch_bounds__(DTHREADS, R == 64 ? 3 : 4)
 stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t npix,
                   float sigma_low, float sigma_high, unsigned max_iter, CeConst kc,
-                  const __grid_constant__ DeepPre pre, float *__restrict__ out,
+                  const __grid_constant__ DeepPre pre, int aligned16, float *__restrict__ out,
                   unsigned long long *__restrict__ rejected_total) {
+    using G = Geom<R>;
     extern __shared__ __align__(16) float deep_smem[];
+    const float **ptrs = reinterpret_cast<const float **>(deep_smem + 2 * G::STAGE);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float *col = deep_smem + warp * (K * CH * 32) + lane;
-    unsigned local_rej = 0;
+    const int p = lane >> 2;  // pixel of the warp
+    const int l = lane & 3;   // lane of the pixel's quad
     const bool has_bias = PRE && pre.bias != nullptr;
     const bool has_dark = PRE && pre.dark != nullptr;
     const bool median_only = PRE && pre.median_only != 0;
+    unsigned local_rej = 0;
 
-    const size_t n_groups = (npix + 31) / 32;
-    constexpr int DEEP_WARPS = deep_warps<K>();
-    const size_t warp_global = (size_t)blockIdx.x * DEEP_WARPS + warp;
-    const size_t warp_stride = (size_t)gridDim.x * DEEP_WARPS;
-    for (size_t g = warp_global; g < n_groups; g += warp_stride) {
-        const size_t p = g * 32 + lane;
-        const bool active = p < npix;
+    for (int f = threadIdx.x; f < AB_MAX_FRAMES; f += DTHREADS) ptrs[f] = ft.p[f];
+    __syncthreads();
 
-        // ---------------------------------------------------------------- phase 1
-        Pack8 npk{0};  // (the chunk loop stays rolled: one copy of the sorting network)
-        int n_tot = 0;
-        bool have_c = false;
-        double cd = 0.0, S1 = 0.0, S2 = 0.0;
-        float pivot_acc = 0.0f, spread_acc = 0.0f;
-        int pivot_cnt = 0;
-        // calibration.rs:160-162,199-206: frame - bias, then - dark * ratio (median-combine callers)
-        const float pre_b = (active && has_bias) ? pre.bias[p] : 0.0f;
-        const float pre_d = (active && has_dark) ? pre.dark[p] * pre.dark_ratio : 0.0f;
-        auto fetch = [&](int f) -> float {
-            if (!(active && f < n_frames)) return CUDART_INF_F;
-            float v = __ldcs(ft.p[f] + p);
-            if (has_bias) v -= pre_b;
-            if (has_dark) v -= pre_d;
-            return v;
-        };
-        float nxt[CH];
+    const size_t n_tiles = (npix + TILE_PX - 1) / TILE_PX;
+    size_t tile = blockIdx.x;
+    if (tile < n_tiles) fill_stage<R>(deep_smem, ptrs, n_frames, npix, tile, aligned16 != 0);
+    int buf = 0;
+    for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        cp_async_wait_all();
+        __syncthreads();  // tile `tile` has landed; every warp is done with the other stage
+        {  // the next tile streams in while this one is worked on (no sample registers live yet)
+            const size_t next = tile + gridDim.x;
+            if (next < n_tiles)
+                fill_stage<R>(deep_smem + (buf ^ 1) * G::STAGE, ptrs, n_frames, npix, next,
+                              aligned16 != 0);
+        }
+        float *region = deep_smem + buf * G::STAGE + warp * G::REGION;
+        const size_t pix = tile * TILE_PX + warp * DPX + p;
+        const bool in_image = pix < npix;
+
+        // ---------------------------------------------------------------- samples -> registers
+        // lane l takes frames [R l, R l + R), rotated by l rows so that the quad's four loads of
+        // a step fall in different banks (word = 8 f + p)
+        float s[R];
+        {
+            const float *src = region + (R * l + l) * 8 + p;
 #pragma unroll
-        for (int j = 0; j < CH; ++j) nxt[j] = fetch(j);
-#pragma unroll 1
-        for (int k = 0; k < K; ++k) {
-            float s[CH];
-            int nk = 0;
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                const bool fin = fabsf(nxt[j]) < CUDART_INF_F;
-                nk += fin ? 1 : 0;
-                s[j] = fin ? nxt[j] : CUDART_INF_F;
+            for (int j = 0; j < R; ++j) {
+                if (j < R - 3) s[j] = src[j * 8];
+                else s[j] = src[(j + l >= R ? j - R : j) * 8];
             }
-            if (k + 1 < K) {  // next chunk's loads fly while this one is sorted
+        }
+        if constexpr (PRE) {  // calibration.rs:160-162,199-206: frame - bias, then - dark * ratio
+            const float pre_b = (in_image && has_bias) ? pre.bias[pix] : 0.0f;
+            const float pre_d = (in_image && has_dark) ? pre.dark[pix] * pre.dark_ratio : 0.0f;
+            if (has_bias) {
 #pragma unroll
-                for (int j = 0; j < CH; ++j) nxt[j] = fetch((k + 1) * CH + j);
+                for (int j = 0; j < R; ++j) s[j] -= pre_b;
             }
-            abk::sort_network<CH, DEEP_MN, DEEP_MD>(s, kc);
-            float *dst = col + (size_t)k * CH * 32;
+            if (has_dark) {
 #pragma unroll
-            for (int j = 0; j < CH; ++j) dst[j * 32] = s[j];
-            npk.set(k, nk);
-            n_tot += nk;
-            if (nk > 0) {
-                const float mk = dst[(nk >> 1) * 32];  // chunk median (own column: no sync needed)
-                pivot_acc += mk;
-                spread_acc += dst[((3 * nk) >> 2) * 32] - dst[(nk >> 2) * 32];
-                ++pivot_cnt;
-                if (!have_c) {
-                    have_c = true;
-                    cd = (double)mk;
+                for (int j = 0; j < R; ++j) s[j] -= pre_d;
+            }
+        }
+        __syncwarp();  // the whole warp has read its part of the stage: it is scratch from here on
+
+        // non-finite samples (combine.rs:170-175 drops them) -> +inf; n = finite samples of the pixel
+        int n;
+        {
+            float probe = 0.0f;
+#pragma unroll
+            for (int j = 0; j < R; ++j) probe = __fmaf_rn(s[j], 0.0f, probe);  // NaN iff any non-finite
+            const bool dirty = n_frames < G::FR || __any_sync(FULL, !(probe == 0.0f));
+            if (dirty) {
+                int nl = 0;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const bool fin = fabsf(s[j]) < CUDART_INF_F;
+                    nl += fin ? 1 : 0;
+                    s[j] = fin ? s[j] : CUDART_INF_F;
                 }
-            }
-            if (!median_only) {
-#pragma unroll
-                for (int j = 0; j < CH; ++j) {
-                    if (j < nk) {
-                        const double d = (double)s[j] - cd;
-                        S1 += d;
-                        S2 += d * d;
-                    }
-                }
+                nl += __shfl_xor_sync(FULL, nl, 1);
+                nl += __shfl_xor_sync(FULL, nl, 2);
+                n = nl;
+            } else {
+                n = G::FR;
             }
         }
 
-        int n[K];
+        // ---------------------------------------------------------------- sort + merge
+        abk::sort_network<R, AB_DEEP_MN, AB_DEEP_MD>(s, kc);
+#pragma unroll 1
+        for (int level = 0; level < 2; ++level) {
+            flip_stage<R>(s, level ? 3 : 1, (lane & (level ? 2 : 1)) != 0, kc);
+            if (level) straight_stage<R>(s, 1, (lane & 1) != 0, kc);
+            halfclean<R, R / 2>(s, kc);
+        }
+        // rank g of the pixel is now register g % R of lane g / R; mirror it in shared memory
+        float *srt = region + p * G::PITCH;
+        {
+            float *dst = srt + l * G::LANE_PITCH;
 #pragma unroll
-        for (int k = 0; k < K; ++k) n[k] = npk.get(k);
+            for (int j = 0; j < R; j += 4)
+                *reinterpret_cast<float4 *>(dst + j) = make_float4(s[j], s[j + 1], s[j + 2], s[j + 3]);
+        }
+        __syncwarp();
+        auto S = [&](int g) -> float { return srt[g + 4 * (g >> G::LOG2R)]; };
 
-        float result = 0.0f;
+        // ---------------------------------------------------------------- iteration 0
+        const int h = n >> 1;
+        const float med = n > 0 ? S(h) : 0.0f;  // upper median (combine.rs:38-40); n == 1: the sample
+        float result = med;                      // n == 0 -> 0, n == 1 -> the sample (combine.rs:21-26)
         unsigned rejected = 0;
-        if (median_only) {  // median_combine_row_major, calibration.rs:108-116
-            if (n_tot > 0)
-                result = select_rank<K>(col, n, n_tot, n_tot >> 1, pivot_acc / (float)pivot_cnt);
-        } else if (n_tot == 1) {  // combine.rs:24-26
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                if (n[k]) result = at(col, k, 0);
-        } else if (n_tot >= 2) {
-            int len = n_tot;
-            float last_center = 0.0f;
-            int a[K], b[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                a[k] = 0;
-                b[k] = n[k];
-            }
-            for (unsigned it = 0; it < max_iter; ++it) {
-                if (len < 2) break;
-                float center, sigma;
-                if (it == 0) {
-                    // ------------------------------------------------------------ phase 2
-                    const float inv = 1.0f / (float)pivot_cnt;
-                    const float med = select_rank<K>(col, n, n_tot, n_tot >> 1, pivot_acc * inv);
-                    const float mad =
-                        select_mad<K>(col, n, med, n_tot >> 1, 0.5f * spread_acc * inv);
-                    center = med;
-                    sigma = fmaxf((float)((double)mad * abk::MAD_TO_SIGMA), 1e-10f);
-                } else {
-                    const double mean = abk::div_small((double)len * cd + S1, len);
-                    const double dm = mean - cd;
-                    double ss = (S2 - 2.0 * dm * S1) + (double)len * dm * dm;
-                    ss = fmax(ss, 0.0);
-                    center = (float)mean;
-                    sigma = fmaxf((float)sqrt(abk::div_small(ss, len > 2 ? len - 1 : 1)), 1e-10f);
+        if (!median_only) {
+            int a = 0, b = n;
+            bool active = n >= 2 && max_iter > 0;
+            float sigma = 0.0f, last_center = 0.0f;
+            if (__any_sync(FULL, active)) {
+                // MAD = min_t max(med - S[t], S[t+h] - med), t in [0, n-h): first t whose right
+                // term reaches the left one, then the better of t and t-1
+                const int W = n - h;
+#if AB_DEEP_MAD4
+                // quad-cooperative search for t* = first t in [0, W) with right(t) >= left(t) (W if
+                // none): the lanes probe the last element of four consecutive blocks of `st`
+                // candidates; the count of leading "false" picks the block
+                int lo_t = 0;
+#pragma unroll 1
+                for (int st = G::FR / 8;; st = st > 2 ? st >> 2 : 1) {
+                    const int q = lo_t + (l + 1) * st - 1;
+                    const bool below = active && q < W && !(S(q + h) - med >= med - S(q));
+                    const unsigned bq = (__ballot_sync(FULL, below) >> (4 * p)) & 0xfu;
+                    lo_t += __popc(bq) * st;
+                    if (st == 1) break;
                 }
-                last_center = center;
-                // ---------------------------------------------------------------- phase 3
-                const float lo = -sigma_low * sigma;
-                const float hi = sigma_high * sigma;
+                lo_t = min(lo_t, W);
+#else
+                int lo_t = 0, hi_t = active ? W : 0;
+#pragma unroll 1
+                for (int r = 0; r < G::LOG2R + 2; ++r) {
+                    const int mid = (lo_t + hi_t) >> 1;
+                    if (lo_t < hi_t) {
+                        if (S(mid + h) - med >= med - S(mid)) hi_t = mid;
+                        else lo_t = mid + 1;
+                    }
+                }
+#endif
+                float mad = CUDART_INF_F;
+                if (active && lo_t < W) mad = fmaxf(med - S(lo_t), S(lo_t + h) - med);
+                if (active && lo_t > 0)
+                    mad = fminf(mad, fmaxf(med - S(lo_t - 1), S(lo_t - 1 + h) - med));
+                sigma = fmaxf((float)((double)mad * abk::MAD_TO_SIGMA), 1e-10f);
+            }
+            const double c0 = (double)med;
+            double D1 = 0.0, D2 = 0.0, D2_fresh = 0.0;
+            float center = med;
+            for (unsigned it = 0;; ++it) {
+                // ---- one clip pass (combine.rs:62-82) for the quads still iterating
                 int removed = 0;
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    int ak = a[k], bk = b[k];
+                if (it < max_iter && __any_sync(FULL, active)) {
+                    if (active && b - a < 2) active = false;  // combine.rs:33-35
+                    if (active) last_center = center;
+                    const float lo = -sigma_low * sigma;
+                    const float hi = sigma_high * sigma;
+                    // negated compares: NaN bounds reject everything, like `dev >= lo && dev <= hi`
+                    int na = a, nb = b;
+                    bool search = active;
 #pragma unroll 1
-                    while (ak < bk) {
-                        const float v = at(col, k, ak);
-                        if (v - center >= lo) break;
-                        const double d = (double)v - cd;
-                        S1 -= d;
-                        S2 -= d * d;
-                        ++ak;
-                        ++removed;
+                    while (__any_sync(FULL, search)) {
+                        const int g = na + l;
+                        const bool rj = search && g < nb && !(S(g) - center >= lo);
+                        const unsigned q = (__ballot_sync(FULL, rj) >> (4 * p)) & 0xfu;
+                        const int cnt = q == 0xfu ? 4 : __ffs(~q) - 1;
+                        if (search) na += cnt;
+                        search = search && cnt == 4 && na < nb;
                     }
+                    search = active && na < nb;
 #pragma unroll 1
-                    while (bk > ak) {
-                        const float v = at(col, k, bk - 1);
-                        if (v - center <= hi) break;
-                        const double d = (double)v - cd;
-                        S1 -= d;
-                        S2 -= d * d;
-                        --bk;
-                        ++removed;
+                    while (__any_sync(FULL, search)) {
+                        const int g = nb - 1 - l;
+                        const bool rj = search && g >= na && !(S(g) - center <= hi);
+                        const unsigned q = (__ballot_sync(FULL, rj) >> (4 * p)) & 0xfu;
+                        const int cnt = q == 0xfu ? 4 : __ffs(~q) - 1;
+                        if (search) nb -= cnt;
+                        search = search && cnt == 4 && nb > na;
                     }
-                    a[k] = ak;
-                    b[k] = bk;
+                    if (active) {
+                        removed = (b - a) - (nb - na);
+                        rejected += (unsigned)removed;
+                    }
+                    const int a_old = a, b_old = b;
+                    if (active) {
+                        a = na;
+                        b = nb;
+                        if (removed == 0) active = false;  // combine.rs:80-82
+                    }
+                    // ---- moments of the survivors
+                    if (it > 0 && __any_sync(FULL, removed > 0)) {
+                        double r1 = 0.0, r2 = 0.0;
+                        if (removed > 0) {
+#pragma unroll 1
+                            for (int g = a_old + l; g < a; g += DL) {
+                                const double d = (double)S(g) - c0;
+                                r1 += d;
+                                r2 = fma(d, d, r2);
+                            }
+#pragma unroll 1
+                            for (int g = b + l; g < b_old; g += DL) {
+                                const double d = (double)S(g) - c0;
+                                r1 += d;
+                                r2 = fma(d, d, r2);
+                            }
+                        }
+                        r1 = quad_sum(r1);
+                        r2 = quad_sum(r2);
+                        D1 -= r1;
+                        D2 -= r2;
+                    }
                 }
-                rejected += (unsigned)removed;
-                len -= removed;
-                if (removed == 0) break;
+                const bool first = it == 0;
+                // a downdate that left less than 1/1024 of the last fresh D2 has cancelled ~10 bits
+                const bool stale = !first && active && D2 * 1024.0 < D2_fresh;
+                if (first || __any_sync(FULL, stale)) {
+                    const int a_loc = a - R * l, b_loc = b - R * l;
+                    double m1[2] = {0.0, 0.0}, m2[2] = {0.0, 0.0};
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        const bool in = a_loc <= j && j < b_loc;
+                        const double d = (double)(in ? s[j] : med) - c0;
+                        m1[j & 1] += d;
+                        m2[j & 1] = fma(d, d, m2[j & 1]);
+                    }
+                    const double f1 = quad_sum(m1[0] + m1[1]);
+                    const double f2 = quad_sum(m2[0] + m2[1]);
+                    if (first || stale) {
+                        D1 = f1;
+                        D2 = f2;
+                        D2_fresh = f2;
+                    }
+                }
+                if (it + 1 >= max_iter || !__any_sync(FULL, active)) break;
+                // ---- center / sigma of the next iteration (combine.rs:49-61)
+                {
+                    const int len = max(b - a, 1);
+                    const double mean = abk::div_small((double)len * c0 + D1, len);
+                    const double dm = mean - c0;
+                    double ss = (D2 - 2.0 * dm * D1) + (double)len * dm * dm;
+                    ss = fmax(ss, 0.0);
+                    if (active) {
+                        center = (float)mean;
+                        // (float)max(sd, 1e-10) == max((float)sd, (float)1e-10): rounding is monotone
+                        sigma = fmaxf((float)sqrt(abk::div_small(ss, len > 2 ? len - 1 : 1)), 1e-10f);
+                    }
+                }
             }
-            if (len == 0)
-                result = isfinite(last_center) ? last_center : 0.0f;  // combine.rs:85-88
-            else
-                result = (float)abk::div_small((double)len * cd + S1, len);
+            const int len = b - a;
+            if (n >= 2) {
+                if (len == 0) result = isfinite(last_center) ? last_center : 0.0f;  // combine.rs:85-88
+                else result = (float)abk::div_small((double)len * c0 + D1, len);
+            }
         }
-        if (active) {
-            __stcs(out + p, result);
+        if (in_image && l == 0) {
+            __stcs(out + pix, result);
             local_rej += rejected;
         }
     }
-    const unsigned w = __reduce_add_sync(0xffffffffu, local_rej);
+    cp_async_wait_all();
+    const unsigned w = __reduce_add_sync(FULL, local_rej);
     if (lane == 0 && w) atomicAdd(rejected_total, (unsigned long long)w);
 }
 
 }  // namespace
 
-template <int K, bool PRE>
-static ab_status launch_deep_k(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix, float sl,
+template <int R, bool PRE>
+static ab_status launch_deep_r(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix, float sl,
                                float sh, unsigned max_iter, const DeepPre &pre, float *d_out,
                                unsigned long long *d_rej, cudaStream_t stream) {
-    constexpr int DEEP_WARPS = deep_warps<K>();
-    const size_t smem = (size_t)DEEP_WARPS * K * CH * 32 * sizeof(float);
-    auto kern = stack_deep_kernel<K, PRE>;
-    AB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    using G = Geom<R>;
+    auto kern = stack_deep_kernel<R, PRE>;
+    AB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
     int per_sm = 0;
-    AB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEEP_WARPS * 32, smem));
+    AB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DTHREADS, G::SMEM));
     if (per_sm < 1) per_sm = 1;
-    const size_t need = (npix + DEEP_WARPS * 32 - 1) / (DEEP_WARPS * 32);
-    size_t grid = (size_t)ctx->sm_count * per_sm;  // persistent: one wave, groups strided
-    if (grid > need) grid = need;
+    const size_t n_tiles = (npix + TILE_PX - 1) / TILE_PX;
+    size_t grid = (size_t)ctx->sm_count * per_sm;  // persistent: one wave, tiles strided
+    if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, DEEP_WARPS * 32, smem, stream>>>(ft, n_frames, npix, sl, sh, max_iter,
-                                                           CeConst{1, -1}, pre, d_out, d_rej);
+    int aligned16 = 1;
+    for (int f = 0; f < n_frames; ++f)
+        if (reinterpret_cast<uintptr_t>(ft.p[f]) & 15u) aligned16 = 0;
+    kern<<<(unsigned)grid, DTHREADS, G::SMEM, stream>>>(ft, n_frames, npix, sl, sh, max_iter,
+                                                       CeConst{1, -1}, pre, aligned16, d_out, d_rej);
     AB_LAUNCH_CHECK(ctx);
     return AB_OK;
 }
@@ -440,20 +469,17 @@ static ab_status launch_deep_k(ab_ctx *ctx, const FrameTable &ft, int n_frames, 
 ab_status ab_stack_launch_deep(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix,
                                float sl, float sh, unsigned max_iter, const DeepPre &pre,
                                float *d_out, unsigned long long *d_rej, cudaStream_t stream) {
-    const int K = (n_frames + CH - 1) / CH;
     const bool use_pre = pre.bias || pre.dark || pre.median_only;
-#define AB_DEEP_CASE(k)                                                                         \
-    case k:                                                                                     \
-        return use_pre ? launch_deep_k<k, true>(ctx, ft, n_frames, npix, sl, sh, max_iter, pre,     \
-                                                d_out, d_rej, stream)                           \
-                       : launch_deep_k<k, false>(ctx, ft, n_frames, npix, sl, sh, max_iter, pre,    \
-                                                 d_out, d_rej, stream);
-    switch (K) {
-        AB_DEEP_CASE(1) AB_DEEP_CASE(2) AB_DEEP_CASE(3) AB_DEEP_CASE(4) AB_DEEP_CASE(5)
-        AB_DEEP_CASE(6) AB_DEEP_CASE(7) AB_DEEP_CASE(8)
-        default:
-            break;
-    }
+    if (n_frames < 1 || n_frames > AB_MAX_FRAMES)
+        return ab_fail(ctx, AB_ERR_UNSUPPORTED, "deep stack: %d frames", n_frames);
+#define AB_DEEP_CASE(r)                                                                              \
+    return use_pre ? launch_deep_r<r, true>(ctx, ft, n_frames, npix, sl, sh, max_iter, pre, d_out,   \
+                                            d_rej, stream)                                           \
+                   : launch_deep_r<r, false>(ctx, ft, n_frames, npix, sl, sh, max_iter, pre, d_out,  \
+                                             d_rej, stream);
+    if (n_frames <= 32) { AB_DEEP_CASE(8) }
+    if (n_frames <= 64) { AB_DEEP_CASE(16) }
+    if (n_frames <= 128) { AB_DEEP_CASE(32) }
+    AB_DEEP_CASE(64)
 #undef AB_DEEP_CASE
-    return ab_fail(ctx, AB_ERR_UNSUPPORTED, "deep stack: %d frames", n_frames);
 }

@@ -1046,8 +1046,10 @@ ab_status launch_mix(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, f
 // Default mix per frame count (tuned on B200 at P = 32).
 constexpr int DEFAULT_MN = 1, DEFAULT_MD = 2;
 
-// P = 32 also carries alternative mixes (AB_STACK_MIX=1..7) for A/B measurements; they are
-// instantiated in stack_inst_mix*.cu.
+// Developer builds (-DAB_DEV_VARIANTS, `python -m astroburst_b200.build --variant NAME
+// AB_DEV_VARIANTS ...`) also carry alternative mixes for P = 32 (AB_STACK_MIX=1..7) for A/B
+// measurements, instantiated in stack_inst_mix*.cu; the shipped library has the default only.
+#ifdef AB_DEV_VARIANTS
 #define AB_MIX_LIST(X) X(1, 0, 1) X(2, 1, 3) X(3, 2, 5) X(4, 3, 5) X(5, 2, 3) X(6, 3, 4) X(7, 1, 1)
 #define AB_MIX_EXTERN(idx, mn, md)                                                               \
     extern template ab_status launch_mix<32, mn, md>(ab_ctx *, const FrameTable &, size_t, float, \
@@ -1055,11 +1057,13 @@ constexpr int DEFAULT_MN = 1, DEFAULT_MD = 2;
                                                      unsigned long long *, cudaStream_t);
 AB_MIX_LIST(AB_MIX_EXTERN)
 #undef AB_MIX_EXTERN
+#endif
 
 template <int P>
 ab_status launch_tile(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, float sh,
                       unsigned max_iter, float *d_out, unsigned long long *d_rej,
                       cudaStream_t stream) {
+#ifdef AB_DEV_VARIANTS
     if constexpr (P == 32) {
 #define AB_MIX_CASE(idx, mn, md)                                                                 \
     case idx:                                                                                    \
@@ -1071,6 +1075,7 @@ ab_status launch_tile(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, 
         }
 #undef AB_MIX_CASE
     }
+#endif
     return launch_mix<P, DEFAULT_MN, DEFAULT_MD>(ctx, ft, npix, sl, sh, max_iter, d_out, d_rej,
                                                  stream);
 }

@@ -1148,7 +1148,7 @@ ab_status ab_detect_stars_dev(ab_ctx *ctx, const float *d_img, size_t rows, size
                               double sigma_threshold, ab_star *stars, size_t max_stars,
                               ab_detection_info *info, void *stream) {
     if (!ctx || !info || (max_stars && !stars) || (rows * cols && !d_img)) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     std::vector<ab_star> found;
     double bm, bs;
@@ -1165,7 +1165,7 @@ ab_status ab_detect_stars(ab_ctx *ctx, const float *img, size_t rows, size_t col
                           double sigma_threshold, ab_star *stars, size_t max_stars,
                           ab_detection_info *info) {
     if (!ctx || !info || (max_stars && !stars) || (rows * cols && !img)) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     std::vector<ab_star> found;
     double bm = 0.0, bs = 1.0;
@@ -1186,7 +1186,7 @@ ab_status ab_detect_stars(ab_ctx *ctx, const float *img, size_t rows, size_t col
 ab_status ab_estimate_background(ab_ctx *ctx, const float *img, size_t rows, size_t cols,
                                  size_t tile_size, double *median, double *sigma) {
     if (!ctx || !img || !median || !sigma) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     *median = 0.0;
     *sigma = 1.0;
@@ -1229,7 +1229,7 @@ ab_status ab_estimate_background(ab_ctx *ctx, const float *img, size_t rows, siz
 ab_status ab_normalize_for_detection(ab_ctx *ctx, const float *img, size_t len, float *out) {
     if (!ctx || (len && (!img || !out))) return AB_ERR_INVALID;
     if (len == 0) return AB_OK;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     float *d = nullptr;
     ab_status st = upload(ctx, 0, img, len, &d);
@@ -1254,7 +1254,7 @@ ab_status ab_normalize_for_detection(ab_ctx *ctx, const float *img, size_t len, 
 ab_status ab_align_affine_dev(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t rows,
                               size_t cols, int n_threads, ab_align_result *out, void *stream) {
     if (!ctx || !out || !d_ref || !d_tgt) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     return align_on_device(ctx, d_ref, d_tgt, rows, cols, n_threads, (cudaStream_t)stream, out);
 }
@@ -1262,7 +1262,7 @@ ab_status ab_align_affine_dev(ab_ctx *ctx, const float *d_ref, const float *d_tg
 ab_status ab_align_affine(ab_ctx *ctx, const float *ref, const float *tgt, size_t rows, size_t cols,
                           int n_threads, ab_align_result *out) {
     if (!ctx || !out || !ref || !tgt) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     // both planes side by side in scratch slot 0
     const size_t plane = (rows * cols * 4 + 255) / 256 * 256;
@@ -1281,7 +1281,7 @@ ab_status ab_match_stars(ab_ctx *ctx, const double *ref_xy, size_t n_ref, const 
     if (!ctx || !n_matches || (n_ref && !ref_xy) || (n_tgt && !tgt_xy)) return AB_ERR_INVALID;
     if (n_ref > MAX_STARS || n_tgt > MAX_STARS)
         return ab_fail(ctx, AB_ERR_INVALID, "at most %d stars per list (MAX_STARS)", MAX_STARS);
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     std::vector<Pt> rs(n_ref), ts(n_tgt);
     for (size_t i = 0; i < n_ref; ++i) rs[i] = {ref_xy[2 * i], ref_xy[2 * i + 1]};

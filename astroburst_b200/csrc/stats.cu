@@ -656,7 +656,7 @@ ab_status ab_image_stats_dev(ab_ctx *ctx, const float *d_data, size_t len, int m
                              double known_min, double known_max, ab_image_stats *out,
                              void *stream) {
     if (!ctx || !out || (len && !d_data)) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     return stats_dispatch(ctx, d_data, len, mode, known_min, known_max, (cudaStream_t)stream, out);
 }
@@ -664,7 +664,7 @@ ab_status ab_image_stats_dev(ab_ctx *ctx, const float *d_data, size_t len, int m
 ab_status ab_compute_image_stats(ab_ctx *ctx, const float *data, size_t len, int mode,
                                  double known_min, double known_max, ab_image_stats *out) {
     if (!ctx || !out || (len && !data)) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     if (len == 0) {
         stats_default(out);
@@ -686,7 +686,7 @@ ab_status ab_image_stats_sharded_dev(ab_ctx *ctx, const float *d_data, size_t le
     if (!ctx || !out || !allreduce || (len && !d_data)) return AB_ERR_INVALID;
     if (len >= ((size_t)1 << 32))
         return ab_fail(ctx, AB_ERR_UNSUPPORTED, "bands of 2^32 pixels or more are not supported");
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     cudaStream_t s = (cudaStream_t)stream;
     Reducer rd;
@@ -740,14 +740,14 @@ ab_status ab_histogram_u32_dev(ab_ctx *ctx, const float *d_data, size_t len, siz
                                double dmin, double dmax, uint32_t *bins, double *edges,
                                void *stream) {
     if (!ctx || !bins || !edges || (len && !d_data)) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     return histogram_impl(ctx, d_data, len, n_bins, dmin, dmax, bins, edges, (cudaStream_t)stream);
 }
 ab_status ab_histogram_u32(ab_ctx *ctx, const float *data, size_t len, size_t n_bins, double dmin,
                            double dmax, uint32_t *bins, double *edges) {
     if (!ctx || !bins || !edges || (len && !data)) return AB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     float *d = nullptr;
     if (len) {

@@ -165,62 +165,79 @@ def stack_frame_sharded(local_frames, n_frames: int, rows: int, cols: int, confi
 
 
 # ---------------------------------------------------------------------------------------------------
-# Peer-memory variant of the frame-sharded stack -- NOT CONFIRMED ON HARDWARE.
-# r1's first attempt mapped the peers' cubes with torch's tensor rebuild (which opens the IPC handle
-# under the OWNER's device) and faulted when another GPU dereferenced the mapping.  This version
-# opens the handles itself under the CONSUMER's device (ab_ipc_open, lazy peer access).  The
-# staged path above (reshard_frames_to_bands + stack) is the validated one.
-class PeerCubes:
-    """Base device pointers of every rank's frame cube, addressable from this rank's device."""
+# Peer-memory path (shard.cu): frame-sharded stacks read the owners' HBM over NVLink inside the
+# stack kernel -- transfer and compute are one kernel, no staging copy, no NCCL on the data path.
+class DeviceCube:
+    """A cudaMalloc'd [n, rows, cols] f32 block owned by the library (ab_dev_alloc), exportable
+    with CUDA IPC.  `tensor()` views it as a torch tensor (__cuda_array_interface__) for filling."""
 
-    def __init__(self, local_frames, ctx: Context | None = None, group=None):
+    def __init__(self, shape, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.shape = tuple(int(x) for x in shape)
+        self.nbytes = 4 * int(np.prod(self.shape)) if len(self.shape) else 4
+        p = C.c_void_p()
+        self.ctx.check(lib().ab_dev_alloc(self.ctx.handle, max(self.nbytes, 1), C.byref(p)))
+        self.ptr = int(p.value)
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": "<f4", "data": (self.ptr, False),
+                                         "version": 2, "strides": None}
+
+    def tensor(self):
+        import torch
+
+        return torch.as_tensor(self, device=torch.device("cuda", self.ctx.device))
+
+    def ipc_handle(self) -> bytes:
+        buf = (C.c_char * 64)()
+        self.ctx.check(lib().ab_ipc_export(self.ctx.handle, self.ptr, buf))
+        return bytes(buf.raw)
+
+    def free(self):
+        if self.ptr:
+            self.ctx.check(lib().ab_dev_free(self.ctx.handle, self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PeerCubes:
+    """Every rank's exported block, mapped into this process (ab_ipc_open under this rank's device):
+    `base[q]` = rank q's block as a device pointer valid here.  `local` is a DeviceCube.  The handle
+    bytes travel over torch.distributed (any host channel would do)."""
+
+    def __init__(self, local: DeviceCube, group=None):
         import torch
         import torch.distributed as dist
 
-        self.ctx = ctx or default_context(local_frames.device.index)
-        self.local = local_frames  # keeps the exported allocation alive
+        self.ctx = local.ctx
+        self.local = local
         self.group = group
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        if not local_frames.is_contiguous():
-            raise ValueError("local_frames must be contiguous")
-        torch.cuda.synchronize(local_frames.device)  # the frames are complete before anyone maps them
-        shared = local_frames.untyped_storage()._share_cuda_()  # (device, handle, size, offset, ...)
-        handle, seg_offset = bytes(shared[1]), int(shared[3])
-        offset = seg_offset + local_frames.storage_offset() * local_frames.element_size()
+        self.world, self.rank = world, rank
+        torch.cuda.synchronize(self.ctx.device)  # the block is complete before anyone maps it
         gathered = [None] * world
-        dist.all_gather_object(gathered, (handle, offset), group=group)
+        dist.all_gather_object(gathered, local.ipc_handle(), group=group)
         self._opened = []
         self.base = []
-        for r in range(world):
-            if r == rank:
-                self.base.append(local_frames.data_ptr())
+        for q in range(world):
+            if q == rank:
+                self.base.append(local.ptr)
                 continue
-            h, off = gathered[r]
-            # torch >= 2.5 prefixes the 64 handle bytes with (version, kind): kind 'c' = cudaMalloc block
-            if len(h) == 66 and h[1:2] == b"c":
-                h = h[2:]
-            if len(h) != 64:
-                raise RuntimeError(f"unsupported CUDA IPC handle ({len(h)} bytes, prefix {h[:2]!r}): "
-                                   "expandable segments are not mappable with cudaIpcOpenMemHandle")
             p = C.c_void_p()
-            self.ctx.check(lib().ab_ipc_open(self.ctx.handle, h, C.byref(p)))
+            self.ctx.check(lib().ab_ipc_open(self.ctx.handle, gathered[q], C.byref(p)))
             self._opened.append(p)
-            self.base.append(int(p.value) + off)
+            self.base.append(int(p.value))
         dist.barrier(group)
 
-    def band_pointers(self, n_frames: int, rows: int, cols: int, elem: int = 4):
-        """This rank's row band of every frame, inside the owners' cubes -> (pointers, (r0, r1))."""
-        import torch.distributed as dist
-
-        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
-        return band_pointers_in_cubes(self.base, n_frames, rows, cols, rank, world, elem)
-
     def close(self):
-        """Unmap the peers' cubes (every rank, before any owner frees its frames)."""
+        """Unmap the peers' blocks (every rank, before any owner frees its block)."""
         import torch
         import torch.distributed as dist
 
-        torch.cuda.synchronize(self.local.device)
+        torch.cuda.synchronize(self.ctx.device)
         for p in self._opened:
             self.ctx.check(lib().ab_ipc_close(self.ctx.handle, p))
         self._opened = []
@@ -228,8 +245,8 @@ class PeerCubes:
 
 
 def band_pointers_in_cubes(bases, n_frames: int, rows: int, cols: int, rank: int, world: int, elem: int = 4):
-    """Pointer arithmetic of the peer-memory stack: frame f's band of `rank` starts at its owner's
-    cube base + ((index of f among the owner's frames) * rows + r0) * cols elements."""
+    """Pointer arithmetic of the peer-memory stack (same rule as shard.cu): frame f's band of `rank`
+    starts at its owner's cube base + ((index of f among the owner's frames) * rows + r0) * cols."""
     r0, r1 = row_band(rows, rank, world)
     counts = [0] * world
     ptrs = []
@@ -240,23 +257,27 @@ def band_pointers_in_cubes(bases, n_frames: int, rows: int, cols: int, rank: int
     return ptrs, (r0, r1)
 
 
-def stack_frame_sharded_p2p(cubes: PeerCubes, n_frames: int, rows: int, cols: int, config, stream: int = 0,
-                            group=None, out=None, rej=None):
-    """Config 5 without the staging copy (UNCONFIRMED, see above): each rank's stack kernel reads its
-    row band of every frame straight from the owners' HBM, so the NVLink transfer overlaps the
-    per-pixel work load by load -- one kernel instead of all-to-all + kernel.  Same kernel and same
-    samples as stack_frame_sharded, only the addresses differ."""
-    import torch
+def stack_frame_sharded_p2p(cubes: PeerCubes, n_frames: int, rows: int, cols: int, config, out_ptr: int,
+                            rejected_targets=(), stream: int = 0):
+    """Config 5 as ONE kernel per rank (ab_stack_frame_sharded_dev): this rank's row band of every
+    frame is read from the owners' HBM; its reject count is added to every pointer in
+    `rejected_targets` (own counter + the peers' mapped counters) by a peer-atomic epilogue.
+    Returns (r0, r1).  Bit-identical to the single-GPU stack of all frames."""
+    bases = (C.c_void_p * cubes.world)(*[int(b) for b in cubes.base])
+    tg = (C.c_void_p * max(len(rejected_targets), 1))(*[int(t) for t in rejected_targets])
+    cfg = config.to_c()
+    cubes.ctx.check(lib().ab_stack_frame_sharded_dev(
+        cubes.ctx.handle, bases, cubes.world, cubes.rank, int(n_frames), int(rows), int(cols), C.byref(cfg),
+        int(out_ptr) if out_ptr else None, tg, len(rejected_targets), int(stream) if stream else None))
+    return row_band(rows, cubes.rank, cubes.world)
 
-    from .core import stack_images_device
 
-    ptrs, (r0, r1) = cubes.band_pointers(n_frames, rows, cols)
-    dev = cubes.local.device
-    if out is None:
-        out = torch.empty((r1 - r0, cols), dtype=torch.float32, device=dev)
-    if rej is None:
-        rej = torch.zeros(1, dtype=torch.int64, device=dev)
-    if r1 > r0:
-        stack_images_device(ptrs, out.numel(), config, out.data_ptr(), rej.data_ptr(), stream, cubes.ctx)
-    allreduce_rejected(rej, group)
-    return out, rej, (r0, r1)
+def reshard_frames_to_bands_p2p(cubes: PeerCubes, n_frames: int, rows: int, cols: int, band_cube_ptr: int,
+                                stream: int = 0):
+    """Staged alternative behind the C ABI (ab_reshard_frames_to_bands_dev): pull this rank's band of
+    every frame into a local [n_frames, band_rows, cols] cube."""
+    bases = (C.c_void_p * cubes.world)(*[int(b) for b in cubes.base])
+    cubes.ctx.check(lib().ab_reshard_frames_to_bands_dev(
+        cubes.ctx.handle, bases, cubes.world, cubes.rank, int(n_frames), int(rows), int(cols),
+        int(band_cube_ptr) if band_cube_ptr else None, int(stream) if stream else None))
+    return row_band(rows, cubes.rank, cubes.world)

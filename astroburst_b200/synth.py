@@ -37,8 +37,11 @@ def render_stars(rows: int, cols: int, x, y, flux, sigma: float = 1.3) -> np.nda
 
 
 def stack_frames(n_frames: int, rows: int, cols: int, seed: int = 42, nan_border: int = 8,
-                 n_stars: int | None = None, cosmic_fraction: float = 2e-4) -> np.ndarray:
-    """-> float32 [n_frames, rows, cols]."""
+                 n_stars: int | None = None, cosmic_fraction: float = 2e-4,
+                 border: tuple | None = None) -> np.ndarray:
+    """-> float32 [n_frames, rows, cols].  `border` = (top, bottom, left, right) NaN strip widths
+    in frames k % 8 == 0, instead of the symmetric `nan_border` (row-band samples of a larger
+    frame)."""
     if n_stars is None:
         n_stars = max(int(6000 * rows * cols / 4096 ** 2), 4)
     x, y, flux = star_catalogue(rows, cols, n_stars, seed)
@@ -52,7 +55,17 @@ def stack_frames(n_frames: int, rows: int, cols: int, seed: int = 42, nan_border
             idx = rng.integers(0, rows * cols, n_cr)
             f.reshape(-1)[idx] += rng.uniform(5000.0, 50000.0, n_cr)
         f = f.astype(np.float32)
-        if nan_border and k % 8 == 0:
+        if border is not None and k % 8 == 0:
+            t, bt, lf, rt = (int(x) for x in border)
+            if t:
+                f[:t, :] = np.nan
+            if bt:
+                f[-bt:, :] = np.nan
+            if lf:
+                f[:, :lf] = np.nan
+            if rt:
+                f[:, -rt:] = np.nan
+        elif nan_border and k % 8 == 0:
             b = min(nan_border, rows // 4, cols // 4)
             if b:
                 f[:b, :] = np.nan

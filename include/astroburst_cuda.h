@@ -35,6 +35,7 @@ extern "C" {
 
 #define AB_ABI_VERSION 1
 #define AB_MAX_FRAMES 256      /* frames per stack call (register path <= 64, deep path <= 256) */
+#define AB_MAX_RANKS 16        /* GPUs of one box a frame-sharded stack can span */
 #define AB_MAX_BLEND_WEIGHTS 32
 #define AB_CURVE_LUT_SIZE 4096 /* core/imaging/curves.rs:66 */
 
@@ -160,14 +161,16 @@ int ab_ctx_device(ab_ctx *ctx);
 uint64_t ab_ctx_launch_count(ab_ctx *ctx);
 ab_status ab_ctx_synchronize(ab_ctx *ctx);
 /* cudaDeviceEnablePeerAccess from this context's device to `peer_device` (idempotent;
- * AB_ERR_UNSUPPORTED when the two GPUs are not P2P-capable).  Groundwork for reading a
- * frame-sharded stack's row bands straight from the owners' HBM instead of re-sharding first
- * (used together with ab_ipc_open, unconfirmed on hardware). */
+ * AB_ERR_UNSUPPORTED when the two GPUs are not P2P-capable).  Only needed when several GPUs are
+ * driven from ONE process; across processes ab_ipc_open enables peer access itself. */
 ab_status ab_ctx_enable_peer_access(ab_ctx *ctx, int peer_device);
-/* CUDA IPC import of another process's allocation (64 handle bytes from cudaIpcGetMemHandle) under
- * this context's device, with lazy peer access to the exporting GPU; ab_ipc_close unmaps it.
- * Used by the peer-memory variant of the frame-sharded deep stack, which is
- * NOT yet confirmed on hardware. */
+/* CUDA IPC: ab_ipc_export writes the 64 handle bytes (cudaIpcGetMemHandle) of a cudaMalloc'd block
+ * (`dev_ptr` = its base, e.g. from ab_dev_alloc); ab_ipc_open maps another process's block under
+ * this context's device with lazy peer access to the exporting GPU; ab_ipc_close unmaps it.  The
+ * host exchanges the handle bytes over whatever channel it has (the reference's Rust side would
+ * use its own IPC; the Python mirror uses torch.distributed).  Peer mappings feed
+ * ab_stack_frame_sharded_dev / ab_reshard_frames_to_bands_dev below. */
+ab_status ab_ipc_export(ab_ctx *ctx, const void *dev_ptr, void *handle64_out);
 ab_status ab_ipc_open(ab_ctx *ctx, const void *handle64, void **dev_ptr);
 ab_status ab_ipc_close(ab_ctx *ctx, void *dev_ptr);
 
@@ -203,6 +206,35 @@ ab_status ab_stack_sigma_clip_dev(ab_ctx *ctx, const float *const *d_frames, siz
 ab_status ab_stack_images(ab_ctx *ctx, const float *const *frames, size_t n_frames, size_t rows,
                           size_t cols, const ab_stack_config *cfg, float *out,
                           uint64_t *rejected_pixels, int32_t *offsets);
+/* ---- frame-sharded stacks over the GPUs of one box (BASELINE config 5)
+ * Partition rules: rank r of `world` owns the contiguous block of frames f with
+ * ab_frame_owner(f, n_frames, world) == r (f * world / n_frames; f % world when n_frames < world),
+ * stored in frame order as one [n_local, rows, cols] f32 cube, and combines row band
+ * [r0, r1) = ab_row_band(rows, r, world) of ALL frames (contiguous bands, sizes differ by <= 1 row).
+ * cube_bases: HOST array of `world` device pointers, entry q = base of rank q's cube as addressable
+ * from this context's device (its own allocation for q == rank, an ab_ipc_open mapping otherwise).
+ *
+ * ab_stack_frame_sharded_dev: stack_images (combine.rs:94-193, align == false) of this rank's
+ * band, reading the foreign frames straight from their owners' HBM over NVLink inside the stack
+ * kernel (no staging copy, no collective on the data path).  d_out_band: (r1-r0)*cols f32.
+ * StackResult.rejected_pixels: this rank's count is ADDED (system-scope atomics) to each of the
+ * n_targets device words d_rejected_targets[i] -- pass every rank's counter (own + peer mappings)
+ * and each rank holds the global sum once all ranks' calls have completed; the caller zeroes the
+ * counters beforehand and orders steps across ranks (e.g. one counter per step in flight).
+ * n_targets == 0 drops the count.  Bit-identical to the single-GPU stack of all frames.
+ *
+ * ab_reshard_frames_to_bands_dev: the staged alternative -- copies this rank's band of every frame
+ * into d_band_cube [n_frames, r1-r0, cols] (pull copies over NVLink, one 2-D copy per owner). */
+void ab_row_band(size_t rows, int rank, int world, size_t *r0, size_t *r1);
+int ab_frame_owner(size_t f, size_t n_frames, int world);
+ab_status ab_stack_frame_sharded_dev(ab_ctx *ctx, const float *const *cube_bases, int world,
+                                     int rank, size_t n_frames, size_t rows, size_t cols,
+                                     const ab_stack_config *cfg, float *d_out_band,
+                                     uint64_t *const *d_rejected_targets, int n_targets,
+                                     void *stream);
+ab_status ab_reshard_frames_to_bands_dev(ab_ctx *ctx, const float *const *cube_bases, int world,
+                                         int rank, size_t n_frames, size_t rows, size_t cols,
+                                         float *d_band_cube, void *stream);
 /* One pixel's sample list through the same device code path (combine.rs:14-92); n <= 256.
  * Used by the parity tests for the reference's sigma_clip_combine unit tests. */
 ab_status ab_sigma_clip_combine(ab_ctx *ctx, const float *values, size_t n, float sigma_low,

@@ -138,7 +138,7 @@ void correlate_single(const View &a, const View &b, double *dx, double *dy, doub
             if (std::isfinite(v)) var_sum += (v - mean) * (v - mean);
         sigma = std::sqrt(var_sum / (count > 1.0 ? count - 1.0 : 1.0));
     }
-    const double eps = 2.220446049250313e-16;
+    const double eps = 1e-15;  // FftFloat::epsilon_val() for f64, math/fft.rs:57 (normalization.rs:166, subpixel.rs:55)
     *conf = std::fabs(sigma) < eps ? 0.0 : (sf[best] - mean) / sigma;
     auto unwrap = [](size_t peak, size_t size) {
         return peak > size / 2 ? (double)peak - (double)size : (double)peak;

@@ -33,3 +33,16 @@ def test_reference_arm_prints_the_contract_line():
 def test_reference_arm_other_ranks_do_nothing():
     r = _run({"RANK": "3", "WORLD_SIZE": "8", "LOCAL_RANK": "3"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_uses_all_host_threads_under_torchrun_env():
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm must still use every host core (r1's
+    multi-GPU vs_reference was void because it ran on one thread) and carry the GPU arm's config."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    r = _run({"OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "8", "LOCAL_RANK": "0"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert d["config"] == bench.CONFIG

@@ -2,18 +2,15 @@
 committed HST M16 crops against the committed vectors -- FITS decode, image statistics, auto-STF,
 STF u8 preview, star detection, and the linked-STF -> SCNR -> RGB8 compose tail.
 
-These fixtures were added after round 1's GPU budget was spent, so this file has not run on a B200
-yet: the tests are marked xfail(strict=False) until a GPU run confirms them (an unexpected pass is
-reported as XPASS and is the expected outcome -- every operator involved is already bit-exact
-against the oracle on synthetic inputs)."""
+Confirmed on B200 at the end of round 1 (5 xpassed in GPUTEST_r01); the provisional xfail markers
+are gone, so a regression fails."""
 import os
 import sys
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="new in r1 after the GPU budget ended: unconfirmed on B200")]
+pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 sys.path.insert(0, GOLD)
 

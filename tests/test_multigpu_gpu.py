@@ -123,23 +123,38 @@ def _p2p_worker(rank, world, port, q):
     ctx = ab.default_context(rank)
     s = torch.cuda.current_stream().cuda_stream
     res = {}
-    for key, nf in (("fs16", 16), ("fs40", 40)):
-        fr = synth.stack_frames(nf, 64, 512, seed=11, nan_border=3)
+    # register path (16), deep path (40, 256 frames), ragged band width (cols not a multiple of 32)
+    for key, nf, rows, cols in (("fs16", 16, 64, 512), ("fs40", 40, 64, 512), ("fs256", 256, 10, 330)):
+        fr = synth.stack_frames(nf, rows, cols, seed=11, nan_border=3)
         mine = [f for f in range(nf) if parallel.frame_owner(f, nf, world) == rank]
-        local = torch.from_numpy(np.ascontiguousarray(fr[mine])).to(dev)
-        cubes = parallel.PeerCubes(local, ctx)
-        band, rj, _ = parallel.stack_frame_sharded_p2p(cubes, nf, 64, 512, ab.StackConfig(3.0, 3.0, 5, False), s)
+        local = parallel.DeviceCube((len(mine), rows, cols), ctx)
+        local.tensor().copy_(torch.from_numpy(np.ascontiguousarray(fr[mine])))
+        counter = parallel.DeviceCube((2,), ctx)            # 8 bytes = one u64 counter
+        counter.tensor().zero_()
+        cubes = parallel.PeerCubes(local)                   # (barrier inside: counters are zero everywhere)
+        counters = parallel.PeerCubes(counter)
+        r0, r1 = parallel.row_band(rows, rank, world)
+        out = torch.empty((r1 - r0, cols), dtype=torch.float32, device=dev)
+        parallel.stack_frame_sharded_p2p(cubes, nf, rows, cols, ab.StackConfig(3.0, 3.0, 5, False),
+                                         out.data_ptr(), rejected_targets=counters.base, stream=s)
+        band_cube = torch.empty((nf, r1 - r0, cols), dtype=torch.float32, device=dev)
+        parallel.reshard_frames_to_bands_p2p(cubes, nf, rows, cols, band_cube.data_ptr(), stream=s)
         torch.cuda.synchronize()
-        res[key] = (band.cpu().numpy(), int(rj))
+        dist.barrier()                                      # every rank's fan-out has landed
+        rej = int(counter.tensor().view(torch.int64)[0].item())
+        res[key] = (out.cpu().numpy(), rej, bool(np.array_equal(band_cube.cpu().numpy(), fr[:, r0:r1], equal_nan=True)))
+        counters.close()
         cubes.close()
+        counter.free()
+        local.free()
     q.put((rank, res))
     dist.destroy_process_group()
 
 
-@pytest.mark.xfail(strict=False, reason="peer-memory stack: re-designed after r1's GPU budget ended, unconfirmed on B200")
 def test_frame_sharded_stack_with_peer_memory_loads(orc):
-    """The frame-sharded stack reading its row bands straight from the owners' HBM (no staging copy)
-    equals the oracle, register and deep paths."""
+    """The frame-sharded stack reading its row bands straight from the owners' HBM over NVLink (one
+    kernel, no staging copy; reject counts fanned out with peer atomics) equals the oracle on the
+    register and deep paths; the pull re-shard behind the C ABI reproduces the bands."""
     import torch
     import torch.multiprocessing as mp
 
@@ -154,15 +169,16 @@ def test_frame_sharded_stack_with_peer_memory_loads(orc):
     for p in procs:
         p.start()
     try:
-        out = dict(q.get(timeout=90) for _ in procs)
+        out = dict(q.get(timeout=180) for _ in procs)
     finally:
         for p in procs:
-            p.join(timeout=20)
+            p.join(timeout=30)
             if p.is_alive():
                 p.kill()
-    for key, nf in (("fs16", 16), ("fs40", 40)):
-        fr = synth.stack_frames(nf, 64, 512, seed=11, nan_border=3)
+    for key, nf, rows, cols in (("fs16", 16, 64, 512), ("fs40", 40, 64, 512), ("fs256", 256, 10, 330)):
+        fr = synth.stack_frames(nf, rows, cols, seed=11, nan_border=3)
         want_img, want_rej = orc.stack_images(list(fr), 3.0, 3.0, 5)
         got = np.concatenate([out[0][key][0], out[1][key][0]])
-        assert np.array_equal(got, want_img)
-        assert out[0][key][1] == out[1][key][1] == want_rej
+        assert np.array_equal(got, want_img), key
+        assert out[0][key][1] == out[1][key][1] == want_rej, key
+        assert out[0][key][2] and out[1][key][2], key

@@ -157,3 +157,22 @@ def test_band_pointers_in_cubes():
             if r1 > r0:
                 assert p == cubes[o][seen[o], r0].data_ptr()
             seen[o] += 1
+
+
+def test_c_abi_partition_rules_match_the_python_mirror():
+    """ab_row_band / ab_frame_owner (shard.cu) == parallel.row_band / frame_owner (no GPU needed)."""
+    import ctypes as C
+
+    from astroburst_b200 import _lib
+    from astroburst_b200.parallel import frame_owner, row_band
+
+    lib = _lib.lib()
+    for rows in (0, 1, 7, 64, 4096, 4099):
+        for world in (1, 2, 3, 8, 16):
+            for rank in range(world):
+                r0, r1 = C.c_size_t(), C.c_size_t()
+                lib.ab_row_band(rows, rank, world, C.byref(r0), C.byref(r1))
+                assert (r0.value, r1.value) == row_band(rows, rank, world)
+    for n in (1, 3, 8, 40, 255, 256):
+        for world in (1, 2, 5, 8):
+            assert [lib.ab_frame_owner(f, n, world) for f in range(n)] == [frame_owner(f, n, world) for f in range(n)]

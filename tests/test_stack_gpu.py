@@ -197,3 +197,107 @@ def test_full_size_properties(ab, orc):
     ab.stack_images_device([f.data_ptr() for f in same], rows * cols, cfg, out2.data_ptr(), rej2.data_ptr(), s)
     torch.cuda.synchronize()
     assert torch.equal(out2, frames[1]) and int(rej2) == 0
+
+
+# ---- deep path (33..256 frames, stack_deep.cu): far outliers, ragged / unaligned input, gaps
+@pytest.mark.parametrize("n", [33, 100, 256])
+def test_deep_far_outliers(ab, orc, n):
+    """a far finite outlier must not wreck the f64 moments of the later iterations
+    (they are accumulated after iteration 0's clip and never contain it)."""
+    rng = np.random.default_rng(7 + n)
+    cases = [
+        (rng.normal(1000.0, 30.0, n), 1e12),
+        (rng.normal(0.05, 0.005, n), 1e7),
+        (rng.normal(999.0, 5.0, n), 1e30),
+        (rng.normal(100.0, 1.0, n), float(np.finfo(np.float32).max)),
+        (rng.normal(1e-3, 1e-4, n), 1e7),
+    ]
+    for v, outlier in cases:
+        v = v.astype(np.float32)
+        v[n // 3] = outlier
+        for it in (1, 2, 5):
+            want = orc.sigma_clip_combine(v, 3.0, 3.0, it)
+            assert ab.sigma_clip_combine(v, 3.0, 3.0, it) == want, (n, outlier, it)
+            assert 1 <= want[1] < n // 2
+
+
+@pytest.mark.parametrize("n_frames,rows,cols", [(256, 9, 37), (200, 5, 70), (129, 7, 33), (65, 6, 50), (40, 11, 29)])
+def test_deep_ragged_unaligned_and_gaps(ab, orc, n_frames, rows, cols):
+    """Pixel counts that are not a multiple of the 32-pixel tile, frames at 4-byte (not 16-byte)
+    aligned device addresses, per-pixel varying finite counts (NaN / +-inf gaps), all-NaN pixels."""
+    import torch
+    from astroburst_b200 import synth
+
+    fr = synth.stack_frames(n_frames, rows, cols, seed=n_frames, nan_border=0, cosmic_fraction=4e-3)
+    rng = np.random.default_rng(n_frames)
+    gaps = rng.random(fr.shape) < 0.07
+    fr[gaps] = np.nan
+    fr[rng.random(fr.shape) < 0.002] = np.inf
+    fr[rng.random(fr.shape) < 0.002] = -np.inf
+    fr[:, 1, 2] = np.nan                     # no finite sample at all -> 0
+    fr[: n_frames - 1, 2, 3] = np.nan        # exactly one finite sample
+    fr[: n_frames - 2, 3, 4] = np.nan        # two
+    fr[::2, 4, :] = np.nan                   # half the frames missing along a row
+    want, want_rej = orc.stack_images(list(fr), 3.0, 3.0, 5)
+    res = ab.stack_images(list(fr), ab.StackConfig(3.0, 3.0, 5, False))
+    assert res.rejected_pixels == want_rej and np.array_equal(res.image, want)
+    # device entry point, every frame starting 4 bytes off a 16-byte boundary
+    dev = torch.device("cuda:0")
+    npix = rows * cols
+    pad = (npix + 1 + 3) // 4 * 4
+    flat = torch.zeros(n_frames * pad + 4, dtype=torch.float32, device=dev)
+    ptrs = []
+    for f in range(n_frames):
+        v = flat[f * pad + 1: f * pad + 1 + npix]
+        v.copy_(torch.from_numpy(fr[f].reshape(-1)))
+        assert v.data_ptr() % 16 == 4
+        ptrs.append(v.data_ptr())
+    out = torch.empty(npix, dtype=torch.float32, device=dev)
+    rej = torch.zeros(1, dtype=torch.int64, device=dev)
+    ab.stack_images_device(ptrs, npix, ab.StackConfig(3.0, 3.0, 5, False), out.data_ptr(), rej.data_ptr(),
+                           torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(rej) == want_rej and np.array_equal(out.cpu().numpy().reshape(rows, cols), want)
+
+
+def test_deep_band_properties_at_config5_size(ab, orc):
+    """256 frames x (64 x 4096) band (1/64 of BASELINE config 5): oracle on sampled rows,
+    frame-order invariance, sigma / iteration sweep."""
+    import torch
+
+    dev = torch.device("cuda:0")
+    n, rows, cols = 256, 64, 4096
+    g = torch.Generator(device=dev)
+    g.manual_seed(99)
+    cube = torch.randn((n, rows, cols), generator=g, device=dev) * 12.0 + 1000.0
+    idx = torch.randint(0, cube.numel(), (cube.numel() // 5000,), generator=g, device=dev)
+    cube.view(-1)[idx] += torch.rand(idx.numel(), generator=g, device=dev) * 45000.0 + 5000.0
+    cube[::8, :3, :] = float("nan")          # frame-uniform gap rows (registration borders)
+    s = torch.cuda.current_stream().cuda_stream
+    out = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+    rej = torch.zeros(1, dtype=torch.int64, device=dev)
+    for (sl, sh, it) in ((3.0, 3.0, 5), (2.0, 2.5, 2), (3.0, 3.0, 0)):
+        cfg = ab.StackConfig(sl, sh, it, False)
+        ab.stack_images_device([cube[f].data_ptr() for f in range(n)], rows * cols, cfg, out.data_ptr(),
+                               rej.data_ptr(), s)
+        torch.cuda.synchronize()
+        for r0 in (0, 2, 40):
+            band = [cube[f, r0:r0 + 2].cpu().numpy() for f in range(n)]
+            want, _ = orc.stack_images(band, sl, sh, it)
+            assert np.array_equal(out[r0:r0 + 2].cpu().numpy(), want), (sl, sh, it, r0)
+        want_all, want_rej = orc.stack_images([cube[f, :8].cpu().numpy() for f in range(n)], sl, sh, it)
+        rej8 = torch.zeros(1, dtype=torch.int64, device=dev)
+        out8 = torch.empty((8, cols), dtype=torch.float32, device=dev)
+        ab.stack_images_device([cube[f].data_ptr() for f in range(n)], 8 * cols, cfg, out8.data_ptr(),
+                               rej8.data_ptr(), s)
+        torch.cuda.synchronize()
+        assert int(rej8) == want_rej and np.array_equal(out8.cpu().numpy(), want_all)
+    perm = torch.randperm(n).tolist()
+    out2 = torch.empty_like(out)
+    rej2 = torch.zeros_like(rej)
+    ab.stack_images_device([cube[f].data_ptr() for f in range(n)], rows * cols, ab.StackConfig(3.0, 3.0, 5, False),
+                           out.data_ptr(), rej.data_ptr(), s)
+    ab.stack_images_device([cube[f].data_ptr() for f in perm], rows * cols, ab.StackConfig(3.0, 3.0, 5, False),
+                           out2.data_ptr(), rej2.data_ptr(), s)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2) and int(rej) == int(rej2)

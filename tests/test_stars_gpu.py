@@ -171,7 +171,6 @@ def test_detect_stars_band_parallel_fill_is_order_exact(al, orc, monkeypatch):
         same_detection(al.detect_stars(img, 3.5), want)
 
 
-@pytest.mark.xfail(strict=False, reason="added after r1's GPU budget ended: unconfirmed on B200")
 @pytest.mark.parametrize("shape,tile", [((700, 900), 300), ((1100, 600), 512)])
 def test_background_tiles_beyond_the_on_chip_capacity(al, orc, shape, tile):
     """Caller-chosen tiles above 65,536 px run the global-memory pixel source of the tile kernel

@@ -48,9 +48,13 @@ using abk::CeConst;
 
 constexpr int DL = 4;        // lanes per pixel
 constexpr int DPX = 32 / DL; // pixels per warp
-constexpr int DWARPS = 4;    // warps per block
+#ifndef AB_DEEP_WARPS
+#define AB_DEEP_WARPS 4
+#endif
+constexpr int DWARPS = AB_DEEP_WARPS;  // warps per block
 constexpr int DTHREADS = DWARPS * 32;
 constexpr int TILE_PX = DWARPS * DPX;  // 32 pixels = one 128-byte line per frame
+constexpr int ROW_CHUNKS = TILE_PX / 4;  // 16-byte chunks of one frame row of a tile
 constexpr unsigned FULL = 0xffffffffu;
 
 template <int R>
@@ -85,25 +89,25 @@ static __device__ __noinline__ void fill_stage(float *stage, const float *const 
                                                size_t npix, size_t tile, bool aligned16) {
     using G = Geom<R>;
     const size_t px0 = tile * TILE_PX;
-    const int k = (int)threadIdx.x & 7;
-    const size_t px = px0 + 4 * k;
-    float *dst0 = stage + (k >> 1) * G::REGION + (k & 1) * 4;
-    const int f0 = (int)threadIdx.x >> 3;  // this thread's rows: f0, f0 + 16, ...
+    constexpr int ITERS = (G::FR * ROW_CHUNKS) / DTHREADS;
     if (aligned16 && px0 + TILE_PX <= npix) {
 #pragma unroll
-        for (int it = 0; it < (G::FR * 8) / DTHREADS; ++it) {
-            const int f = f0 + it * (DTHREADS / 8);
-            float *dst = dst0 + f * 8;
-            if (f < n_frames) cp_async16(dst, ptrs[f] + px);
+        for (int it = 0; it < ITERS; ++it) {
+            const int c = it * DTHREADS + (int)threadIdx.x;
+            const int f = c / ROW_CHUNKS, k = c % ROW_CHUNKS;
+            float *dst = stage + (k >> 1) * G::REGION + f * 8 + (k & 1) * 4;
+            if (f < n_frames) cp_async16(dst, ptrs[f] + px0 + 4 * k);
             else  // rows past the frame count: +inf sorts last and counts as "not finite"
                 *reinterpret_cast<float4 *>(dst) =
                     make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
         }
     } else {  // unaligned frames or the ragged last tile: 4-byte copies, pixels past the end untouched
 #pragma unroll 1
-        for (int it = 0; it < (G::FR * 8) / DTHREADS; ++it) {
-            const int f = f0 + it * (DTHREADS / 8);
-            float *dst = dst0 + f * 8;
+        for (int it = 0; it < ITERS; ++it) {
+            const int c = it * DTHREADS + (int)threadIdx.x;
+            const int f = c / ROW_CHUNKS, k = c % ROW_CHUNKS;
+            float *dst = stage + (k >> 1) * G::REGION + f * 8 + (k & 1) * 4;
+            const size_t px = px0 + 4 * k;
 #pragma unroll 1
             for (int e = 0; e < 4; ++e) {
                 if (f >= n_frames) dst[e] = CUDART_INF_F;
@@ -174,7 +178,7 @@ __device__ __forceinline__ double quad_sum(double v) {
 
 // PRE = false is the plain stack (no calibration terms, no median-only mode compiled in).
 template <int R, bool PRE>
-__global__ void __launch_bounds__(DTHREADS, R == 64 ? 3 : 4)
+__global__ void __launch_bounds__(DTHREADS, (R == 64 ? 12 : 16) / DWARPS)
 stack_deep_kernel(const __grid_constant__ FrameTable ft, int n_frames, size_t npix,
                   float sigma_low, float sigma_high, unsigned max_iter, CeConst kc,
                   const __grid_constant__ DeepPre pre, int aligned16, float *__restrict__ out,

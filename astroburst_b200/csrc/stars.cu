@@ -28,9 +28,10 @@
 #include <cstdint>
 #include <cstring>
 #include <cstdlib>
-#include <thread>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <math_constants.h>
 
 #include "ab_internal.h"
@@ -342,7 +343,7 @@ row_count_kernel(const float *__restrict__ img, size_t rows, size_t cols, Norm n
 __global__ void __launch_bounds__(256)
 row_compact_kernel(const float *__restrict__ img, size_t rows, size_t cols, Norm nm, double thr,
                    const unsigned long long *__restrict__ row_offsets, unsigned *__restrict__ out_col,
-                   float *__restrict__ out_val) {
+                   float *__restrict__ out_val, unsigned *__restrict__ out_row) {
     const size_t r = blockIdx.x;
     __shared__ unsigned warp_tot[8];
     __shared__ unsigned run;
@@ -367,6 +368,7 @@ row_compact_kernel(const float *__restrict__ img, size_t rows, size_t cols, Norm
             const unsigned long long pos = base + before + __popc(bal & ((1u << lane) - 1u));
             out_col[pos] = (unsigned)x;
             out_val[pos] = v;
+            out_row[pos] = (unsigned)r;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -375,6 +377,34 @@ row_compact_kernel(const float *__restrict__ img, size_t rows, size_t cols, Norm
             run += tot;
         }
         __syncthreads();
+    }
+}
+
+// exclusive prefix sum of the per-row counts -> row offsets (rows + 1 entries), one block
+__global__ void __launch_bounds__(1024)
+row_offsets_kernel(const unsigned *__restrict__ row_counts, size_t rows,
+                   unsigned long long *__restrict__ row_offsets) {
+    __shared__ unsigned long long part[1024];
+    const size_t per = (rows + blockDim.x - 1) / blockDim.x;
+    const size_t b = (size_t)threadIdx.x * per, e = b + per < rows ? b + per : rows;
+    unsigned long long sum = 0;
+    for (size_t r = b; r < e; ++r) sum += row_counts[r];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (unsigned t = 0; t < blockDim.x; ++t) {
+            const unsigned long long v = part[t];
+            part[t] = run;
+            run += v;
+        }
+        row_offsets[rows] = run;
+    }
+    __syncthreads();
+    unsigned long long run = part[threadIdx.x];
+    for (size_t r = b; r < e; ++r) {
+        row_offsets[r] = run;
+        run += row_counts[r];
     }
 }
 
@@ -422,195 +452,235 @@ tri_match_kernel(const double *__restrict__ r_mid, const double *__restrict__ r_
 }
 
 // ------------------------------------------------------------------------- host-side pieces
-struct SparseImage {  // above-threshold pixels in raster order
-    size_t rows = 0, cols = 0;
-    std::vector<unsigned long long> row_off;  // rows + 1
-    std::vector<unsigned> col;
-    std::vector<float> val;
-    // index of pixel (r, c) in the list or -1
-    long long find(size_t r, size_t c) const {
-        const unsigned *b = col.data() + row_off[r], *e = col.data() + row_off[r + 1];
-        const unsigned *it = std::lower_bound(b, e, (unsigned)c);
-        return (it != e && *it == c) ? (long long)(it - col.data()) : -1;
-    }
-};
-
 inline size_t f2us(double x) {  // Rust `f64 as usize`
     if (!(x > 0.0)) return 0;
     if (x >= 18446744073709551615.0) return SIZE_MAX;
     return (size_t)x;
 }
 
-// star_detection.rs:105-248 on the sparse list: identical visiting order, identical f64 sums.
-//
-// The reference's raster scan + BFS is sequential, but connected components are disjoint: the
-// BFS of a component (from its first interior pixel in raster order) does not depend on any other
-// component.  So the list is cut into row bands of equal pixel count, one host thread per band
-// grows the components that lie entirely inside its band (it never touches a pixel of another
-// band), components that cross a band edge are grown afterwards by the sequential algorithm, and
-// the stars are put back into discovery order by their seed index.
-struct Filler {
-    const SparseImage &sp;
-    double bg_median, bg_sigma;
-    std::vector<unsigned> row_idx;  // row of every sparse pixel
-    std::vector<char> visited;      // 0 free, 1 taken, 2 part of a band-crossing component
-    struct Found {
-        unsigned long long seed;
-        ab_star star;
-    };
-
-    Filler(const SparseImage &s, double med, double sig)
-        : sp(s), bg_median(med), bg_sigma(sig), row_idx(s.col.size()), visited(s.col.size(), 0) {
-        for (size_t r = 0; r < sp.rows; ++r)
-            for (unsigned long long p = sp.row_off[r]; p < sp.row_off[r + 1]; ++p) row_idx[p] = (unsigned)r;
-    }
-    // the up-to-three list entries of row `r` in columns c-1, c, c+1 (-1 where absent): one search
-    void three(long long r, size_t c, long long out3[3]) const {
-        out3[0] = out3[1] = out3[2] = -1;
-        if (r < 0 || r >= (long long)sp.rows) return;
-        const unsigned *b = sp.col.data() + sp.row_off[r], *e = sp.col.data() + sp.row_off[r + 1];
-        const unsigned lo = c ? (unsigned)(c - 1) : 0u;
-        for (const unsigned *it = std::lower_bound(b, e, lo); it != e && *it <= c + 1; ++it)
-            out3[*it + 1 - c] = (long long)(it - sp.col.data());
-    }
-    // BFS from `seed` in the reference's neighbour order.  With a band [r0, r1) given, pixels of
-    // other rows are not touched; returns false when the component reaches outside the band.
-    bool grow(long long seed, size_t r0, size_t r1, std::vector<long long> &comp) {
-        bool inside = true;
-        comp.clear();
-        comp.push_back(seed);  // `comp` is the BFS queue and, when done, the visiting order
-        visited[seed] = 1;
-        for (size_t head = 0; head < comp.size(); ++head) {
-            const long long cur = comp[head];
-            const size_t cr = row_idx[cur], cc = sp.col[cur];
-            long long up[3], dn[3];
-            three((long long)cr - 1, cc, up);
-            three((long long)cr + 1, cc, dn);
-            const long long left =
-                ((unsigned long long)cur > sp.row_off[cr] && sp.col[cur - 1] + 1 == cc) ? cur - 1 : -1;
-            const long long right =
-                ((unsigned long long)cur + 1 < sp.row_off[cr + 1] && sp.col[cur + 1] == cc + 1) ? cur + 1 : -1;
-            // star_detection.rs:123: N, S, W, E, NW, NE, SW, SE
-            const long long nb[8] = {up[1], dn[1], left, right, up[0], up[2], dn[0], dn[2]};
-            for (int k = 0; k < 8; ++k) {
-                const long long q = nb[k];
-                if (q < 0) continue;
-                const size_t qr = row_idx[q];
-                if (qr < r0 || qr >= r1) {
-                    inside = false;
-                    continue;
-                }
-                if (visited[q]) continue;
-                visited[q] = 1;
-                comp.push_back(q);
-            }
-        }
-        return inside;
-    }
-    // star_detection.rs:142-214: moments of one component in BFS order
-    bool measure(const std::vector<long long> &comp, ab_star *out) const {
-        const size_t npix = comp.size();
-        if (npix < 3 || npix > 5000) return false;
-        double sum_flux = 0.0, sum_x = 0.0, sum_y = 0.0, peak_val = 0.0;
-        for (long long q : comp) {
-            const double w = std::fmax((double)sp.val[q] - bg_median, 0.0);
-            sum_flux += w;
-            sum_x += (double)sp.col[q] * w;
-            sum_y += (double)row_idx[q] * w;
-            peak_val = std::fmax(peak_val, w);
-        }
-        if (sum_flux <= 0.0) return false;
-        const double cx = sum_x / sum_flux, cy = sum_y / sum_flux;
-        double sum_r2 = 0.0, sum_xx = 0.0, sum_yy = 0.0, sum_xy = 0.0;
-        for (long long q : comp) {
-            const double w = std::fmax((double)sp.val[q] - bg_median, 0.0);
-            const double dx = (double)sp.col[q] - cx;
-            const double dy = (double)row_idx[q] - cy;
-            sum_r2 += (dx * dx + dy * dy) * w;
-            sum_xx += dx * dx * w;
-            sum_yy += dy * dy * w;
-            sum_xy += dx * dy * w;
-        }
-        const double sigma_star = std::sqrt(sum_r2 / (2.0 * sum_flux));
-        const double fwhm = sigma_star * 2.3548200450309493;
-        if (fwhm < 0.5 || fwhm > 30.0) return false;
-        const double ixx = sum_xx / sum_flux, iyy = sum_yy / sum_flux, ixy = sum_xy / sum_flux;
-        const double trace = ixx + iyy;
-        const double det = std::fmax(ixx * iyy - ixy * ixy, 0.0);
-        const double disc = std::sqrt(std::fmax((trace * trace / 4.0) - det, 0.0));
-        const double lambda1 = trace / 2.0 + disc;
-        const double lambda2 = std::fmax(trace / 2.0 - disc, 0.0);
-        double ecc = 0.0;
-        if (lambda1 > 1e-15) {
-            ecc = std::sqrt(1.0 - lambda2 / lambda1);
-            ecc = ecc < 0.0 ? 0.0 : (ecc > 1.0 ? 1.0 : ecc);
-        }
-        const double snr = bg_sigma <= DBL_EPSILON ? 0.0 : peak_val / bg_sigma;  // confidence.rs:3-8
-        *out = {cx, cy, sum_flux, fwhm, ecc, peak_val, (uint64_t)npix, snr};
-        return true;
-    }
-    // seeds of rows [r0, r1) in raster order; banded = stay inside the band
-    void scan(size_t r0, size_t r1, bool banded, std::vector<Found> &found) {
-        std::vector<long long> comp;
-        const size_t rows = sp.rows, cols = sp.cols;
-        for (size_t r = std::max(r0, (size_t)1); r < r1 && r + 1 < rows; ++r) {
-            for (unsigned long long p = sp.row_off[r]; p < sp.row_off[r + 1]; ++p) {
-                const size_t c = sp.col[p];
-                if (c < 1 || c + 1 >= cols || visited[p]) continue;  // seeds are interior pixels
-                const bool inside = banded ? grow((long long)p, r0, r1, comp) : grow((long long)p, 0, rows, comp);
-                if (!inside) {  // leave it to the sequential pass
-                    for (long long q : comp) visited[q] = 2;
-                    continue;
-                }
-                ab_star st;
-                if (measure(comp, &st)) found.push_back({p, st});
-            }
-        }
-    }
+// ------------------------------------------------------------------------- components on the device
+// star_detection.rs:105-214 on the sparse above-threshold list, bit-identical to the reference's
+// serial raster scan + BFS:
+//   1. union-find CCL (8-connectivity) over the sparse pixels: every pixel links to its W / NW /
+//      N / NE neighbours (one binary search in the previous row), atomicMin hooks, then a flatten
+//      pass that also counts npix per root and takes the smallest INTERIOR pixel of the component
+//      -- the pixel at which the reference's scan discovers it (seeds are interior pixels,
+//      components may contain border pixels, star_detection.rs:108-140);
+//   2. components with 3 <= npix <= 5000 (:142-145; larger blobs are flood-filled and dropped by
+//      the reference, so only their size matters) get a slot in discovery order (prefix sum over
+//      the seed flags) and a slice of the visiting-order queue;
+//   3. one 8-lane group per component replays the reference's BFS from the seed: lane j looks up
+//      neighbour j of the queue head in the reference's order N, S, W, E, NW, NE, SW, SE, and the
+//      unvisited ones are appended in that order (ballot + rank), so the queue IS the reference's
+//      `component` vector; the f64 moments are then accumulated over it sequentially, expression
+//      by expression as :147-175 (no FMA contraction: -fmad=false), hence bit-identical sums;
+//   4. stable radix sort by flux descending (input in discovery order = the reference's stable
+//      sort_by, :215).  The greedy 3-px dedup (:217-248) stays host scalar code on the sorted list.
+struct CompRec {
+    unsigned seed, off, npix, pad;
+};
+struct StarRec {
+    ab_star st;
 };
 
-void flood_fill_stars(const SparseImage &sp, double bg_median, double bg_sigma,
-                      std::vector<ab_star> &out) {
-    Filler fl(sp, bg_median, bg_sigma);
-    const size_t rows = sp.rows, nfg = sp.col.size();
-    std::vector<Filler::Found> found;
-    unsigned n_thr = std::thread::hardware_concurrency();
-    n_thr = n_thr > 16 ? 16 : n_thr;
-    bool forced = false;  // AB_FILL_THREADS=n: exactly n bands whatever the image size (tests)
-    if (const char *e = std::getenv("AB_FILL_THREADS")) {
-        n_thr = (unsigned)std::min(64, std::max(1, std::atoi(e)));
-        forced = true;
+__device__ __forceinline__ unsigned uf_find(const unsigned *parent, unsigned x) {
+    for (;;) {
+        const unsigned p = __ldcg(parent + x);
+        if (p == x) return x;
+        x = p;
     }
-    if (n_thr > 1 && (forced ? rows >= 2 * (size_t)n_thr : (nfg >= 20000 && rows >= 64 * (size_t)n_thr))) {
-        // band edges at equal shares of the sparse pixels
-        std::vector<size_t> edge(n_thr + 1, rows);
-        edge[0] = 0;
-        for (unsigned t = 1; t < n_thr; ++t) {
-            const unsigned long long want = (unsigned long long)nfg * t / n_thr;
-            edge[t] = (size_t)(std::lower_bound(sp.row_off.begin(), sp.row_off.end(), want) -
-                               sp.row_off.begin());
-            if (edge[t] > rows) edge[t] = rows;
-            if (edge[t] < edge[t - 1]) edge[t] = edge[t - 1];
+}
+__device__ __forceinline__ void uf_unite(unsigned *parent, unsigned a, unsigned b) {
+    for (;;) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a > b) {
+            const unsigned t = a;
+            a = b;
+            b = t;
         }
-        std::vector<std::vector<Filler::Found>> part(n_thr);
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < n_thr; ++t)
-            pool.emplace_back([&, t] { fl.scan(edge[t], edge[t + 1], true, part[t]); });
-        for (auto &th : pool) th.join();
-        for (auto &v : part) found.insert(found.end(), v.begin(), v.end());
-        for (auto &v : fl.visited)
-            if (v == 2) v = 0;
+        const unsigned old = atomicMin(parent + b, a);  // hook the larger root under the smaller
+        if (old == b) return;
+        b = old;
     }
-    fl.scan(0, rows, false, found);  // everything (sequential mode) or the band-crossing components
-    std::sort(found.begin(), found.end(),
-              [](const Filler::Found &a, const Filler::Found &b) { return a.seed < b.seed; });
-    std::vector<ab_star> stars;
-    stars.reserve(found.size());
-    for (const auto &f : found) stars.push_back(f.star);
-    std::stable_sort(stars.begin(), stars.end(),
-                     [](const ab_star &a, const ab_star &b) { return a.flux > b.flux; });
-    // greedy dedup on a 3-px grid (star_detection.rs:219-248); the grid is a flat hash of cell ->
-    // chain of kept stars (same decisions as the reference's HashMap<(usize, usize), Vec<usize>>)
+}
+// first list index of row `r` whose column is >= c
+__device__ __forceinline__ unsigned long long row_lower_bound(const unsigned *__restrict__ col,
+                                                              const unsigned long long *__restrict__ ro,
+                                                              size_t r, unsigned c) {
+    unsigned long long lo = __ldg(ro + r), hi = __ldg(ro + r + 1);
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (__ldg(col + mid) < c) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void ccl_init_kernel(unsigned *parent, unsigned *npix, unsigned *seed, unsigned char *vis,
+                                unsigned *flag, unsigned *size, unsigned n) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        parent[i] = i;
+        npix[i] = 0;
+        seed[i] = 0xffffffffu;
+        vis[i] = 0;
+        flag[i] = 0;
+        size[i] = 0;
+    }
+}
+__global__ void ccl_union_kernel(const unsigned *__restrict__ col, const unsigned *__restrict__ rowi,
+                                 const unsigned long long *__restrict__ ro, unsigned *parent, unsigned n) {
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const unsigned r = __ldg(rowi + p), c = __ldg(col + p);
+    if ((unsigned long long)p > __ldg(ro + r) && __ldg(col + p - 1) + 1 == c) uf_unite(parent, p, p - 1);
+    if (r > 0) {
+        const unsigned long long e = __ldg(ro + r);
+        for (unsigned long long q = row_lower_bound(col, ro, r - 1, c ? c - 1 : 0u);
+             q < e && __ldg(col + q) <= c + 1; ++q)
+            uf_unite(parent, p, (unsigned)q);
+    }
+}
+__global__ void ccl_flatten_kernel(const unsigned *__restrict__ col, const unsigned *__restrict__ rowi,
+                                   unsigned *parent, unsigned *npix, unsigned *seed, unsigned n,
+                                   unsigned rows, unsigned cols) {
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const unsigned root = uf_find(parent, p);
+    parent[p] = root;
+    atomicAdd(npix + root, 1u);
+    const unsigned r = __ldg(rowi + p), c = __ldg(col + p);
+    if (r >= 1 && r + 1 < rows && c >= 1 && c + 1 < cols) atomicMin(seed + root, p);
+}
+// flag / size at the seed position of every component the reference measures
+__global__ void ccl_mark_kernel(const unsigned *__restrict__ parent, const unsigned *__restrict__ npix,
+                                const unsigned *__restrict__ seed, unsigned *flag, unsigned *size,
+                                unsigned n) {
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || parent[p] != p) return;
+    const unsigned sd = seed[p], np = npix[p];
+    if (sd != 0xffffffffu && np >= 3 && np <= 5000) {
+        flag[sd] = 1;
+        size[sd] = np;
+    }
+}
+__global__ void ccl_emit_kernel(const unsigned *__restrict__ flag, const unsigned *__restrict__ size,
+                                const unsigned *__restrict__ slot, const unsigned *__restrict__ off,
+                                CompRec *comps, unsigned n) {
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n && flag[p]) comps[slot[p]] = {p, off[p], size[p], 0u};
+}
+
+// One 8-lane group per component: BFS replay + moments.  keys[k] = ~bits(flux) (ascending radix
+// sort = flux descending), all ones for components the reference drops (:177-179, :199-201).
+__global__ void __launch_bounds__(128)
+ccl_measure_kernel(const unsigned *__restrict__ col, const unsigned *__restrict__ rowi,
+                   const float *__restrict__ val, const unsigned long long *__restrict__ ro,
+                   const CompRec *__restrict__ comps, unsigned n_comp, unsigned rows, unsigned cols,
+                   double bg_median, double bg_sigma, unsigned *queue, unsigned char *vis,
+                   StarRec *stars, unsigned long long *keys, unsigned *order, unsigned *n_valid) {
+    const unsigned lane = threadIdx.x & 31, j = lane & 7, g = lane >> 3;
+    const unsigned gmask = 0xffu << (8 * g);
+    const unsigned groups = gridDim.x * (blockDim.x >> 3);
+    const int dr = (j == 0 || j == 4 || j == 5) ? -1 : ((j == 1 || j == 6 || j == 7) ? 1 : 0);
+    const int dc = (j == 2 || j == 4 || j == 6) ? -1 : ((j == 3 || j == 5 || j == 7) ? 1 : 0);
+    for (unsigned k = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; k < n_comp; k += groups) {
+        const CompRec cr = comps[k];
+        unsigned *qu = queue + cr.off;
+        if (j == 0) {
+            qu[0] = cr.seed;
+            vis[cr.seed] = 1;
+        }
+        __syncwarp(gmask);
+        unsigned head = 0, tail = 1;
+        while (head < tail) {
+            const unsigned cur = __ldcg(qu + head);
+            const unsigned r = __ldg(rowi + cur), c = __ldg(col + cur);
+            const long long nr = (long long)r + dr, nc = (long long)c + dc;
+            unsigned q = 0xffffffffu;
+            if (nr >= 0 && nc >= 0 && nr < (long long)rows && nc < (long long)cols) {
+                if (dr == 0) {
+                    const long long cand = (long long)cur + dc;
+                    if (cand >= (long long)__ldg(ro + r) && cand < (long long)__ldg(ro + r + 1) &&
+                        __ldg(col + cand) == (unsigned)nc)
+                        q = (unsigned)cand;
+                } else {
+                    const unsigned long long lb = row_lower_bound(col, ro, (size_t)nr, (unsigned)nc);
+                    if (lb < __ldg(ro + nr + 1) && __ldg(col + lb) == (unsigned)nc) q = (unsigned)lb;
+                }
+            }
+            const bool fresh = q != 0xffffffffu && __ldcg(vis + q) == 0;
+            const unsigned bal = (__ballot_sync(gmask, fresh) >> (8 * g)) & 0xffu;
+            if (fresh) {
+                qu[tail + __popc(bal & ((1u << j) - 1u))] = q;
+                vis[q] = 1;
+            }
+            tail += __popc(bal);
+            ++head;
+            __syncwarp(gmask);
+        }
+        // moments in visiting order (every lane of the group computes the same scalars)
+        double sum_flux = 0.0, sum_x = 0.0, sum_y = 0.0, peak_val = 0.0;
+        for (unsigned i = 0; i < cr.npix; ++i) {
+            const unsigned p = __ldcg(qu + i);
+            const double w = fmax((double)__ldg(val + p) - bg_median, 0.0);
+            sum_flux += w;
+            sum_x += (double)__ldg(col + p) * w;
+            sum_y += (double)__ldg(rowi + p) * w;
+            peak_val = fmax(peak_val, w);
+        }
+        bool ok = sum_flux > 0.0;
+        ab_star st = {};
+        if (ok) {
+            const double cx = sum_x / sum_flux, cy = sum_y / sum_flux;
+            double sum_r2 = 0.0, sum_xx = 0.0, sum_yy = 0.0, sum_xy = 0.0;
+            for (unsigned i = 0; i < cr.npix; ++i) {
+                const unsigned p = __ldcg(qu + i);
+                const double w = fmax((double)__ldg(val + p) - bg_median, 0.0);
+                const double dx = (double)__ldg(col + p) - cx;
+                const double dy = (double)__ldg(rowi + p) - cy;
+                sum_r2 += (dx * dx + dy * dy) * w;
+                sum_xx += dx * dx * w;
+                sum_yy += dy * dy * w;
+                sum_xy += dx * dy * w;
+            }
+            const double sigma_star = sqrt(sum_r2 / (2.0 * sum_flux));
+            const double fwhm = sigma_star * 2.3548200450309493;
+            ok = !(fwhm < 0.5 || fwhm > 30.0);
+            const double ixx = sum_xx / sum_flux, iyy = sum_yy / sum_flux, ixy = sum_xy / sum_flux;
+            const double trace = ixx + iyy;
+            const double det = fmax(ixx * iyy - ixy * ixy, 0.0);
+            const double disc = sqrt(fmax((trace * trace / 4.0) - det, 0.0));
+            const double lambda1 = trace / 2.0 + disc;
+            const double lambda2 = fmax(trace / 2.0 - disc, 0.0);
+            double ecc = 0.0;
+            if (lambda1 > 1e-15) {
+                ecc = sqrt(1.0 - lambda2 / lambda1);
+                ecc = ecc < 0.0 ? 0.0 : (ecc > 1.0 ? 1.0 : ecc);
+            }
+            const double snr = bg_sigma <= DBL_EPSILON ? 0.0 : peak_val / bg_sigma;  // confidence.rs:3-8
+            st = {cx, cy, sum_flux, fwhm, ecc, peak_val, (uint64_t)cr.npix, snr};
+        }
+        if (j == 0) {
+            stars[k].st = st;
+            keys[k] = ok ? ~(unsigned long long)__double_as_longlong(sum_flux) : ~0ull;
+            order[k] = k;
+            if (ok) atomicAdd(n_valid, 1u);
+        }
+    }
+}
+__global__ void ccl_gather_kernel(const StarRec *__restrict__ stars, const unsigned *__restrict__ order,
+                                  ab_star *__restrict__ out, unsigned n) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = stars[order[i]].st;
+}
+
+// greedy dedup on a 3-px grid (star_detection.rs:217-248) over the flux-sorted list; the grid is a
+// flat hash of cell -> chain of kept stars (same decisions as the reference's
+// HashMap<(usize, usize), Vec<usize>>)
+void dedup_stars(const std::vector<ab_star> &stars, std::vector<ab_star> &out) {
     const double dedup_r2 = 9.0, cell = 3.0;
     size_t cap = 16;
     while (cap < stars.size() * 2) cap <<= 1;
@@ -712,41 +782,113 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
 
     row_count_kernel<<<(unsigned)rows, 256, 0, s>>>(d_img, rows, cols, nm, threshold, d_rc);
     AB_LAUNCH_CHECK(ctx);
-    std::vector<unsigned> h_rc(rows);
-    AB_CUDA(ctx, cudaMemcpyAsync(h_rc.data(), d_rc, rows * 4, cudaMemcpyDeviceToHost, s));
+    row_offsets_kernel<<<1, 1024, 0, s>>>(d_rc, rows, d_ro);
+    AB_LAUNCH_CHECK(ctx);
+    unsigned long long nfg64 = 0;
+    AB_CUDA(ctx, cudaMemcpyAsync(&nfg64, d_ro + rows, 8, cudaMemcpyDeviceToHost, s));
     AB_CUDA(ctx, cudaStreamSynchronize(s));
-    SparseImage sp;
-    sp.rows = rows;
-    sp.cols = cols;
-    sp.row_off.resize(rows + 1);
-    sp.row_off[0] = 0;
-    for (size_t r = 0; r < rows; ++r) sp.row_off[r + 1] = sp.row_off[r] + h_rc[r];
-    const size_t nfg = (size_t)sp.row_off[rows];
     const double t_count = ms_since(t1);
     const auto t2 = now();
+    if (nfg64 >= 0xffffffffull)
+        return ab_fail(ctx, AB_ERR_UNSUPPORTED, "detector: %llu pixels above the threshold", nfg64);
+    const unsigned nfg = (unsigned)nfg64;
+    std::vector<ab_star> sorted;
+    unsigned n_comp = 0;
     if (nfg) {
-        AB_CUDA(ctx, cudaMemcpyAsync(d_ro, sp.row_off.data(), (rows + 1) * 8, cudaMemcpyHostToDevice, s));
-        const size_t lists = (nfg * 4 + 255) / 256 * 256;
-        st = ab_scratch_reserve(ctx, 2, lists * 2);
+        // scratch slot 2, all sized by nfg: col | val | row | parent | npix | seed | flag | size |
+        // slot | off | queue | vis, then (components <= nfg / 3) comps | stars | keys x2 | order x2
+        const size_t a4 = ((size_t)nfg * 4 + 255) / 256 * 256;
+        const size_t max_comp = (size_t)nfg / 3 + 1;
+        const size_t b_comp = (max_comp * sizeof(CompRec) + 255) / 256 * 256;
+        const size_t b_star = (max_comp * sizeof(StarRec) + 255) / 256 * 256;
+        const size_t b_k8 = (max_comp * 8 + 255) / 256 * 256, b_k4 = (max_comp * 4 + 255) / 256 * 256;
+        size_t tmp_scan = 0, tmp_sort = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (unsigned *)nullptr, (unsigned *)nullptr, (int)nfg, s);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (unsigned long long *)nullptr,
+                                        (unsigned long long *)nullptr, (unsigned *)nullptr,
+                                        (unsigned *)nullptr, (int)max_comp, 0, 64, s);
+        const size_t b_tmp = (std::max(tmp_scan, tmp_sort) + 255) / 256 * 256;
+        const size_t total = 12 * a4 + b_comp + 2 * b_star + 2 * b_k8 + 2 * b_k4 + b_tmp + 256;
+        st = ab_scratch_reserve(ctx, 2, total);
         if (st != AB_OK) return st;
-        unsigned *d_col = reinterpret_cast<unsigned *>(ctx->d_scratch[2]);
-        float *d_val = reinterpret_cast<float *>(static_cast<char *>(ctx->d_scratch[2]) + lists);
+        char *q = static_cast<char *>(ctx->d_scratch[2]);
+        auto take = [&](size_t bytes) {
+            char *r = q;
+            q += bytes;
+            return r;
+        };
+        unsigned *d_col = (unsigned *)take(a4);
+        float *d_val = (float *)take(a4);
+        unsigned *d_row = (unsigned *)take(a4), *d_parent = (unsigned *)take(a4);
+        unsigned *d_npix = (unsigned *)take(a4), *d_seed = (unsigned *)take(a4);
+        unsigned *d_flag = (unsigned *)take(a4), *d_size = (unsigned *)take(a4);
+        unsigned *d_slot = (unsigned *)take(a4), *d_off = (unsigned *)take(a4);
+        unsigned *d_queue = (unsigned *)take(a4);
+        unsigned char *d_vis = (unsigned char *)take(a4);
+        CompRec *d_comps = (CompRec *)take(b_comp);
+        StarRec *d_stars = (StarRec *)take(b_star);
+        ab_star *d_sorted = (ab_star *)take(b_star);
+        unsigned long long *d_keys = (unsigned long long *)take(b_k8), *d_keys2 = (unsigned long long *)take(b_k8);
+        unsigned *d_order = (unsigned *)take(b_k4), *d_order2 = (unsigned *)take(b_k4);
+        void *d_tmp = take(b_tmp);
+        unsigned *d_nvalid = (unsigned *)take(256);
+
         row_compact_kernel<<<(unsigned)rows, 256, 0, s>>>(d_img, rows, cols, nm, threshold, d_ro, d_col,
-                                                         d_val);
+                                                         d_val, d_row);
         AB_LAUNCH_CHECK(ctx);
-        sp.col.resize(nfg);
-        sp.val.resize(nfg);
-        AB_CUDA(ctx, cudaMemcpyAsync(sp.col.data(), d_col, nfg * 4, cudaMemcpyDeviceToHost, s));
-        AB_CUDA(ctx, cudaMemcpyAsync(sp.val.data(), d_val, nfg * 4, cudaMemcpyDeviceToHost, s));
+        const unsigned nb = (nfg + 255) / 256;
+        ccl_init_kernel<<<nb, 256, 0, s>>>(d_parent, d_npix, d_seed, d_vis, d_flag, d_size, nfg);
+        AB_LAUNCH_CHECK(ctx);
+        ccl_union_kernel<<<nb, 256, 0, s>>>(d_col, d_row, d_ro, d_parent, nfg);
+        AB_LAUNCH_CHECK(ctx);
+        ccl_flatten_kernel<<<nb, 256, 0, s>>>(d_col, d_row, d_parent, d_npix, d_seed, nfg, (unsigned)rows,
+                                             (unsigned)cols);
+        AB_LAUNCH_CHECK(ctx);
+        ccl_mark_kernel<<<nb, 256, 0, s>>>(d_parent, d_npix, d_seed, d_flag, d_size, nfg);
+        AB_LAUNCH_CHECK(ctx);
+        size_t tb = b_tmp;
+        AB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_flag, d_slot, (int)nfg, s));
+        tb = b_tmp;
+        AB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_size, d_off, (int)nfg, s));
+        ctx->launches.fetch_add(2, std::memory_order_relaxed);
+        unsigned last[2] = {0, 0};
+        AB_CUDA(ctx, cudaMemcpyAsync(&last[0], d_slot + (nfg - 1), 4, cudaMemcpyDeviceToHost, s));
+        AB_CUDA(ctx, cudaMemcpyAsync(&last[1], d_flag + (nfg - 1), 4, cudaMemcpyDeviceToHost, s));
+        AB_CUDA(ctx, cudaMemsetAsync(d_nvalid, 0, 4, s));
         AB_CUDA(ctx, cudaStreamSynchronize(s));
+        n_comp = last[0] + last[1];
+        if (n_comp) {
+            ccl_emit_kernel<<<nb, 256, 0, s>>>(d_flag, d_size, d_slot, d_off, d_comps, nfg);
+            AB_LAUNCH_CHECK(ctx);
+            const unsigned mb = (unsigned)std::min<size_t>(((size_t)n_comp + 15) / 16, (size_t)ctx->sm_count * 16);
+            ccl_measure_kernel<<<mb, 128, 0, s>>>(d_col, d_row, d_val, d_ro, d_comps, n_comp, (unsigned)rows,
+                                                 (unsigned)cols, bg_median, bg_sigma, d_queue, d_vis,
+                                                 d_stars, d_keys, d_order, d_nvalid);
+            AB_LAUNCH_CHECK(ctx);
+            tb = b_tmp;
+            AB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_keys, d_keys2, d_order, d_order2,
+                                                         (int)n_comp, 0, 64, s));
+            ctx->launches.fetch_add(1, std::memory_order_relaxed);
+            unsigned n_valid = 0;
+            AB_CUDA(ctx, cudaMemcpyAsync(&n_valid, d_nvalid, 4, cudaMemcpyDeviceToHost, s));
+            AB_CUDA(ctx, cudaStreamSynchronize(s));
+            if (n_valid) {
+                ccl_gather_kernel<<<(n_valid + 255) / 256, 256, 0, s>>>(d_stars, d_order2, d_sorted, n_valid);
+                AB_LAUNCH_CHECK(ctx);
+                sorted.resize(n_valid);
+                AB_CUDA(ctx, cudaMemcpyAsync(sorted.data(), d_sorted, (size_t)n_valid * sizeof(ab_star),
+                                             cudaMemcpyDeviceToHost, s));
+                AB_CUDA(ctx, cudaStreamSynchronize(s));
+            }
+        }
     }
-    const double t_compact = ms_since(t2);
+    const double t_ccl = ms_since(t2);
     const auto t3 = now();
-    flood_fill_stars(sp, bg_median, bg_sigma, stars);
+    dedup_stars(sorted, stars);
     if (trace)
-        fprintf(stderr, "[ab] detect %zux%zu: tiles %.2f ms, count %.2f ms, compact+D2H %.2f ms (%zu px), "
-                        "host fill %.2f ms (%zu stars)\n",
-                rows, cols, t_bg, t_count, t_compact, nfg, ms_since(t3), stars.size());
+        fprintf(stderr, "[ab] detect %zux%zu: tiles %.2f ms, count %.2f ms, compact+CCL+measure+sort %.2f ms "
+                        "(%u px, %u components), host dedup %.2f ms (%zu stars)\n",
+                rows, cols, t_bg, t_count, t_ccl, nfg, n_comp, ms_since(t3), stars.size());
     return AB_OK;
 }
 

@@ -158,17 +158,42 @@ def test_align_falls_back_to_phase_correlation(al, orc):
         assert r.matched_stars == 0 and r.inliers == 0
 
 
-def test_detect_stars_band_parallel_fill_is_order_exact(al, orc, monkeypatch):
-    """The host flood fill runs row bands on several threads and re-grows band-crossing components
-    sequentially; star lists must equal the oracle's (order, f64 parameters) for any band count --
-    including bands thinner than the stars, where most components cross an edge."""
+def test_detect_components_on_device_are_order_exact(al, orc):
+    """Connected components, visiting order and f64 moments now run on the device (union-find CCL +
+    a replay of the reference's BFS per component): star lists must equal the oracle's -- count,
+    order, npix and every f64 parameter -- on shapes where the visiting order matters."""
     img = star_field(600, 700, 150, seed=21)
-    img[100:140, 200:260] += 500.0  # one big blob crossing many bands
+    img[100:140, 200:260] += 500.0            # a 2400-px blob (kept: <= 5000 px)
+    img[300:380, 400:480] += 400.0            # a 6400-px blob (flood-filled, then dropped: > 5000 px)
+    img[200:230, 100] += 300.0                # U shape: two arms joined at the bottom -> the seed is
+    img[200:230, 110] += 300.0                # not the only raster-first pixel of its component
+    img[229, 100:111] += 300.0
+    img[0:4, 300:305] += 350.0                # touches the top border (seeded from row 1)
+    img[500:520, 696:700] += 350.0            # touches the right border
+    img[-1, 10:40] += 350.0                   # border-only pixels: never seeded
+    img[450, 50:53] += 200.0                  # exactly 3 px
+    img[460, 60:62] += 200.0                  # 2 px: dropped
+    img[470:475:2, 70:75:2] += 200.0          # diagonal-only contacts are NOT connected at distance 2
+    img[480, 80] += 200.0                     # 8-connectivity: a diagonal chain is one component
+    img[481, 81] += 200.0
+    img[482, 82] += 200.0
+    img[483, 81] += 200.0
     want = orc.detect_stars(img, 3.5)
     assert len(want.stars) > 50
-    for n in ("1", "3", "16", "64"):
-        monkeypatch.setenv("AB_FILL_THREADS", n)
-        same_detection(al.detect_stars(img, 3.5), want)
+    same_detection(al.detect_stars(img, 3.5), want)
+    for sigma in (2.0, 5.0, 12.0):
+        same_detection(al.detect_stars(img, sigma), orc.detect_stars(img, sigma))
+    # dense noise just above the threshold: thousands of tiny irregular components
+    rng = np.random.default_rng(3)
+    noisy = rng.normal(100.0, 5.0, (512, 640)).astype(np.float32)
+    same_detection(al.detect_stars(noisy, 1.0), orc.detect_stars(noisy, 1.0))
+    same_detection(al.detect_stars(noisy, 0.3), orc.detect_stars(noisy, 0.3))   # one percolating blob
+    # nothing above the threshold / everything above it
+    flat = np.full((64, 80), 7.0, np.float32)
+    same_detection(al.detect_stars(flat, 3.5), orc.detect_stars(flat, 3.5))
+    step = flat.copy()
+    step[:, 40:] = 500.0
+    same_detection(al.detect_stars(step, 3.5), orc.detect_stars(step, 3.5))
 
 
 @pytest.mark.parametrize("shape,tile", [((700, 900), 300), ((1100, 600), 512)])

@@ -78,6 +78,28 @@ class DetectionInfoC(C.Structure):
                 ("image_height", C.c_uint64), ("n_stars", C.c_uint64)]
 
 
+class SubframeConfigC(C.Structure):
+    """SubframeWeightConfig, core/analysis/subframe.rs:24-50 (defaults in __init__)."""
+    _fields_ = [(n, C.c_double) for n in ("fwhm_weight", "eccentricity_weight", "snr_weight",
+                                          "noise_weight", "max_fwhm", "max_eccentricity", "min_snr")] + [
+        ("min_stars", C.c_uint64)]
+
+    def __init__(self, fwhm_weight=1.0, eccentricity_weight=0.5, snr_weight=1.0, noise_weight=0.3,
+                 max_fwhm=8.0, max_eccentricity=0.7, min_snr=5.0, min_stars=5):
+        super().__init__(fwhm_weight, eccentricity_weight, snr_weight, noise_weight, max_fwhm,
+                         max_eccentricity, min_snr, min_stars)
+
+
+class SubframeMetricsC(C.Structure):
+    """SubframeMetrics minus the path strings, subframe.rs:9-22."""
+    _fields_ = [("star_count", C.c_uint64)] + [(n, C.c_double) for n in (
+        "median_fwhm", "median_eccentricity", "median_snr", "background_median", "background_sigma",
+        "noise_ratio", "weight")] + [("accepted", C.c_int32)]
+
+    def as_tuple(self):
+        return tuple(getattr(self, n) for n, _ in self._fields_)
+
+
 class AlignResultC(C.Structure):
     _fields_ = [("transform", AffineC), ("matched_stars", C.c_uint64), ("inliers", C.c_uint64),
                 ("residual_px", C.c_double), ("method", C.c_int32)]
@@ -169,6 +191,10 @@ SIGNATURES = {
     # calibration
     "ab_median_combine": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz, _sz, _vp, _vp, C.c_float, _vp]),
     "ab_median_combine_dev": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz, _vp, _vp, C.c_float, _vp, _vp]),
+    "ab_sigma_clipped_mean_stack": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz, _sz, C.c_float, C.c_float,
+                                              C.c_uint32, _vp, _vp]),
+    "ab_sigma_clipped_mean_stack_dev": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz, C.c_float, C.c_float,
+                                                  C.c_uint32, _vp, _vp, _vp]),
     "ab_normalize_flat": (C.c_int, [_vp, _vp, _sz]),
     "ab_normalize_flat_dev": (C.c_int, [_vp, _vp, _sz, _vp]),
     "ab_calibrate_image": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
@@ -215,6 +241,9 @@ SIGNATURES = {
     # stars / alignment
     "ab_detect_stars": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, _vp, _sz, _vp]),
     "ab_detect_stars_dev": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, _vp, _sz, _vp, _vp]),
+    "ab_analyze_subframe": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
+    "ab_analyze_subframe_dev": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _vp, _vp]),
+    "ab_normalize_weights": (None, [_vp, _sz]),
     "ab_estimate_background": (C.c_int, [_vp, _vp, _sz, _sz, _sz, C.POINTER(C.c_double),
                                          C.POINTER(C.c_double)]),
     "ab_normalize_for_detection": (C.c_int, [_vp, _vp, _sz, _vp]),

@@ -8,8 +8,8 @@ from typing import List
 
 import numpy as np
 
-from ._lib import (AlignResultC, AstroBurstError, Context, DetectionInfoC, StarC, default_context,
-                   lib)
+from ._lib import (AlignResultC, AstroBurstError, Context, DetectionInfoC, StarC, SubframeConfigC,
+                   SubframeMetricsC, default_context, lib)
 
 METHODS = ("affine", "rigid", "phase_correlation", "identity")  # affine.rs:101-118
 
@@ -134,3 +134,27 @@ def area_downsample(img: np.ndarray, out_rows: int, out_cols: int, ctx=None) -> 
     ctx.check(lib().ab_area_downsample(ctx.handle, a.ctypes.data, a.shape[0], a.shape[1],
                                        out_rows, out_cols, out.ctypes.data))
     return out
+
+
+# ---- core::analysis::subframe (subframe.rs:52-158)
+SubframeWeightConfig = SubframeConfigC
+
+
+def analyze_subframe(image, config: SubframeConfigC | None = None, ctx: Context | None = None) -> SubframeMetricsC:
+    """analyze_subframe, subframe.rs:52-118 (the path strings stay with the caller)."""
+    ctx = ctx or default_context()
+    d = _f32(image)
+    cfg = config or SubframeConfigC()
+    out = SubframeMetricsC()
+    ctx.check(lib().ab_analyze_subframe(ctx.handle, d.ctypes.data, d.shape[0], d.shape[1], C.addressof(cfg),
+                                        C.addressof(out)))
+    return out
+
+
+def normalize_weights(metrics):
+    """normalize_weights, subframe.rs:147-158, in place on a list of SubframeMetricsC."""
+    arr = (SubframeMetricsC * len(metrics))(*metrics)
+    lib().ab_normalize_weights(arr, len(metrics))
+    for m, a in zip(metrics, arr):
+        m.weight = a.weight
+    return metrics

@@ -118,3 +118,25 @@ def subtract_dark(image, master_dark, exposure_ratio: float, ctx=None) -> np.nda
 def divide_flat(image, master_flat, ctx=None) -> np.ndarray:
     """calibration.rs:27-45."""
     return _calibrate(image, None, None, master_flat, 1.0, False, ctx)
+
+
+def sigma_clipped_mean_stack(frames: Sequence[np.ndarray], sigma_low: float = 2.5, sigma_high: float = 3.0,
+                             max_iterations: int = 5, ctx: Optional[Context] = None):
+    """sigma_clipped_mean_stack of the batch pipeline (core/imaging/calibration_pipeline.rs:317-378;
+    BatchStackConfig defaults :27-36) -> (stacked image, per-frame rejection counts).  Every sample
+    takes part (NaN ordered last), MAD-based clip in every iteration, f32 mean in frame order."""
+    ctx = ctx or default_context()
+    fr = [_f32(f) for f in frames]
+    if not fr:
+        raise AstroBurstError(_lib.AB_ERR_INVALID, "no frames")
+    rows, cols = fr[0].shape
+    for f in fr[1:]:
+        if f.shape != (rows, cols):  # run_batch_pipeline, calibration_pipeline.rs:131-141
+            raise AstroBurstError(_lib.AB_ERR_INVALID, "All frames must match")
+    ptrs = (C.c_void_p * len(fr))(*[f.ctypes.data for f in fr])
+    out = np.empty((rows, cols), np.float32)
+    counts = np.zeros(len(fr), np.uint64)
+    ctx.check(lib().ab_sigma_clipped_mean_stack(ctx.handle, ptrs, len(fr), rows, cols, C.c_float(sigma_low),
+                                                C.c_float(sigma_high), int(max_iterations), out.ctypes.data,
+                                                counts.ctypes.data))
+    return out, [int(c) for c in counts]

@@ -31,6 +31,7 @@ struct ab_ctx {
     static constexpr size_t SMALL_BYTES = 1 << 20;
     int stack_variant = 0;     // AB_STACK_VARIANT: 0 TMA-staged (default), 2 plain coalesced loads
     int stack_mix = 0;         // AB_STACK_MIX: 0 default compare-exchange mix, 1..7 A/B variants (P = 32)
+    bool stats_host_walks = false;  // AB_STATS_HOST_WALKS=1: percentile walks on the host (A/B; the sharded path always does)
     bool force_tma1d = false;  // AB_STACK_FORCE_TMA1D=1: per-frame bulk copies instead of the tensor map
     void *encode_tmap_fn = nullptr;  // cuTensorMapEncodeTiled, resolved lazily
     // work-queue counters of the stack kernels (one per launch in flight, round-robin)

@@ -54,6 +54,8 @@ ab_status ab_ctx_create(int device, ab_ctx **out) {
         ctx->stack_variant = e ? atoi(e) : 0;
         e = getenv("AB_STACK_FORCE_TMA1D");
         ctx->force_tma1d = e && e[0] == '1';
+        e = getenv("AB_STATS_HOST_WALKS");
+        ctx->stats_host_walks = e && e[0] == '1';
         e = getenv("AB_STACK_MIX");
         ctx->stack_mix = e ? atoi(e) : 0;
     }
@@ -324,7 +326,12 @@ ab_status ab_stack_images(ab_ctx *ctx, const float *const *frames, size_t n_fram
     for (size_t f = 1; f < n_frames; ++f) {
         AB_CUDA(ctx, cudaMemcpyAsync(d_raw, frames[f], npix * sizeof(float), cudaMemcpyHostToDevice, s));
         ab_phase_result pc;
-        if ((st = ab_phase_correlate_on(ctx, d_ref, d_raw, rows, cols, s, &pc)) != AB_OK) return st;
+        // align == 1: the reference's operand order (bit parity with combine.rs:118-147, including its
+        // sign convention, see the header); align == 2: operands swapped, so the measured offset is
+        // the one shift_image_subpixel needs to bring the frame ONTO the reference
+        if ((st = (cfg->align == 2 ? ab_phase_correlate_on(ctx, d_raw, d_ref, rows, cols, s, &pc)
+                                   : ab_phase_correlate_on(ctx, d_ref, d_raw, rows, cols, s, &pc))) != AB_OK)
+            return st;
         float *d_al = reinterpret_cast<float *>(base + f * plane_bytes);
         if ((st = ab_shift_bicubic_dev(ctx, d_raw, rows, cols, pc.dy, pc.dx, d_al, s)) != AB_OK)
             return st;

@@ -1284,6 +1284,86 @@ ab_status ab_detect_stars_on(ab_ctx *ctx, const float *d_img, size_t rows, size_
     return detect_on_device(ctx, d_img, rows, cols, nm, sigma_threshold, s, stars, bg_median, bg_sigma);
 }
 
+// ---- subframe scoring (core/analysis/subframe.rs:52-171): the detector + host scalar medians
+namespace {
+// median_of, subframe.rs:160-171: finite values, stable sort, even count -> mean of the middle two
+double subframe_median(const std::vector<ab_star> &stars, double ab_star::*field) {
+    std::vector<double> vals;
+    for (const ab_star &s : stars)
+        if (std::isfinite(s.*field)) vals.push_back(s.*field);
+    if (vals.empty()) return 0.0;
+    std::stable_sort(vals.begin(), vals.end());
+    const size_t mid = vals.size() / 2;
+    return vals.size() % 2 == 0 ? (vals[mid - 1] + vals[mid]) / 2.0 : vals[mid];
+}
+// compute_weight, subframe.rs:120-145
+double subframe_weight(double fwhm, double ecc, double snr, double noise, const ab_subframe_config &c) {
+    const double fwhm_score = fwhm > 0.5 ? 1.0 / fwhm : 0.0;
+    const double ecc_score = 1.0 - ecc;
+    const double snr_score = std::fmax(std::log(snr), 0.0);  // f64::max ignores NaN
+    const double noise_score = 1.0 / (1.0 + noise * 10.0);
+    const double total = c.fwhm_weight + c.eccentricity_weight + c.snr_weight + c.noise_weight;
+    if (total < 1e-15) return 0.0;
+    const double raw = c.fwhm_weight * fwhm_score + c.eccentricity_weight * ecc_score +
+                       c.snr_weight * snr_score + c.noise_weight * noise_score;
+    return std::fmax(raw / total, 0.0);
+}
+ab_status analyze_subframe_on(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols,
+                              const ab_subframe_config &cfg, cudaStream_t s, ab_subframe_metrics *out) {
+    std::vector<ab_star> stars;
+    double bm = 0.0, bs = 1.0;
+    Norm nm{0, 0.0, 1.0};
+    ab_status st = detect_on_device(ctx, d_img, rows, cols, nm, 4.0, s, stars, &bm, &bs);  // DETECTION_SIGMA :6
+    if (st != AB_OK) return st;
+    *out = {};
+    out->star_count = stars.size();
+    out->background_median = bm;
+    out->background_sigma = bs;
+    const size_t min_needed = std::min<size_t>(5, (size_t)cfg.min_stars);  // MIN_STARS_FOR_METRICS :7
+    if (stars.size() < min_needed) return AB_OK;
+    out->median_fwhm = subframe_median(stars, &ab_star::fwhm);
+    out->median_eccentricity = subframe_median(stars, &ab_star::eccentricity);
+    out->median_snr = subframe_median(stars, &ab_star::snr);
+    out->noise_ratio = bm > 1e-15 ? bs / bm : 0.0;
+    out->weight = subframe_weight(out->median_fwhm, out->median_eccentricity, out->median_snr,
+                                  out->noise_ratio, cfg);
+    out->accepted = (stars.size() >= (size_t)cfg.min_stars && out->median_fwhm <= cfg.max_fwhm &&
+                     out->median_eccentricity <= cfg.max_eccentricity && out->median_snr >= cfg.min_snr)
+                        ? 1
+                        : 0;
+    return AB_OK;
+}
+}  // namespace
+
+extern "C" {
+ab_status ab_analyze_subframe_dev(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols,
+                                  const ab_subframe_config *cfg, ab_subframe_metrics *out, void *stream) {
+    if (!ctx || !cfg || !out || ((rows * cols) && !d_img)) return AB_ERR_INVALID;
+    CtxLock lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    return analyze_subframe_on(ctx, d_img, rows, cols, *cfg, (cudaStream_t)stream, out);
+}
+ab_status ab_analyze_subframe(ab_ctx *ctx, const float *img, size_t rows, size_t cols,
+                              const ab_subframe_config *cfg, ab_subframe_metrics *out) {
+    if (!ctx || !cfg || !out || ((rows * cols) && !img)) return AB_ERR_INVALID;
+    CtxLock lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    float *d = nullptr;
+    if (rows * cols) {
+        ab_status st = upload(ctx, 0, img, rows * cols, &d);
+        if (st != AB_OK) return st;
+    }
+    return analyze_subframe_on(ctx, d, rows, cols, *cfg, ctx->stream, out);
+}
+void ab_normalize_weights(ab_subframe_metrics *metrics, size_t n) {
+    if (!metrics) return;
+    double max_w = 0.0;
+    for (size_t i = 0; i < n; ++i) max_w = std::fmax(max_w, metrics[i].weight);
+    if (max_w > 1e-15)
+        for (size_t i = 0; i < n; ++i) metrics[i].weight /= max_w;
+}
+}  // extern "C"
+
 extern "C" {
 
 ab_status ab_detect_stars_dev(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols,

@@ -195,6 +195,15 @@ hist_kernel(const float *__restrict__ data, size_t len, F f, unsigned *__restric
     }
 }
 
+// Same pass with the classifier read from device memory: the device-chained statistics path
+// (stats_hist_chained) computes each pass's parameters in a one-block "walk" kernel on the same
+// stream, so the sweeps follow each other without a host round trip.
+template <typename F>
+__global__ void __launch_bounds__(HT_THREADS, 1)
+hist_ctl_kernel(const float *__restrict__ data, size_t len, const F *__restrict__ f_dev,
+                const int *__restrict__ skip, unsigned *__restrict__ histA,
+                unsigned *__restrict__ histB, HistPartial *__restrict__ partials);
+
 // `((x) as usize).min(last)` for x = f64.  The f64 -> u32 conversion saturates like Rust's `as`
 // (negative and NaN -> 0, >= 2^32 -> u32::MAX), so the clamp to the last bin is exact for every x.
 __device__ __forceinline__ unsigned bin_of(double x) {
@@ -236,6 +245,307 @@ struct MadRefineF {  // stats.rs:164-193
     }
     __device__ bool is_below(float v) const { return fabsf(v - med) < lo_f32; }
 };
+
+template <typename F>
+__global__ void __launch_bounds__(HT_THREADS, 1)
+hist_ctl_kernel(const float *__restrict__ data, size_t len, const F *__restrict__ f_dev,
+                const int *__restrict__ skip, unsigned *__restrict__ histA,
+                unsigned *__restrict__ histB, HistPartial *__restrict__ partials) {
+    extern __shared__ unsigned packed[];
+    if (*skip) {  // no valid pixel: nothing to classify
+        if (threadIdx.x == 0) partials[blockIdx.x] = {0.0, 0ull, 0ull};
+        return;
+    }
+    const F f = *f_dev;
+    for (unsigned i = threadIdx.x; i < HIST_BINS / 2; i += HT_THREADS) packed[i] = 0;
+    __syncthreads();
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(data) & 15) == 0;
+    const size_t n4 = vec_ok ? len / 4 : 0;
+    const size_t stride = (size_t)gridDim.x * HT_THREADS;
+    const size_t tid = (size_t)blockIdx.x * HT_THREADS + threadIdx.x;
+    double sum = 0.0;
+    unsigned cnt = 0, below = 0;
+    auto one = [&](float v) {
+        if (!valid_px(v)) return;
+        const double dv = (double)v;
+        if constexpr (F::kSum) {
+            sum += dv;
+            ++cnt;
+        }
+        if constexpr (F::kA) {
+            const unsigned a = f.bin_a(v, dv);
+            const unsigned sh = (a & 1u) << 4;
+            const unsigned old = atomicAdd(&packed[a >> 1], 1u << sh);
+            if (((old >> sh) & 0xffffu) == HALF_FLUSH - 1u) {
+                atomicAdd(&histA[a], HALF_FLUSH);
+                atomicSub(&packed[a >> 1], HALF_FLUSH << sh);
+            }
+        }
+        if constexpr (F::kB) {
+            unsigned b;
+            if (f.bin_b(v, dv, b)) atomicAdd(&histB[b], 1u);
+        }
+        if constexpr (F::kBelow) below += f.is_below(v) ? 1u : 0u;
+    };
+    auto four = [&](const float4 &v) { one(v.x); one(v.y); one(v.z); one(v.w); };
+    const float4 *d4 = reinterpret_cast<const float4 *>(data);
+    size_t i = tid;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 v0 = __ldcs(d4 + i);
+        const float4 v1 = __ldcs(d4 + i + stride);
+        const float4 v2 = __ldcs(d4 + i + 2 * stride);
+        const float4 v3 = __ldcs(d4 + i + 3 * stride);
+        four(v0); four(v1); four(v2); four(v3);
+    }
+    for (; i < n4; i += stride) four(__ldcs(d4 + i));
+    for (size_t j = n4 * 4 + tid; j < len; j += stride) one(data[j]);
+    __syncthreads();
+    if constexpr (F::kA) {
+        for (unsigned w = threadIdx.x; w < HIST_BINS / 2; w += HT_THREADS) {
+            const unsigned c = packed[w];
+            if (c & 0xffffu) atomicAdd(&histA[2 * w], c & 0xffffu);
+            if (c >> 16) atomicAdd(&histA[2 * w + 1], c >> 16);
+        }
+    }
+    __shared__ HistPartial sh[HT_THREADS / 32];
+    unsigned long long cnt64 = cnt, below64 = below;
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, o);
+        cnt64 += __shfl_down_sync(0xffffffffu, cnt64, o);
+        below64 += __shfl_down_sync(0xffffffffu, below64, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = {sum, cnt64, below64};
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        HistPartial r = sh[0];
+        for (int w = 1; w < HT_THREADS / 32; ++w) {
+            r.sum += sh[w].sum;
+            r.count += sh[w].count;
+            r.below += sh[w].below;
+        }
+        partials[blockIdx.x] = r;
+    }
+}
+
+// ---- device-side percentile walks (stats.rs:299-353 on the device, one 1,024-thread block).
+// All of it is integer counting plus a handful of IEEE f64 operations (no contraction:
+// -fmad=false), so the values equal the host walk's bit for bit.
+struct StatsCtl {
+    ValueHistF f1;
+    RefineDevF f2;
+    MadRefineF f3;
+    double global_min, global_max, range, bin_width, mean;
+    double median_bin_lo, refine_range, median, dev_bw, mad_region_lo, mad_refine_range;
+    unsigned long long total_valid, half_count, count_before_median;
+    int empty;
+    ab_image_stats out;
+};
+constexpr int WK_THREADS = 1024, WK_PER = HIST_BINS / WK_THREADS;
+
+// first bin i with cum(i) >= target (cum inclusive): *idx, *cum = cum(i), *cnt = hist[i].
+// All threads of the block call it; returns false when the total stays below the target.
+__device__ bool block_find_cum(const unsigned *__restrict__ hist, unsigned long long target,
+                               unsigned *idx, unsigned long long *cum, unsigned long long *cnt) {
+    __shared__ unsigned long long part[WK_THREADS];
+    __shared__ unsigned long long res[3];
+    __shared__ int found;
+    const unsigned b0 = threadIdx.x * WK_PER;
+    unsigned long long sum = 0;
+    for (int j = 0; j < WK_PER; ++j) sum += hist[b0 + j];
+    part[threadIdx.x] = sum;
+    if (threadIdx.x == 0) found = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // exclusive scan of the 1,024 chunk sums
+        unsigned long long run = 0;
+        for (int t = 0; t < WK_THREADS; ++t) {
+            const unsigned long long v = part[t];
+            part[t] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    const unsigned long long before = part[threadIdx.x];
+    if (before < target && before + sum >= target) {  // exactly one chunk crosses the target
+        unsigned long long run = before;
+        for (int j = 0; j < WK_PER; ++j) {
+            const unsigned long long c = hist[b0 + j];
+            run += c;
+            if (run >= target) {
+                res[0] = b0 + j;
+                res[1] = run;
+                res[2] = c;
+                found = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const bool ok = found != 0;
+    if (ok) {
+        *idx = (unsigned)res[0];
+        *cum = res[1];
+        *cnt = res[2];
+    }
+    __syncthreads();
+    return ok;
+}
+__device__ __forceinline__ double walk_frac(unsigned long long cum, unsigned long long target,
+                                            unsigned long long count) {
+    const unsigned long long overshoot = cum - target;
+    return count > 0 ? 1.0 - ((double)overshoot / (double)count) : 0.5;
+}
+// resolve_rank_in_hist, stats.rs:333-353 (all threads)
+__device__ double block_resolve_rank(const unsigned *hist, unsigned long long rank, double region_lo,
+                                     double sub_bin_width) {
+    if (rank == 0) return region_lo;
+    unsigned idx = 0;
+    unsigned long long cum = 0, cnt = 0;
+    if (block_find_cum(hist, rank, &idx, &cum, &cnt))
+        return region_lo + ((double)idx + walk_frac(cum, rank, cnt)) * sub_bin_width;
+    return region_lo + (double)HIST_BINS * sub_bin_width;
+}
+
+// after the scan pass (or with a caller-known range): range, bin width, pass-1 classifier
+__global__ void __launch_bounds__(WK_THREADS)
+walk_range_kernel(const ScanPartial *__restrict__ sp, unsigned n_partials, int known, double kmin,
+                  double kmax, StatsCtl *ctl) {
+    if (threadIdx.x != 0) return;
+    double lo = kmin, hi = kmax;
+    int empty = 0;
+    if (!known) {
+        lo = DBL_MAX;
+        hi = -DBL_MAX;
+        unsigned long long c = 0;
+        for (unsigned i = 0; i < n_partials; ++i) {
+            if (sp[i].count) {
+                lo = fmin(lo, (double)sp[i].mn);
+                hi = fmax(hi, (double)sp[i].mx);
+            }
+            c += sp[i].count;
+        }
+        empty = c == 0;
+    }
+    ctl->empty = empty;
+    ctl->global_min = lo;
+    ctl->global_max = hi;
+    const double range = fmax(hi - lo, 1e-30);
+    ctl->range = range;
+    ctl->bin_width = range / (double)HIST_BINS;
+    ctl->f1.lo = lo;
+    ctl->f1.inv = (double)HIST_BINS / range;
+}
+// after pass 1 (value histogram + sum): median bin, coarse median, pass-2 classifier
+__global__ void __launch_bounds__(WK_THREADS)
+walk_value_kernel(const unsigned *__restrict__ histA, const HistPartial *__restrict__ hp,
+                  unsigned n_partials, StatsCtl *ctl) {
+    __shared__ unsigned long long tot;
+    __shared__ double gsum;
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        unsigned long long c = 0;
+        for (unsigned i = 0; i < n_partials; ++i) {
+            s += hp[i].sum;
+            c += hp[i].count;
+        }
+        tot = c;
+        gsum = s;
+    }
+    __syncthreads();
+    const unsigned long long total = tot;
+    if (ctl->empty || total == 0) {
+        if (threadIdx.x == 0) ctl->empty = 1;
+        return;
+    }
+    const double bin_width = ctl->bin_width, gmin = ctl->global_min, range = ctl->range;
+    const unsigned long long target = (unsigned long long)ceil((double)total * 0.5);
+    unsigned idx = HIST_BINS - 1;
+    unsigned long long cum = 0, cnt = 0;
+    const bool ok = block_find_cum(histA, target, &idx, &cum, &cnt);
+    if (threadIdx.x == 0) {
+        // find_percentile_bin (:299-309) / interpolate_percentile (:311-331)
+        const unsigned median_bin = ok ? idx : HIST_BINS - 1;
+        unsigned long long before = 0;
+        if (ok) before = cum - cnt;
+        else
+            for (unsigned i = 0; i < HIST_BINS - 1; ++i) before += histA[i];
+        const double coarse = ok ? gmin + ((double)idx + walk_frac(cum, target, cnt)) * bin_width
+                                 : gmin + (double)HIST_BINS * bin_width;
+        const double lo = gmin + (double)median_bin * bin_width, hi = lo + bin_width;
+        const double refine_range = fmax(hi - lo, 1e-30);
+        ctl->total_valid = total;
+        ctl->mean = gsum / (double)total;
+        ctl->half_count = target;
+        ctl->count_before_median = before;
+        ctl->median_bin_lo = lo;
+        ctl->refine_range = refine_range;
+        ctl->dev_bw = range / (double)HIST_BINS;
+        ctl->f2.bin_lo = lo;
+        ctl->f2.bin_hi = hi;
+        ctl->f2.refine_inv = (double)HIST_BINS / refine_range;
+        ctl->f2.dev_inv = (double)HIST_BINS / range;
+        ctl->f2.coarse_med = (float)coarse;
+    }
+}
+// after pass 2 (deviation histogram A + median-refine histogram B): median, MAD region, pass-3 classifier
+__global__ void __launch_bounds__(WK_THREADS)
+walk_refine_kernel(const unsigned *__restrict__ histA, const unsigned *__restrict__ histB, StatsCtl *ctl) {
+    if (ctl->empty) return;
+    const unsigned long long half = ctl->half_count, before = ctl->count_before_median;
+    const unsigned long long rank = half > before ? half - before : 0;
+    const double median = block_resolve_rank(histB, rank, ctl->median_bin_lo,
+                                             ctl->refine_range / (double)HIST_BINS);
+    unsigned idx = HIST_BINS - 1;
+    unsigned long long cum = 0, cnt = 0;
+    const bool ok = block_find_cum(histA, half, &idx, &cum, &cnt);  // ceil(total * 0.5) again
+    if (threadIdx.x == 0) {
+        const unsigned mad_bin = ok ? idx : HIST_BINS - 1;
+        const unsigned expand_lo = mad_bin > 0 ? mad_bin - 1 : 0;
+        const unsigned expand_hi = min(mad_bin + 2, HIST_BINS);
+        const double dev_bw = ctl->dev_bw;
+        const double region_lo = (double)expand_lo * dev_bw, region_hi = (double)expand_hi * dev_bw;
+        const double mrr = fmax(region_hi - region_lo, 1e-30);
+        ctl->median = median;
+        ctl->mad_region_lo = region_lo;
+        ctl->mad_refine_range = mrr;
+        ctl->f3.region_lo = region_lo;
+        ctl->f3.refine_inv = (double)HIST_BINS / mrr;
+        ctl->f3.med = (float)median;
+        ctl->f3.lo_f32 = (float)region_lo;
+        ctl->f3.hi_f32 = (float)region_hi;
+    }
+}
+// after pass 3 (MAD-refine histogram B + count below): MAD, sigma, the ImageStats
+__global__ void __launch_bounds__(WK_THREADS)
+walk_mad_kernel(const unsigned *__restrict__ histB, const HistPartial *__restrict__ hp,
+                unsigned n_partials, StatsCtl *ctl) {
+    if (ctl->empty) {
+        if (threadIdx.x == 0) ctl->out = {0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0};  // ImageStats::default, stats.rs:45-47
+        return;
+    }
+    __shared__ unsigned long long below_sh;
+    if (threadIdx.x == 0) {
+        unsigned long long b = 0;
+        for (unsigned i = 0; i < n_partials; ++i) b += hp[i].below;
+        below_sh = b;
+    }
+    __syncthreads();
+    const unsigned long long half = ctl->half_count, below = below_sh;
+    const unsigned long long rank = half > below ? half - below : 0;
+    const double mad = block_resolve_rank(histB, rank, ctl->mad_region_lo,
+                                          ctl->mad_refine_range / (double)HIST_BINS);
+    if (threadIdx.x == 0) {
+        ab_image_stats o;
+        o.min = ctl->global_min;
+        o.max = ctl->global_max;
+        o.median = ctl->median;
+        o.mad = mad;
+        o.sigma = fmax(mad * MAD_TO_SIGMA, 1e-30);
+        o.mean = ctl->mean;
+        o.valid_count = ctl->total_valid;
+        ctl->out = o;
+    }
+}
 
 // ---- radix select on float bit patterns (exact path)
 // key(v) = bits(v) for mode 0, bits(|v - center|) for mode 1; only valid pixels take part.
@@ -570,6 +880,54 @@ ab_status hist_core(ab_ctx *ctx, const float *d, size_t len, double global_min, 
     return AB_OK;
 }
 
+// stats.rs:75-210 with every percentile walk on the device: scan, walk, 3 x (sweep, walk) queued
+// back to back on `s`, ONE synchronisation for the 56-byte result.  `known`: the caller's range
+// (compute_image_stats_with_known_range, :25-41) replaces the scan pass.
+ab_status stats_hist_chained(ab_ctx *ctx, const float *d, size_t len, bool known, double kmin,
+                             double kmax, cudaStream_t s, ab_image_stats *out) {
+    Small sm(ctx);
+    // control block + host mirror of the result in the small scratch blocks ([640 KiB, +4 KiB))
+    StatsCtl *ctl = reinterpret_cast<StatsCtl *>(sm.d + (640 << 10));
+    ab_image_stats *h_out = reinterpret_cast<ab_image_stats *>(sm.h + (640 << 10));
+    ScanPartial *d_sp = reinterpret_cast<ScanPartial *>(sm.d);
+    HistPartial *d_hp = reinterpret_cast<HistPartial *>(sm.d + (32 << 10));
+    unsigned n_sp = 0;
+    if (!known) {
+        n_sp = grid_for(ctx, len, 16);
+        scan_kernel<<<n_sp, ST_THREADS, 0, s>>>(d, len, d_sp);
+        AB_LAUNCH_CHECK(ctx);
+    }
+    walk_range_kernel<<<1, WK_THREADS, 0, s>>>(d_sp, n_sp, known ? 1 : 0, kmin, kmax, ctl);
+    AB_LAUNCH_CHECK(ctx);
+    size_t blocks = (len / 16 + HT_THREADS - 1) / HT_THREADS + 1;
+    if (blocks > (size_t)ctx->sm_count) blocks = (size_t)ctx->sm_count;
+    const unsigned grid = (unsigned)blocks;
+    constexpr int smem = (int)(HIST_BINS / 2 * sizeof(unsigned));
+    AB_CUDA(ctx, cudaFuncSetAttribute(hist_ctl_kernel<ValueHistF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AB_CUDA(ctx, cudaFuncSetAttribute(hist_ctl_kernel<RefineDevF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AB_CUDA(ctx, cudaFuncSetAttribute(hist_ctl_kernel<MadRefineF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const size_t hist_bytes = 2 * HIST_BINS * sizeof(unsigned);
+    AB_CUDA(ctx, cudaMemsetAsync(sm.dA, 0, hist_bytes, s));
+    hist_ctl_kernel<ValueHistF><<<grid, HT_THREADS, smem, s>>>(d, len, &ctl->f1, &ctl->empty, sm.dA, sm.dB, d_hp);
+    AB_LAUNCH_CHECK(ctx);
+    walk_value_kernel<<<1, WK_THREADS, 0, s>>>(sm.dA, d_hp, grid, ctl);
+    AB_LAUNCH_CHECK(ctx);
+    AB_CUDA(ctx, cudaMemsetAsync(sm.dA, 0, hist_bytes, s));
+    hist_ctl_kernel<RefineDevF><<<grid, HT_THREADS, smem, s>>>(d, len, &ctl->f2, &ctl->empty, sm.dA, sm.dB, d_hp);
+    AB_LAUNCH_CHECK(ctx);
+    walk_refine_kernel<<<1, WK_THREADS, 0, s>>>(sm.dA, sm.dB, ctl);
+    AB_LAUNCH_CHECK(ctx);
+    AB_CUDA(ctx, cudaMemsetAsync(sm.dB, 0, HIST_BINS * sizeof(unsigned), s));
+    hist_ctl_kernel<MadRefineF><<<grid, HT_THREADS, smem, s>>>(d, len, &ctl->f3, &ctl->empty, sm.dA, sm.dB, d_hp);
+    AB_LAUNCH_CHECK(ctx);
+    walk_mad_kernel<<<1, WK_THREADS, 0, s>>>(sm.dB, d_hp, grid, ctl);
+    AB_LAUNCH_CHECK(ctx);
+    AB_CUDA(ctx, cudaMemcpyAsync(h_out, &ctl->out, sizeof(ab_image_stats), cudaMemcpyDeviceToHost, s));
+    AB_CUDA(ctx, cudaStreamSynchronize(s));
+    *out = *h_out;
+    return AB_OK;
+}
+
 // stats.rs:43-73
 ab_status stats_exact(ab_ctx *ctx, const float *d, size_t len, cudaStream_t s, ab_image_stats *out) {
     double mn, mx, sum;
@@ -601,6 +959,7 @@ ab_status stats_exact(ab_ctx *ctx, const float *d, size_t len, cudaStream_t s, a
 ab_status stats_hist(ab_ctx *ctx, const float *d, size_t len, cudaStream_t s, ab_image_stats *out) {
     double mn, mx, sum;
     unsigned long long n;
+    if (!ctx->stats_host_walks) return stats_hist_chained(ctx, d, len, false, 0.0, 0.0, s, out);
     ab_status st = run_scan(ctx, d, len, s, &mn, &mx, &sum, &n);  // scan_minmax, stats.rs:212-231
     if (st != AB_OK) return st;
     if (n == 0) {
@@ -628,6 +987,7 @@ ab_status stats_dispatch(ab_ctx *ctx, const float *d, size_t len, int mode, doub
             if (len <= 4000000) return stats_exact(ctx, d, len, s, out);
             if (!std::isfinite(kmin) || !std::isfinite(kmax) || kmin >= kmax)
                 return stats_hist(ctx, d, len, s, out);
+            if (!ctx->stats_host_walks) return stats_hist_chained(ctx, d, len, true, kmin, kmax, s, out);
             return hist_core(ctx, d, len, kmin, kmax, s, out);
         default:
             return len > 4000000 ? stats_hist(ctx, d, len, s, out) : stats_exact(ctx, d, len, s, out);

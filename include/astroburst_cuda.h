@@ -110,6 +110,22 @@ typedef struct {
     uint64_t n_stars; /* stars found; may exceed the caller's capacity */
 } ab_detection_info;
 
+/* mirrors SubframeWeightConfig, core/analysis/subframe.rs:24-50
+ * (defaults 1.0, 0.5, 1.0, 0.3, 8.0, 0.7, 5.0, 5) */
+typedef struct {
+    double fwhm_weight, eccentricity_weight, snr_weight, noise_weight;
+    double max_fwhm, max_eccentricity, min_snr;
+    uint64_t min_stars;
+} ab_subframe_config;
+
+/* mirrors SubframeMetrics (minus the path strings), subframe.rs:9-22 */
+typedef struct {
+    uint64_t star_count;
+    double median_fwhm, median_eccentricity, median_snr;
+    double background_median, background_sigma, noise_ratio, weight;
+    int32_t accepted;
+} ab_subframe_metrics;
+
 /* mirrors AffineAlignResult, core/alignment/affine.rs:93-110.
  * method: 0 affine, 1 rigid, 2 phase_correlation, 3 identity */
 typedef struct {
@@ -198,7 +214,14 @@ ab_status ab_stack_sigma_clip(ab_ctx *ctx, const float *const *frames, size_t n_
 ab_status ab_stack_sigma_clip_dev(ab_ctx *ctx, const float *const *d_frames, size_t n_frames,
                                   size_t npix, const ab_stack_config *cfg, float *d_out,
                                   uint64_t *d_rejected, void *stream);
-/* stack_images with config.align honoured (combine.rs:118-147): every frame i >= 1 is
+/* NOTE on align: align = 1 reproduces the reference bit for bit, INCLUDING its sign convention --
+ * phase_correlate(reference, target) peaks at MINUS the content displacement (forward DFT,
+ * a * conj(b)) and shift_image_subpixel(target, dy, dx) then moves the frame AWAY from the
+ * reference, which the reference's own (never-run) tests contradict.
+ * align = 2 is an opt-in correction outside parity: the correlation runs with the operands
+ * swapped, so every frame is shifted ONTO frame 0.  Use 2 when registration quality matters, 1
+ * when the output must equal upstream's.
+ * stack_images with config.align honoured (combine.rs:118-147): every frame i >= 1 is
  * phase-correlated against frame 0 (core/stacking/align.rs:84-97) and shifted with the bicubic
  * sampler (align.rs:36-57) before the combine.  offsets: NULL or 2*n_frames int32 =
  * StackResult.offsets as (dy, dx) pairs = (round(dy), round(dx)), (0,0) for frame 0.
@@ -302,6 +325,22 @@ ab_status ab_median_combine_dev(ab_ctx *ctx, const float *const *d_frames, size_
  * no pixel is finite and positive. */
 ab_status ab_normalize_flat(ab_ctx *ctx, float *data, size_t len);
 ab_status ab_normalize_flat_dev(ab_ctx *ctx, float *d_data, size_t len, void *stream);
+/* sigma_clipped_mean_stack, core/imaging/calibration_pipeline.rs:317-378 (the batch pipeline's
+ * clip; NOT combine.rs): every sample takes part (NaN ordered last, math/median.rs:4-13); each of
+ * up to max_iterations rounds (while >= 3 samples) takes the upper median and the upper-median MAD,
+ * sigma = (mad as f64 * 1.4826) as f32, stops when sigma < 1e-10, keeps the samples with
+ * -sigma_low < (v - median) / sigma < sigma_high (f32, strict) and stops when nothing was removed;
+ * out = f32 sum of the survivors in frame order / their count (0 when none survive);
+ * rejection_counts[f] = samples of frame f rejected over the whole image (n_frames u64,
+ * overwritten).  n_frames <= AB_MAX_FRAMES.  BatchStackConfig defaults: 2.5, 3.0, 5. */
+ab_status ab_sigma_clipped_mean_stack(ab_ctx *ctx, const float *const *frames, size_t n_frames,
+                                      size_t rows, size_t cols, float sigma_low, float sigma_high,
+                                      uint32_t max_iterations, float *out,
+                                      uint64_t *rejection_counts);
+ab_status ab_sigma_clipped_mean_stack_dev(ab_ctx *ctx, const float *const *d_frames, size_t n_frames,
+                                          size_t npix, float sigma_low, float sigma_high,
+                                          uint32_t max_iterations, float *d_out,
+                                          uint64_t *d_rejection_counts, void *stream);
 /* CalibrationConfig (:8-13); masters may be NULL.  clamp_negative = 1: calibrate_image (:47-83,
  * `if v < 0.0 { 0.0 }`); 0: the unclamped subtract_bias / subtract_dark / divide_flat (:15-45). */
 typedef struct ab_calibration_config {
@@ -462,6 +501,18 @@ ab_status ab_detect_stars(ab_ctx *ctx, const float *img, size_t rows, size_t col
 ab_status ab_detect_stars_dev(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols,
                               double sigma_threshold, ab_star *stars, size_t max_stars,
                               ab_detection_info *info, void *stream);
+/* analyze_subframe, core/analysis/subframe.rs:52-118: detect_stars at sigma 4.0,
+ * medians of fwhm / eccentricity / snr over the finite values (even count: mean of the two middle
+ * ones), noise ratio, compute_weight (:120-145) and the acceptance test.  Fewer than
+ * min(5, cfg->min_stars) stars -> zero metrics, weight 0, not accepted (:65-79).
+ * ab_normalize_weights = normalize_weights (:147-158): divide by the largest weight when it is
+ * > 1e-15 (host scalar code, no context needed). */
+ab_status ab_analyze_subframe(ab_ctx *ctx, const float *img, size_t rows, size_t cols,
+                              const ab_subframe_config *cfg, ab_subframe_metrics *out);
+ab_status ab_analyze_subframe_dev(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols,
+                                  const ab_subframe_config *cfg, ab_subframe_metrics *out,
+                                  void *stream);
+void ab_normalize_weights(ab_subframe_metrics *metrics, size_t n);
 /* estimate_background, star_detection.rs:32-84 */
 ab_status ab_estimate_background(ab_ctx *ctx, const float *img, size_t rows, size_t cols,
                                  size_t tile_size, double *median, double *sigma);

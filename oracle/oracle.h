@@ -84,6 +84,9 @@ int orc_fits_decode(const uint8_t *data, size_t n_pixels, int bitpix, double bsc
 int orc_fits_encode(const float *data, size_t n_pixels, int bitpix, double bzero, double bscale, uint8_t *out);
 
 /* ---- calibration (core/stacking/calibration.rs) ---- */
+int orc_sigma_clipped_mean_stack(const float *const *frames, size_t n_frames, size_t rows, size_t cols,
+                                 float sigma_low, float sigma_high, size_t max_iterations, float *out,
+                                 uint64_t *rejection_counts);
 int orc_median_combine(const float *const *frames, size_t n_frames, size_t rows, size_t cols,
                        const float *bias, const float *dark, float dark_ratio, float *out);
 void orc_normalize_flat(float *data, size_t len);
@@ -147,6 +150,21 @@ int orc_resample_image(const float *img, size_t src_rows, size_t src_cols, size_
 void orc_estimate_background(const float *img, size_t rows, size_t cols, size_t tile_size,
                              double *median, double *sigma);
 /* returns number of stars found (may exceed max_out; only max_out are written) */
+/* SubframeWeightConfig / SubframeMetrics, core/analysis/subframe.rs:9-50 */
+typedef struct {
+    double fwhm_weight, eccentricity_weight, snr_weight, noise_weight, max_fwhm, max_eccentricity, min_snr;
+    uint64_t min_stars;
+} orc_subframe_config;
+typedef struct {
+    uint64_t star_count;
+    double median_fwhm, median_eccentricity, median_snr, background_median, background_sigma, noise_ratio,
+        weight;
+    int32_t accepted;
+} orc_subframe_metrics;
+void orc_analyze_subframe(const float *img, size_t rows, size_t cols, const orc_subframe_config *cfg,
+                          orc_subframe_metrics *out);
+double orc_subframe_weight(double fwhm, double ecc, double snr, double noise, const orc_subframe_config *cfg);
+void orc_normalize_weights(orc_subframe_metrics *m, size_t n);
 size_t orc_detect_stars(const float *img, size_t rows, size_t cols, double sigma_threshold,
                         orc_star *out, size_t max_out, double *bg_median, double *bg_sigma);
 void orc_normalize_for_detection(const float *img, size_t len, float *out);

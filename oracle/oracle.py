@@ -206,6 +206,21 @@ def median_combine(frames, bias=None, dark=None, dark_ratio=1.0):
     return out
 
 
+def sigma_clipped_mean_stack(frames, sigma_low=2.5, sigma_high=3.0, max_iterations=5):
+    """calibration_pipeline.rs:317-378 -> (image, per-frame rejection counts)."""
+    fr = [_f32(f) for f in frames]
+    if not fr:
+        raise ValueError("no frames")
+    rows, cols = fr[0].shape
+    ptrs = (C.c_void_p * len(fr))(*[f.ctypes.data for f in fr])
+    out = np.empty((rows, cols), np.float32)
+    counts = np.zeros(len(fr), np.uint64)
+    lib().orc_sigma_clipped_mean_stack(ptrs, C.c_size_t(len(fr)), C.c_size_t(rows), C.c_size_t(cols),
+                                       C.c_float(sigma_low), C.c_float(sigma_high),
+                                       C.c_size_t(max_iterations), _p(out), _p(counts))
+    return out, [int(c) for c in counts]
+
+
 def normalize_flat(data):
     out = _f32(data).copy()
     lib().orc_normalize_flat(_p(out), C.c_size_t(out.size))
@@ -466,6 +481,49 @@ def detect_stars(img, sigma_threshold, max_out=1 << 20) -> DetectionResult:
         for s in buf[: min(n, max_out)]
     ]
     return DetectionResult(stars, med.value, sig.value, sigma_threshold, d.shape[1], d.shape[0])
+
+
+class SubframeConfig(C.Structure):
+    """SubframeWeightConfig defaults, subframe.rs:37-50."""
+    _fields_ = [(n, C.c_double) for n in ("fwhm_weight", "eccentricity_weight", "snr_weight", "noise_weight",
+                                          "max_fwhm", "max_eccentricity", "min_snr")] + [("min_stars", C.c_uint64)]
+
+    def __init__(self, fwhm_weight=1.0, eccentricity_weight=0.5, snr_weight=1.0, noise_weight=0.3,
+                 max_fwhm=8.0, max_eccentricity=0.7, min_snr=5.0, min_stars=5):
+        super().__init__(fwhm_weight, eccentricity_weight, snr_weight, noise_weight, max_fwhm,
+                         max_eccentricity, min_snr, min_stars)
+
+
+class SubframeMetrics(C.Structure):
+    _fields_ = [("star_count", C.c_uint64)] + [(n, C.c_double) for n in (
+        "median_fwhm", "median_eccentricity", "median_snr", "background_median", "background_sigma",
+        "noise_ratio", "weight")] + [("accepted", C.c_int32)]
+
+    def as_tuple(self):
+        return tuple(getattr(self, n) for n, _ in self._fields_)
+
+
+def analyze_subframe(img, config: SubframeConfig | None = None) -> SubframeMetrics:
+    d = _f32(img)
+    cfg = config or SubframeConfig()
+    out = SubframeMetrics()
+    lib().orc_analyze_subframe(_p(d), C.c_size_t(d.shape[0]), C.c_size_t(d.shape[1]), C.byref(cfg), C.byref(out))
+    return out
+
+
+def subframe_weight(fwhm, ecc, snr, noise, config: SubframeConfig | None = None) -> float:
+    cfg = config or SubframeConfig()
+    lib().orc_subframe_weight.restype = C.c_double
+    return lib().orc_subframe_weight(C.c_double(fwhm), C.c_double(ecc), C.c_double(snr), C.c_double(noise),
+                                     C.byref(cfg))
+
+
+def normalize_weights(weights):
+    m = (SubframeMetrics * len(weights))()
+    for i, w in enumerate(weights):
+        m[i].weight = w
+    lib().orc_normalize_weights(m, C.c_size_t(len(weights)))
+    return [x.weight for x in m]
 
 
 def normalize_for_detection(img):

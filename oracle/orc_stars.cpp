@@ -204,4 +204,61 @@ size_t orc_detect_stars(const float *img, size_t rows, size_t cols, double sigma
     return n;
 }
 
+// core/analysis/subframe.rs:52-171 -- analyze_subframe (metrics only; the path strings stay with
+// the caller), compute_weight, median_of, normalize_weights.
+void orc_analyze_subframe(const float *img, size_t rows, size_t cols, const orc_subframe_config *cfg,
+                          orc_subframe_metrics *out) {
+    std::vector<orc_star> buf(rows * cols / 3 + 16);
+    double bm = 0.0, bs = 1.0;
+    size_t n = orc_detect_stars(img, rows, cols, 4.0, buf.data(), buf.size(), &bm, &bs);  // :6
+    n = std::min(n, buf.size());
+    *out = {};
+    out->star_count = n;
+    out->background_median = bm;
+    out->background_sigma = bs;
+    if (n < std::min<size_t>(5, (size_t)cfg->min_stars)) return;  // :65-79
+    auto median_of = [&](double orc_star::*field) {  // :160-171
+        std::vector<double> vals;
+        for (size_t i = 0; i < n; ++i)
+            if (std::isfinite(buf[i].*field)) vals.push_back(buf[i].*field);
+        if (vals.empty()) return 0.0;
+        std::stable_sort(vals.begin(), vals.end());
+        const size_t mid = vals.size() / 2;
+        return vals.size() % 2 == 0 ? (vals[mid - 1] + vals[mid]) / 2.0 : vals[mid];
+    };
+    const double fwhm = median_of(&orc_star::fwhm), ecc = median_of(&orc_star::eccentricity);
+    const double snr = median_of(&orc_star::snr);
+    const double noise = bm > 1e-15 ? bs / bm : 0.0;
+    out->median_fwhm = fwhm;
+    out->median_eccentricity = ecc;
+    out->median_snr = snr;
+    out->noise_ratio = noise;
+    out->weight = orc_subframe_weight(fwhm, ecc, snr, noise, cfg);
+    out->accepted = (n >= (size_t)cfg->min_stars && fwhm <= cfg->max_fwhm && ecc <= cfg->max_eccentricity &&
+                     snr >= cfg->min_snr)
+                        ? 1
+                        : 0;
+}
+
+// compute_weight, subframe.rs:120-145
+double orc_subframe_weight(double fwhm, double ecc, double snr, double noise, const orc_subframe_config *c) {
+    const double fwhm_score = fwhm > 0.5 ? 1.0 / fwhm : 0.0;
+    const double ecc_score = 1.0 - ecc;
+    const double snr_score = std::fmax(std::log(snr), 0.0);
+    const double noise_score = 1.0 / (1.0 + noise * 10.0);
+    const double total = c->fwhm_weight + c->eccentricity_weight + c->snr_weight + c->noise_weight;
+    if (total < 1e-15) return 0.0;
+    const double raw = c->fwhm_weight * fwhm_score + c->eccentricity_weight * ecc_score +
+                       c->snr_weight * snr_score + c->noise_weight * noise_score;
+    return std::fmax(raw / total, 0.0);
+}
+
+// normalize_weights, subframe.rs:147-158
+void orc_normalize_weights(orc_subframe_metrics *m, size_t n) {
+    double max_w = 0.0;
+    for (size_t i = 0; i < n; ++i) max_w = std::fmax(max_w, m[i].weight);
+    if (max_w > 1e-15)
+        for (size_t i = 0; i < n; ++i) m[i].weight /= max_w;
+}
+
 }  // extern "C"

@@ -113,3 +113,36 @@ def test_device_band_entry_point(cal, orc):
                                           torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), orc.median_combine(fr)[8:24])
+
+
+# ---- sigma_clipped_mean_stack of the batch pipeline (calibration_pipeline.rs:317-378)
+@pytest.mark.parametrize("n_frames,rows,cols", [(3, 20, 31), (8, 33, 40), (12, 40, 64), (20, 24, 50), (33, 16, 48),
+                                                (64, 12, 40), (100, 9, 33), (200, 6, 21)])
+def test_sigma_clipped_mean_stack_matches_oracle(n_frames, rows, cols, orc):
+    """Bit-exact image (f32 sum in frame order) and per-frame rejection counts, every frame-count
+    class of the kernel (register network 8/16/32/64, rolled sort 128/256)."""
+    from astroburst_b200 import calibration
+
+    rng = np.random.default_rng(n_frames)
+    fr = rng.normal(1.0, 0.02, (n_frames, rows, cols)).astype(np.float32)
+    fr[rng.random(fr.shape) < 0.01] += 3.0                         # outliers
+    fr[rng.random(fr.shape) < 0.004] = np.nan                      # NaN takes part (ordered last)
+    fr[rng.random(fr.shape) < 0.002] = np.inf
+    fr[:, 1, 2] = 0.5                                              # MAD 0 -> sigma < 1e-10 ends the loop
+    fr[: n_frames // 2 + 1, 2, 3] = np.nan                         # NaN median -> everything rejected -> 0
+    for sl, sh, it in ((2.5, 3.0, 5), (1.0, 1.5, 3), (3.0, 3.0, 1), (2.5, 3.0, 0)):
+        want, want_cnt = orc.sigma_clipped_mean_stack(list(fr), sl, sh, it)
+        got, got_cnt = calibration.sigma_clipped_mean_stack(list(fr), sl, sh, it)
+        assert got_cnt == want_cnt, (sl, sh, it)
+        assert np.array_equal(got, want, equal_nan=True), (sl, sh, it)
+    assert got[2, 3] == 0.0 or it == 0
+
+
+def test_sigma_clipped_mean_stack_errors():
+    import astroburst_b200 as ab
+    from astroburst_b200 import calibration
+
+    with pytest.raises(ab.AstroBurstError):
+        calibration.sigma_clipped_mean_stack([])
+    with pytest.raises(ab.AstroBurstError):
+        calibration.sigma_clipped_mean_stack([np.zeros((4, 4), np.float32), np.zeros((4, 5), np.float32)])

@@ -112,3 +112,35 @@ def test_stack_images_with_align(orc):
     assert abs(res.rejected_pixels - want_rej) <= max(4, want_rej // 1000)
     # (with the literal sign convention the frames are shifted AWAY from the reference frame --
     # see the module docstring and DESIGN.md; reproduced faithfully, not "fixed")
+
+
+def test_align_2_registers_frames_onto_the_reference(al):
+    """align = 2 (opt-in, outside parity): operands of the phase correlation swapped, so frames are
+    shifted ONTO frame 0.  A stack of integer-shifted copies then reproduces frame 0 in the interior,
+    while align = 1 (upstream's sign convention, bit parity) smears it."""
+    import astroburst_b200 as ab
+    import ctypes as C
+    from astroburst_b200._lib import StackConfigC, lib
+
+    base = star_field(256, 256, 8)
+    frames = [base] + [shift_array(base, dy, dx) for dy, dx in ((3, -2), (-4, 5), (6, 1), (-1, -6))]
+    ctx = ab.default_context()
+
+    def run(align):
+        cfg = StackConfigC(3.0, 3.0, 5, align)
+        ptrs = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
+        out = np.empty_like(base)
+        rej = C.c_uint64(0)
+        offs = np.zeros((len(frames), 2), np.int32)
+        ctx.check(lib().ab_stack_images(ctx.handle, ptrs, len(frames), 256, 256, C.byref(cfg), out.ctypes.data,
+                                        C.byref(rej), offs.ctypes.data))
+        return out, offs
+
+    fixed, offs2 = run(2)
+    upstream, offs1 = run(1)
+    assert [tuple(o) for o in offs2[1:]] == [(3, -2), (-4, 5), (6, 1), (-1, -6)]   # the content displacement
+    assert [tuple(o) for o in offs1[1:]] == [(-3, 2), (4, -5), (-6, -1), (1, 6)]   # upstream: its negative
+    core = (slice(16, -16), slice(16, -16))
+    err2 = np.abs(fixed[core] - base[core]).max()
+    err1 = np.abs(upstream[core] - base[core]).max()
+    assert err2 < 1e-2 * base[core].max() and err1 > 10 * max(err2, 1.0)

@@ -204,3 +204,22 @@ def test_background_tiles_beyond_the_on_chip_capacity(al, orc, shape, tile):
     img[:9, :] = 0.0
     img[13, 17] = np.nan
     assert al.estimate_background(img, tile) == orc.estimate_background(img, tile)
+
+
+# ---- subframe scoring (core/analysis/subframe.rs:52-158)
+def test_analyze_subframe_matches_oracle(al, orc):
+    from astroburst_b200 import alignment
+
+    imgs = [star_field(400, 500, 120, seed=4), star_field(300, 300, 40, seed=9),
+            np.full((64, 64), 10.0, np.float32), reference_test_image(300, 300)]
+    got = []
+    for img in imgs:
+        g, w = alignment.analyze_subframe(img), orc.analyze_subframe(img)
+        assert g.as_tuple() == w.as_tuple()
+        got.append(g)
+    cfg_g = alignment.SubframeWeightConfig(max_fwhm=2.0, min_stars=500, snr_weight=0.0)
+    cfg_o = orc.SubframeConfig(max_fwhm=2.0, min_stars=500, snr_weight=0.0)
+    assert alignment.analyze_subframe(imgs[0], cfg_g).as_tuple() == orc.analyze_subframe(imgs[0], cfg_o).as_tuple()
+    want = orc.normalize_weights([g.weight for g in got])
+    alignment.normalize_weights(got)
+    assert [g.weight for g in got] == want and max(want) == 1.0

@@ -134,6 +134,7 @@ class MaskedStretchInfoC(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int)
+ALLREDUCE_DEV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p)
 
 
 def library_path() -> str:
@@ -225,6 +226,8 @@ SIGNATURES = {
     "ab_image_stats_dev": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_double, C.c_double, _vp, _vp]),
     "ab_image_stats_sharded_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, C.c_int, C.c_double, C.c_double,
                                              _vp, _vp]),
+    "ab_image_stats_sharded_chained_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, C.c_int, C.c_double,
+                                                     C.c_double, _vp, _vp]),
     "ab_histogram_u32": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, C.c_double, _vp, _vp]),
     "ab_histogram_u32_dev": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, C.c_double, _vp, _vp, _vp]),
     "ab_downsample_histogram": (C.c_int, [_vp, _sz, _sz, _vp]),
@@ -249,6 +252,8 @@ SIGNATURES = {
     "ab_normalize_for_detection": (C.c_int, [_vp, _vp, _sz, _vp]),
     "ab_align_affine": (C.c_int, [_vp, _vp, _vp, _sz, _sz, C.c_int, _vp]),
     "ab_align_affine_dev": (C.c_int, [_vp, _vp, _vp, _sz, _sz, C.c_int, _vp, _vp]),
+    "ab_align_ref_stars_dev": (C.c_int, [_vp, _vp, _sz, _sz, _vp, C.POINTER(C.c_size_t), _vp]),
+    "ab_align_affine_with_ref_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _sz, _sz, C.c_int, _vp, _vp]),
     "ab_match_stars": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, C.POINTER(C.c_size_t)]),
     "ab_ransac_affine": (C.c_int, [_vp, _sz, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),
     # preview / export tail, LRGB, star mask, masked stretch

@@ -1143,6 +1143,7 @@ ab_status fallback(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t r
     out->inliers = 0;
     out->residual_px = 0.0;
     out->method = 3;
+    if (!d_ref) return AB_OK;  // no reference plane on this GPU
     ab_phase_result pc;
     ab_status st = ab_phase_correlate_on(ctx, d_ref, d_tgt, rows, cols, s, &pc);
     if (st != AB_OK) return st;
@@ -1223,22 +1224,29 @@ ab_status match_stars(ab_ctx *ctx, const std::vector<Pt> &rs, const std::vector<
     return AB_OK;
 }
 
-ab_status align_on_device(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t rows,
-                          size_t cols, int n_threads, cudaStream_t s, ab_align_result *out) {
-    std::vector<ab_star> rst, tst;
+// the (up to) 120 brightest stars of a plane as the aligner sees it: normalize_for_detection fused
+// into the detector's loads, detect_stars at 3.5 sigma, top MAX_STARS by flux (affine.rs:133-147)
+ab_status align_star_points(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols, cudaStream_t s,
+                            std::vector<Pt> &pts) {
+    std::vector<ab_star> st;
     double bm, bs;
-    Norm nr, nt;
-    ab_status st = normalize_params(ctx, d_ref, rows * cols, s, &nr);
+    Norm nm;
+    ab_status rc = normalize_params(ctx, d_img, rows * cols, s, &nm);
+    if (rc != AB_OK) return rc;
+    rc = detect_on_device(ctx, d_img, rows, cols, nm, DETECTION_SIGMA, s, st, &bm, &bs);
+    if (rc != AB_OK) return rc;
+    pts.clear();
+    for (size_t i = 0; i < std::min(st.size(), (size_t)MAX_STARS); ++i) pts.push_back({st[i].x, st[i].y});
+    return AB_OK;
+}
+
+// align_channel_affine (affine.rs:129-212) from the reference's star list onwards
+ab_status align_with_ref_points(ab_ctx *ctx, const std::vector<Pt> &rs, const float *d_ref,
+                                const float *d_tgt, size_t rows, size_t cols, int n_threads,
+                                cudaStream_t s, ab_align_result *out) {
+    std::vector<Pt> ts;
+    ab_status st = align_star_points(ctx, d_tgt, rows, cols, s, ts);
     if (st != AB_OK) return st;
-    st = detect_on_device(ctx, d_ref, rows, cols, nr, DETECTION_SIGMA, s, rst, &bm, &bs);
-    if (st != AB_OK) return st;
-    st = normalize_params(ctx, d_tgt, rows * cols, s, &nt);
-    if (st != AB_OK) return st;
-    st = detect_on_device(ctx, d_tgt, rows, cols, nt, DETECTION_SIGMA, s, tst, &bm, &bs);
-    if (st != AB_OK) return st;
-    std::vector<Pt> rs, ts;
-    for (size_t i = 0; i < std::min(rst.size(), (size_t)MAX_STARS); ++i) rs.push_back({rst[i].x, rst[i].y});
-    for (size_t i = 0; i < std::min(tst.size(), (size_t)MAX_STARS); ++i) ts.push_back({tst[i].x, tst[i].y});
     if (rs.size() < MIN_MATCHES_RIGID || ts.size() < MIN_MATCHES_RIGID)
         return fallback(ctx, d_ref, d_tgt, rows, cols, s, out);
     std::vector<Match> matches;
@@ -1255,6 +1263,14 @@ ab_status align_on_device(ab_ctx *ctx, const float *d_ref, const float *d_tgt, s
         return AB_OK;
     }
     return fallback(ctx, d_ref, d_tgt, rows, cols, s, out);
+}
+
+ab_status align_on_device(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t rows,
+                          size_t cols, int n_threads, cudaStream_t s, ab_align_result *out) {
+    std::vector<Pt> rs;
+    ab_status st = align_star_points(ctx, d_ref, rows, cols, s, rs);
+    if (st != AB_OK) return st;
+    return align_with_ref_points(ctx, rs, d_ref, d_tgt, rows, cols, n_threads, s, out);
 }
 
 ab_status upload(ab_ctx *ctx, int slot, const float *h, size_t len, float **d) {
@@ -1479,6 +1495,39 @@ ab_status ab_align_affine_dev(ab_ctx *ctx, const float *d_ref, const float *d_tg
     CtxLock lk(ctx->mu);
     DeviceGuard g(ctx->device);
     return align_on_device(ctx, d_ref, d_tgt, rows, cols, n_threads, (cudaStream_t)stream, out);
+}
+
+// The reference plane's star list once (align_channels_cmd aligns every channel against the same
+// reference, cmd/compose/blend.rs:263-296; the reference re-detects it per pair, :279): xy_out =
+// up to 120 (x, y) pairs, *n_out = stars written.  ab_align_affine_with_ref_dev then equals
+// ab_align_affine_dev(ref, tgt) bit for bit.  A frames-across-GPUs run broadcasts these <= 1920
+// bytes instead of the reference frame.
+ab_status ab_align_ref_stars_dev(ab_ctx *ctx, const float *d_ref, size_t rows, size_t cols,
+                                 double *xy_out, size_t *n_out, void *stream) {
+    if (!ctx || !d_ref || !xy_out || !n_out) return AB_ERR_INVALID;
+    CtxLock lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    std::vector<Pt> pts;
+    ab_status st = align_star_points(ctx, d_ref, rows, cols, (cudaStream_t)stream, pts);
+    if (st != AB_OK) return st;
+    for (size_t i = 0; i < pts.size(); ++i) {
+        xy_out[2 * i] = pts[i].x;
+        xy_out[2 * i + 1] = pts[i].y;
+    }
+    *n_out = pts.size();
+    return AB_OK;
+}
+// d_ref may be NULL when the reference plane is not on this GPU: the phase-correlation fallback
+// (affine.rs:243-270) then cannot run and the result falls back to identity (method 3).
+ab_status ab_align_affine_with_ref_dev(ab_ctx *ctx, const double *ref_xy, size_t n_ref,
+                                       const float *d_ref, const float *d_tgt, size_t rows, size_t cols,
+                                       int n_threads, ab_align_result *out, void *stream) {
+    if (!ctx || !out || !d_tgt || (n_ref && !ref_xy)) return AB_ERR_INVALID;
+    CtxLock lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    std::vector<Pt> rs;
+    for (size_t i = 0; i < std::min(n_ref, (size_t)MAX_STARS); ++i) rs.push_back({ref_xy[2 * i], ref_xy[2 * i + 1]});
+    return align_with_ref_points(ctx, rs, d_ref, d_tgt, rows, cols, n_threads, (cudaStream_t)stream, out);
 }
 
 ab_status ab_align_affine(ab_ctx *ctx, const float *ref, const float *tgt, size_t rows, size_t cols,

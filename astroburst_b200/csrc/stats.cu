@@ -338,9 +338,52 @@ struct StatsCtl {
     double global_min, global_max, range, bin_width, mean;
     double median_bin_lo, refine_range, median, dev_bw, mad_region_lo, mad_refine_range;
     unsigned long long total_valid, half_count, count_before_median;
+    // per-pass scalars, folded from the block partials and (sharded images) all-reduced in place
+    double mm[2];                   // {-min, max} of the valid pixels: one MAX all-reduce covers both
+    unsigned long long scan_count;  // valid pixels seen by the scan pass
+    double hsum;                    // pass 1: f64 sum of the valid pixels
+    unsigned long long hcnt[2];     // {valid count, count below the MAD region}
     int empty;
     ab_image_stats out;
 };
+// cross-rank reduction of DEVICE buffers on the stream (sharded images); null = single GPU.
+// dtype 0 f64 / 1 u64 / 2 u32, op 0 sum / 1 min / 2 max (ab_allreduce_dev_fn in the header)
+struct DevReducer {
+    ab_allreduce_dev_fn fn = nullptr;
+    void *user = nullptr;
+    ab_status run(ab_ctx *ctx, void *d_buf, size_t count, int dtype, int op, cudaStream_t s) const {
+        if (!fn) return AB_OK;
+        if (fn(user, d_buf, count, dtype, op, (void *)s) != 0)
+            return ab_fail(ctx, AB_ERR_INVALID, "device all-reduce callback failed");
+        return AB_OK;
+    }
+};
+__global__ void fold_scan_kernel(const ScanPartial *__restrict__ sp, unsigned n, StatsCtl *ctl) {
+    double lo = DBL_MAX, hi = -DBL_MAX;
+    unsigned long long c = 0;
+    for (unsigned i = 0; i < n; ++i) {
+        if (sp[i].count) {
+            lo = fmin(lo, (double)sp[i].mn);
+            hi = fmax(hi, (double)sp[i].mx);
+        }
+        c += sp[i].count;
+    }
+    ctl->mm[0] = -lo;
+    ctl->mm[1] = hi;
+    ctl->scan_count = c;
+}
+__global__ void fold_hist_kernel(const HistPartial *__restrict__ hp, unsigned n, StatsCtl *ctl) {
+    double s = 0.0;
+    unsigned long long c = 0, b = 0;
+    for (unsigned i = 0; i < n; ++i) {
+        s += hp[i].sum;
+        c += hp[i].count;
+        b += hp[i].below;
+    }
+    ctl->hsum = s;
+    ctl->hcnt[0] = c;
+    ctl->hcnt[1] = b;
+}
 constexpr int WK_THREADS = 1024, WK_PER = HIST_BINS / WK_THREADS;
 
 // first bin i with cum(i) >= target (cum inclusive): *idx, *cum = cum(i), *cnt = hist[i].
@@ -407,24 +450,13 @@ __device__ double block_resolve_rank(const unsigned *hist, unsigned long long ra
 }
 
 // after the scan pass (or with a caller-known range): range, bin width, pass-1 classifier
-__global__ void __launch_bounds__(WK_THREADS)
-walk_range_kernel(const ScanPartial *__restrict__ sp, unsigned n_partials, int known, double kmin,
-                  double kmax, StatsCtl *ctl) {
-    if (threadIdx.x != 0) return;
+__global__ void walk_range_kernel(int known, double kmin, double kmax, StatsCtl *ctl) {
     double lo = kmin, hi = kmax;
     int empty = 0;
     if (!known) {
-        lo = DBL_MAX;
-        hi = -DBL_MAX;
-        unsigned long long c = 0;
-        for (unsigned i = 0; i < n_partials; ++i) {
-            if (sp[i].count) {
-                lo = fmin(lo, (double)sp[i].mn);
-                hi = fmax(hi, (double)sp[i].mx);
-            }
-            c += sp[i].count;
-        }
-        empty = c == 0;
+        lo = -ctl->mm[0];
+        hi = ctl->mm[1];
+        empty = ctl->scan_count == 0;
     }
     ctl->empty = empty;
     ctl->global_min = lo;
@@ -437,23 +469,12 @@ walk_range_kernel(const ScanPartial *__restrict__ sp, unsigned n_partials, int k
 }
 // after pass 1 (value histogram + sum): median bin, coarse median, pass-2 classifier
 __global__ void __launch_bounds__(WK_THREADS)
-walk_value_kernel(const unsigned *__restrict__ histA, const HistPartial *__restrict__ hp,
-                  unsigned n_partials, StatsCtl *ctl) {
-    __shared__ unsigned long long tot;
-    __shared__ double gsum;
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        unsigned long long c = 0;
-        for (unsigned i = 0; i < n_partials; ++i) {
-            s += hp[i].sum;
-            c += hp[i].count;
-        }
-        tot = c;
-        gsum = s;
-    }
-    __syncthreads();
-    const unsigned long long total = tot;
-    if (ctl->empty || total == 0) {
+walk_value_kernel(const unsigned *__restrict__ histA, StatsCtl *ctl) {
+    const unsigned long long total = ctl->hcnt[0];
+    const double gsum = ctl->hsum;
+    const int was_empty = ctl->empty;
+    __syncthreads();  // every thread has read `empty` before thread 0 may overwrite it
+    if (was_empty || total == 0) {
         if (threadIdx.x == 0) ctl->empty = 1;
         return;
     }
@@ -517,20 +538,12 @@ walk_refine_kernel(const unsigned *__restrict__ histA, const unsigned *__restric
 }
 // after pass 3 (MAD-refine histogram B + count below): MAD, sigma, the ImageStats
 __global__ void __launch_bounds__(WK_THREADS)
-walk_mad_kernel(const unsigned *__restrict__ histB, const HistPartial *__restrict__ hp,
-                unsigned n_partials, StatsCtl *ctl) {
+walk_mad_kernel(const unsigned *__restrict__ histB, StatsCtl *ctl) {
     if (ctl->empty) {
-        if (threadIdx.x == 0) ctl->out = {0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0};  // ImageStats::default, stats.rs:45-47
+        if (threadIdx.x == 0) ctl->out = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0};  // ImageStats::default(), like stats_default
         return;
     }
-    __shared__ unsigned long long below_sh;
-    if (threadIdx.x == 0) {
-        unsigned long long b = 0;
-        for (unsigned i = 0; i < n_partials; ++i) b += hp[i].below;
-        below_sh = b;
-    }
-    __syncthreads();
-    const unsigned long long half = ctl->half_count, below = below_sh;
+    const unsigned long long half = ctl->half_count, below = ctl->hcnt[1];
     const unsigned long long rank = half > below ? half - below : 0;
     const double mad = block_resolve_rank(histB, rank, ctl->mad_region_lo,
                                           ctl->mad_refine_range / (double)HIST_BINS);
@@ -882,45 +895,73 @@ ab_status hist_core(ab_ctx *ctx, const float *d, size_t len, double global_min, 
 
 // stats.rs:75-210 with every percentile walk on the device: scan, walk, 3 x (sweep, walk) queued
 // back to back on `s`, ONE synchronisation for the 56-byte result.  `known`: the caller's range
-// (compute_image_stats_with_known_range, :25-41) replaces the scan pass.
+// (compute_image_stats_with_known_range, :25-41) replaces the scan pass.  With a DevReducer the
+// image is a row band of a larger one: the folded scalars and the histograms are all-reduced in
+// place on the stream between a sweep and its walk, every rank then walks identical data.
 ab_status stats_hist_chained(ab_ctx *ctx, const float *d, size_t len, bool known, double kmin,
-                             double kmax, cudaStream_t s, ab_image_stats *out) {
+                             double kmax, cudaStream_t s, ab_image_stats *out,
+                             const DevReducer &rd = DevReducer()) {
     Small sm(ctx);
     // control block + host mirror of the result in the small scratch blocks ([640 KiB, +4 KiB))
     StatsCtl *ctl = reinterpret_cast<StatsCtl *>(sm.d + (640 << 10));
     ab_image_stats *h_out = reinterpret_cast<ab_image_stats *>(sm.h + (640 << 10));
     ScanPartial *d_sp = reinterpret_cast<ScanPartial *>(sm.d);
     HistPartial *d_hp = reinterpret_cast<HistPartial *>(sm.d + (32 << 10));
-    unsigned n_sp = 0;
+    ab_status st;
     if (!known) {
-        n_sp = grid_for(ctx, len, 16);
-        scan_kernel<<<n_sp, ST_THREADS, 0, s>>>(d, len, d_sp);
+        const unsigned n_sp = len ? grid_for(ctx, len, 16) : 0;
+        if (n_sp) {
+            scan_kernel<<<n_sp, ST_THREADS, 0, s>>>(d, len, d_sp);
+            AB_LAUNCH_CHECK(ctx);
+        }
+        fold_scan_kernel<<<1, 1, 0, s>>>(d_sp, n_sp, ctl);
         AB_LAUNCH_CHECK(ctx);
+        if ((st = rd.run(ctx, ctl->mm, 2, 0, 2, s)) != AB_OK) return st;
+        if ((st = rd.run(ctx, &ctl->scan_count, 1, 1, 0, s)) != AB_OK) return st;
     }
-    walk_range_kernel<<<1, WK_THREADS, 0, s>>>(d_sp, n_sp, known ? 1 : 0, kmin, kmax, ctl);
+    walk_range_kernel<<<1, 1, 0, s>>>(known ? 1 : 0, kmin, kmax, ctl);
     AB_LAUNCH_CHECK(ctx);
     size_t blocks = (len / 16 + HT_THREADS - 1) / HT_THREADS + 1;
     if (blocks > (size_t)ctx->sm_count) blocks = (size_t)ctx->sm_count;
-    const unsigned grid = (unsigned)blocks;
+    const unsigned grid = len ? (unsigned)blocks : 0;
     constexpr int smem = (int)(HIST_BINS / 2 * sizeof(unsigned));
     AB_CUDA(ctx, cudaFuncSetAttribute(hist_ctl_kernel<ValueHistF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     AB_CUDA(ctx, cudaFuncSetAttribute(hist_ctl_kernel<RefineDevF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     AB_CUDA(ctx, cudaFuncSetAttribute(hist_ctl_kernel<MadRefineF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const size_t hist_bytes = 2 * HIST_BINS * sizeof(unsigned);
+    // ---- pass 1: value histogram + sum
     AB_CUDA(ctx, cudaMemsetAsync(sm.dA, 0, hist_bytes, s));
-    hist_ctl_kernel<ValueHistF><<<grid, HT_THREADS, smem, s>>>(d, len, &ctl->f1, &ctl->empty, sm.dA, sm.dB, d_hp);
+    if (grid) {
+        hist_ctl_kernel<ValueHistF><<<grid, HT_THREADS, smem, s>>>(d, len, &ctl->f1, &ctl->empty, sm.dA, sm.dB, d_hp);
+        AB_LAUNCH_CHECK(ctx);
+    }
+    fold_hist_kernel<<<1, 1, 0, s>>>(d_hp, grid, ctl);
     AB_LAUNCH_CHECK(ctx);
-    walk_value_kernel<<<1, WK_THREADS, 0, s>>>(sm.dA, d_hp, grid, ctl);
+    if ((st = rd.run(ctx, sm.dA, HIST_BINS, 2, 0, s)) != AB_OK) return st;
+    if ((st = rd.run(ctx, &ctl->hsum, 1, 0, 0, s)) != AB_OK) return st;
+    if ((st = rd.run(ctx, ctl->hcnt, 2, 1, 0, s)) != AB_OK) return st;
+    walk_value_kernel<<<1, WK_THREADS, 0, s>>>(sm.dA, ctl);
     AB_LAUNCH_CHECK(ctx);
+    // ---- pass 2: deviation histogram (A) + median-refine histogram (B)
     AB_CUDA(ctx, cudaMemsetAsync(sm.dA, 0, hist_bytes, s));
-    hist_ctl_kernel<RefineDevF><<<grid, HT_THREADS, smem, s>>>(d, len, &ctl->f2, &ctl->empty, sm.dA, sm.dB, d_hp);
-    AB_LAUNCH_CHECK(ctx);
+    if (grid) {
+        hist_ctl_kernel<RefineDevF><<<grid, HT_THREADS, smem, s>>>(d, len, &ctl->f2, &ctl->empty, sm.dA, sm.dB, d_hp);
+        AB_LAUNCH_CHECK(ctx);
+    }
+    if ((st = rd.run(ctx, sm.dA, 2 * HIST_BINS, 2, 0, s)) != AB_OK) return st;  // A and B are adjacent
     walk_refine_kernel<<<1, WK_THREADS, 0, s>>>(sm.dA, sm.dB, ctl);
     AB_LAUNCH_CHECK(ctx);
+    // ---- pass 3: MAD-refine histogram (B) + count below the region
     AB_CUDA(ctx, cudaMemsetAsync(sm.dB, 0, HIST_BINS * sizeof(unsigned), s));
-    hist_ctl_kernel<MadRefineF><<<grid, HT_THREADS, smem, s>>>(d, len, &ctl->f3, &ctl->empty, sm.dA, sm.dB, d_hp);
+    if (grid) {
+        hist_ctl_kernel<MadRefineF><<<grid, HT_THREADS, smem, s>>>(d, len, &ctl->f3, &ctl->empty, sm.dA, sm.dB, d_hp);
+        AB_LAUNCH_CHECK(ctx);
+    }
+    fold_hist_kernel<<<1, 1, 0, s>>>(d_hp, grid, ctl);
     AB_LAUNCH_CHECK(ctx);
-    walk_mad_kernel<<<1, WK_THREADS, 0, s>>>(sm.dB, d_hp, grid, ctl);
+    if ((st = rd.run(ctx, sm.dB, HIST_BINS, 2, 0, s)) != AB_OK) return st;
+    if ((st = rd.run(ctx, ctl->hcnt, 2, 1, 0, s)) != AB_OK) return st;
+    walk_mad_kernel<<<1, WK_THREADS, 0, s>>>(sm.dB, ctl);
     AB_LAUNCH_CHECK(ctx);
     AB_CUDA(ctx, cudaMemcpyAsync(h_out, &ctl->out, sizeof(ab_image_stats), cudaMemcpyDeviceToHost, s));
     AB_CUDA(ctx, cudaStreamSynchronize(s));
@@ -1074,6 +1115,25 @@ ab_status ab_image_stats_sharded_dev(ab_ctx *ctx, const float *d_data, size_t le
         }
     }
     return hist_core(ctx, d_data, len, mn, mx, s, out, rd);
+}
+
+// The same with every reduction on the device and on the stream (NCCL through the callback): no
+// host round trip between the sweeps, one synchronisation for the result.
+ab_status ab_image_stats_sharded_chained_dev(ab_ctx *ctx, const float *d_data, size_t len,
+                                             ab_allreduce_dev_fn allreduce, void *user,
+                                             int use_known_range, double known_min, double known_max,
+                                             ab_image_stats *out, void *stream) {
+    if (!ctx || !out || !allreduce || (len && !d_data)) return AB_ERR_INVALID;
+    if (len >= ((size_t)1 << 32))
+        return ab_fail(ctx, AB_ERR_UNSUPPORTED, "bands of 2^32 pixels or more are not supported");
+    CtxLock lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    DevReducer rd;
+    rd.fn = allreduce;
+    rd.user = user;
+    const bool known = use_known_range && std::isfinite(known_min) && std::isfinite(known_max) &&
+                       known_min < known_max;
+    return stats_hist_chained(ctx, d_data, len, known, known_min, known_max, (cudaStream_t)stream, out, rd);
 }
 
 // build_histogram, stats.rs:378-421: bins = n_bins u32, edges = n_bins + 1 f64 (host outputs)

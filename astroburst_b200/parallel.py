@@ -12,7 +12,7 @@ from typing import Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import ALLREDUCE_FN, Context, ImageStatsC, default_context, lib
+from ._lib import ALLREDUCE_DEV_FN, ALLREDUCE_FN, Context, ImageStatsC, default_context, lib
 
 _NP = {0: np.float64, 1: np.uint64, 2: np.float64, 3: np.float64}
 
@@ -76,6 +76,52 @@ def compute_image_stats_sharded(band_ptr: int, band_len: int, allreduce, known_r
     kmin, kmax = known_range if known_range is not None else (0.0, 0.0)
     ctx.check(lib().ab_image_stats_sharded_dev(
         ctx.handle, int(band_ptr) if band_len else None, int(band_len), allreduce, None,
+        1 if known_range is not None else 0, kmin, kmax, C.addressof(out),
+        int(stream) if stream else None))
+    return out
+
+
+class _DevView:
+    """__cuda_array_interface__ view of a raw device buffer (what the C callback hands over)."""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+def make_allreduce_dev(device, group=None):
+    """ctypes callback for ab_image_stats_sharded_chained_dev: one torch.distributed (NCCL)
+    all-reduce of a DEVICE buffer, in place, enqueued on the caller's stream.  u64 / u32 buffers are
+    summed as int64 / int32 (same bits: two's complement, counts stay far below the sign bit)."""
+    import torch
+    import torch.distributed as dist
+
+    ops = {0: dist.ReduceOp.SUM, 1: dist.ReduceOp.MIN, 2: dist.ReduceOp.MAX}
+    types = {0: "<f8", 1: "<i8", 2: "<i4"}
+
+    def _cb(user, buf, count, dtype, op, stream):
+        try:
+            t = torch.as_tensor(_DevView(int(buf), int(count), types[dtype]), device=device)
+            st = torch.cuda.ExternalStream(int(stream)) if stream else torch.cuda.default_stream(device)
+            with torch.cuda.stream(st):
+                dist.all_reduce(t, op=ops[op], group=group)
+            return 0
+        except Exception:  # never unwind through the C frame
+            return 1
+
+    return ALLREDUCE_DEV_FN(_cb)
+
+
+def compute_image_stats_sharded_chained(band_ptr: int, band_len: int, allreduce_dev, known_range=None,
+                                        stream: int = 0, ctx: Context | None = None) -> ImageStatsC:
+    """compute_image_stats of a row-band sharded image with every reduction on the device and on
+    the stream (NCCL through `allreduce_dev` = make_allreduce_dev(...)); same results as
+    compute_image_stats_sharded, no host round trip between the sweeps."""
+    ctx = ctx or default_context()
+    out = ImageStatsC()
+    kmin, kmax = known_range if known_range is not None else (0.0, 0.0)
+    ctx.check(lib().ab_image_stats_sharded_chained_dev(
+        ctx.handle, int(band_ptr) if band_len else None, int(band_len), allreduce_dev, None,
         1 if known_range is not None else 0, kmin, kmax, C.addressof(out),
         int(stream) if stream else None))
     return out

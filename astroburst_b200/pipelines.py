@@ -1,0 +1,183 @@
+"""Device-resident compositions of the hot-path operators in the order the reference's commands fix
+(SURVEY 8(a) A19), for BASELINE configs 3 and 4.  Inputs and outputs are device pointers / torch
+tensors; every pixel sweep is one `_dev` entry point of the C ABI, every scalar step is the host
+scalar code the reference runs between them.
+
+config 4 (`color_chain`): blend_channels_cmd (cmd/compose/blend.rs:129-223) -> compute_auto_wb_cmd
+(cmd/compose/color.rs:188-224) -> calibrate_and_scnr_cmd (color.rs:98-185) -> apply_tone_composite_cmd
+with linked STF + curves (cmd/processing/curves.rs:58-191).  Works on a ROW BAND: the pointwise
+sweeps need nothing from other bands, the statistics come from `stats_fn`, which is either the
+single-GPU ab_image_stats_dev or the sharded, NCCL-reduced variant (parallel.py).
+
+config 3 (`align_and_warp`): align_channels_cmd with alignMethod = "affine"
+(cmd/compose/blend.rs:226-348): every target frame is registered against the reference frame
+(align_channel_affine, affine.rs:129-212) and resampled with warp_image (affine.rs:663-690).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import (AlignResultC, AutoStfConfigC, BlendWeightC, Context, ImageStatsC, LevelsParamsC, ScnrConfigC,
+                   StfParamsC, ToneChainC, default_context, lib)
+
+PAR_THRESHOLD = 4_000_000  # cmd/compose/color.rs:19
+
+
+def stats_single_gpu(ctx: Context, stream: int):
+    """stats_fn for an image that lives whole on one GPU: compute_image_stats /
+    compute_image_stats_with_known_range (stats.rs:15-41)."""
+
+    def fn(ptr: int, n: int, known_range=None) -> ImageStatsC:
+        st = ImageStatsC()
+        mode, (kmin, kmax) = (3, known_range) if known_range is not None else (0, (0.0, 0.0))
+        ctx.check(lib().ab_image_stats_dev(ctx.handle, ptr, n, mode, kmin, kmax, C.addressof(st),
+                                           stream if stream else None))
+        return st
+
+    return fn
+
+
+def stats_sharded(ctx: Context, stream: int, allreduce_dev, total_pixels: int):
+    """stats_fn for a row-band sharded image: histogram algorithm with the reductions
+    on the device.  `total_pixels` decides, like the reference, between the exact and the histogram
+    algorithm -- sharded images are far above the 4,000,000-pixel switch, anything else is refused."""
+    if total_pixels <= PAR_THRESHOLD:
+        raise ValueError("sharded statistics implement the histogram algorithm (> 4,000,000 px) only")
+
+    def fn(ptr: int, n: int, known_range=None) -> ImageStatsC:
+        from . import parallel
+
+        return parallel.compute_image_stats_sharded_chained(ptr, n, allreduce_dev, known_range, stream, ctx)
+
+    return fn
+
+
+def auto_wb_factors(sr: ImageStatsC, sg: ImageStatsC, sb: ImageStatsC):
+    """compute_auto_wb_cmd, cmd/compose/color.rs:188-224 -> (r_factor, g_factor, b_factor)."""
+
+    def stability(med, mad):
+        return mad / med if med > 1e-10 else float(np.finfo(np.float64).max)
+
+    stab_r, stab_g, stab_b = stability(sr.median, sr.mad), stability(sg.median, sg.mad), stability(sb.median, sb.mad)
+    if stab_r <= stab_g and stab_r <= stab_b:
+        m = max(sr.median, 1e-10)
+        return 1.0, m / max(sg.median, 1e-10), m / max(sb.median, 1e-10)
+    if stab_b <= stab_g:
+        m = max(sb.median, 1e-10)
+        return m / max(sr.median, 1e-10), m / max(sg.median, 1e-10), 1.0
+    m = max(sg.median, 1e-10)
+    return m / max(sr.median, 1e-10), 1.0, m / max(sb.median, 1e-10)
+
+
+@dataclass
+class ColorChainResult:
+    stats_blend: tuple          # ImageStats of the blended R, G, B (blend.rs:187-193)
+    factors: tuple              # white-balance factors as applied (f32, floored at 1e-6)
+    stats_balanced: tuple       # after WB (+ SCNR re-stat of G, color.rs:142-155)
+    stf: StfParamsC             # linked auto-STF (helpers.rs:185-202)
+    launches: int
+    lut: object = None          # device LUT of the curve: keep it alive until the stream has drained
+
+
+def color_chain(ch_ptrs: Sequence[int], n: int, rows: int, cols: int, weights, curve_points,
+                r_ptr: int, g_ptr: int, b_ptr: int, stats_fn: Callable, total_pixels: Optional[int] = None,
+                scnr_after_wb=(0, 0.5, 0), ctx: Context | None = None, stream: int = 0) -> ColorChainResult:
+    """The config-4 colour chain on `n` = rows * cols pixels (one row band, or the whole image).
+    ch_ptrs: device planes of the input channels; r/g/b_ptr: three device planes that receive the
+    result (they are also the working planes).  weights: [(channel_idx, r, g, b), ...].
+    scnr_after_wb: (method, amount, preserve_luminance) of calibrate_and_scnr_cmd."""
+    ctx = ctx or default_context()
+    h = ctx.handle
+    s = stream if stream else None
+    l0 = ctx.launch_count
+    total_pixels = total_pixels or n
+    # ---- blend_channels_cmd: blend + 3 x compute_image_stats
+    w = (BlendWeightC * len(weights))(*[BlendWeightC(*x) for x in weights])
+    ptrs = (C.c_void_p * len(ch_ptrs))(*[int(p) for p in ch_ptrs])
+    lens = (C.c_size_t * len(ch_ptrs))(*([n] * len(ch_ptrs)))
+    ctx.check(lib().ab_blend_channels_dev(h, ptrs, lens, len(ch_ptrs), w, len(weights), rows, cols, r_ptr, g_ptr,
+                                          b_ptr, s))
+    s_r, s_g, s_b = stats_fn(r_ptr, n), stats_fn(g_ptr, n), stats_fn(b_ptr, n)
+    stats_blend = (s_r, s_g, s_b)
+    # ---- compute_auto_wb_cmd -> calibrate_and_scnr_cmd
+    fac = [max(np.float32(f), np.float32(1e-6)) for f in auto_wb_factors(s_r, s_g, s_b)]   # color.rs:115-117
+    bal = []
+    for ptr, f, st in ((r_ptr, fac[0], s_r), (g_ptr, fac[1], s_g), (b_ptr, fac[2], s_b)):
+        ctx.check(lib().ab_scale_dev(h, ptr, n, C.c_float(float(f)), ptr, s))             # calibrate_channel :21-49
+        if total_pixels <= PAR_THRESHOLD:
+            bal.append(stats_fn(ptr, n))
+        else:  # factor >= 0 here (floored at 1e-6): known range = orig range * factor (f64)
+            bal.append(stats_fn(ptr, n, (st.min * float(f), st.max * float(f))))
+    method, amount, preserve = scnr_after_wb
+    if amount > 1e-7:
+        cfg = ScnrConfigC(method, amount, preserve)
+        ctx.check(lib().ab_apply_scnr_dev(h, r_ptr, g_ptr, b_ptr, n, C.addressof(cfg), s))
+        if preserve:
+            bal = [stats_fn(r_ptr, n), stats_fn(g_ptr, n), stats_fn(b_ptr, n)]
+        else:
+            bal[1] = stats_fn(g_ptr, n)
+    # ---- apply_tone_composite_cmd, linked STF: combined stats normalise all three channels
+    combined = ImageStatsC()
+    lib().ab_linked_stats(C.addressof(bal[0]), C.addressof(bal[1]), C.addressof(bal[2]), C.addressof(combined))
+    cfg_stf = AutoStfConfigC(0.25, -2.8)
+    stf = StfParamsC()
+    lib().ab_auto_stf(C.addressof(combined), C.addressof(cfg_stf), C.addressof(stf))
+    import torch
+
+    lut_host = np.empty(4096, np.float32)
+    pts = np.ascontiguousarray(curve_points, dtype=np.float64)
+    ctx.check(lib().ab_spline_lut(pts.ctypes.data, len(pts), lut_host.ctypes.data))
+    lut = torch.from_numpy(lut_host).to(torch.device("cuda", ctx.device))
+    tc = ToneChainC()
+    for k in range(3):
+        tc.stf[k], tc.stats[k] = stf, combined
+        tc.levels[k] = LevelsParamsC(0.0, 1.0, 1.0)
+        tc.lut[k] = lut.data_ptr()
+    tc.apply_scnr, tc.scnr = 0, ScnrConfigC(0, 0.0, 0)
+    ctx.check(lib().ab_tone_composite_dev(h, r_ptr, g_ptr, b_ptr, n, C.addressof(tc), r_ptr, g_ptr, b_ptr, s))
+    return ColorChainResult(stats_blend, tuple(float(f) for f in fac), tuple(bal), stf, ctx.launch_count - l0, lut)
+
+
+# ------------------------------------------------------------------------------------- config 3
+def align_and_warp(ref_ptr: int, tgt_ptr: int, out_ptr: int, rows: int, cols: int, n_threads: int = 8,
+                   ctx: Context | None = None, stream: int = 0) -> AlignResultC:
+    """One target frame of align_channels_cmd (affine): align_channel_affine(ref, tgt) then
+    warp_image(tgt, transform) into `out_ptr` (blend.rs:263-296)."""
+    ctx = ctx or default_context()
+    res = AlignResultC()
+    s = stream if stream else None
+    ctx.check(lib().ab_align_affine_dev(ctx.handle, ref_ptr, tgt_ptr, rows, cols, n_threads, C.addressof(res), s))
+    ctx.check(lib().ab_warp_affine_bicubic_dev(ctx.handle, tgt_ptr, rows, cols, C.addressof(res.transform), rows, cols,
+                                               out_ptr, s))
+    return res
+
+
+def align_ref_stars(ref_ptr: int, rows: int, cols: int, ctx: Context | None = None, stream: int = 0) -> np.ndarray:
+    """The reference frame's star list as the aligner sees it (<= 120 (x, y) pairs, f64), computed
+    once for all targets (ab_align_ref_stars_dev)."""
+    ctx = ctx or default_context()
+    xy = np.zeros((120, 2), np.float64)
+    n = C.c_size_t(0)
+    ctx.check(lib().ab_align_ref_stars_dev(ctx.handle, ref_ptr, rows, cols, xy.ctypes.data, C.byref(n),
+                                           stream if stream else None))
+    return xy[: n.value].copy()
+
+
+def align_and_warp_with_ref(ref_xy: np.ndarray, ref_ptr: Optional[int], tgt_ptr: int, out_ptr: int, rows: int,
+                            cols: int, n_threads: int = 8, ctx: Context | None = None, stream: int = 0) -> AlignResultC:
+    """align_and_warp with the reference's star list given (broadcast to the GPU that holds the
+    target); `ref_ptr` = None when the reference plane is not on this GPU."""
+    ctx = ctx or default_context()
+    res = AlignResultC()
+    s = stream if stream else None
+    xy = np.ascontiguousarray(ref_xy, dtype=np.float64)
+    ctx.check(lib().ab_align_affine_with_ref_dev(ctx.handle, xy.ctypes.data, len(xy), ref_ptr, tgt_ptr, rows, cols,
+                                                 n_threads, C.addressof(res), s))
+    ctx.check(lib().ab_warp_affine_bicubic_dev(ctx.handle, tgt_ptr, rows, cols, C.addressof(res.transform), rows, cols,
+                                               out_ptr, s))
+    return res

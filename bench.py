@@ -15,7 +15,9 @@ threads (torchrun exports OMP_NUM_THREADS=1: the arm resets it).
 After the headline the line carries `secondary` objects (skipped with --no-secondary):
 `config5` = BASELINE config 5 (256 x 4096^2 deep stack, frames sharded over the ranks, each rank's
 stack kernel reading the foreign frames from their owners' HBM over NVLink) with the single-GPU
-time of the same stack measured in the same run, and `multi_gpu_matches_oracle` (world > 1).
+time of the same stack measured in the same run; `config4` / `config3` = the colour chain on
+3 x 13759 x 12451 row-banded over the ranks and the 16-frame 8192^2 detect + align + warp pipeline
+(bench_configs.py); and `multi_gpu_matches_oracle` (world > 1).
 """
 from __future__ import annotations
 
@@ -583,9 +585,15 @@ def main():
                 okp = run_multi_gpu_parity(torch, dist, ab, ctx, dev, rank, world)
                 secondary["multi_gpu_matches_oracle"] = okp
             secondary["config5"] = run_config5(torch, dist, ab, ctx, dev, rank, world, args.c5_steps)
-            if world > 1 and "matches_oracle_on_sample" in secondary["config5"]:
+            import bench_configs
+
+            secondary["config4"] = bench_configs.run_config4(torch, dist, ab, ctx, dev, rank, world)
+            secondary["config3"] = bench_configs.run_config3(torch, dist, ab, ctx, dev, rank, world)
+            if world > 1:
                 secondary["multi_gpu_matches_oracle"] = bool(
-                    secondary["multi_gpu_matches_oracle"] and secondary["config5"]["matches_oracle_on_sample"])
+                    secondary["multi_gpu_matches_oracle"]
+                    and secondary["config5"].get("matches_oracle_on_sample", rank != 0)
+                    and secondary["config4"]["matches_oracle"] and secondary["config3"]["matches_oracle"])
         except Exception as e:  # the headline stands on its own; a failed secondary is reported, not hidden
             secondary["error"] = f"{type(e).__name__}: {e}"
         if rank == 0:

@@ -452,6 +452,17 @@ ab_status ab_image_stats_sharded_dev(ab_ctx *ctx, const float *d_data, size_t le
                                      ab_allreduce_fn allreduce, void *user, int use_known_range,
                                      double known_min, double known_max, ab_image_stats *out,
                                      void *stream);
+/* The same with the reductions on the DEVICE and on `stream`: `allreduce` all-reduces a device
+ * buffer in place over all ranks, asynchronously on `stream` (dtype 0: f64, 1: u64, 2: u32; op 0:
+ * sum, 1: min, 2: max; returns 0 on success) -- one ncclAllReduce per call.  The sweeps and the
+ * device-side percentile walks then follow each other without a host round trip; the call
+ * synchronises once, for the result.  Same results as ab_image_stats_sharded_dev. */
+typedef int (*ab_allreduce_dev_fn)(void *user, void *d_buf, size_t count, int dtype, int op,
+                                   void *stream);
+ab_status ab_image_stats_sharded_chained_dev(ab_ctx *ctx, const float *d_data, size_t len,
+                                             ab_allreduce_dev_fn allreduce, void *user,
+                                             int use_known_range, double known_min, double known_max,
+                                             ab_image_stats *out, void *stream);
 /* build_histogram / compute_histogram_with_stats, stats.rs:373-421: n_bins must be 65536
  * (HISTOGRAM_BINS); bins = n_bins u32, edges = n_bins + 1 f64, both HOST buffers */
 ab_status ab_histogram_u32(ab_ctx *ctx, const float *data, size_t len, size_t n_bins, double dmin,
@@ -526,6 +537,18 @@ ab_status ab_align_affine(ab_ctx *ctx, const float *ref, const float *tgt, size_
                           int n_threads, ab_align_result *out);
 ab_status ab_align_affine_dev(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t rows,
                               size_t cols, int n_threads, ab_align_result *out, void *stream);
+/* The reference plane's star list once: align_channels_cmd (cmd/compose/blend.rs:263-296) aligns
+ * every channel against the same reference, and the reference re-detects it for every pair
+ * (affine.rs:133-140).  xy_out: room for 120 (x, y) pairs; *n_out = pairs written.
+ * ab_align_affine_with_ref_dev(ref_xy, ...) equals ab_align_affine_dev(ref, tgt) bit for bit;
+ * d_ref may be NULL when the reference plane lives on another GPU (frames spread over GPUs,
+ * the star list broadcast): the phase-correlation fallback then yields identity (method 3). */
+ab_status ab_align_ref_stars_dev(ab_ctx *ctx, const float *d_ref, size_t rows, size_t cols,
+                                 double *xy_out, size_t *n_out, void *stream);
+ab_status ab_align_affine_with_ref_dev(ab_ctx *ctx, const double *ref_xy, size_t n_ref,
+                                       const float *d_ref, const float *d_tgt, size_t rows,
+                                       size_t cols, int n_threads, ab_align_result *out,
+                                       void *stream);
 /* build_triangles + match_triangles, affine.rs:279-384, on (x, y) star lists (<= 120 each);
  * matches_out receives (ref x, ref y, tgt x, tgt y) per match */
 ab_status ab_match_stars(ab_ctx *ctx, const double *ref_xy, size_t n_ref, const double *tgt_xy,

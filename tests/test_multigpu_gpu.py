@@ -38,6 +38,13 @@ def _worker(rank, world, port, q):
     kr = parallel.compute_image_stats_sharded(band.data_ptr(), band.numel(), cb, known_range=(5.0, 40000.0),
                                               stream=s, ctx=ctx)
     res["stats_kr"] = (kr.min, kr.max, kr.median, kr.mad, kr.sigma, int(kr.valid_count))
+    # the same with every reduction on the device / on the stream (NCCL through the device callback)
+    cbd = parallel.make_allreduce_dev(dev)
+    sd = parallel.compute_image_stats_sharded_chained(band.data_ptr(), band.numel(), cbd, stream=s, ctx=ctx)
+    res["stats_dev"] = (sd.min, sd.max, sd.median, sd.mad, sd.sigma, sd.mean, int(sd.valid_count))
+    kd = parallel.compute_image_stats_sharded_chained(band.data_ptr(), band.numel(), cbd, known_range=(5.0, 40000.0),
+                                                      stream=s, ctx=ctx)
+    res["stats_kr_dev"] = (kd.min, kd.max, kd.median, kd.mad, kd.sigma, int(kd.valid_count))
     # --- sharded stack: each rank combines its row band of all frames, counters are all-reduced
     f0, f1 = parallel.row_band(96, rank, world)
     t = [torch.from_numpy(f[f0:f1].copy()).to(dev) for f in frames]
@@ -94,6 +101,10 @@ def test_sharded_equals_single_gpu(orc):
         assert abs(got[5] - one.mean) <= 1e-12 * abs(one.mean)
     o = orc.compute_image_stats_with_known_range(img, 5.0, 40000.0)
     assert out[0]["stats_kr"] == out[1]["stats_kr"] == (o.min, o.max, o.median, o.mad, o.sigma, o.valid_count)
+    for r in (0, 1):
+        got = out[r]["stats_dev"]
+        assert got[:5] == want and got[6] == one.valid_count and abs(got[5] - one.mean) <= 1e-12 * abs(one.mean)
+        assert out[r]["stats_kr_dev"] == (o.min, o.max, o.median, o.mad, o.sigma, o.valid_count)
     frames = synth.stack_frames(n, 96, cols, seed=3, nan_border=4)
     want_img, want_rej = orc.stack_images(list(frames), 3.0, 3.0, 5)
     got_img = np.concatenate([out[0]["stack_band"], out[1]["stack_band"]])

@@ -158,6 +158,9 @@ SIGNATURES = {
     "ab_ipc_export": (C.c_int, [_vp, _vp, _vp]),
     "ab_ipc_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "ab_ipc_close": (C.c_int, [_vp, _vp]),
+    "ab_peer_export": (C.c_int, [_vp, _vp]),
+    "ab_peer_connect": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "ab_peer_disconnect": (C.c_int, [_vp]),
     "ab_host_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
     "ab_host_free": (C.c_int, [_vp]),
     "ab_dev_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
@@ -228,6 +231,7 @@ SIGNATURES = {
                                              _vp, _vp]),
     "ab_image_stats_sharded_chained_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, C.c_int, C.c_double,
                                                      C.c_double, _vp, _vp]),
+    "ab_image_stats_peer_dev": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_double, C.c_double, _vp, _vp]),
     "ab_histogram_u32": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, C.c_double, _vp, _vp]),
     "ab_histogram_u32_dev": (C.c_int, [_vp, _vp, _sz, _sz, C.c_double, C.c_double, _vp, _vp, _vp]),
     "ab_downsample_histogram": (C.c_int, [_vp, _sz, _sz, _vp]),

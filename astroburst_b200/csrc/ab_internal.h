@@ -28,7 +28,7 @@ struct ab_ctx {
     // small device + pinned host blocks for scalars (counters, stats partials)
     void *d_small = nullptr;
     void *h_small = nullptr;
-    static constexpr size_t SMALL_BYTES = 1 << 20;
+    static constexpr size_t SMALL_BYTES = 2 << 20;
     int stack_variant = 0;     // AB_STACK_VARIANT: 0 TMA-staged (default), 2 plain coalesced loads
     int stack_mix = 0;         // AB_STACK_MIX: 0 default compare-exchange mix, 1..7 A/B variants (P = 32)
     bool stats_host_walks = false;  // AB_STATS_HOST_WALKS=1: percentile walks on the host (A/B; the sharded path always does)
@@ -38,6 +38,10 @@ struct ab_ctx {
     static constexpr unsigned WORK_COUNTERS = 256;
     unsigned *d_work_counters = nullptr;
     std::atomic<unsigned> work_seq{0};
+    // peer group (shard.cu): every rank's d_small mapped here, for in-kernel collectives over NVLink
+    int peer_world = 0, peer_rank = 0;
+    char *peer_small[AB_MAX_RANKS] = {};
+    unsigned long long peer_epoch = 0;  // barriers issued so far (same sequence on every rank)
     // Calls on one context serialize on `mu`.  Recursive: host-buffer entry points hold it while
     // they call the _dev entry points, which take it themselves (they share d_small, the phase
     // correlation state and the scratch slots with every other call on the context).
@@ -105,6 +109,26 @@ void ab_phasecorr_release(ab_ctx *ctx);
 ab_status ab_phase_correlate_on(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t rows,
                                 size_t cols, cudaStream_t s, ab_phase_result *out);
 
+// ---- shard.cu: all-reduce of regions of d_small over the peer group, enqueued on `s` (no host
+// round trip, no NCCL): barrier, every rank sums the peers' copies in rank order, barrier.
+// Offsets are bytes inside d_small; the result goes to `dst_off` (never in place).
+constexpr size_t AB_SMALL_PEER_FLAGS = 896 << 10;   // u64 flag[AB_MAX_RANKS], then u32 error
+constexpr size_t AB_SMALL_REDUCED = 1024 << 10;     // 512 KiB: reduced histograms A | B
+struct PeerScalarOp {  // up to 8 scalars per call: kind 0 f64 sum, 1 u64 sum, 2 f64 max
+    size_t src_off[8], dst_off[8];
+    int kind[8];
+    int n = 0;
+    void add(size_t src, size_t dst, int k) {
+        src_off[n] = src;
+        dst_off[n] = dst;
+        kind[n++] = k;
+    }
+};
+// `count` u32 words (0 = none) and the scalars of `op` under ONE barrier pair
+ab_status ab_peer_allreduce(ab_ctx *ctx, size_t src_off, size_t dst_off, size_t count,
+                            const PeerScalarOp &op, cudaStream_t s);
+ab_status ab_peer_check(ab_ctx *ctx);  // after a synchronisation: did a barrier time out?
+
 // ---- stack.cu
 struct FrameTable {
     const float *p[AB_MAX_FRAMES];
@@ -115,6 +139,7 @@ struct DeepPre {
     const float *dark = nullptr;  // v -= dark[p] * dark_ratio
     float dark_ratio = 1.0f;
     int median_only = 0;          // 1: upper median of the finite samples (calibration masters)
+    int peer_frames = 0;          // 1: some frames live in a peer GPU's HBM (ab_stack_frame_sharded_dev)
 };
 ab_status ab_stack_launch_deep(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix,
                                float sigma_low, float sigma_high, unsigned max_iter,
@@ -122,4 +147,4 @@ ab_status ab_stack_launch_deep(ab_ctx *ctx, const FrameTable &ft, int n_frames, 
                                cudaStream_t stream);
 ab_status ab_stack_launch(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix,
                           float sigma_low, float sigma_high, unsigned max_iter, float *d_out,
-                          unsigned long long *d_rejected, cudaStream_t stream);
+                          unsigned long long *d_rejected, cudaStream_t stream, bool peer_frames = false);

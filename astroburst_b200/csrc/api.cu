@@ -65,6 +65,7 @@ ab_status ab_ctx_create(int device, ab_ctx **out) {
         ok = ok && cudaEventCreateWithFlags(&ctx->copy_events[i], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaMalloc(&ctx->d_small, ab_ctx::SMALL_BYTES) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_small, 0, ab_ctx::SMALL_BYTES) == cudaSuccess;  // peer barrier flags start at 0
     ok = ok && cudaMalloc(&ctx->d_work_counters, ab_ctx::WORK_COUNTERS * sizeof(unsigned)) == cudaSuccess;
     ok = ok && cudaMallocHost(&ctx->h_small, ab_ctx::SMALL_BYTES) == cudaSuccess;
     if (!ok) {
@@ -86,6 +87,7 @@ void ab_ctx_destroy(ab_ctx *ctx) {
             if (ctx->copy_streams[i]) cudaStreamDestroy(ctx->copy_streams[i]);
         }
         ab_phasecorr_release(ctx);
+        ab_peer_disconnect(ctx);
         if (ctx->d_small) cudaFree(ctx->d_small);
         if (ctx->d_work_counters) cudaFree(ctx->d_work_counters);
         if (ctx->h_small) cudaFreeHost(ctx->h_small);

@@ -67,9 +67,157 @@ ab_status band_pointers(ab_ctx *ctx, const float *const *cube_bases, int world, 
     return AB_OK;
 }
 
+// ---------------------------------------------------------------------------- peer collectives
+// Cross-GPU barrier over the mapped d_small blocks: rank r stores the epoch into flag[r] of EVERY
+// rank (release, system scope), then waits until its own flag[q] has reached the epoch for every q
+// (acquire).  A bounded spin: a missing peer sets the error word instead of hanging the GPU.
+struct PeerArgs {
+    char *small[AB_MAX_RANKS];
+    int world, rank;
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void peer_barrier_kernel(PeerArgs pa, unsigned long long epoch) {
+    const int q = threadIdx.x;
+    if (q >= pa.world) return;
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned long long *>(pa.small[q] + AB_SMALL_PEER_FLAGS) + pa.rank, epoch);
+    const unsigned long long *mine =
+        reinterpret_cast<const unsigned long long *>(pa.small[pa.rank] + AB_SMALL_PEER_FLAGS) + q;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mine) < epoch) {
+        if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer never arrived
+            *reinterpret_cast<unsigned *>(pa.small[pa.rank] + AB_SMALL_PEER_FLAGS + AB_MAX_RANKS * 8) = 1u;
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+// dst[i] = sum over ranks (in rank order) of src[i]; every rank computes the whole result itself
+__global__ void __launch_bounds__(1024)
+peer_sum_u32_kernel(PeerArgs pa, size_t src_off, size_t dst_off, size_t count) {
+    unsigned *dst = reinterpret_cast<unsigned *>(pa.small[pa.rank] + dst_off);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count / 4; i += stride) {
+        uint4 acc = make_uint4(0, 0, 0, 0);
+        for (int q = 0; q < pa.world; ++q) {
+            const uint4 v = __ldcv(reinterpret_cast<const uint4 *>(pa.small[q] + src_off) + i);
+            acc.x += v.x;
+            acc.y += v.y;
+            acc.z += v.z;
+            acc.w += v.w;
+        }
+        reinterpret_cast<uint4 *>(dst)[i] = acc;
+    }
+}
+__global__ void peer_scalars_kernel(PeerArgs pa, PeerScalarOp op) {
+    const int k = threadIdx.x;
+    if (k >= op.n) return;
+    char *me = pa.small[pa.rank];
+    if (op.kind[k] == 1) {
+        unsigned long long acc = 0;
+        for (int q = 0; q < pa.world; ++q)
+            acc += __ldcv(reinterpret_cast<const unsigned long long *>(pa.small[q] + op.src_off[k]));
+        *reinterpret_cast<unsigned long long *>(me + op.dst_off[k]) = acc;
+    } else {
+        double acc = __ldcv(reinterpret_cast<const double *>(pa.small[0] + op.src_off[k]));
+        for (int q = 1; q < pa.world; ++q) {
+            const double v = __ldcv(reinterpret_cast<const double *>(pa.small[q] + op.src_off[k]));
+            acc = op.kind[k] == 2 ? fmax(acc, v) : acc + v;
+        }
+        *reinterpret_cast<double *>(me + op.dst_off[k]) = acc;
+    }
+}
+PeerArgs peer_args(ab_ctx *ctx) {
+    PeerArgs pa{};
+    pa.world = ctx->peer_world;
+    pa.rank = ctx->peer_rank;
+    for (int q = 0; q < ctx->peer_world; ++q) pa.small[q] = ctx->peer_small[q];
+    return pa;
+}
+ab_status peer_barrier(ab_ctx *ctx, cudaStream_t s) {
+    peer_barrier_kernel<<<1, 32, 0, s>>>(peer_args(ctx), ++ctx->peer_epoch);
+    AB_LAUNCH_CHECK(ctx);
+    return AB_OK;
+}
+
 }  // namespace
 
+ab_status ab_peer_allreduce(ab_ctx *ctx, size_t src_off, size_t dst_off, size_t count,
+                            const PeerScalarOp &op, cudaStream_t s) {
+    if (ctx->peer_world < 1) return ab_fail(ctx, AB_ERR_INVALID, "no peer group (ab_peer_connect)");
+    if ((count & 3) || (src_off & 15) || (dst_off & 15)) return ab_fail(ctx, AB_ERR_INVALID, "peer all-reduce alignment");
+    ab_status st = peer_barrier(ctx, s);  // every rank's sources are complete
+    if (st != AB_OK) return st;
+    if (count) {
+        peer_sum_u32_kernel<<<32, 1024, 0, s>>>(peer_args(ctx), src_off, dst_off, count);
+        AB_LAUNCH_CHECK(ctx);
+    }
+    if (op.n) {
+        peer_scalars_kernel<<<1, 32, 0, s>>>(peer_args(ctx), op);
+        AB_LAUNCH_CHECK(ctx);
+    }
+    return peer_barrier(ctx, s);  // every rank has read every source: they may be overwritten
+}
+ab_status ab_peer_check(ab_ctx *ctx) {
+    if (ctx->peer_world < 1) return AB_OK;
+    unsigned err = 0;
+    AB_CUDA(ctx, cudaMemcpy(&err, ctx->peer_small[ctx->peer_rank] + AB_SMALL_PEER_FLAGS + AB_MAX_RANKS * 8, 4,
+                            cudaMemcpyDeviceToHost));
+    if (err) return ab_fail(ctx, AB_ERR_CUDA, "peer barrier timed out (a rank of the peer group did not arrive)");
+    return AB_OK;
+}
+
 extern "C" {
+
+// ---- peer group: every rank exports its context's scratch block, all ranks map all blocks
+ab_status ab_peer_export(ab_ctx *ctx, void *handle64_out) {
+    if (!ctx || !handle64_out) return AB_ERR_INVALID;
+    return ab_ipc_export(ctx, ctx->d_small, handle64_out);
+}
+ab_status ab_peer_connect(ab_ctx *ctx, const void *handles64, int world, int rank) {
+    if (!ctx || !handles64 || world < 1 || world > AB_MAX_RANKS || rank < 0 || rank >= world)
+        return AB_ERR_INVALID;
+    CtxLock lk(ctx->mu);
+    if (ctx->peer_world) return ab_fail(ctx, AB_ERR_INVALID, "peer group already connected");
+    DeviceGuard g(ctx->device);
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) {
+            ctx->peer_small[q] = static_cast<char *>(ctx->d_small);
+            continue;
+        }
+        void *p = nullptr;
+        ab_status st = ab_ipc_open(ctx, static_cast<const char *>(handles64) + 64 * q, &p);
+        if (st != AB_OK) {
+            for (int k = 0; k < q; ++k)
+                if (k != rank && ctx->peer_small[k]) cudaIpcCloseMemHandle(ctx->peer_small[k]);
+            return st;
+        }
+        ctx->peer_small[q] = static_cast<char *>(p);
+    }
+    ctx->peer_world = world;
+    ctx->peer_rank = rank;
+    ctx->peer_epoch = 0;
+    return AB_OK;
+}
+ab_status ab_peer_disconnect(ab_ctx *ctx) {
+    if (!ctx) return AB_ERR_INVALID;
+    CtxLock lk(ctx->mu);
+    if (!ctx->peer_world) return AB_OK;
+    DeviceGuard g(ctx->device);
+    cudaDeviceSynchronize();
+    for (int q = 0; q < ctx->peer_world; ++q)
+        if (q != ctx->peer_rank && ctx->peer_small[q]) cudaIpcCloseMemHandle(ctx->peer_small[q]);
+    for (int q = 0; q < AB_MAX_RANKS; ++q) ctx->peer_small[q] = nullptr;
+    ctx->peer_world = 0;
+    return AB_OK;
+}
 
 void ab_row_band(size_t rows, int rank, int world, size_t *r0, size_t *r1) {
     size_t a = 0, b = 0;
@@ -121,7 +269,7 @@ ab_status ab_stack_frame_sharded_dev(ab_ctx *ctx, const float *const *cube_bases
                                       static_cast<char *>(ctx->d_small) + (776 << 10)) +
                                   (ctx->work_seq.fetch_add(1) % 64);
     st = ab_stack_launch(ctx, ft, (int)n_frames, npix, cfg->sigma_low, cfg->sigma_high,
-                         cfg->max_iterations, d_out_band, d_local, s);
+                         cfg->max_iterations, d_out_band, d_local, s, world > 1);
     if (st != AB_OK) return st;
     if (n_targets) {
         RejTargets t{};

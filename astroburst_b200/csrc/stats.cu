@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -343,6 +344,11 @@ struct StatsCtl {
     unsigned long long scan_count;  // valid pixels seen by the scan pass
     double hsum;                    // pass 1: f64 sum of the valid pixels
     unsigned long long hcnt[2];     // {valid count, count below the MAD region}
+    // the same after the cross-rank reduction (what the walks read; = the local values on one GPU)
+    double mm_r[2];
+    unsigned long long scan_count_r;
+    double hsum_r;
+    unsigned long long hcnt_r[2];
     int empty;
     ab_image_stats out;
 };
@@ -351,6 +357,7 @@ struct StatsCtl {
 struct DevReducer {
     ab_allreduce_dev_fn fn = nullptr;
     void *user = nullptr;
+    bool peer = false;  // reduce over the peer group (shard.cu) instead of the callback
     ab_status run(ab_ctx *ctx, void *d_buf, size_t count, int dtype, int op, cudaStream_t s) const {
         if (!fn) return AB_OK;
         if (fn(user, d_buf, count, dtype, op, (void *)s) != 0)
@@ -358,31 +365,47 @@ struct DevReducer {
         return AB_OK;
     }
 };
+// one warp: lane l folds partials l, l + 32, ... in order, then a fixed xor tree -- deterministic,
+// and a few microseconds instead of a serial walk over up to 444 global-memory entries
 __global__ void fold_scan_kernel(const ScanPartial *__restrict__ sp, unsigned n, StatsCtl *ctl) {
     double lo = DBL_MAX, hi = -DBL_MAX;
     unsigned long long c = 0;
-    for (unsigned i = 0; i < n; ++i) {
+    for (unsigned i = threadIdx.x; i < n; i += 32) {
         if (sp[i].count) {
             lo = fmin(lo, (double)sp[i].mn);
             hi = fmax(hi, (double)sp[i].mx);
         }
         c += sp[i].count;
     }
-    ctl->mm[0] = -lo;
-    ctl->mm[1] = hi;
-    ctl->scan_count = c;
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (threadIdx.x == 0) {
+        ctl->mm[0] = ctl->mm_r[0] = -lo;
+        ctl->mm[1] = ctl->mm_r[1] = hi;
+        ctl->scan_count = ctl->scan_count_r = c;
+    }
 }
 __global__ void fold_hist_kernel(const HistPartial *__restrict__ hp, unsigned n, StatsCtl *ctl) {
     double s = 0.0;
     unsigned long long c = 0, b = 0;
-    for (unsigned i = 0; i < n; ++i) {
+    for (unsigned i = threadIdx.x; i < n; i += 32) {
         s += hp[i].sum;
         c += hp[i].count;
         b += hp[i].below;
     }
-    ctl->hsum = s;
-    ctl->hcnt[0] = c;
-    ctl->hcnt[1] = b;
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (threadIdx.x == 0) {
+        ctl->hsum = ctl->hsum_r = s;
+        ctl->hcnt[0] = ctl->hcnt_r[0] = c;
+        ctl->hcnt[1] = ctl->hcnt_r[1] = b;
+    }
 }
 constexpr int WK_THREADS = 1024, WK_PER = HIST_BINS / WK_THREADS;
 
@@ -399,13 +422,26 @@ __device__ bool block_find_cum(const unsigned *__restrict__ hist, unsigned long 
     part[threadIdx.x] = sum;
     if (threadIdx.x == 0) found = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {  // exclusive scan of the 1,024 chunk sums
-        unsigned long long run = 0;
-        for (int t = 0; t < WK_THREADS; ++t) {
-            const unsigned long long v = part[t];
-            part[t] = run;
-            run += v;
+    {  // exclusive scan of the 1,024 chunk sums: warp scans + a scan of the 32 warp totals
+        __shared__ unsigned long long wtot[32];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        unsigned long long inc = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
         }
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = wtot[lane], winc = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long v = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += v;
+            }
+            wtot[lane] = winc - w;
+        }
+        __syncthreads();
+        part[threadIdx.x] = wtot[warp] + inc - sum;
     }
     __syncthreads();
     const unsigned long long before = part[threadIdx.x];
@@ -454,9 +490,9 @@ __global__ void walk_range_kernel(int known, double kmin, double kmax, StatsCtl 
     double lo = kmin, hi = kmax;
     int empty = 0;
     if (!known) {
-        lo = -ctl->mm[0];
-        hi = ctl->mm[1];
-        empty = ctl->scan_count == 0;
+        lo = -ctl->mm_r[0];
+        hi = ctl->mm_r[1];
+        empty = ctl->scan_count_r == 0;
     }
     ctl->empty = empty;
     ctl->global_min = lo;
@@ -470,8 +506,8 @@ __global__ void walk_range_kernel(int known, double kmin, double kmax, StatsCtl 
 // after pass 1 (value histogram + sum): median bin, coarse median, pass-2 classifier
 __global__ void __launch_bounds__(WK_THREADS)
 walk_value_kernel(const unsigned *__restrict__ histA, StatsCtl *ctl) {
-    const unsigned long long total = ctl->hcnt[0];
-    const double gsum = ctl->hsum;
+    const unsigned long long total = ctl->hcnt_r[0];
+    const double gsum = ctl->hsum_r;
     const int was_empty = ctl->empty;
     __syncthreads();  // every thread has read `empty` before thread 0 may overwrite it
     if (was_empty || total == 0) {
@@ -543,7 +579,7 @@ walk_mad_kernel(const unsigned *__restrict__ histB, StatsCtl *ctl) {
         if (threadIdx.x == 0) ctl->out = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0};  // ImageStats::default(), like stats_default
         return;
     }
-    const unsigned long long half = ctl->half_count, below = ctl->hcnt[1];
+    const unsigned long long half = ctl->half_count, below = ctl->hcnt_r[1];
     const unsigned long long rank = half > below ? half - below : 0;
     const double mad = block_resolve_rank(histB, rank, ctl->mad_region_lo,
                                           ctl->mad_refine_range / (double)HIST_BINS);
@@ -903,8 +939,19 @@ ab_status stats_hist_chained(ab_ctx *ctx, const float *d, size_t len, bool known
                              const DevReducer &rd = DevReducer()) {
     Small sm(ctx);
     // control block + host mirror of the result in the small scratch blocks ([640 KiB, +4 KiB))
-    StatsCtl *ctl = reinterpret_cast<StatsCtl *>(sm.d + (640 << 10));
-    ab_image_stats *h_out = reinterpret_cast<ab_image_stats *>(sm.h + (640 << 10));
+    constexpr size_t ctl_off = 640 << 10, offA = 128 << 10, offB = 384 << 10;
+    StatsCtl *ctl = reinterpret_cast<StatsCtl *>(sm.d + ctl_off);
+    ab_image_stats *h_out = reinterpret_cast<ab_image_stats *>(sm.h + ctl_off);
+    // the histograms the walks read: the local ones, or (peer group) the reduced copies
+    unsigned *wA = rd.peer ? reinterpret_cast<unsigned *>(sm.d + AB_SMALL_REDUCED) : sm.dA;
+    unsigned *wB = rd.peer ? wA + HIST_BINS : sm.dB;
+    auto hist_scalars = [&]() {
+        PeerScalarOp op;
+        op.add(ctl_off + offsetof(StatsCtl, hsum), ctl_off + offsetof(StatsCtl, hsum_r), 0);
+        op.add(ctl_off + offsetof(StatsCtl, hcnt), ctl_off + offsetof(StatsCtl, hcnt_r), 1);
+        op.add(ctl_off + offsetof(StatsCtl, hcnt) + 8, ctl_off + offsetof(StatsCtl, hcnt_r) + 8, 1);
+        return op;
+    };
     ScanPartial *d_sp = reinterpret_cast<ScanPartial *>(sm.d);
     HistPartial *d_hp = reinterpret_cast<HistPartial *>(sm.d + (32 << 10));
     ab_status st;
@@ -914,10 +961,17 @@ ab_status stats_hist_chained(ab_ctx *ctx, const float *d, size_t len, bool known
             scan_kernel<<<n_sp, ST_THREADS, 0, s>>>(d, len, d_sp);
             AB_LAUNCH_CHECK(ctx);
         }
-        fold_scan_kernel<<<1, 1, 0, s>>>(d_sp, n_sp, ctl);
+        fold_scan_kernel<<<1, 32, 0, s>>>(d_sp, n_sp, ctl);
         AB_LAUNCH_CHECK(ctx);
-        if ((st = rd.run(ctx, ctl->mm, 2, 0, 2, s)) != AB_OK) return st;
-        if ((st = rd.run(ctx, &ctl->scan_count, 1, 1, 0, s)) != AB_OK) return st;
+        if (rd.peer) {
+            PeerScalarOp op;
+            op.add(ctl_off + offsetof(StatsCtl, mm), ctl_off + offsetof(StatsCtl, mm_r), 2);
+            op.add(ctl_off + offsetof(StatsCtl, mm) + 8, ctl_off + offsetof(StatsCtl, mm_r) + 8, 2);
+            op.add(ctl_off + offsetof(StatsCtl, scan_count), ctl_off + offsetof(StatsCtl, scan_count_r), 1);
+            if ((st = ab_peer_allreduce(ctx, 0, 0, 0, op, s)) != AB_OK) return st;
+        }
+        if ((st = rd.run(ctx, ctl->mm_r, 2, 0, 2, s)) != AB_OK) return st;
+        if ((st = rd.run(ctx, &ctl->scan_count_r, 1, 1, 0, s)) != AB_OK) return st;
     }
     walk_range_kernel<<<1, 1, 0, s>>>(known ? 1 : 0, kmin, kmax, ctl);
     AB_LAUNCH_CHECK(ctx);
@@ -935,12 +989,14 @@ ab_status stats_hist_chained(ab_ctx *ctx, const float *d, size_t len, bool known
         hist_ctl_kernel<ValueHistF><<<grid, HT_THREADS, smem, s>>>(d, len, &ctl->f1, &ctl->empty, sm.dA, sm.dB, d_hp);
         AB_LAUNCH_CHECK(ctx);
     }
-    fold_hist_kernel<<<1, 1, 0, s>>>(d_hp, grid, ctl);
+    fold_hist_kernel<<<1, 32, 0, s>>>(d_hp, grid, ctl);
     AB_LAUNCH_CHECK(ctx);
+    if (rd.peer && (st = ab_peer_allreduce(ctx, offA, AB_SMALL_REDUCED, HIST_BINS, hist_scalars(), s)) != AB_OK)
+        return st;
     if ((st = rd.run(ctx, sm.dA, HIST_BINS, 2, 0, s)) != AB_OK) return st;
-    if ((st = rd.run(ctx, &ctl->hsum, 1, 0, 0, s)) != AB_OK) return st;
-    if ((st = rd.run(ctx, ctl->hcnt, 2, 1, 0, s)) != AB_OK) return st;
-    walk_value_kernel<<<1, WK_THREADS, 0, s>>>(sm.dA, ctl);
+    if ((st = rd.run(ctx, &ctl->hsum_r, 1, 0, 0, s)) != AB_OK) return st;
+    if ((st = rd.run(ctx, ctl->hcnt_r, 2, 1, 0, s)) != AB_OK) return st;
+    walk_value_kernel<<<1, WK_THREADS, 0, s>>>(wA, ctl);
     AB_LAUNCH_CHECK(ctx);
     // ---- pass 2: deviation histogram (A) + median-refine histogram (B)
     AB_CUDA(ctx, cudaMemsetAsync(sm.dA, 0, hist_bytes, s));
@@ -948,8 +1004,10 @@ ab_status stats_hist_chained(ab_ctx *ctx, const float *d, size_t len, bool known
         hist_ctl_kernel<RefineDevF><<<grid, HT_THREADS, smem, s>>>(d, len, &ctl->f2, &ctl->empty, sm.dA, sm.dB, d_hp);
         AB_LAUNCH_CHECK(ctx);
     }
+    if (rd.peer && (st = ab_peer_allreduce(ctx, offA, AB_SMALL_REDUCED, 2 * HIST_BINS, PeerScalarOp(), s)) != AB_OK)
+        return st;
     if ((st = rd.run(ctx, sm.dA, 2 * HIST_BINS, 2, 0, s)) != AB_OK) return st;  // A and B are adjacent
-    walk_refine_kernel<<<1, WK_THREADS, 0, s>>>(sm.dA, sm.dB, ctl);
+    walk_refine_kernel<<<1, WK_THREADS, 0, s>>>(wA, wB, ctl);
     AB_LAUNCH_CHECK(ctx);
     // ---- pass 3: MAD-refine histogram (B) + count below the region
     AB_CUDA(ctx, cudaMemsetAsync(sm.dB, 0, HIST_BINS * sizeof(unsigned), s));
@@ -957,16 +1015,19 @@ ab_status stats_hist_chained(ab_ctx *ctx, const float *d, size_t len, bool known
         hist_ctl_kernel<MadRefineF><<<grid, HT_THREADS, smem, s>>>(d, len, &ctl->f3, &ctl->empty, sm.dA, sm.dB, d_hp);
         AB_LAUNCH_CHECK(ctx);
     }
-    fold_hist_kernel<<<1, 1, 0, s>>>(d_hp, grid, ctl);
+    fold_hist_kernel<<<1, 32, 0, s>>>(d_hp, grid, ctl);
     AB_LAUNCH_CHECK(ctx);
+    if (rd.peer && (st = ab_peer_allreduce(ctx, offB, AB_SMALL_REDUCED + HIST_BINS * sizeof(unsigned), HIST_BINS,
+                                           hist_scalars(), s)) != AB_OK)
+        return st;
     if ((st = rd.run(ctx, sm.dB, HIST_BINS, 2, 0, s)) != AB_OK) return st;
-    if ((st = rd.run(ctx, ctl->hcnt, 2, 1, 0, s)) != AB_OK) return st;
-    walk_mad_kernel<<<1, WK_THREADS, 0, s>>>(sm.dB, ctl);
+    if ((st = rd.run(ctx, ctl->hcnt_r, 2, 1, 0, s)) != AB_OK) return st;
+    walk_mad_kernel<<<1, WK_THREADS, 0, s>>>(wB, ctl);
     AB_LAUNCH_CHECK(ctx);
     AB_CUDA(ctx, cudaMemcpyAsync(h_out, &ctl->out, sizeof(ab_image_stats), cudaMemcpyDeviceToHost, s));
     AB_CUDA(ctx, cudaStreamSynchronize(s));
     *out = *h_out;
-    return AB_OK;
+    return rd.peer ? ab_peer_check(ctx) : AB_OK;
 }
 
 // stats.rs:43-73
@@ -1131,6 +1192,22 @@ ab_status ab_image_stats_sharded_chained_dev(ab_ctx *ctx, const float *d_data, s
     DevReducer rd;
     rd.fn = allreduce;
     rd.user = user;
+    const bool known = use_known_range && std::isfinite(known_min) && std::isfinite(known_max) &&
+                       known_min < known_max;
+    return stats_hist_chained(ctx, d_data, len, known, known_min, known_max, (cudaStream_t)stream, out, rd);
+}
+
+// The same over the peer group: no callback, the reductions are kernels reading the peers' blocks.
+ab_status ab_image_stats_peer_dev(ab_ctx *ctx, const float *d_data, size_t len, int use_known_range,
+                                  double known_min, double known_max, ab_image_stats *out, void *stream) {
+    if (!ctx || !out || (len && !d_data)) return AB_ERR_INVALID;
+    if (len >= ((size_t)1 << 32))
+        return ab_fail(ctx, AB_ERR_UNSUPPORTED, "bands of 2^32 pixels or more are not supported");
+    CtxLock lk(ctx->mu);
+    if (ctx->peer_world < 1) return ab_fail(ctx, AB_ERR_INVALID, "no peer group (ab_peer_connect)");
+    DeviceGuard g(ctx->device);
+    DevReducer rd;
+    rd.peer = true;
     const bool known = use_known_range && std::isfinite(known_min) && std::isfinite(known_max) &&
                        known_min < known_max;
     return stats_hist_chained(ctx, d_data, len, known, known_min, known_max, (cudaStream_t)stream, out, rd);

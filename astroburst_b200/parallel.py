@@ -127,6 +127,46 @@ def compute_image_stats_sharded_chained(band_ptr: int, band_len: int, allreduce_
     return out
 
 
+def connect_peer_group(ctx: Context | None = None, group=None) -> None:
+    """Set up the library's peer group (shard.cu): every rank exports its context's scratch block,
+    the 64-byte handles travel over torch.distributed, every rank maps all blocks.  From then on the
+    sharded statistics reduce inside kernels over NVLink (compute_image_stats_peer)."""
+    import torch.distributed as dist
+
+    ctx = ctx or default_context()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    buf = (C.c_char * 64)()
+    ctx.check(lib().ab_peer_export(ctx.handle, buf))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, bytes(buf.raw), group=group)
+    blob = b"".join(gathered)
+    ctx.check(lib().ab_peer_connect(ctx.handle, blob, world, rank))
+    dist.barrier(group)
+
+
+def disconnect_peer_group(ctx: Context | None = None, group=None) -> None:
+    import torch.distributed as dist
+
+    ctx = ctx or default_context()
+    ctx.synchronize()
+    dist.barrier(group)  # nobody is inside a peer collective any more
+    ctx.check(lib().ab_peer_disconnect(ctx.handle))
+    dist.barrier(group)
+
+
+def compute_image_stats_peer(band_ptr: int, band_len: int, known_range=None, stream: int = 0,
+                             ctx: Context | None = None) -> ImageStatsC:
+    """compute_image_stats of a row-band sharded image over the peer group (connect_peer_group):
+    counters and histograms are summed by kernels that read the peers' blocks over NVLink."""
+    ctx = ctx or default_context()
+    out = ImageStatsC()
+    kmin, kmax = known_range if known_range is not None else (0.0, 0.0)
+    ctx.check(lib().ab_image_stats_peer_dev(ctx.handle, int(band_ptr) if band_len else None, int(band_len),
+                                            1 if known_range is not None else 0, kmin, kmax, C.addressof(out),
+                                            int(stream) if stream else None))
+    return out
+
+
 def allreduce_rejected(rejected_tensor, group=None):
     """StackResult.rejected_pixels of a row-band sharded stack = sum over ranks (in place)."""
     import torch.distributed as dist

@@ -57,6 +57,20 @@ def stats_sharded(ctx: Context, stream: int, allreduce_dev, total_pixels: int):
     return fn
 
 
+def stats_peer(ctx: Context, stream: int, total_pixels: int):
+    """stats_fn for a row-band sharded image over the library's peer group (parallel.connect_peer_group):
+    reductions inside kernels over NVLink, no NCCL, no host callback."""
+    if total_pixels <= PAR_THRESHOLD:
+        raise ValueError("sharded statistics implement the histogram algorithm (> 4,000,000 px) only")
+
+    def fn(ptr: int, n: int, known_range=None) -> ImageStatsC:
+        from . import parallel
+
+        return parallel.compute_image_stats_peer(ptr, n, known_range, stream, ctx)
+
+    return fn
+
+
 def auto_wb_factors(sr: ImageStatsC, sg: ImageStatsC, sb: ImageStatsC):
     """compute_auto_wb_cmd, cmd/compose/color.rs:188-224 -> (r_factor, g_factor, b_factor)."""
 

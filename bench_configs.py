@@ -86,30 +86,41 @@ def run_config4(torch, dist, ab, ctx, dev, rank, world, reps=3, rows=13759, cols
     total = rows * cols
     src = [c4_band(torch, dev, k, r0, r1, rows, cols) for k in range(3)]
     out = [torch.empty((r1 - r0, cols), dtype=torch.float32, device=dev) for _ in range(3)]
-    if world > 1:
-        cb = parallel.make_allreduce_dev(dev)
-        stats_fn = pipelines.stats_sharded(ctx, stream, cb, total)
-    else:
-        stats_fn = pipelines.stats_single_gpu(ctx, stream)
+    ms_nccl = None
     res_box = [None]
 
-    def chain():
+    def chain(stats_fn):
         res_box[0] = pipelines.color_chain([s.data_ptr() for s in src], n, r1 - r0, cols, C4_WEIGHTS, C4_CURVE,
                                            out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), stats_fn,
                                            total_pixels=total, ctx=ctx, stream=stream)
 
-    chain()  # warm-up (allocations, NCCL channels)
-    ms = _wall_max(torch, dist, world, dev, chain, reps)
+    if world > 1:
+        # statistics reduced (a) by NCCL through the device callback, (b) by the library's own
+        # kernels over peer memory (NVLink) -- (b) is the product path, (a) is timed beside it
+        cb = parallel.make_allreduce_dev(dev)
+        fn_nccl = pipelines.stats_sharded(ctx, stream, cb, total)
+        chain(fn_nccl)
+        ms_nccl = _wall_max(torch, dist, world, dev, lambda: chain(fn_nccl), max(reps - 1, 1))
+        parallel.connect_peer_group(ctx)
+        stats_fn = pipelines.stats_peer(ctx, stream, total)
+    else:
+        stats_fn = pipelines.stats_single_gpu(ctx, stream)
+    chain(stats_fn)  # warm-up
+    ms = _wall_max(torch, dist, world, dev, lambda: chain(stats_fn), reps)
     res = res_box[0]
+    if world > 1:
+        parallel.disconnect_peer_group(ctx)
     algo = 20.56e9 * (total / (13759 * 12451))  # 20.56 GB at the full size
     peak = _peak()
     info = {"workload": f"3-channel blend + WB + SCNR + linked STF + curve, {rows}x{cols} f32, row-banded over "
                         f"{world} GPU(s); 7 image statistics (3 blend, 3 WB known-range, G re-stat)"
-                        + (" reduced with NCCL on the device" if world > 1 else ""),
+                        + (" reduced inside kernels over peer memory (NVLink), no NCCL" if world > 1 else ""),
             "ms_total": ms, "value": total / (ms * 1e-3) / 1e6, "unit": "Mpix/s",
             "algorithmic_bytes": int(algo), "ideal_ms_at_measured_peak": algo / peak / 1e6 / world,
             "frac_of_roofline": algo / (ms * 1e-3) / 1e9 / (peak * world), "gpu_launches": int(res.launches),
             "timing": "wall clock between device synchronisations, max over ranks, best of reps"}
+    if ms_nccl is not None:
+        info["ms_total_with_nccl_callback_stats"] = ms_nccl
     # ---- parity: (a) statistics of the blended R plane, whole image, against the oracle; (b) final
     # pixels of sampled rows of every rank's band with the oracle chain on the same statistics
     okt = torch.ones(1, dtype=torch.int32, device=dev)

@@ -190,6 +190,17 @@ ab_status ab_ipc_export(ab_ctx *ctx, const void *dev_ptr, void *handle64_out);
 ab_status ab_ipc_open(ab_ctx *ctx, const void *handle64, void **dev_ptr);
 ab_status ab_ipc_close(ab_ctx *ctx, void *dev_ptr);
 
+/* Peer group: the collectives of the sharded paths without NCCL and without host round trips.
+ * Every rank exports its context's scratch block (ab_peer_export: 64 handle bytes), the host
+ * gathers the handles of all ranks in rank order (world * 64 bytes) and every rank calls
+ * ab_peer_connect; from then on ab_image_stats_peer_dev reduces its counters and histograms inside
+ * kernels that read the peers' blocks over NVLink (barrier flags in the same blocks; a peer that
+ * never arrives makes the call fail after ~2 s instead of hanging the GPU).  All ranks must issue
+ * the same sequence of peer calls.  ab_peer_disconnect before any rank destroys its context. */
+ab_status ab_peer_export(ab_ctx *ctx, void *handle64_out);
+ab_status ab_peer_connect(ab_ctx *ctx, const void *handles64, int world, int rank);
+ab_status ab_peer_disconnect(ab_ctx *ctx);
+
 /* pinned host memory, so host-buffer entry points overlap copies with kernels */
 ab_status ab_host_alloc(size_t bytes, void **out);
 ab_status ab_host_free(void *p);
@@ -463,6 +474,11 @@ ab_status ab_image_stats_sharded_chained_dev(ab_ctx *ctx, const float *d_data, s
                                              ab_allreduce_dev_fn allreduce, void *user,
                                              int use_known_range, double known_min, double known_max,
                                              ab_image_stats *out, void *stream);
+/* The same over the peer group (ab_peer_connect): reductions are kernels that sum the peers'
+ * counters / histograms over NVLink in rank order -- no callback, no NCCL, one synchronisation. */
+ab_status ab_image_stats_peer_dev(ab_ctx *ctx, const float *d_data, size_t len, int use_known_range,
+                                  double known_min, double known_max, ab_image_stats *out,
+                                  void *stream);
 /* build_histogram / compute_histogram_with_stats, stats.rs:373-421: n_bins must be 65536
  * (HISTOGRAM_BINS); bins = n_bins u32, edges = n_bins + 1 f64, both HOST buffers */
 ab_status ab_histogram_u32(ab_ctx *ctx, const float *data, size_t len, size_t n_bins, double dmin,

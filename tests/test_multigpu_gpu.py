@@ -45,6 +45,16 @@ def _worker(rank, world, port, q):
     kd = parallel.compute_image_stats_sharded_chained(band.data_ptr(), band.numel(), cbd, known_range=(5.0, 40000.0),
                                                       stream=s, ctx=ctx)
     res["stats_kr_dev"] = (kd.min, kd.max, kd.median, kd.mad, kd.sigma, int(kd.valid_count))
+    # and over the library's peer group: reductions inside kernels over NVLink, no NCCL
+    parallel.connect_peer_group(ctx)
+    sp = parallel.compute_image_stats_peer(band.data_ptr(), band.numel(), stream=s, ctx=ctx)
+    res["stats_peer"] = (sp.min, sp.max, sp.median, sp.mad, sp.sigma, sp.mean, int(sp.valid_count))
+    kp = parallel.compute_image_stats_peer(band.data_ptr(), band.numel(), known_range=(5.0, 40000.0), stream=s, ctx=ctx)
+    res["stats_kr_peer"] = (kp.min, kp.max, kp.median, kp.mad, kp.sigma, int(kp.valid_count))
+    for _ in range(20):  # many epochs: the barrier flags only ever grow
+        sp2 = parallel.compute_image_stats_peer(band.data_ptr(), band.numel(), stream=s, ctx=ctx)
+    res["stats_peer_again"] = (sp2.min, sp2.max, sp2.median, sp2.mad, sp2.sigma, sp2.mean, int(sp2.valid_count))
+    parallel.disconnect_peer_group(ctx)
     # --- sharded stack: each rank combines its row band of all frames, counters are all-reduced
     f0, f1 = parallel.row_band(96, rank, world)
     t = [torch.from_numpy(f[f0:f1].copy()).to(dev) for f in frames]
@@ -105,6 +115,11 @@ def test_sharded_equals_single_gpu(orc):
         got = out[r]["stats_dev"]
         assert got[:5] == want and got[6] == one.valid_count and abs(got[5] - one.mean) <= 1e-12 * abs(one.mean)
         assert out[r]["stats_kr_dev"] == (o.min, o.max, o.median, o.mad, o.sigma, o.valid_count)
+        got = out[r]["stats_peer"]
+        assert got[:5] == want and got[6] == one.valid_count and abs(got[5] - one.mean) <= 1e-12 * abs(one.mean)
+        assert out[r]["stats_kr_peer"] == (o.min, o.max, o.median, o.mad, o.sigma, o.valid_count)
+        assert out[r]["stats_peer_again"] == out[r]["stats_peer"]
+    assert out[0]["stats_peer"] == out[1]["stats_peer"]   # rank-ordered sums: identical bits on every rank
     frames = synth.stack_frames(n, 96, cols, seed=3, nan_border=4)
     want_img, want_rej = orc.stack_images(list(frames), 3.0, 3.0, 5)
     got_img = np.concatenate([out[0]["stack_band"], out[1]["stack_band"]])

@@ -136,7 +136,9 @@ def test_arcsinh(im, orc):
     for factor, gamma in ((10.0, 1.0), (50.0, 1.0), (500.0, 0.5), (1.0, 2.2)):
         a = im.arcsinh_stretch_with_stats(d, 900.0, 30000.0, factor, gamma)
         b = orc.arcsinh_stretch_with_stats(d, 900.0, 30000.0, factor, gamma)
-        assert close(a, b, 2e-5) and np.abs(a - b).max() < 2e-6   # libm vs CUDA asinh/powf: <= 2 ulp of [0,1]
+        # north_star tolerance 1e-5 relative; measured on B200: max rel 4.8e-7, max abs 2.4e-7 (libm vs CUDA
+        # log1pf / hypotf / powf, <= 2 ulp of [0, 1])
+        assert close(a, b, 1e-5) and np.abs(a - b).max() < 1e-6
     assert np.array_equal(im.arcsinh_stretch_with_stats(d, 0.0, 1.0, 0.0), d, equal_nan=True)   # factor 0 -> clone
     assert not im.arcsinh_stretch_with_stats(d, 5.0, 5.0, 10.0).any()                            # range < 1e-10 -> zeros
     r = im.arcsinh_stretch_with_stats(np.array([[np.nan, -0.5, 0.5]], np.float32), 0.0, 1.0, 10.0)

@@ -894,6 +894,27 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
 
 // affine.rs:24-53: percentiles of a strided sample -> (lo, inv_range); on=0 when the reference
 // returns the image unchanged
+// the two ranks of the sorted finite samples (affine.rs:36-41); non-finite samples were replaced by
+// +inf before the sort, *n_fin counts the finite ones
+__global__ void sample_ranks_kernel(const float *__restrict__ sorted, const unsigned *__restrict__ n_fin,
+                                    float *__restrict__ out2) {
+    const size_t n = *n_fin;
+    if (n < 100) return;
+    out2[0] = sorted[n / 100];
+    out2[1] = sorted[n * 999 / 1000];
+}
+__global__ void sample_finite_kernel(const float *__restrict__ img, size_t step, float *__restrict__ out,
+                                     size_t n_out, unsigned *__restrict__ n_fin) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool fin = false;
+    if (i < n_out) {
+        const float v = img[i * step];
+        fin = fabsf(v) < CUDART_INF_F;
+        out[i] = fin ? v : CUDART_INF_F;
+    }
+    const unsigned c = __popc(__ballot_sync(0xffffffffu, fin));
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_fin, c);
+}
 ab_status normalize_params(ab_ctx *ctx, const float *d_img, size_t len, cudaStream_t s, Norm *nm) {
     nm->on = 0;
     nm->lo = 0.0;
@@ -901,25 +922,36 @@ ab_status normalize_params(ab_ctx *ctx, const float *d_img, size_t len, cudaStre
     if (len == 0) return AB_OK;
     const size_t step = std::max(len / 100000, (size_t)1);
     const size_t n_s = (len + step - 1) / step;
-    ab_status st = ab_scratch_reserve(ctx, 2, n_s * 4 + 256);
+    if (n_s >= ((size_t)1 << 31)) return ab_fail(ctx, AB_ERR_UNSUPPORTED, "normalize_for_detection: too many samples");
+    // strided sample, finite filter, radix sort and the two rank reads all on the device: one
+    // 16-byte D2H instead of the whole sample and two host selections
+    size_t tmp_sort = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, (float *)nullptr, (float *)nullptr, (int)n_s, 0, 32, s);
+    const size_t b_keys = (n_s * 4 + 255) / 256 * 256, b_tmp = (tmp_sort + 255) / 256 * 256;
+    ab_status st = ab_scratch_reserve(ctx, 2, 2 * b_keys + b_tmp + 512);
     if (st != AB_OK) return st;
-    float *d_s = static_cast<float *>(ctx->d_scratch[2]);
-    sample_kernel<<<(unsigned)((n_s + 255) / 256), 256, 0, s>>>(d_img, len, step, d_s, n_s);
+    char *base = static_cast<char *>(ctx->d_scratch[2]);
+    float *d_s = reinterpret_cast<float *>(base), *d_sorted = reinterpret_cast<float *>(base + b_keys);
+    void *d_tmp = base + 2 * b_keys;
+    unsigned *d_nfin = reinterpret_cast<unsigned *>(base + 2 * b_keys + b_tmp);
+    float *d_out2 = reinterpret_cast<float *>(d_nfin + 4);
+    AB_CUDA(ctx, cudaMemsetAsync(d_nfin, 0, 64, s));
+    sample_finite_kernel<<<(unsigned)((n_s + 255) / 256), 256, 0, s>>>(d_img, step, d_s, n_s, d_nfin);
     AB_LAUNCH_CHECK(ctx);
-    std::vector<float> samples(n_s);
-    AB_CUDA(ctx, cudaMemcpyAsync(samples.data(), d_s, n_s * 4, cudaMemcpyDeviceToHost, s));
+    size_t tb = b_tmp;
+    AB_CUDA(ctx, cub::DeviceRadixSort::SortKeys(d_tmp, tb, d_s, d_sorted, (int)n_s, 0, 32, s));
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    sample_ranks_kernel<<<1, 1, 0, s>>>(d_sorted, d_nfin, d_out2);
+    AB_LAUNCH_CHECK(ctx);
+    struct {
+        unsigned n_fin, pad[3];
+        float v[2];
+    } h;
+    AB_CUDA(ctx, cudaMemcpyAsync(&h, d_nfin, sizeof(h), cudaMemcpyDeviceToHost, s));
     AB_CUDA(ctx, cudaStreamSynchronize(s));
-    size_t w = 0;
-    for (size_t i = 0; i < n_s; ++i)
-        if (std::isfinite(samples[i])) samples[w++] = samples[i];
-    samples.resize(w);
-    if (samples.size() < 100) return AB_OK;
-    // affine.rs:36-41 sorts the samples and reads two ranks; two selections give the same values
-    const size_t k_lo = samples.size() / 100, k_hi = samples.size() * 999 / 1000;
-    std::nth_element(samples.begin(), samples.begin() + k_hi, samples.end());
-    std::nth_element(samples.begin(), samples.begin() + k_lo, samples.begin() + k_hi);
-    const double lo = (double)samples[k_lo];
-    const double hi = (double)samples[k_hi];
+    if (h.n_fin < 100) return AB_OK;
+    const double lo = (double)h.v[0];
+    const double hi = (double)h.v[1];
     const double range = hi - lo;
     if (range < 1e-15) return AB_OK;
     nm->on = 1;
@@ -935,43 +967,11 @@ struct Pt {
 struct Match {
     double rx, ry, tx, ty;
 };
-struct Tri {
-    int idx[3];
-    double ratio_mid, ratio_long;
-};
 constexpr double TRIANGLE_TOLERANCE = 0.02;
 constexpr size_t MIN_MATCHES_AFFINE = 6, MIN_MATCHES_RIGID = 4, RANSAC_ITERATIONS = 2000;
 constexpr double RANSAC_INLIER_PX = 3.0, DETECTION_SIGMA = 3.5, MIN_TRIANGLE_SIDE = 15.0;
 constexpr double MIN_INLIER_RATIO = 0.20, MAX_RESIDUAL_PX = 5.0, MAX_OFFSET_FRACTION = 0.40;
 constexpr double MAX_ROTATION_DEG = 30.0, MIN_SCALE = 0.70, MAX_SCALE = 1.40;
-
-inline double pdist(Pt a, Pt b) {
-    const double dx = a.x - b.x, dy = a.y - b.y;
-    return std::sqrt(dx * dx + dy * dy);
-}
-std::vector<Tri> build_triangles(const std::vector<Pt> &s) {
-    std::vector<Tri> tris;
-    const int n = (int)s.size();
-    if (n < 3) return tris;
-    const int limit = std::min(n, 60);
-    for (int i = 0; i < limit; ++i)
-        for (int j = i + 1; j < limit; ++j)
-            for (int k = j + 1; k < limit; ++k) {
-                double sides[3] = {pdist(s[i], s[j]), pdist(s[j], s[k]), pdist(s[i], s[k])};
-                std::stable_sort(sides, sides + 3);
-                if (sides[0] < MIN_TRIANGLE_SIDE) continue;
-                tris.push_back({{i, j, k}, sides[1] / sides[0], sides[2] / sides[0]});
-            }
-    return tris;
-}
-void sort_triangle_vertices(const std::vector<Pt> &s, const int idx[3], unsigned char out[3]) {
-    const int i = idx[0], j = idx[1], k = idx[2];
-    std::pair<int, double> v[3] = {{i, pdist(s[j], s[k])}, {j, pdist(s[i], s[k])}, {k, pdist(s[i], s[j])}};
-    std::stable_sort(v, v + 3, [](const std::pair<int, double> &a, const std::pair<int, double> &b) {
-        return a.second < b.second;
-    });
-    for (int q = 0; q < 3; ++q) out[q] = (unsigned char)v[q].first;
-}
 
 ab_affine aff_identity() { return {1.0, 0.0, 0.0, 0.0, 1.0, 0.0}; }
 inline void amap(const ab_affine &t, double x, double y, double *px, double *py) {
@@ -1155,54 +1155,115 @@ ab_status fallback(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t r
     return AB_OK;
 }
 
-// match_triangles (affine.rs:320-384): votes on the GPU, greedy 1-1 assignment on the host.
-// Equal-vote pairs are taken in (ref index, tgt index) order (the reference's order is the
+// build_triangles + the vertex ordering of match_triangles (affine.rs:279-318, :332-346) for one star
+// list: thread t = the t-th triple i < j < k of the first 60 stars in colexicographic order
+// (t = C(k,3) + C(j,2) + i).  Triangles the reference drops (shortest side < 15 px, or a vertex
+// beyond the list) get descriptor `bad` = +inf (reference list) / -inf (target list): |+-inf - x|
+// and |inf - (-inf)| are +inf > tolerance, so they never vote.  Votes are sums, so the order in
+// which the triangles sit in the arrays does not matter.
+constexpr int TRI_LIMIT = 60, TRI_MAX = TRI_LIMIT * (TRI_LIMIT - 1) * (TRI_LIMIT - 2) / 6;  // 34,220
+__device__ __forceinline__ double dev_pdist(double ax, double ay, double bx, double by) {
+    const double dx = ax - bx, dy = ay - by;
+    return sqrt(dx * dx + dy * dy);
+}
+__global__ void build_tri_kernel(const double *__restrict__ xy, int n_stars, double bad, double min_side,
+                                 double *__restrict__ mid, double *__restrict__ lng,
+                                 unsigned char *__restrict__ srt) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= TRI_MAX) return;
+    int k = 2;
+    while ((k + 1) * k * (k - 1) / 6 <= t) ++k;  // largest k with C(k,3) <= t
+    int rem = t - k * (k - 1) * (k - 2) / 6;
+    int j = 1;
+    while ((j + 1) * j / 2 <= rem) ++j;          // largest j with C(j,2) <= rem
+    const int i = rem - j * (j - 1) / 2;
+    const int limit = n_stars < TRI_LIMIT ? n_stars : TRI_LIMIT;
+    double m = bad, l = bad;
+    unsigned char v0 = 0, v1 = 0, v2 = 0;
+    if (k < limit) {
+        const double xi = xy[2 * i], yi = xy[2 * i + 1], xj = xy[2 * j], yj = xy[2 * j + 1];
+        const double xk = xy[2 * k], yk = xy[2 * k + 1];
+        const double dij = dev_pdist(xi, yi, xj, yj), djk = dev_pdist(xj, yj, xk, yk), dik = dev_pdist(xi, yi, xk, yk);
+        // stable ascending sort of (dij, djk, dik)  [std::stable_sort == insertion order on ties]
+        double a = dij, b = djk, c = dik;
+        if (b < a) { const double x = a; a = b; b = x; }
+        if (c < b) {
+            const double x = b; b = c; c = x;
+            if (b < a) { const double y = a; a = b; b = y; }
+        }
+        if (!(a < min_side)) {
+            m = b / a;
+            l = c / a;
+            // vertices ordered by the length of the opposite side, stable: (i, djk), (j, dik), (k, dij)
+            int p0 = i, p1 = j, p2 = k;
+            double q0 = djk, q1 = dik, q2 = dij;
+            if (q1 < q0) { const double x = q0; q0 = q1; q1 = x; const int y = p0; p0 = p1; p1 = y; }
+            if (q2 < q1) {
+                const double x = q1; q1 = q2; q2 = x; const int y = p1; p1 = p2; p2 = y;
+                if (q1 < q0) { const double x2 = q0; q0 = q1; q1 = x2; const int y2 = p0; p0 = p1; p1 = y2; }
+            }
+            v0 = (unsigned char)p0;
+            v1 = (unsigned char)p1;
+            v2 = (unsigned char)p2;
+        }
+    }
+    mid[t] = m;
+    lng[t] = l;
+    srt[3 * t] = v0;
+    srt[3 * t + 1] = v1;
+    srt[3 * t + 2] = v2;
+}
+
+// match_triangles (affine.rs:320-384): triangles and votes on the GPU, greedy 1-1 assignment on the
+// host.  Equal-vote pairs are taken in (ref index, tgt index) order (the reference's order is the
 // HashMap iteration order, i.e. unspecified).
 ab_status match_stars(ab_ctx *ctx, const std::vector<Pt> &rs, const std::vector<Pt> &ts,
                       cudaStream_t s, std::vector<Match> &matches) {
     matches.clear();
-    const std::vector<Tri> rt = build_triangles(rs), tt = build_triangles(ts);
-    if (rt.empty() || tt.empty()) return AB_OK;
-    auto pack = [](const std::vector<Pt> &st, const std::vector<Tri> &tr, std::vector<double> &mid,
-                   std::vector<double> &lng, std::vector<unsigned char> &srt) {
-        mid.resize(tr.size());
-        lng.resize(tr.size());
-        srt.resize(tr.size() * 3);
-        for (size_t a = 0; a < tr.size(); ++a) {
-            mid[a] = tr[a].ratio_mid;
-            lng[a] = tr[a].ratio_long;
-            sort_triangle_vertices(st, tr[a].idx, &srt[3 * a]);
-        }
-    };
-    std::vector<double> rmid, rlng, tmid, tlng;
-    std::vector<unsigned char> rsrt, tsrt;
-    pack(rs, rt, rmid, rlng, rsrt);
-    pack(ts, tt, tmid, tlng, tsrt);
-    const size_t nr = rt.size(), nt = tt.size();
+    if (rs.size() < 3 || ts.size() < 3) return AB_OK;
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
-    const size_t o_rl = al(nr * 8), o_rs = o_rl + al(nr * 8), o_tm = o_rs + al(nr * 3);
-    const size_t o_tl = o_tm + al(nt * 8), o_ts = o_tl + al(nt * 8), o_v = o_ts + al(nt * 3);
+    const size_t b8 = al((size_t)TRI_MAX * 8), b3 = al((size_t)TRI_MAX * 3), bxy = al(2 * MAX_STARS * 8);
+    const size_t o_rxy = 0, o_txy = bxy, o_rm = 2 * bxy, o_rl = o_rm + b8, o_rs = o_rl + b8, o_tm = o_rs + b3;
+    const size_t o_tl = o_tm + b8, o_ts = o_tl + b8, o_v = o_ts + b3;
     const size_t total = o_v + MAX_STARS * MAX_STARS * 4;
     ab_status st = ab_scratch_reserve(ctx, 2, total);
     if (st != AB_OK) return st;
     char *b = static_cast<char *>(ctx->d_scratch[2]);
-    AB_CUDA(ctx, cudaMemcpyAsync(b, rmid.data(), nr * 8, cudaMemcpyHostToDevice, s));
-    AB_CUDA(ctx, cudaMemcpyAsync(b + o_rl, rlng.data(), nr * 8, cudaMemcpyHostToDevice, s));
-    AB_CUDA(ctx, cudaMemcpyAsync(b + o_rs, rsrt.data(), nr * 3, cudaMemcpyHostToDevice, s));
-    AB_CUDA(ctx, cudaMemcpyAsync(b + o_tm, tmid.data(), nt * 8, cudaMemcpyHostToDevice, s));
-    AB_CUDA(ctx, cudaMemcpyAsync(b + o_tl, tlng.data(), nt * 8, cudaMemcpyHostToDevice, s));
-    AB_CUDA(ctx, cudaMemcpyAsync(b + o_ts, tsrt.data(), nt * 3, cudaMemcpyHostToDevice, s));
+    static_assert(sizeof(Pt) == 16, "Pt is two doubles");
+    AB_CUDA(ctx, cudaMemcpyAsync(b + o_rxy, rs.data(), rs.size() * sizeof(Pt), cudaMemcpyHostToDevice, s));
+    AB_CUDA(ctx, cudaMemcpyAsync(b + o_txy, ts.data(), ts.size() * sizeof(Pt), cudaMemcpyHostToDevice, s));
     AB_CUDA(ctx, cudaMemsetAsync(b + o_v, 0, MAX_STARS * MAX_STARS * 4, s));
-    const unsigned grid = (unsigned)std::min<size_t>((nr + 255) / 256, (size_t)ctx->sm_count * 2);
+    const bool trace = std::getenv("AB_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        cudaStreamSynchronize(s);
+        fprintf(stderr, "[ab]   match: %s at %.3f ms\n", what,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
+    const unsigned tb = (TRI_MAX + 127) / 128;
+    build_tri_kernel<<<tb, 128, 0, s>>>(reinterpret_cast<double *>(b + o_rxy), (int)rs.size(), (double)INFINITY,
+                                       MIN_TRIANGLE_SIDE, reinterpret_cast<double *>(b + o_rm),
+                                       reinterpret_cast<double *>(b + o_rl),
+                                       reinterpret_cast<unsigned char *>(b + o_rs));
+    AB_LAUNCH_CHECK(ctx);
+    build_tri_kernel<<<tb, 128, 0, s>>>(reinterpret_cast<double *>(b + o_txy), (int)ts.size(), -(double)INFINITY,
+                                       MIN_TRIANGLE_SIDE, reinterpret_cast<double *>(b + o_tm),
+                                       reinterpret_cast<double *>(b + o_tl),
+                                       reinterpret_cast<unsigned char *>(b + o_ts));
+    AB_LAUNCH_CHECK(ctx);
+    lap("triangles built");
+    const unsigned grid = (unsigned)std::min<size_t>((TRI_MAX + 255) / 256, (size_t)ctx->sm_count * 2);
     AB_CUDA(ctx, cudaFuncSetAttribute(tri_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       MAX_STARS * MAX_STARS * 4));
     tri_match_kernel<<<grid, 256, MAX_STARS * MAX_STARS * 4, s>>>(
-        reinterpret_cast<double *>(b), reinterpret_cast<double *>(b + o_rl),
-        reinterpret_cast<unsigned char *>(b + o_rs), (int)nr, reinterpret_cast<double *>(b + o_tm),
-        reinterpret_cast<double *>(b + o_tl), reinterpret_cast<unsigned char *>(b + o_ts), (int)nt,
+        reinterpret_cast<double *>(b + o_rm), reinterpret_cast<double *>(b + o_rl),
+        reinterpret_cast<unsigned char *>(b + o_rs), TRI_MAX, reinterpret_cast<double *>(b + o_tm),
+        reinterpret_cast<double *>(b + o_tl), reinterpret_cast<unsigned char *>(b + o_ts), TRI_MAX,
         TRIANGLE_TOLERANCE, reinterpret_cast<unsigned *>(b + o_v));
     AB_LAUNCH_CHECK(ctx);
     std::vector<unsigned> votes(MAX_STARS * MAX_STARS);
+    lap("votes counted");
     AB_CUDA(ctx, cudaMemcpyAsync(votes.data(), b + o_v, votes.size() * 4, cudaMemcpyDeviceToHost, s));
     AB_CUDA(ctx, cudaStreamSynchronize(s));
     struct PV {
@@ -1244,21 +1305,32 @@ ab_status align_star_points(ab_ctx *ctx, const float *d_img, size_t rows, size_t
 ab_status align_with_ref_points(ab_ctx *ctx, const std::vector<Pt> &rs, const float *d_ref,
                                 const float *d_tgt, size_t rows, size_t cols, int n_threads,
                                 cudaStream_t s, ab_align_result *out) {
+    const bool trace = std::getenv("AB_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(now() - t0).count();
+    };
+    const auto t0 = now();
     std::vector<Pt> ts;
     ab_status st = align_star_points(ctx, d_tgt, rows, cols, s, ts);
     if (st != AB_OK) return st;
+    const double t_det = ms_since(t0);
     if (rs.size() < MIN_MATCHES_RIGID || ts.size() < MIN_MATCHES_RIGID)
         return fallback(ctx, d_ref, d_tgt, rows, cols, s, out);
+    const auto t1 = now();
     std::vector<Match> matches;
     st = match_stars(ctx, rs, ts, s, matches);
     if (st != AB_OK) return st;
+    const double t_match = ms_since(t1);
     if (matches.size() < MIN_MATCHES_RIGID) return fallback(ctx, d_ref, d_tgt, rows, cols, s, out);
+    const auto t2 = now();
     ab_align_result r;
-    if (matches.size() >= MIN_MATCHES_AFFINE && ransac(matches, 0, n_threads, &r) && sane(r, rows, cols)) {
-        *out = r;
-        return AB_OK;
-    }
-    if (ransac(matches, 1, n_threads, &r) && sane(r, rows, cols)) {
+    bool done = matches.size() >= MIN_MATCHES_AFFINE && ransac(matches, 0, n_threads, &r) && sane(r, rows, cols);
+    if (!done) done = ransac(matches, 1, n_threads, &r) && sane(r, rows, cols);
+    if (trace)
+        fprintf(stderr, "[ab] align %zux%zu: normalise+detect %.2f ms, triangles+votes+assign %.2f ms (%zu matches), "
+                        "ransac %.2f ms\n", rows, cols, t_det, t_match, matches.size(), ms_since(t2));
+    if (done) {
         *out = r;
         return AB_OK;
     }

@@ -425,30 +425,38 @@ __global__ void normalize_kernel(const float *__restrict__ img, size_t len, Norm
 
 // ------------------------------------------------------------------------- triangle matching
 constexpr int MAX_STARS = 120;  // affine.rs:8
-// votes[ri * MAX_STARS + ti] over all (ref tri, tgt tri) pairs within tolerance (affine.rs:327-348)
+// votes[ri * MAX_STARS + ti] over all (ref tri, tgt tri) pairs within tolerance (affine.rs:327-348).
+// 2-D grid: blockIdx.x = 256 reference triangles (one per thread), blockIdx.y = a chunk of target
+// triangles staged in shared memory (every thread reads the same entry: broadcast).  Matches are
+// rare (tolerance 0.02 on both ratios), so they go straight to the L2-resident vote matrix.
+constexpr int TRI_CHUNK = 1024;
 __global__ void __launch_bounds__(256)
 tri_match_kernel(const double *__restrict__ r_mid, const double *__restrict__ r_long,
                  const unsigned char *__restrict__ r_sorted, int n_ref, const double *__restrict__ t_mid,
                  const double *__restrict__ t_long, const unsigned char *__restrict__ t_sorted,
                  int n_tgt, double tol, unsigned *__restrict__ votes) {
-    extern __shared__ unsigned sv[];  // MAX_STARS x MAX_STARS votes (57.6 KB, opt-in dynamic)
-    for (int i = threadIdx.x; i < MAX_STARS * MAX_STARS; i += blockDim.x) sv[i] = 0;
-    __syncthreads();
-    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_ref; a += gridDim.x * blockDim.x) {
-        const double rm = r_mid[a], rl = r_long[a];
-        const int r0 = r_sorted[3 * a], r1 = r_sorted[3 * a + 1], r2 = r_sorted[3 * a + 2];
-        for (int b = 0; b < n_tgt; ++b) {
-            const double d_mid = fabs(rm - __ldg(t_mid + b));
-            const double d_long = fabs(rl - __ldg(t_long + b));
-            if (d_mid > tol || d_long > tol) continue;
-            atomicAdd(&sv[r0 * MAX_STARS + t_sorted[3 * b]], 1u);
-            atomicAdd(&sv[r1 * MAX_STARS + t_sorted[3 * b + 1]], 1u);
-            atomicAdd(&sv[r2 * MAX_STARS + t_sorted[3 * b + 2]], 1u);
-        }
+    __shared__ double s_mid[TRI_CHUNK], s_long[TRI_CHUNK];
+    __shared__ unsigned char s_srt[3 * TRI_CHUNK];
+    const int b0 = blockIdx.y * TRI_CHUNK, nb = min(TRI_CHUNK, n_tgt - b0);
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        s_mid[i] = t_mid[b0 + i];
+        s_long[i] = t_long[b0 + i];
     }
+    for (int i = threadIdx.x; i < 3 * nb; i += blockDim.x) s_srt[i] = t_sorted[3 * b0 + i];
     __syncthreads();
-    for (int i = threadIdx.x; i < MAX_STARS * MAX_STARS; i += blockDim.x)
-        if (sv[i]) atomicAdd(&votes[i], sv[i]);
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_ref) return;
+    const double rm = r_mid[a], rl = r_long[a];
+    if (!(fabs(rm) < CUDART_INF)) return;  // a triangle the reference drops
+    const int r0 = r_sorted[3 * a], r1 = r_sorted[3 * a + 1], r2 = r_sorted[3 * a + 2];
+    for (int b = 0; b < nb; ++b) {
+        const double d_mid = fabs(rm - s_mid[b]);
+        const double d_long = fabs(rl - s_long[b]);
+        if (d_mid > tol || d_long > tol) continue;
+        atomicAdd(&votes[r0 * MAX_STARS + s_srt[3 * b]], 1u);
+        atomicAdd(&votes[r1 * MAX_STARS + s_srt[3 * b + 1]], 1u);
+        atomicAdd(&votes[r2 * MAX_STARS + s_srt[3 * b + 2]], 1u);
+    }
 }
 
 // ------------------------------------------------------------------------- host-side pieces
@@ -680,7 +688,7 @@ __global__ void ccl_gather_kernel(const StarRec *__restrict__ stars, const unsig
 // greedy dedup on a 3-px grid (star_detection.rs:217-248) over the flux-sorted list; the grid is a
 // flat hash of cell -> chain of kept stars (same decisions as the reference's
 // HashMap<(usize, usize), Vec<usize>>)
-void dedup_stars(const std::vector<ab_star> &stars, std::vector<ab_star> &out) {
+void dedup_stars(const std::vector<ab_star> &stars, std::vector<ab_star> &out, size_t max_keep = SIZE_MAX) {
     const double dedup_r2 = 9.0, cell = 3.0;
     size_t cap = 16;
     while (cap < stars.size() * 2) cap <<= 1;
@@ -689,7 +697,7 @@ void dedup_stars(const std::vector<ab_star> &stars, std::vector<ab_star> &out) {
     auto key_of = [](size_t gy, size_t gx) { return ((unsigned long long)gy << 32) ^ (unsigned long long)gx; };
     auto slot_of = [&](unsigned long long k) { return (size_t)((k * 0x9E3779B97F4A7C15ull) >> 20) & (cap - 1); };
     out.clear();
-    for (size_t i = 0; i < stars.size(); ++i) {
+    for (size_t i = 0; i < stars.size() && out.size() < max_keep; ++i) {
         const ab_star &s = stars[i];
         const size_t gx = f2us(s.x / cell), gy = f2us(s.y / cell);
         bool too_close = false;
@@ -717,9 +725,11 @@ void dedup_stars(const std::vector<ab_star> &stars, std::vector<ab_star> &out) {
 }
 
 // device scratch of the detector inside ctx scratch slot 1
+// max_keep: the caller only needs the first `max_keep` stars of the result (the aligner: 120) -- the
+// greedy dedup walks the flux-sorted list in order, so a prefix of it is enough
 ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols, Norm nm,
                            double sigma_threshold, cudaStream_t s, std::vector<ab_star> &stars,
-                           double *bg_median_out, double *bg_sigma_out) {
+                           double *bg_median_out, double *bg_sigma_out, size_t max_keep = SIZE_MAX) {
     stars.clear();
     if (rows < 3 || cols < 3) {  // star_detection.rs:89-98
         *bg_median_out = 0.0;
@@ -875,16 +885,25 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
             if (n_valid) {
                 ccl_gather_kernel<<<(n_valid + 255) / 256, 256, 0, s>>>(d_stars, d_order2, d_sorted, n_valid);
                 AB_LAUNCH_CHECK(ctx);
-                sorted.resize(n_valid);
-                AB_CUDA(ctx, cudaMemcpyAsync(sorted.data(), d_sorted, (size_t)n_valid * sizeof(ab_star),
-                                             cudaMemcpyDeviceToHost, s));
-                AB_CUDA(ctx, cudaStreamSynchronize(s));
+                // the whole list, or (max_keep given) prefixes of it until the dedup has enough
+                size_t have = 0, want = max_keep == SIZE_MAX ? n_valid : std::min<size_t>(n_valid, 8 * max_keep + 64);
+                for (;;) {
+                    sorted.resize(want);
+                    AB_CUDA(ctx, cudaMemcpyAsync(sorted.data() + have, d_sorted + have, (want - have) * sizeof(ab_star),
+                                                 cudaMemcpyDeviceToHost, s));
+                    AB_CUDA(ctx, cudaStreamSynchronize(s));
+                    have = want;
+                    if (have == n_valid) break;
+                    dedup_stars(sorted, stars, max_keep);
+                    if (stars.size() >= max_keep) break;
+                    want = std::min<size_t>(n_valid, have * 4);
+                }
             }
         }
     }
     const double t_ccl = ms_since(t2);
     const auto t3 = now();
-    dedup_stars(sorted, stars);
+    dedup_stars(sorted, stars, max_keep);
     if (trace)
         fprintf(stderr, "[ab] detect %zux%zu: tiles %.2f ms, count %.2f ms, compact+CCL+measure+sort %.2f ms "
                         "(%u px, %u components), host dedup %.2f ms (%zu stars)\n",
@@ -1253,10 +1272,8 @@ ab_status match_stars(ab_ctx *ctx, const std::vector<Pt> &rs, const std::vector<
                                        reinterpret_cast<unsigned char *>(b + o_ts));
     AB_LAUNCH_CHECK(ctx);
     lap("triangles built");
-    const unsigned grid = (unsigned)std::min<size_t>((TRI_MAX + 255) / 256, (size_t)ctx->sm_count * 2);
-    AB_CUDA(ctx, cudaFuncSetAttribute(tri_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      MAX_STARS * MAX_STARS * 4));
-    tri_match_kernel<<<grid, 256, MAX_STARS * MAX_STARS * 4, s>>>(
+    const dim3 grid((TRI_MAX + 255) / 256, (TRI_MAX + TRI_CHUNK - 1) / TRI_CHUNK);
+    tri_match_kernel<<<grid, 256, 0, s>>>(
         reinterpret_cast<double *>(b + o_rm), reinterpret_cast<double *>(b + o_rl),
         reinterpret_cast<unsigned char *>(b + o_rs), TRI_MAX, reinterpret_cast<double *>(b + o_tm),
         reinterpret_cast<double *>(b + o_tl), reinterpret_cast<unsigned char *>(b + o_ts), TRI_MAX,
@@ -1294,7 +1311,7 @@ ab_status align_star_points(ab_ctx *ctx, const float *d_img, size_t rows, size_t
     Norm nm;
     ab_status rc = normalize_params(ctx, d_img, rows * cols, s, &nm);
     if (rc != AB_OK) return rc;
-    rc = detect_on_device(ctx, d_img, rows, cols, nm, DETECTION_SIGMA, s, st, &bm, &bs);
+    rc = detect_on_device(ctx, d_img, rows, cols, nm, DETECTION_SIGMA, s, st, &bm, &bs, MAX_STARS);
     if (rc != AB_OK) return rc;
     pts.clear();
     for (size_t i = 0; i < std::min(st.size(), (size_t)MAX_STARS); ++i) pts.push_back({st[i].x, st[i].y});

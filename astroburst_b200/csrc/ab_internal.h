@@ -35,8 +35,15 @@ struct ab_ctx {
     bool force_tma1d = false;  // AB_STACK_FORCE_TMA1D=1: per-frame bulk copies instead of the tensor map
     void *encode_tmap_fn = nullptr;  // cuTensorMapEncodeTiled, resolved lazily
     // work-queue counters of the stack kernels (one per launch in flight, round-robin)
+    // Each launch takes slot i = seq % 256 of a ring of {work counter, finished-block ticket,
+    // reject accumulator} triples that start at zero, and clears slot (i + 128) % 256 -- used 128
+    // launches ago -- on its way: no memset launches around the stack kernel.
     static constexpr unsigned WORK_COUNTERS = 256;
-    unsigned *d_work_counters = nullptr;
+    struct StackSlot {
+        unsigned work, done;
+        unsigned long long rejected;
+    };
+    StackSlot *d_work_counters = nullptr;
     std::atomic<unsigned> work_seq{0};
     // peer group (shard.cu): every rank's d_small mapped here, for in-kernel collectives over NVLink
     int peer_world = 0, peer_rank = 0;

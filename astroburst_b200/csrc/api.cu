@@ -66,7 +66,8 @@ ab_status ab_ctx_create(int device, ab_ctx **out) {
     }
     ok = ok && cudaMalloc(&ctx->d_small, ab_ctx::SMALL_BYTES) == cudaSuccess;
     ok = ok && cudaMemset(ctx->d_small, 0, ab_ctx::SMALL_BYTES) == cudaSuccess;  // peer barrier flags start at 0
-    ok = ok && cudaMalloc(&ctx->d_work_counters, ab_ctx::WORK_COUNTERS * sizeof(unsigned)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_work_counters, ab_ctx::WORK_COUNTERS * sizeof(ab_ctx::StackSlot)) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_work_counters, 0, ab_ctx::WORK_COUNTERS * sizeof(ab_ctx::StackSlot)) == cudaSuccess;
     ok = ok && cudaMallocHost(&ctx->h_small, ab_ctx::SMALL_BYTES) == cudaSuccess;
     if (!ok) {
         ab_ctx_destroy(ctx);

@@ -58,8 +58,12 @@ AB_DECL(36) AB_DECL(40) AB_DECL(48) AB_DECL(56) AB_DECL(64)
 ab_status ab_stack_launch(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix,
                           float sigma_low, float sigma_high, unsigned max_iter, float *d_out,
                           unsigned long long *d_rejected, cudaStream_t stream, bool peer_frames) {
-    AB_CUDA(ctx, cudaMemsetAsync(d_rejected, 0, sizeof(unsigned long long), stream));
-    if (npix == 0) return AB_OK;
+    // (the register kernels publish the count themselves, see launch_mix; only the empty image
+    // and the deep path zero it here)
+    if (npix == 0) {
+        AB_CUDA(ctx, cudaMemsetAsync(d_rejected, 0, sizeof(unsigned long long), stream));
+        return AB_OK;
+    }
     if (n_frames > AB_MAX_FRAMES)
         return ab_fail(ctx, AB_ERR_UNSUPPORTED, "n_frames %d > AB_MAX_FRAMES %d", n_frames,
                        AB_MAX_FRAMES);
@@ -78,6 +82,7 @@ ab_status ab_stack_launch(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_
             break;
     }
 #undef AB_CASE
+    AB_CUDA(ctx, cudaMemsetAsync(d_rejected, 0, sizeof(unsigned long long), stream));
     DeepPre pre{};
     pre.peer_frames = peer_frames ? 1 : 0;
     return ab_stack_launch_deep(ctx, ft, n_frames, npix, sigma_low, sigma_high, max_iter, pre, d_out,

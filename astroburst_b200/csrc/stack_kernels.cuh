@@ -848,8 +848,9 @@ template <int P, int MN, int MD, bool kTensorMap>
 __global__ void __launch_bounds__(tma_warps<P>() * 32, 1)
 stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__ TmapParam tmap,
                   unsigned n_groups, float sigma_low, float sigma_high, unsigned max_iter, CeConst k,
-                  unsigned *__restrict__ work_counter, float *__restrict__ out,
-                  unsigned long long *__restrict__ rejected_total) {
+                  ab_ctx::StackSlot *__restrict__ slot, ab_ctx::StackSlot *__restrict__ stale_slot,
+                  float *__restrict__ out, unsigned long long *__restrict__ rejected_total) {
+    unsigned *work_counter = &slot->work;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr unsigned TW = tma_warps<P>();
     const int lane = threadIdx.x & 31;
@@ -964,7 +965,23 @@ stack_wtma_kernel(const __grid_constant__ FrameTable ft, const __grid_constant__
     }
     if (count) drain_dynamic<P>(sm.q, count, lane, sigma_low, sigma_high, max_iter, out, local_rej);
     const unsigned w = __reduce_add_sync(0xffffffffu, local_rej);
-    if (lane == 0 && w) atomicAdd(rejected_total, (unsigned long long)w);
+    if (lane == 0 && w) atomicAdd(&slot->rejected, (unsigned long long)w);
+    // StackResult.rejected_pixels without a memset before the launch: the counts meet in the slot's
+    // accumulator (zero since it was cleared 128 launches ago); the block that finishes last
+    // publishes the total and block 0 clears the slot the launch after next-but-127 will use
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            stale_slot->work = 0;
+            stale_slot->done = 0;
+            stale_slot->rejected = 0;
+        }
+        __threadfence();
+        if (atomicAdd(&slot->done, 1u) == gridDim.x - 1) {
+            __threadfence();
+            *rejected_total = atomicAdd(&slot->rejected, 0ull);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1012,8 +1029,10 @@ ab_status launch_mix(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, f
         if (cube) cube = ab_make_stack_tmap(ctx, ft.p[0], npix, (size_t)stride, P, 32, &tm);
         // scattered frames: P small bulk copies per group measured slower (1.18 ms) than plain
         // coalesced loads (0.92 ms) -> only the tensor-map form is used unless forced
-        if (!cube && !ctx->force_tma1d)
+        if (!cube && !ctx->force_tma1d) {
+            AB_CUDA(ctx, cudaMemsetAsync(d_rej, 0, sizeof(unsigned long long), stream));
             return launch_ldg<P, MN, MD>(ctx, ft, npix, sl, sh, max_iter, d_out, d_rej, stream);
+        }
         constexpr int TW = tma_warps<P>();
         const size_t smem = sizeof(WarpTmaSmem<P>) * TW;
         constexpr int threads = TW * 32;
@@ -1026,12 +1045,14 @@ ab_status launch_mix(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, f
         size_t grid = (size_t)ctx->sm_count * per_sm;
         const size_t need = (groups + TW - 1) / TW;
         if (grid > need) grid = need;
-        unsigned *counter =
-            ctx->d_work_counters + (ctx->work_seq.fetch_add(1) % ab_ctx::WORK_COUNTERS);
-        AB_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
+        const unsigned seq = ctx->work_seq.fetch_add(1);
+        ab_ctx::StackSlot *slot = ctx->d_work_counters + (seq % ab_ctx::WORK_COUNTERS);
+        ab_ctx::StackSlot *stale = ctx->d_work_counters + ((seq + ab_ctx::WORK_COUNTERS / 2) % ab_ctx::WORK_COUNTERS);
         kern<<<(unsigned)grid, threads, smem, stream>>>(ft, tm, (unsigned)groups, sl, sh, max_iter,
-                                                        CeConst{1, -1}, counter, d_out, d_rej);
+                                                        CeConst{1, -1}, slot, stale, d_out, d_rej);
         AB_LAUNCH_CHECK(ctx);
+    } else {
+        AB_CUDA(ctx, cudaMemsetAsync(d_rej, 0, sizeof(unsigned long long), stream));
     }
     const size_t done = groups * 32;
     if (done < npix) {  // ragged tail (or everything, for unaligned frames): plain loads

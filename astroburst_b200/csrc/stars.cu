@@ -80,6 +80,7 @@ __device__ __forceinline__ float tile_load(const TileCtx &t, unsigned i) {
 }
 struct FromGlobal {
     TileCtx t;
+    __device__ __forceinline__ int slots() const { return 1; }
     template <typename Fn>
     __device__ __forceinline__ void for_each(Fn fn) const {
         const unsigned n_px = (unsigned)(t.th * t.tw);
@@ -100,24 +101,52 @@ struct OnChip {
             const unsigned i = (unsigned)j * OC_THREADS + threadIdx.x;
             rv[j] = i < n_px ? tile_load(t, i) : CUDART_NAN_F;
         }
-        for (int j = OC_REG; j < n_slots; ++j) {
+        int j = OC_REG;
+        for (; j + 8 <= n_slots; j += 8) {  // 8 loads in flight per thread
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned i = (unsigned)(j + u) * OC_THREADS + threadIdx.x;
+                v[u] = i < n_px ? tile_load(t, i) : CUDART_NAN_F;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) smw[(j + u - OC_REG) * OC_THREADS + threadIdx.x] = v[u];
+        }
+        for (; j < n_slots; ++j) {
             const unsigned i = (unsigned)j * OC_THREADS + threadIdx.x;
             smw[(j - OC_REG) * OC_THREADS + threadIdx.x] = i < n_px ? tile_load(t, i) : CUDART_NAN_F;
         }
     }
+    __device__ __forceinline__ int slots() const { return n_slots; }
     template <typename Fn>
     __device__ __forceinline__ void for_each(Fn fn) const {
 #pragma unroll
         for (int j = 0; j < OC_REG; ++j)
             if (j < n_slots) fn(rv[j]);
-        for (int j = OC_REG; j < n_slots; ++j) fn(sm[(j - OC_REG) * OC_THREADS + threadIdx.x]);
+        const float *p = sm + threadIdx.x;
+        int j = OC_REG;
+        for (; j + 4 <= n_slots; j += 4, p += 4 * OC_THREADS) {
+            const float a = p[0], b = p[OC_THREADS], c = p[2 * OC_THREADS], d = p[3 * OC_THREADS];
+            fn(a);
+            fn(b);
+            fn(c);
+            fn(d);
+        }
+        for (; j < n_slots; ++j, p += OC_THREADS) fn(p[0]);
     }
 };
+constexpr int FS_SAMPLES = 2048, FS_CAP = 6144;  // sampled-bracket selection (on-chip tiles)
 struct Sel {  // shared scratch of one block
     unsigned hist[256];
     unsigned bin, cum;
     unsigned long long total;
     unsigned maxkey;
+    // sampled-bracket selection: one value per thread sampled once per tile, its keys sorted per
+    // statistic, the keys between two sample quantiles collected in one pass over the tile
+    float *samp_v;     // FS_SAMPLES sampled pixel values (NaN = none), null = fast path off
+    unsigned *bracket; // FS_CAP keys; the sample's sorted keys live here until the bracket is chosen
+    unsigned n_samp, n_tot, n_lo, n_br;
+    unsigned *fallbacks;  // optional global counter of statistics that took the radix select
 };
 
 // key of one pixel for the current selection, or false when the pixel is not in the set.
@@ -204,6 +233,228 @@ __device__ __forceinline__ unsigned tile_max_below(const Src &src, Sel &s, int m
     return r;
 }
 
+// ---- sampled-bracket selection -----------------------------------------------------------------
+// A radix select reads the whole tile 4 times per order statistic (and the detector needs 6
+// statistics + 3 counts per tile).  Here a sorted 2,048-value sample gives two keys that bracket
+// the median with ~99 % probability; ONE pass over the tile counts the keys below the bracket, the
+// retained keys in total, and collects the bracket's keys (a few thousand) in shared memory -- each
+// warp into its own segment, so the pass has no atomics -- where the exact order statistics are
+// selected.  Whenever the bracket misses (or a segment overflows) the caller falls back to the
+// radix select, so the result is always exact.
+constexpr int FS_SEG = FS_CAP / (OC_THREADS / 32);  // bracket keys per warp
+__device__ __forceinline__ unsigned hist_find_warp(const unsigned *hist, unsigned k, unsigned *cum_out) {
+    // bin b with cum(b-1) <= k < cum(b) over 256 bins; warp 0 only (all 32 lanes)
+    const int lane = threadIdx.x & 31;
+    unsigned loc[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        loc[j] = hist[lane * 8 + j];
+        sum += loc[j];
+    }
+    unsigned inc = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    unsigned run = inc - sum;  // keys in the bins before this lane's
+    const bool mine = run <= k && k < inc;
+    unsigned b = 0xffffffffu, cum = 0;
+    if (mine) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (b == 0xffffffffu && k < run + loc[j]) {
+                b = lane * 8 + j;
+                cum = run;
+            }
+            run += (b == 0xffffffffu) ? loc[j] : 0u;
+        }
+    }
+    const unsigned who = __ballot_sync(0xffffffffu, mine);
+    const int src = who ? __ffs(who) - 1 : 31;
+    b = __shfl_sync(0xffffffffu, b, src);
+    cum = __shfl_sync(0xffffffffu, cum, src);
+    if (!who) {  // k beyond the total: last bin (callers never ask for it)
+        b = 255;
+        cum = __shfl_sync(0xffffffffu, inc, 31) - hist[255];
+    }
+    *cum_out = cum;
+    return b;
+}
+// k-th smallest (0-based) of the bracket (every warp scans its own segment of `mine` keys);
+// *less = keys strictly below it
+__device__ __forceinline__ unsigned bracket_select(const unsigned *seg, unsigned mine, Sel &s, unsigned k,
+                                                   unsigned *less) {
+    unsigned prefix = 0, mask = 0, below = 0;
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        if (threadIdx.x < 256) s.hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (unsigned i = lane; i < mine; i += 32) {
+            const unsigned key = seg[i];
+            if ((key & mask) == prefix) atomicAdd(&s.hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned cum;
+            const unsigned b = hist_find_warp(s.hist, k, &cum);
+            if (threadIdx.x == 0) {
+                s.bin = b;
+                s.cum = cum;
+            }
+        }
+        __syncthreads();
+        k -= s.cum;
+        below += s.cum;
+        prefix |= s.bin << shift;
+        mask |= 0xffu << shift;
+        __syncthreads();
+    }
+    *less = below;
+    return prefix;
+}
+// ascending bitonic sort of FS_SAMPLES u32 in shared memory, one comparator per thread and stage
+__device__ __forceinline__ void sort_samples(unsigned *sk) {
+    for (unsigned size = 2; size <= FS_SAMPLES; size <<= 1)
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            const unsigned t = threadIdx.x, p = 2 * t - (t & (stride - 1)), q = p + stride;
+            const unsigned a = sk[p], b = sk[q];
+            const bool up = (p & size) == 0;
+            if ((a > b) == up) {
+                sk[p] = b;
+                sk[q] = a;
+            }
+        }
+    __syncthreads();
+}
+// two values per thread from pseudo-random slots of its column (a spatially spread sample), sorted
+// by value once per tile: samp_v[0..n_samp) ascending, the rest +inf
+template <typename Src>
+__device__ __forceinline__ void tile_sample(const Src &src, Sel &s) {
+    if (!s.samp_v) return;
+    const unsigned ns = (unsigned)max(src.slots(), 1);
+    const unsigned w0 = (threadIdx.x * 2654435761u >> 16) % ns, w1 = (w0 + (ns >> 1)) % ns;
+    unsigned idx = 0;
+    float p0 = CUDART_INF_F, p1 = CUDART_INF_F;
+    src.for_each([&](float v) {
+        const bool ok = v > 1e-7f && v < CUDART_INF_F;
+        if (ok && idx >= w0 && p0 == CUDART_INF_F) p0 = v;
+        if (ok && idx >= w1 && idx != w0 && p1 == CUDART_INF_F) p1 = v;
+        ++idx;
+    });
+    if (ns < 2) p1 = CUDART_INF_F;
+    if (threadIdx.x == 0) s.n_samp = 0;
+    __syncthreads();
+    unsigned c = (p0 < CUDART_INF_F) + (p1 < CUDART_INF_F);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s.n_samp, c);
+    s.samp_v[threadIdx.x] = p0;
+    s.samp_v[threadIdx.x + OC_THREADS] = p1;
+    sort_samples(reinterpret_cast<unsigned *>(s.samp_v));  // positive floats order like their bits
+}
+// Fast (left, right, n): returns false when the caller must use the radix select.
+template <int MODE, typename Src>
+__device__ __forceinline__ bool tile_pair_fast(const Src &src, Sel &s, double median, float L, float H,
+                                               unsigned long long *n_out, float *left, float *right) {
+    if (!s.samp_v) return false;
+    // valid pixel <=> Lq <= v <= Hq (finite, > 1e-7, inside the clip; NaN fails both compares)
+    const float Lq = fmaxf(L, __uint_as_float(__float_as_uint(1e-7f) + 1u)), Hq = fminf(H, 3.402823466e38f);
+    auto key_of = [&](float v) -> unsigned {
+        return __float_as_uint(MODE ? (float)fabs((double)v - median) : v);
+    };
+    // ---- the bracket [lo_key, hi_key] around the sample's median
+    unsigned lo_key = 0u, hi_key = 0xfffffffeu;
+    {
+        // the retained part of the sorted sample: indices [a, b)
+        const unsigned m0 = s.n_samp;
+        unsigned a = 0, b = m0;
+        if (m0) {
+            unsigned l = 0, r = m0;  // first index with value >= Lq
+            while (l < r) {
+                const unsigned mdl = (l + r) >> 1;
+                if (s.samp_v[mdl] < Lq) l = mdl + 1; else r = mdl;
+            }
+            a = l;
+            r = m0;  // first index with value > Hq
+            while (l < r) {
+                const unsigned mdl = (l + r) >> 1;
+                if (s.samp_v[mdl] <= Hq) l = mdl + 1; else r = mdl;
+            }
+            b = l;
+        }
+        const unsigned m = b - a;
+        const int d = (int)(1.25f * sqrtf((float)m)) + 6;  // ~2.5 sigma of the sample median's rank
+        const int i = (int)(m >> 1);
+        if (MODE == 0) {
+            if (m >= 64) {  // (a thin sample brackets everything: small sets fit the bracket whole)
+                if (i - d >= 0) lo_key = __float_as_uint(s.samp_v[a + i - d]);
+                if (i + d < (int)m) hi_key = __float_as_uint(s.samp_v[a + i + d]);
+            }
+            __syncthreads();
+        } else {  // |v - median| keys of the retained samples, sorted in the bracket's space
+            unsigned *sk = s.bracket;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const unsigned j = threadIdx.x + h * OC_THREADS;
+                sk[j] = (j >= a && j < b) ? key_of(s.samp_v[j]) : 0xffffffffu;
+            }
+            sort_samples(sk);
+            if (m >= 64) {
+                if (i - d >= 0) lo_key = sk[i - d];
+                if (i + d < (int)m) hi_key = sk[i + d];
+            }
+            __syncthreads();  // the sample's keys are dead from here: the bracket reuses their space
+        }
+    }
+    // ---- one pass: retained keys in total, keys below the bracket, the bracket's keys
+    if (threadIdx.x == 0) s.n_tot = s.n_lo = s.n_br = s.maxkey = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
+    unsigned *seg = s.bracket + (threadIdx.x >> 5) * FS_SEG;
+    unsigned c_tot = 0, c_lo = 0, mine = 0;  // mine: keys in this warp's segment (warp-uniform)
+    src.for_each([&](float v) {
+        const bool ok = v >= Lq && v <= Hq;
+        const unsigned key = key_of(v);
+        const bool in = ok && key >= lo_key && key <= hi_key;
+        c_tot += ok ? 1u : 0u;
+        c_lo += (ok && key < lo_key) ? 1u : 0u;
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        const unsigned pos = mine + __popc(bal & lt_mask);
+        if (in && pos < FS_SEG) seg[pos] = key;
+        mine += __popc(bal);
+    });
+    c_tot = __reduce_add_sync(0xffffffffu, c_tot);
+    c_lo = __reduce_add_sync(0xffffffffu, c_lo);
+    if (lane == 0) {
+        if (c_tot) atomicAdd(&s.n_tot, c_tot);
+        if (c_lo) atomicAdd(&s.n_lo, c_lo);
+        if (mine) atomicAdd(&s.n_br, mine);
+        if (mine > FS_SEG) s.maxkey = 1;  // (flag: a segment overflowed)
+    }
+    __syncthreads();
+    const unsigned n = s.n_tot, n_lo = s.n_lo, n_br = s.n_br, over = s.maxkey;
+    __syncthreads();
+    *n_out = n;
+    if (n == 0) {
+        *left = *right = 0.0f;
+        return true;
+    }
+    const unsigned mid = n >> 1, lowest = (n & 1u) ? mid : mid - 1;  // ranks wanted: lowest .. mid
+    if (over || lowest < n_lo || mid >= n_lo + n_br) {
+        if (threadIdx.x == 0 && s.fallbacks) atomicAdd(s.fallbacks, 1u);
+        return false;
+    }
+    unsigned less;
+    const unsigned rk = bracket_select(seg, mine, s, mid - n_lo, &less);
+    unsigned lk = rk;
+    if (!(n & 1u) && less == mid - n_lo)  // the lower middle is a smaller key: the next one down
+        lk = bracket_select(seg, mine, s, mid - n_lo - 1, &less);
+    *left = __uint_as_float(lk);
+    *right = __uint_as_float(rk);
+    return true;
+}
+
 // (left, right) = the (n/2 - 1)-th and (n/2)-th order statistics (left == right for odd n)
 template <typename Src>
 __device__ __forceinline__ void tile_median_pair(const Src &src, Sel &s, int mode, double median,
@@ -218,23 +469,35 @@ __device__ __forceinline__ void tile_median_pair(const Src &src, Sel &s, int mod
     *right = __uint_as_float(rk);
 }
 
-// mode 0: exact_median_mut (median.rs:27-44); mode 1: the f32 MAD of sigma_clip.rs:14-17
+// mode 0: exact_median_mut (median.rs:27-44); mode 1: the f32 MAD of sigma_clip.rs:14-17.
+// *n_io: in = the retained count when known (else ~0), out = the retained count.
 template <typename Src>
 __device__ __noinline__ double tile_stat(const Src &src, Sel &s, int mode, double median, float L,
-                                         float H, unsigned long long n) {
+                                         float H, unsigned long long *n_io) {
     float l, r;
-    tile_median_pair(src, s, mode, median, L, H, n, &l, &r);
+    unsigned long long n = *n_io;
+    const bool fast = mode ? tile_pair_fast<1>(src, s, median, L, H, &n, &l, &r)
+                           : tile_pair_fast<0>(src, s, median, L, H, &n, &l, &r);
+    if (!fast) {
+        if (n == ~0ull) n = tile_count(src, s, L, H);
+        if (n > 0) tile_median_pair(src, s, mode, median, L, H, n, &l, &r);
+    }
+    *n_io = n;
+    if (n == 0) return 0.0;
     if (mode == 0) return (n % 2 == 0) ? ((double)l + (double)r) / 2.0 : (double)r;
     const float m = (n % 2 == 0) ? (l + r) / 2.0f : r;  // median_f32_mut
     return (double)m;
 }
 
-// sigma_clipped_stats(&mut vals, 3.0, 2) of one tile + the n >= 8 gate of star_detection.rs:61-66
+// sigma_clipped_stats(&mut vals, 3.0, 2) of one tile + the n >= 8 gate of star_detection.rs:61-66.
+// The retained count of every clip round comes out of the median's own pass over the tile.
 template <typename Src>
 __device__ __forceinline__ void tile_background(const Src &src, Sel &s, double *__restrict__ med_out,
                                                 double *__restrict__ sig_out, int *__restrict__ ok_out) {
     float L = -CUDART_INF_F, H = CUDART_INF_F;
-    unsigned long long n = tile_count(src, s, L, H);
+    tile_sample(src, s);
+    unsigned long long n = ~0ull;
+    double median = tile_stat(src, s, 0, 0.0, L, H, &n);  // median of everything valid (+ its count)
     if (n < 8) {
         if (threadIdx.x == 0) ok_out[blockIdx.x] = 0;
         return;
@@ -242,20 +505,23 @@ __device__ __forceinline__ void tile_background(const Src &src, Sel &s, double *
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
         if (n < 3) break;
-        const double median = tile_stat(src, s, 0, 0.0, L, H, n);
-        const double mad = tile_stat(src, s, 1, median, L, H, n);
+        unsigned long long n_same = n;
+        const double mad = tile_stat(src, s, 1, median, L, H, &n_same);
         const double sig = fmax(mad * MAD_TO_SIGMA, 1e-30);
         const float lo = (float)(median - 3.0 * sig);
         const float hi = (float)(median + 3.0 * sig);
         // retain(v >= lo && v <= hi) on the already retained set
         if (!(lo <= L)) L = lo;  // NaN-safe max
         if (!(hi >= H)) H = hi;
-        n = tile_count(src, s, L, H);
+        n = ~0ull;
+        median = tile_stat(src, s, 0, 0.0, L, H, &n);  // the next round's (or the final) median
     }
-    double median = 0.0, sigma = 1.0;  // sigma_clip.rs:24-26
+    double sigma = 1.0;  // sigma_clip.rs:24-26
     if (n > 0) {
-        median = tile_stat(src, s, 0, 0.0, L, H, n);
-        sigma = fmax(tile_stat(src, s, 1, median, L, H, n) * MAD_TO_SIGMA, 1e-30);
+        unsigned long long n_same = n;
+        sigma = fmax(tile_stat(src, s, 1, median, L, H, &n_same) * MAD_TO_SIGMA, 1e-30);
+    } else {
+        median = 0.0;
     }
     if (threadIdx.x == 0) {
         med_out[blockIdx.x] = median;
@@ -284,6 +550,8 @@ bg_tiles_kernel(const float *__restrict__ img, size_t rows, size_t cols, size_t 
                 size_t tiles_x, Norm nm, double *__restrict__ med_out,
                 double *__restrict__ sig_out, int *__restrict__ ok_out) {
     __shared__ Sel s;
+    if (threadIdx.x == 0) s.samp_v = nullptr;  // tiles beyond the on-chip capacity: radix select only
+    __syncthreads();
     FromGlobal src{tile_of_block(img, rows, cols, step, tiles_x, nm)};
     tile_background(src, s, med_out, sig_out, ok_out);
 }
@@ -291,12 +559,20 @@ bg_tiles_kernel(const float *__restrict__ img, size_t rows, size_t cols, size_t 
 __global__ void __launch_bounds__(OC_THREADS, 1)
 bg_tiles_onchip_kernel(const float *__restrict__ img, size_t rows, size_t cols, size_t step,
                        size_t tiles_x, Norm nm, double *__restrict__ med_out,
-                       double *__restrict__ sig_out, int *__restrict__ ok_out) {
+                       double *__restrict__ sig_out, int *__restrict__ ok_out, unsigned *fallbacks) {
     extern __shared__ float oc_smem[];
     __shared__ Sel s;
     const TileCtx t = tile_of_block(img, rows, cols, step, tiles_x, nm);
     OnChip src;
     src.fill(t, oc_smem);
+    if (threadIdx.x == 0) {  // fast-path scratch behind the tile's shared-memory part
+        const unsigned n_px = (unsigned)(t.th * t.tw);
+        const int slots = (int)((n_px + OC_THREADS - 1) / OC_THREADS);
+        float *tail = oc_smem + (size_t)(slots > OC_REG ? slots - OC_REG : 0) * OC_THREADS;
+        s.samp_v = tail;
+        s.bracket = reinterpret_cast<unsigned *>(tail + FS_SAMPLES);
+        s.fallbacks = fallbacks;
+    }
     __syncthreads();
     tile_background(src, s, med_out, sig_out, ok_out);
 }
@@ -304,14 +580,15 @@ bg_tiles_onchip_kernel(const float *__restrict__ img, size_t rows, size_t cols, 
 // step x step tiles of at most 65,536 px run from the on-chip copy
 ab_status launch_bg_tiles(ab_ctx *ctx, const float *d_img, size_t rows, size_t cols, size_t step,
                           size_t tiles_x, size_t n_tiles, const Norm &nm, double *d_med,
-                          double *d_sig, int *d_ok, cudaStream_t s) {
+                          double *d_sig, int *d_ok, cudaStream_t s, unsigned *d_fb = nullptr) {
     if (step * step <= (size_t)OC_THREADS * (OC_REG + OC_SMEM)) {
         const size_t slots = (std::min(step, rows) * std::min(step, cols) + OC_THREADS - 1) / OC_THREADS;
-        const size_t smem = slots > OC_REG ? (slots - OC_REG) * OC_THREADS * sizeof(float) : 0;
+        const size_t smem = (slots > OC_REG ? (slots - OC_REG) * OC_THREADS * sizeof(float) : 0) +
+                            (FS_SAMPLES + FS_CAP) * sizeof(unsigned);
         AB_CUDA(ctx, cudaFuncSetAttribute(bg_tiles_onchip_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         bg_tiles_onchip_kernel<<<(unsigned)n_tiles, OC_THREADS, smem, s>>>(d_img, rows, cols, step, tiles_x,
-                                                                          nm, d_med, d_sig, d_ok);
+                                                                          nm, d_med, d_sig, d_ok, d_fb);
     } else {
         bg_tiles_kernel<<<(unsigned)n_tiles, BG_THREADS, 0, s>>>(d_img, rows, cols, step, tiles_x, nm,
                                                                 d_med, d_sig, d_ok);
@@ -747,11 +1024,13 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
     const size_t off_sig = n_tiles * 8, off_ok = off_sig + n_tiles * 8;
     const size_t off_rc = (off_ok + n_tiles * 4 + 255) / 256 * 256;
     const size_t off_ro = (off_rc + rows * 4 + 255) / 256 * 256;
-    const size_t fixed = (off_ro + (rows + 1) * 8 + 255) / 256 * 256;
+    const size_t off_fb = (off_ro + (rows + 1) * 8 + 255) / 256 * 256;
+    const size_t fixed = off_fb + 256;
     ab_status st = ab_scratch_reserve(ctx, 1, fixed);
     if (st != AB_OK) return st;
     char *base = static_cast<char *>(ctx->d_scratch[1]);
     double *d_med = reinterpret_cast<double *>(base), *d_sig = reinterpret_cast<double *>(base + off_sig);
+    unsigned *d_fb = reinterpret_cast<unsigned *>(base + off_fb);  // AB_TRACE: radix-select fallbacks
     int *d_ok = reinterpret_cast<int *>(base + off_ok);
     unsigned *d_rc = reinterpret_cast<unsigned *>(base + off_rc);
     unsigned long long *d_ro = reinterpret_cast<unsigned long long *>(base + off_ro);
@@ -763,8 +1042,12 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
         return std::chrono::duration<double, std::milli>(now() - t0).count();
     };
     const auto t_start = now();
-    st = launch_bg_tiles(ctx, d_img, rows, cols, step, tiles_x, n_tiles, nm, d_med, d_sig, d_ok, s);
+    if (trace) AB_CUDA(ctx, cudaMemsetAsync(d_fb, 0, 4, s));
+    st = launch_bg_tiles(ctx, d_img, rows, cols, step, tiles_x, n_tiles, nm, d_med, d_sig, d_ok, s,
+                         trace ? d_fb : nullptr);
     if (st != AB_OK) return st;
+    unsigned h_fb = 0;
+    if (trace) AB_CUDA(ctx, cudaMemcpyAsync(&h_fb, d_fb, 4, cudaMemcpyDeviceToHost, s));
     std::vector<double> h_med(n_tiles), h_sig(n_tiles);
     std::vector<int> h_ok(n_tiles);
     AB_CUDA(ctx, cudaMemcpyAsync(h_med.data(), d_med, n_tiles * 8, cudaMemcpyDeviceToHost, s));
@@ -906,8 +1189,8 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
     dedup_stars(sorted, stars, max_keep);
     if (trace)
         fprintf(stderr, "[ab] detect %zux%zu: tiles %.2f ms, count %.2f ms, compact+CCL+measure+sort %.2f ms "
-                        "(%u px, %u components), host dedup %.2f ms (%zu stars)\n",
-                rows, cols, t_bg, t_count, t_ccl, nfg, n_comp, ms_since(t3), stars.size());
+                        "(%u px, %u components), host dedup %.2f ms (%zu stars); %u of %zu tile statistics by radix select\n",
+                rows, cols, t_bg, t_count, t_ccl, nfg, n_comp, ms_since(t3), stars.size(), h_fb, n_tiles * 6);
     return AB_OK;
 }
 

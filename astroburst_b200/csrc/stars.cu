@@ -1516,6 +1516,142 @@ __global__ void build_tri_kernel(const double *__restrict__ xy, int n_stars, dou
     srt[3 * t + 2] = v2;
 }
 
+// Bucketed variant (the one match_stars launches).  Two triangles can only vote when their mid
+// ratios differ by <= tol, so both lists are counting-sorted by bucket(mid) = floor(mid / (1.001 tol))
+// (clamped to TRI_NBK - 1) and a reference triangle of bucket k meets only the target triangles of
+// buckets k-1 .. k+1 -- one contiguous range of the sorted target list.  The exact f64 test of the
+// brute-force kernel decides inside that range, and votes are sums, so the vote matrix is identical.
+constexpr int TRI_NBK = 4096;
+__device__ __forceinline__ int tri_bucket(double mid, double inv_w) {
+    const double q = mid * inv_w;
+    return q >= (double)(TRI_NBK - 1) ? TRI_NBK - 1 : (int)q;
+}
+__global__ void __launch_bounds__(256)
+tri_hist_kernel(const double *__restrict__ r_mid, const double *__restrict__ t_mid, double inv_w,
+                unsigned *__restrict__ hist) {  // hist[2][TRI_NBK]
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= TRI_MAX) return;
+    const double rm = r_mid[t], tm = t_mid[t];
+    if (fabs(rm) < CUDART_INF) atomicAdd(&hist[tri_bucket(rm, inv_w)], 1u);
+    if (fabs(tm) < CUDART_INF) atomicAdd(&hist[TRI_NBK + tri_bucket(tm, inv_w)], 1u);
+}
+// block 0: reference list, block 1: target list.  start[side][TRI_NBK + 1], cursor[side][TRI_NBK]
+__global__ void __launch_bounds__(1024)
+tri_scan_kernel(const unsigned *__restrict__ hist, unsigned *__restrict__ start, unsigned *__restrict__ cursor) {
+    __shared__ unsigned warp_sum[32];
+    const unsigned *h = hist + blockIdx.x * TRI_NBK;
+    unsigned *st = start + blockIdx.x * (TRI_NBK + 1), *cu = cursor + blockIdx.x * TRI_NBK;
+    constexpr int PER = TRI_NBK / 1024;
+    unsigned loc[PER], sum = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        loc[j] = h[threadIdx.x * PER + j];
+        sum += loc[j];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned inc = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_sum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = warp_sum[lane], winc = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += v;
+        }
+        warp_sum[lane] = winc - w;
+    }
+    __syncthreads();
+    unsigned run = warp_sum[warp] + inc - sum;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        st[threadIdx.x * PER + j] = run;
+        cu[threadIdx.x * PER + j] = run;
+        run += loc[j];
+    }
+    if (threadIdx.x == 1023) st[TRI_NBK] = run;
+}
+struct TriList {
+    double *mid, *lng;
+    unsigned char *srt;
+};
+struct TriSorted {
+    double2 *ml;  // (mid, long) per triangle
+    unsigned char *srt;
+};
+__global__ void __launch_bounds__(256)
+tri_scatter_kernel(TriList r_in, TriList t_in, double inv_w, unsigned *__restrict__ cursor, TriSorted r_out,
+                   TriSorted t_out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= TRI_MAX) return;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const TriList &in = side ? t_in : r_in;
+        const TriSorted &out = side ? t_out : r_out;
+        const double m = in.mid[t];
+        if (!(fabs(m) < CUDART_INF)) continue;
+        const unsigned pos = atomicAdd(&cursor[side * TRI_NBK + tri_bucket(m, inv_w)], 1u);
+        out.ml[pos] = make_double2(m, in.lng[t]);
+        out.srt[3 * pos] = in.srt[3 * t];
+        out.srt[3 * pos + 1] = in.srt[3 * t + 1];
+        out.srt[3 * pos + 2] = in.srt[3 * t + 2];
+    }
+}
+// One thread per bucket-sorted reference triangle; a warp walks the union of its lanes' target
+// ranges, every lane testing the same (broadcast) target triangle.  The ranges of the densest
+// buckets run to thousands of triangles, so blockIdx.y cuts the target list into TRI_SPAN-triangle
+// spans and every warp takes the part of its range inside its span.
+constexpr int TRI_SPAN = 512;
+__global__ void __launch_bounds__(128)
+tri_match_bucketed_kernel(TriSorted ref, TriSorted tgt, const unsigned *__restrict__ start, double inv_w,
+                          double tol, unsigned *__restrict__ votes) {
+    const unsigned n_ref = start[TRI_NBK];
+    const unsigned *t_start = start + (TRI_NBK + 1);
+    const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((a & ~31u) >= n_ref) return;  // whole warp beyond the list
+    const bool live = a < n_ref;
+    double rm = CUDART_INF, rl = CUDART_INF;  // (a dead lane never passes the test)
+    unsigned lo = 0xffffffffu, hi = 0;
+    if (live) {
+        const double2 r = ref.ml[a];
+        rm = r.x;
+        rl = r.y;
+        const int k = tri_bucket(rm, inv_w);
+        lo = t_start[k > 0 ? k - 1 : 0];
+        hi = t_start[k + 2 < TRI_NBK ? k + 2 : TRI_NBK];
+    }
+    const unsigned span0 = blockIdx.y * TRI_SPAN;
+    const unsigned wlo = max(__reduce_min_sync(0xffffffffu, lo), span0);
+    const unsigned whi = min(__reduce_max_sync(0xffffffffu, hi), span0 + TRI_SPAN);
+    if (wlo >= whi) return;
+    int r0 = 0, r1 = 0, r2 = 0;
+    if (live) {
+        r0 = ref.srt[3 * a];
+        r1 = ref.srt[3 * a + 1];
+        r2 = ref.srt[3 * a + 2];
+    }
+    auto test = [&](unsigned b, double2 t) {
+        const double d_mid = fabs(rm - t.x);
+        const double d_long = fabs(rl - t.y);
+        if (d_mid > tol || d_long > tol) return;
+        atomicAdd(&votes[r0 * MAX_STARS + tgt.srt[3 * b]], 1u);
+        atomicAdd(&votes[r1 * MAX_STARS + tgt.srt[3 * b + 1]], 1u);
+        atomicAdd(&votes[r2 * MAX_STARS + tgt.srt[3 * b + 2]], 1u);
+    };
+    unsigned b = wlo;
+    for (; b + 4 <= whi; b += 4) {  // four broadcast loads in flight
+        const double2 t0 = tgt.ml[b], t1 = tgt.ml[b + 1], t2 = tgt.ml[b + 2], t3 = tgt.ml[b + 3];
+        test(b, t0);
+        test(b + 1, t1);
+        test(b + 2, t2);
+        test(b + 3, t3);
+    }
+    for (; b < whi; ++b) test(b, tgt.ml[b]);
+}
+
 // match_triangles (affine.rs:320-384): triangles and votes on the GPU, greedy 1-1 assignment on the
 // host.  Equal-vote pairs are taken in (ref index, tgt index) order (the reference's order is the
 // HashMap iteration order, i.e. unspecified).
@@ -1527,14 +1663,18 @@ ab_status match_stars(ab_ctx *ctx, const std::vector<Pt> &rs, const std::vector<
     const size_t b8 = al((size_t)TRI_MAX * 8), b3 = al((size_t)TRI_MAX * 3), bxy = al(2 * MAX_STARS * 8);
     const size_t o_rxy = 0, o_txy = bxy, o_rm = 2 * bxy, o_rl = o_rm + b8, o_rs = o_rl + b8, o_tm = o_rs + b3;
     const size_t o_tl = o_tm + b8, o_ts = o_tl + b8, o_v = o_ts + b3;
-    const size_t total = o_v + MAX_STARS * MAX_STARS * 4;
+    // votes, then the bucket histograms (cleared with them), then starts / cursors / sorted lists
+    const size_t o_h = o_v + al(MAX_STARS * MAX_STARS * 4), o_st = o_h + al(2 * TRI_NBK * 4);
+    const size_t o_cu = o_st + al(2 * (TRI_NBK + 1) * 4), o_srm = o_cu + al(2 * TRI_NBK * 4);
+    const size_t o_srs = o_srm + 2 * b8, o_stm = o_srs + b3, o_sts = o_stm + 2 * b8;  // (mid, long) pairs + vertices
+    const size_t total = o_sts + b3;
     ab_status st = ab_scratch_reserve(ctx, 2, total);
     if (st != AB_OK) return st;
     char *b = static_cast<char *>(ctx->d_scratch[2]);
     static_assert(sizeof(Pt) == 16, "Pt is two doubles");
     AB_CUDA(ctx, cudaMemcpyAsync(b + o_rxy, rs.data(), rs.size() * sizeof(Pt), cudaMemcpyHostToDevice, s));
     AB_CUDA(ctx, cudaMemcpyAsync(b + o_txy, ts.data(), ts.size() * sizeof(Pt), cudaMemcpyHostToDevice, s));
-    AB_CUDA(ctx, cudaMemsetAsync(b + o_v, 0, MAX_STARS * MAX_STARS * 4, s));
+    AB_CUDA(ctx, cudaMemsetAsync(b + o_v, 0, o_st - o_v, s));
     const bool trace = std::getenv("AB_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
@@ -1543,25 +1683,37 @@ ab_status match_stars(ab_ctx *ctx, const std::vector<Pt> &rs, const std::vector<
         fprintf(stderr, "[ab]   match: %s at %.3f ms\n", what,
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
     };
+    auto dp = [&](size_t off) { return reinterpret_cast<double *>(b + off); };
+    auto bp = [&](size_t off) { return reinterpret_cast<unsigned char *>(b + off); };
+    auto up = [&](size_t off) { return reinterpret_cast<unsigned *>(b + off); };
     const unsigned tb = (TRI_MAX + 127) / 128;
-    build_tri_kernel<<<tb, 128, 0, s>>>(reinterpret_cast<double *>(b + o_rxy), (int)rs.size(), (double)INFINITY,
-                                       MIN_TRIANGLE_SIDE, reinterpret_cast<double *>(b + o_rm),
-                                       reinterpret_cast<double *>(b + o_rl),
-                                       reinterpret_cast<unsigned char *>(b + o_rs));
+    build_tri_kernel<<<tb, 128, 0, s>>>(dp(o_rxy), (int)rs.size(), (double)INFINITY, MIN_TRIANGLE_SIDE, dp(o_rm),
+                                       dp(o_rl), bp(o_rs));
     AB_LAUNCH_CHECK(ctx);
-    build_tri_kernel<<<tb, 128, 0, s>>>(reinterpret_cast<double *>(b + o_txy), (int)ts.size(), -(double)INFINITY,
-                                       MIN_TRIANGLE_SIDE, reinterpret_cast<double *>(b + o_tm),
-                                       reinterpret_cast<double *>(b + o_tl),
-                                       reinterpret_cast<unsigned char *>(b + o_ts));
+    build_tri_kernel<<<tb, 128, 0, s>>>(dp(o_txy), (int)ts.size(), -(double)INFINITY, MIN_TRIANGLE_SIDE, dp(o_tm),
+                                       dp(o_tl), bp(o_ts));
     AB_LAUNCH_CHECK(ctx);
     lap("triangles built");
-    const dim3 grid((TRI_MAX + 255) / 256, (TRI_MAX + TRI_CHUNK - 1) / TRI_CHUNK);
-    tri_match_kernel<<<grid, 256, 0, s>>>(
-        reinterpret_cast<double *>(b + o_rm), reinterpret_cast<double *>(b + o_rl),
-        reinterpret_cast<unsigned char *>(b + o_rs), TRI_MAX, reinterpret_cast<double *>(b + o_tm),
-        reinterpret_cast<double *>(b + o_tl), reinterpret_cast<unsigned char *>(b + o_ts), TRI_MAX,
-        TRIANGLE_TOLERANCE, reinterpret_cast<unsigned *>(b + o_v));
-    AB_LAUNCH_CHECK(ctx);
+    if (std::getenv("AB_TRI_BRUTE")) {  // development switch: the all-pairs kernel (same votes)
+        const dim3 grid((TRI_MAX + 255) / 256, (TRI_MAX + TRI_CHUNK - 1) / TRI_CHUNK);
+        tri_match_kernel<<<grid, 256, 0, s>>>(dp(o_rm), dp(o_rl), bp(o_rs), TRI_MAX, dp(o_tm), dp(o_tl), bp(o_ts),
+                                              TRI_MAX, TRIANGLE_TOLERANCE, up(o_v));
+        AB_LAUNCH_CHECK(ctx);
+    } else {
+        const double inv_w = 1.0 / (TRIANGLE_TOLERANCE * 1.001);
+        const TriList r_in{dp(o_rm), dp(o_rl), bp(o_rs)}, t_in{dp(o_tm), dp(o_tl), bp(o_ts)};
+        const TriSorted r_out{reinterpret_cast<double2 *>(b + o_srm), bp(o_srs)};
+        const TriSorted t_out{reinterpret_cast<double2 *>(b + o_stm), bp(o_sts)};
+        tri_hist_kernel<<<(TRI_MAX + 255) / 256, 256, 0, s>>>(r_in.mid, t_in.mid, inv_w, up(o_h));
+        AB_LAUNCH_CHECK(ctx);
+        tri_scan_kernel<<<2, 1024, 0, s>>>(up(o_h), up(o_st), up(o_cu));
+        AB_LAUNCH_CHECK(ctx);
+        tri_scatter_kernel<<<(TRI_MAX + 255) / 256, 256, 0, s>>>(r_in, t_in, inv_w, up(o_cu), r_out, t_out);
+        AB_LAUNCH_CHECK(ctx);
+        const dim3 grid((TRI_MAX + 127) / 128, (TRI_MAX + TRI_SPAN - 1) / TRI_SPAN);
+        tri_match_bucketed_kernel<<<grid, 128, 0, s>>>(r_out, t_out, up(o_st), inv_w, TRIANGLE_TOLERANCE, up(o_v));
+        AB_LAUNCH_CHECK(ctx);
+    }
     std::vector<unsigned> votes(MAX_STARS * MAX_STARS);
     lap("votes counted");
     AB_CUDA(ctx, cudaMemcpyAsync(votes.data(), b + o_v, votes.size() * 4, cudaMemcpyDeviceToHost, s));

@@ -120,6 +120,30 @@ def test_match_and_ransac_match_oracle(al, orc):
     assert len(al.match_stars(stars, stars)) >= 4
 
 
+@pytest.mark.parametrize("kind", ["uniform", "elongated", "few", "clustered"])
+def test_bucketed_triangle_votes_equal_all_pairs(al, orc, kind, monkeypatch):
+    """The bucket-sorted vote kernel against the all-pairs kernel (AB_TRI_BRUTE) and the oracle: the
+    same matches, also when side ratios run past the last bucket (elongated fields: ratios > 82)."""
+    rng = np.random.default_rng({"uniform": 1, "elongated": 2, "few": 3, "clustered": 4}[kind])
+    if kind == "uniform":
+        ref = rng.uniform(20, 4000, (120, 2))
+    elif kind == "elongated":   # a thin strip: mid / shortest ratios of several hundred
+        ref = np.stack([rng.uniform(0, 8000, 70), rng.uniform(0, 40, 70)], axis=1)
+    elif kind == "few":
+        ref = rng.uniform(20, 600, (7, 2))
+    else:
+        ref = np.concatenate([rng.normal(500, 30, (40, 2)), rng.uniform(0, 3000, (30, 2))])
+    tgt = ref * 1.0005 + np.array([3.25, -7.5]) + rng.normal(0, 0.08, ref.shape)
+    tgt = tgt[rng.permutation(len(tgt))]
+    fast = al.match_stars(ref, tgt)
+    monkeypatch.setenv("AB_TRI_BRUTE", "1")
+    brute = al.match_stars(ref, tgt)
+    monkeypatch.delenv("AB_TRI_BRUTE")
+    assert np.array_equal(fast, brute)
+    assert np.array_equal(fast, orc.match_stars(ref, tgt))
+    assert len(fast) >= 3
+
+
 def test_align_recovers_known_transform(al, orc):
     rows, cols = 1024, 1024
     th = math.radians(0.8)

@@ -87,16 +87,21 @@ def match_stars(ref_xy, tgt_xy, max_matches: int = 256, ctx=None) -> np.ndarray:
     return out[: min(n.value, max_matches)].copy()
 
 
-def ransac_affine(matches, method: str = "affine", n_threads: int = 8):
-    """affine.rs:400-517 -> AlignResultC or None."""
+def ransac_affine(matches, method: str = "affine", n_threads: int = 8, on_gpu: bool = False, ctx=None):
+    """affine.rs:400-517 -> AlignResultC or None.  on_gpu: the affine model's hypotheses on the
+    device (ab_ransac_affine_gpu, what the aligner runs); same result."""
     m = np.ascontiguousarray(matches, np.float64).reshape(-1, 4)
     out = AlignResultC()
     found = C.c_int(0)
-    st = lib().ab_ransac_affine(m.ctypes.data if m.size else None, m.shape[0],
-                                0 if method == "affine" else 1, n_threads, C.addressof(out),
-                                C.byref(found))
-    if st:
-        raise AstroBurstError(st, "ab_ransac_affine")
+    args = (m.ctypes.data if m.size else None, m.shape[0], 0 if method == "affine" else 1, n_threads,
+            C.addressof(out), C.byref(found))
+    if on_gpu:
+        ctx = ctx or default_context()
+        ctx.check(lib().ab_ransac_affine_gpu(ctx.handle, *args))
+    else:
+        st = lib().ab_ransac_affine(*args)
+        if st:
+            raise AstroBurstError(st, "ab_ransac_affine")
     return out if found.value else None
 
 

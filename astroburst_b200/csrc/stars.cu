@@ -1276,15 +1276,15 @@ constexpr double MIN_INLIER_RATIO = 0.20, MAX_RESIDUAL_PX = 5.0, MAX_OFFSET_FRAC
 constexpr double MAX_ROTATION_DEG = 30.0, MIN_SCALE = 0.70, MAX_SCALE = 1.40;
 
 ab_affine aff_identity() { return {1.0, 0.0, 0.0, 0.0, 1.0, 0.0}; }
-inline void amap(const ab_affine &t, double x, double y, double *px, double *py) {
+__host__ __device__ inline void amap(const ab_affine &t, double x, double y, double *px, double *py) {
     *px = t.a * x + t.b * y + t.tx;
     *py = t.c * x + t.d * y + t.ty;
 }
-bool solve_3x3(const double a[3][3], const double b[3], double x[3]) {
+__host__ __device__ inline bool solve_3x3(const double a[3][3], const double b[3], double x[3]) {
     const double det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) -
                        a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
                        a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
-    if (std::fabs(det) < 1e-12) return false;
+    if (fabs(det) < 1e-12) return false;
     const double id = 1.0 / det;
     const double inv[3][3] = {{(a[1][1] * a[2][2] - a[1][2] * a[2][1]) * id,
                                (a[0][2] * a[2][1] - a[0][1] * a[2][2]) * id,
@@ -1298,7 +1298,7 @@ bool solve_3x3(const double a[3][3], const double b[3], double x[3]) {
     for (int i = 0; i < 3; ++i) x[i] = inv[i][0] * b[0] + inv[i][1] * b[1] + inv[i][2] * b[2];
     return true;
 }
-bool solve_ls(const Match *m, size_t n, bool solve_x, double x[3]) {
+__host__ __device__ inline bool solve_ls(const Match *m, size_t n, bool solve_x, double x[3]) {
     double ata[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, atb[3] = {0, 0, 0};
     for (size_t q = 0; q < n; ++q) {
         const double target = solve_x ? m[q].tx : m[q].ty;
@@ -1310,7 +1310,7 @@ bool solve_ls(const Match *m, size_t n, bool solve_x, double x[3]) {
     }
     return solve_3x3(ata, atb, x);
 }
-bool fit_affine(const Match *m, size_t n, ab_affine *t) {
+__host__ __device__ inline bool fit_affine(const Match *m, size_t n, ab_affine *t) {
     if (n < 3) return false;
     double ab[3], cd[3];
     if (!solve_ls(m, n, true, ab) || !solve_ls(m, n, false, cd)) return false;
@@ -1427,6 +1427,143 @@ bool ransac(const std::vector<Match> &matches, int method, int n_threads_in, ab_
     res->residual_px = res_px;
     res->method = method;
     return true;
+}
+// ---- ransac_affine, method "affine", on the device ---------------------------------------------
+// The hypotheses are independent: one thread per RANSAC iteration fits its 3-match sample and
+// counts inliers; atomicMax on (inliers, first iteration wins ties) is exactly the reference's
+// "strictly greater replaces" scan over the chunks in order (affine.rs:426-478); one thread then
+// refits on the winner's inliers and takes the residual.  Only + - * / sqrt in f64 (no FMA
+// contraction: -fmad=false), so every number equals the host code's.  The xorshift sample indices
+// come from the host (a few thousand integer draws, sequential per chunk by construction).
+// The rigid model (atan2 / sin / cos, whose device versions round differently) stays host code.
+struct RansacOut {
+    ab_affine refined;
+    double residual;
+    unsigned long long inliers;
+};
+__device__ __forceinline__ bool is_inlier(const ab_affine &t, const Match &q) {
+    double px, py;
+    amap(t, q.rx, q.ry, &px, &py);
+    const double ex = px - q.tx, ey = py - q.ty;
+    return sqrt(ex * ex + ey * ey) < RANSAC_INLIER_PX;
+}
+__global__ void __launch_bounds__(128)
+ransac_hypotheses_kernel(const Match *__restrict__ m, int n, const unsigned short *__restrict__ samples,
+                         int n_iter, unsigned long long *__restrict__ best_key) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_iter) return;
+    const unsigned short s0 = samples[3 * i], s1 = samples[3 * i + 1], s2 = samples[3 * i + 2];
+    if (s0 == 0xffffu) return;  // no 3 distinct draws in 20 attempts: the iteration is skipped
+    const Match sm[3] = {m[s0], m[s1], m[s2]};
+    ab_affine t;
+    if (!fit_affine(sm, 3, &t)) return;
+    unsigned inl = 0;
+    for (int q = 0; q < n; ++q) inl += is_inlier(t, m[q]) ? 1u : 0u;
+    if (inl) atomicMax(best_key, ((unsigned long long)inl << 32) | (0xffffffffu - (unsigned)i));
+}
+__global__ void ransac_refine_kernel(const Match *__restrict__ m, int n, const unsigned short *__restrict__ samples,
+                                     const unsigned long long *__restrict__ best_key, RansacOut *__restrict__ out) {
+    const unsigned long long key = *best_key;
+    out->inliers = key >> 32;
+    out->residual = 0.0;
+    out->refined = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0};
+    if (key == 0) return;
+    const unsigned i = 0xffffffffu - (unsigned)(key & 0xffffffffu);
+    const Match sm[3] = {m[samples[3 * i]], m[samples[3 * i + 1]], m[samples[3 * i + 2]]};
+    ab_affine best;
+    fit_affine(sm, 3, &best);
+    // fit_affine over the inliers in list order (solve_ls accumulates row by row)
+    ab_affine refined = best;
+    double xs[2][3];
+    bool ok = (key >> 32) >= 3;
+    for (int pass = 0; pass < 2 && ok; ++pass) {
+        double ata[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, atb[3] = {0, 0, 0};
+        for (int q = 0; q < n; ++q) {
+            if (!is_inlier(best, m[q])) continue;
+            const double target = pass == 0 ? m[q].tx : m[q].ty;
+            const double row[3] = {m[q].rx, m[q].ry, 1.0};
+            for (int a = 0; a < 3; ++a) {
+                for (int b = 0; b < 3; ++b) ata[a][b] += row[a] * row[b];
+                atb[a] += row[a] * target;
+            }
+        }
+        ok = solve_3x3(ata, atb, xs[pass]);
+    }
+    if (ok) refined = {xs[0][0], xs[0][1], xs[0][2], xs[1][0], xs[1][1], xs[1][2]};
+    double sum = 0.0;
+    unsigned cnt = 0;
+    for (int q = 0; q < n; ++q) {
+        if (!is_inlier(best, m[q])) continue;
+        double px, py;
+        amap(refined, m[q].rx, m[q].ry, &px, &py);
+        const double ex = px - m[q].tx, ey = py - m[q].ty;
+        sum += sqrt(ex * ex + ey * ey);
+        ++cnt;
+    }
+    out->refined = refined;
+    out->residual = cnt ? sum / (double)cnt : 0.0;
+}
+// method 0 of ransac() with the hypotheses on the device; *found as ransac()'s return value
+ab_status ransac_affine_device(ab_ctx *ctx, const std::vector<Match> &matches, int n_threads_in, cudaStream_t s,
+                               ab_align_result *res, bool *found) {
+    *found = false;
+    const size_t n = matches.size();
+    if (n < 3) return AB_OK;
+    if (n >= 0xffffu) {  // (sample indices travel as u16; star lists hold <= 120 matches)
+        *found = ransac(matches, 0, n_threads_in, res);
+        return AB_OK;
+    }
+    const size_t num_threads = (size_t)std::max(n_threads_in, 1);
+    const size_t chunk = (RANSAC_ITERATIONS + num_threads - 1) / num_threads;
+    const size_t n_iter = chunk * num_threads;
+    std::vector<unsigned short> samples(3 * n_iter);
+    for (size_t tid = 0; tid < num_threads; ++tid) {  // the draws of ransac(), nothing else
+        uint64_t state = 0xDEADBEEFCAFEBABEull + (uint64_t)tid * 0x9E3779B97F4A7C15ull;
+        for (size_t it = 0; it < chunk; ++it) {
+            size_t sample[3], ns = 0;
+            int attempts = 0;
+            while (ns < 3 && attempts < 20) {
+                state ^= state << 13;
+                state ^= state >> 7;
+                state ^= state << 17;
+                const size_t idx = (size_t)(state % (uint64_t)n);
+                bool has = false;
+                for (size_t q = 0; q < ns; ++q) has |= sample[q] == idx;
+                if (!has) sample[ns++] = idx;
+                ++attempts;
+            }
+            unsigned short *o = &samples[3 * (tid * chunk + it)];
+            for (int q = 0; q < 3; ++q) o[q] = ns == 3 ? (unsigned short)sample[q] : (unsigned short)0xffffu;
+        }
+    }
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t o_m = 0, o_s = al(n * sizeof(Match)), o_k = o_s + al(samples.size() * 2), o_o = o_k + 256;
+    ab_status st = ab_scratch_reserve(ctx, 2, o_o + sizeof(RansacOut));  // (the matcher's slot: its data is dead)
+    if (st != AB_OK) return st;
+    char *b = static_cast<char *>(ctx->d_scratch[2]);
+    AB_CUDA(ctx, cudaMemcpyAsync(b + o_m, matches.data(), n * sizeof(Match), cudaMemcpyHostToDevice, s));
+    AB_CUDA(ctx, cudaMemcpyAsync(b + o_s, samples.data(), samples.size() * 2, cudaMemcpyHostToDevice, s));
+    AB_CUDA(ctx, cudaMemsetAsync(b + o_k, 0, 8, s));
+    const Match *d_m = reinterpret_cast<const Match *>(b + o_m);
+    const unsigned short *d_s = reinterpret_cast<const unsigned short *>(b + o_s);
+    unsigned long long *d_k = reinterpret_cast<unsigned long long *>(b + o_k);
+    ransac_hypotheses_kernel<<<(unsigned)((n_iter + 127) / 128), 128, 0, s>>>(d_m, (int)n, d_s, (int)n_iter, d_k);
+    AB_LAUNCH_CHECK(ctx);
+    ransac_refine_kernel<<<1, 1, 0, s>>>(d_m, (int)n, d_s, d_k, reinterpret_cast<RansacOut *>(b + o_o));
+    AB_LAUNCH_CHECK(ctx);
+    RansacOut h;
+    AB_CUDA(ctx, cudaMemcpyAsync(&h, b + o_o, sizeof(h), cudaMemcpyDeviceToHost, s));
+    AB_CUDA(ctx, cudaStreamSynchronize(s));
+    if (h.inliers < MIN_MATCHES_RIGID) return AB_OK;
+    if ((double)h.inliers / (double)n < MIN_INLIER_RATIO) return AB_OK;
+    if (h.residual > MAX_RESIDUAL_PX) return AB_OK;
+    res->transform = h.refined;
+    res->matched_stars = n;
+    res->inliers = h.inliers;
+    res->residual_px = h.residual;
+    res->method = 0;
+    *found = true;
+    return AB_OK;
 }
 bool sane(const ab_align_result &r, size_t rows, size_t cols) {
     const ab_affine &t = r.transform;
@@ -1777,7 +1914,12 @@ ab_status align_with_ref_points(ab_ctx *ctx, const std::vector<Pt> &rs, const fl
     if (matches.size() < MIN_MATCHES_RIGID) return fallback(ctx, d_ref, d_tgt, rows, cols, s, out);
     const auto t2 = now();
     ab_align_result r;
-    bool done = matches.size() >= MIN_MATCHES_AFFINE && ransac(matches, 0, n_threads, &r) && sane(r, rows, cols);
+    bool done = false;
+    if (matches.size() >= MIN_MATCHES_AFFINE) {
+        st = ransac_affine_device(ctx, matches, n_threads, s, &r, &done);
+        if (st != AB_OK) return st;
+        done = done && sane(r, rows, cols);
+    }
     if (!done) done = ransac(matches, 1, n_threads, &r) && sane(r, rows, cols);
     if (trace)
         fprintf(stderr, "[ab] align %zux%zu: normalise+detect %.2f ms, triangles+votes+assign %.2f ms (%zu matches), "
@@ -2104,6 +2246,25 @@ ab_status ab_ransac_affine(const double *matches, size_t n, int method, int n_th
         m[i] = {matches[4 * i], matches[4 * i + 1], matches[4 * i + 2], matches[4 * i + 3]};
     *found = ransac(m, method, n_threads, out) ? 1 : 0;
     return AB_OK;
+}
+// the same result with the hypotheses of the affine model evaluated on the GPU (what ab_align_affine
+// runs); the rigid model is host code in both
+ab_status ab_ransac_affine_gpu(ab_ctx *ctx, const double *matches, size_t n, int method, int n_threads,
+                               ab_align_result *out, int *found) {
+    if (!ctx || !out || !found || (n && !matches)) return AB_ERR_INVALID;
+    CtxLock lk(ctx->mu);
+    std::vector<Match> m(n);
+    for (size_t i = 0; i < n; ++i)
+        m[i] = {matches[4 * i], matches[4 * i + 1], matches[4 * i + 2], matches[4 * i + 3]};
+    if (method != 0) {
+        *found = ransac(m, method, n_threads, out) ? 1 : 0;
+        return AB_OK;
+    }
+    bool f = false;
+    AB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const ab_status st = ransac_affine_device(ctx, m, n_threads, ctx->stream, out, &f);
+    *found = f ? 1 : 0;
+    return st;
 }
 
 }  // extern "C"

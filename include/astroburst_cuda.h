@@ -572,6 +572,12 @@ ab_status ab_match_stars(ab_ctx *ctx, const double *ref_xy, size_t n_ref, const 
 /* ransac_affine, affine.rs:400-517 (host scalar code); *found = 0 where the reference returns None */
 ab_status ab_ransac_affine(const double *matches, size_t n, int method, int n_threads,
                            ab_align_result *out, int *found);
+/* The same function with the 2,000 hypotheses of the affine model evaluated on the GPU (one thread
+ * per iteration, atomicMax on (inliers, earliest iteration), refit on the device) -- the variant
+ * ab_align_affine* run.  Bit-identical to ab_ransac_affine; method 1 (rigid: atan2/sin/cos) is host
+ * code in both. */
+ab_status ab_ransac_affine_gpu(ab_ctx *ctx, const double *matches, size_t n, int method, int n_threads,
+                               ab_align_result *out, int *found);
 
 /* ---------------------------------------------------------------- preview / export tail
  * Preview size of render_rgb_preview(_with_stf), cmd/helpers.rs:222-227: planes that fit max_dim

@@ -113,6 +113,11 @@ def test_match_and_ransac_match_oracle(al, orc):
         for nt in (1, 8, 16):
             r, o = al.ransac_affine(m, method, nt), orc.ransac(om, method, nt)
             assert (r is None) == (o is None)
+            g = al.ransac_affine(m, method, nt, on_gpu=True)   # hypotheses on the device: same bits
+            assert (g is None) == (o is None)
+            if g is not None:
+                assert tuple(getattr(g.transform, k) for k in "a b tx c d ty".split()) == o.transform.as_tuple()
+                assert (g.inliers, g.matched_stars, g.residual_px) == (o.inliers, o.matched_stars, o.residual_px)
             if r is not None:
                 assert tuple(getattr(r.transform, k) for k in "a b tx c d ty".split()) == o.transform.as_tuple()
                 assert (r.inliers, r.matched_stars, r.residual_px) == (o.inliers, o.matched_stars, o.residual_px)
@@ -142,6 +147,24 @@ def test_bucketed_triangle_votes_equal_all_pairs(al, orc, kind, monkeypatch):
     assert np.array_equal(fast, brute)
     assert np.array_equal(fast, orc.match_stars(ref, tgt))
     assert len(fast) >= 3
+
+
+@pytest.mark.parametrize("seed,n,outliers,noise", [(1, 60, 0, 0.05), (2, 60, 25, 0.3), (3, 9, 3, 0.1), (4, 6, 0, 0.0),
+                                                   (5, 120, 80, 1.0), (6, 40, 38, 0.2), (7, 3, 0, 0.0)])
+def test_device_ransac_matches_oracle(al, orc, seed, n, outliers, noise):
+    """ab_ransac_affine_gpu against the oracle on clean, contaminated, tiny and hopeless match lists."""
+    rng = np.random.default_rng(seed)
+    ref = rng.uniform(0, 4000, (n, 2))
+    A = np.array([[0.999, -0.012], [0.011, 1.002]])
+    tgt = ref @ A.T + np.array([-20.5, 14.25]) + rng.normal(0, noise, ref.shape)
+    tgt[:outliers] = rng.uniform(0, 4000, (outliers, 2))
+    m = np.concatenate([ref, tgt], axis=1)
+    for nt in (1, 8, 7):
+        g, o = al.ransac_affine(m, "affine", nt, on_gpu=True), orc.ransac(m, "affine", nt)
+        assert (g is None) == (o is None)
+        if g is not None:
+            assert tuple(getattr(g.transform, k) for k in "a b tx c d ty".split()) == o.transform.as_tuple()
+            assert (g.inliers, g.matched_stars, g.residual_px) == (o.inliers, o.matched_stars, o.residual_px)
 
 
 def test_align_recovers_known_transform(al, orc):

@@ -35,8 +35,9 @@ __device__ __forceinline__ size_t clamp_index(long long idx, size_t len) {
     return (size_t)idx;
 }
 
-__device__ __forceinline__ float bicubic_sample(const float *__restrict__ s, size_t rows,
-                                                size_t cols, double y, double x) {
+// bicubic_sample exactly as written in the reference (any coordinate, any plane size)
+__device__ __noinline__ float bicubic_sample_generic(const float *__restrict__ s, size_t rows,
+                                                     size_t cols, double y, double x) {
     const double fxf = floor(x), fyf = floor(y);
     // `as i64` saturates; NaN -> 0
     const long long ix = (x == x) ? (long long)fxf : 0;
@@ -58,6 +59,57 @@ __device__ __forceinline__ float bicubic_sample(const float *__restrict__ s, siz
         row_val += (double)__ldg(row + c2) * wx2;
         row_val += (double)__ldg(row + c3) * wx3;
         val += row_val * catmull_rom(fy - (double)(j - 1));
+    }
+    return (float)val;
+}
+
+// The two polynomial pieces of catmull_rom.  For a fractional offset f in [0, 1] the four taps sit
+// at |t| = f + 1, f, 1 - f, 2 - f, so the piece each tap takes is known up front; where an argument
+// rounds onto the joint |t| = 1 both pieces give exactly +0, so picking the piece statically
+// returns the same bits as the reference's comparisons (the f64 operations are the same ones).
+__device__ __forceinline__ double cr_near(double a) { return a * a * (1.5 * a - 2.5) + 1.0; }       // |t| <= 1
+__device__ __forceinline__ double cr_far(double a) { return a * (a * (2.5 - 0.5 * a) - 4.0) + 2.0; }  // 1 <= |t| <= 2
+
+// The same value on the common path: coordinates inside a plane of < 2^31 pixels per side, so the
+// tap indices are 32-bit, the fractional parts are x - floor(x) (== x - (double)(i64)floor(x)) and
+// interior pixels need no clamping.  Everything else goes to bicubic_sample_generic.
+__device__ __forceinline__ float bicubic_sample(const float *__restrict__ s, size_t rows,
+                                                size_t cols, double y, double x) {
+    const double fxf = floor(x), fyf = floor(y);
+    const double fx = x - fxf, fy = y - fyf;
+    const bool plain = fxf >= -2.0 && fyf >= -2.0 && fxf <= (double)cols && fyf <= (double)rows &&
+                       fx >= 0.0 && fx <= 1.0 && fy >= 0.0 && fy <= 1.0 && rows < 0x7ffffff0u &&
+                       cols < 0x7ffffff0u;
+    if (!plain) return bicubic_sample_generic(s, rows, cols, y, x);
+    const int ix = (int)fxf, iy = (int)fyf, nc = (int)cols, nr = (int)rows;
+    const double wx0 = cr_far(fx + 1.0), wx1 = cr_near(fx), wx2 = cr_near(fabs(fx - 1.0)),
+                 wx3 = cr_far(fabs(fx - 2.0));
+    const double wy[4] = {cr_far(fy + 1.0), cr_near(fy), cr_near(fabs(fy - 1.0)), cr_far(fabs(fy - 2.0))};
+    double val = 0.0;
+    if (ix >= 1 && iy >= 1 && ix + 2 < nc && iy + 2 < nr) {
+        const float *p = s + (size_t)(iy - 1) * cols + (size_t)(ix - 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j, p += cols) {
+            double row_val = 0.0;
+            row_val += (double)__ldg(p) * wx0;
+            row_val += (double)__ldg(p + 1) * wx1;
+            row_val += (double)__ldg(p + 2) * wx2;
+            row_val += (double)__ldg(p + 3) * wx3;
+            val += row_val * wy[j];
+        }
+    } else {
+        const int c0 = min(max(ix - 1, 0), nc - 1), c1 = min(max(ix, 0), nc - 1), c2 = min(max(ix + 1, 0), nc - 1),
+                  c3 = min(max(ix + 2, 0), nc - 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float *row = s + (size_t)min(max(iy + j - 1, 0), nr - 1) * cols;
+            double row_val = 0.0;
+            row_val += (double)__ldg(row + c0) * wx0;
+            row_val += (double)__ldg(row + c1) * wx1;
+            row_val += (double)__ldg(row + c2) * wx2;
+            row_val += (double)__ldg(row + c3) * wx3;
+            val += row_val * wy[j];
+        }
     }
     return (float)val;
 }

@@ -1881,10 +1881,17 @@ ab_status align_star_points(ab_ctx *ctx, const float *d_img, size_t rows, size_t
     std::vector<ab_star> st;
     double bm, bs;
     Norm nm;
+    const bool trace = std::getenv("AB_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     ab_status rc = normalize_params(ctx, d_img, rows * cols, s, &nm);
     if (rc != AB_OK) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     rc = detect_on_device(ctx, d_img, rows, cols, nm, DETECTION_SIGMA, s, st, &bm, &bs, MAX_STARS);
     if (rc != AB_OK) return rc;
+    if (trace)
+        fprintf(stderr, "[ab]   star points: normalise parameters %.3f ms, detect %.3f ms\n",
+                std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     pts.clear();
     for (size_t i = 0; i < std::min(st.size(), (size_t)MAX_STARS); ++i) pts.push_back({st[i].x, st[i].y});
     return AB_OK;

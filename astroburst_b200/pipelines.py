@@ -183,9 +183,12 @@ def align_ref_stars(ref_ptr: int, rows: int, cols: int, ctx: Context | None = No
 
 
 def align_and_warp_with_ref(ref_xy: np.ndarray, ref_ptr: Optional[int], tgt_ptr: int, out_ptr: int, rows: int,
-                            cols: int, n_threads: int = 8, ctx: Context | None = None, stream: int = 0) -> AlignResultC:
+                            cols: int, n_threads: int = 8, ctx: Context | None = None, stream: int = 0,
+                            warp_stream: Optional[int] = None) -> AlignResultC:
     """align_and_warp with the reference's star list given (broadcast to the GPU that holds the
-    target); `ref_ptr` = None when the reference plane is not on this GPU."""
+    target); `ref_ptr` = None when the reference plane is not on this GPU.  The aligner returns
+    after its last device read of the target, so the warp may go to another stream (`warp_stream`)
+    and overlap the next frame's detection; the caller synchronises that stream before using `out`."""
     ctx = ctx or default_context()
     res = AlignResultC()
     s = stream if stream else None
@@ -193,5 +196,5 @@ def align_and_warp_with_ref(ref_xy: np.ndarray, ref_ptr: Optional[int], tgt_ptr:
     ctx.check(lib().ab_align_affine_with_ref_dev(ctx.handle, xy.ctypes.data, len(xy), ref_ptr, tgt_ptr, rows, cols,
                                                  n_threads, C.addressof(res), s))
     ctx.check(lib().ab_warp_affine_bicubic_dev(ctx.handle, tgt_ptr, rows, cols, C.addressof(res.transform), rows, cols,
-                                               out_ptr, s))
+                                               out_ptr, warp_stream if warp_stream is not None else s))
     return res

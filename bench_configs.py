@@ -239,6 +239,7 @@ def run_config3(torch, dist, ab, ctx, dev, rank, world, reps=2, n_frames=16, R=8
     outs = {f: torch.empty((R, R), dtype=torch.float32, device=dev) for f in mine if f != 0}
     results = {}
     xy_dev = torch.zeros((121, 2), dtype=torch.float64, device=dev)
+    warp_side = torch.cuda.Stream(device=dev)   # warps overlap the next frame's detection
 
     def pipeline():
         # reference star list once, on the rank that holds frame 0, broadcast (<= 1.9 KB) to the others
@@ -257,7 +258,7 @@ def run_config3(torch, dist, ab, ctx, dev, rank, world, reps=2, n_frames=16, R=8
                 continue
             ref_ptr = frames[0].data_ptr() if 0 in frames else None
             results[f] = pipelines.align_and_warp_with_ref(ref_xy, ref_ptr, frames[f].data_ptr(), outs[f].data_ptr(),
-                                                           R, R, 16, ctx, stream)
+                                                           R, R, 16, ctx, stream, warp_stream=warp_side.cuda_stream)
 
     pipeline()
     ms = _wall_max(torch, dist, world, dev, pipeline, reps)

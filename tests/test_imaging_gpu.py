@@ -266,3 +266,34 @@ def test_warp_shift_resample_bit_exact(im, orc):
     ramp = np.arange(2500, dtype=np.float32).reshape(50, 50)                       # affine.rs:789-800
     w = im.warp_image(ramp, (1, 0, 0, 0, 1, 0), 50, 50)
     assert np.abs(w[2:48, 2:48] - ramp[2:48, 2:48]).max() < 0.5
+
+
+def test_bicubic_weight_joints_and_odd_inputs(im, orc):
+    """The statically chosen Catmull-Rom pieces against the reference's comparisons where they could
+    differ: fractions that round onto 0 / 1 (taps exactly on the joints |t| = 1, 2), integer
+    coordinates, non-finite samples and transforms, planes smaller than the 4 x 4 footprint."""
+    img = sky(64, 80, seed=3, pad=False)
+    eps = np.finfo(np.float64).eps
+    for dy, dx in ((-1e-20, -1e-20), (-eps / 4, eps / 4), (1 - eps / 2, 1 - eps / 2), (-0.5, -0.5), (2.0, 3.0),
+                   (1e-300, -1e-300), (0.5 - eps, 63.5), (-0.49999999999999994, 79.49999999999999)):
+        assert np.array_equal(im.shift_image_subpixel(img, dy, dx), orc.shift_image_subpixel(img, dy, dx)), (dy, dx)
+    for t in ((1, 0, 1e-17, 0, 1, 1e-17), (1, 0, 1 - eps / 2, 0, 1, 2 - eps), (1, 1e-18, 0, 1e-18, 1, 0),
+              (1, 0, float("nan"), 0, 1, 0), (float("inf"), 0, 0, 0, 1, 0), (0, 0, 5.0, 0, 0, 7.0), (-1, 0, 70.0, 0, -1, 60.0)):
+        a, b = im.warp_image(img, t, 64, 80), orc.warp_image(img, t, 64, 80)
+        assert np.array_equal(a, b, equal_nan=True), t
+    bad = img.copy()
+    bad[10, 10], bad[20, 30], bad[40, 5] = np.nan, np.inf, -np.inf
+    for t in ((1, 0, 0.25, 0, 1, 0.5), (1, 0, 0, 0, 1, 0)):
+        a, b = im.warp_image(bad, t, 64, 80), orc.warp_image(bad, t, 64, 80)
+        assert np.array_equal(a, b, equal_nan=True) and np.array_equal(np.signbit(a), np.signbit(b))
+    assert np.array_equal(im.shift_image_subpixel(bad, 0.3, -0.7), orc.shift_image_subpixel(bad, 0.3, -0.7), equal_nan=True)
+    for shape in ((1, 1), (2, 3), (3, 2), (4, 4), (1, 9)):
+        tiny = sky(*shape, seed=5, pad=False)
+        assert np.array_equal(im.shift_image_subpixel(tiny, 0.25, -0.25), orc.shift_image_subpixel(tiny, 0.25, -0.25))
+        assert np.array_equal(im.resample_image(tiny, 7, 5), orc.resample_image(tiny, 7, 5))
+        assert np.array_equal(im.warp_image(tiny, (1, 0, 0.5, 0, 1, 0.5), 6, 6), orc.warp_image(tiny, (1, 0, 0.5, 0, 1, 0.5), 6, 6))
+    zeros = np.zeros((32, 32), np.float32)
+    neg = -sky(32, 32, seed=6, pad=False)
+    for plane in (zeros, neg):   # signed zeros of the result
+        a, b = im.shift_image_subpixel(plane, 0.5, 0.5), orc.shift_image_subpixel(plane, 0.5, 0.5)
+        assert np.array_equal(a, b) and np.array_equal(np.signbit(a), np.signbit(b))

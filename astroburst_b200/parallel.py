@@ -367,3 +367,34 @@ def reshard_frames_to_bands_p2p(cubes: PeerCubes, n_frames: int, rows: int, cols
         cubes.ctx.handle, bases, cubes.world, cubes.rank, int(n_frames), int(rows), int(cols),
         int(band_cube_ptr) if band_cube_ptr else None, int(stream) if stream else None))
     return row_band(rows, cubes.rank, cubes.world)
+
+
+# ------------------------------------------------------------------------- host placement
+def bind_to_gpu_numa(device_index: int) -> str:
+    """Restrict this process (one per GPU) to the CPUs NVML reports as local to the GPU, so that
+    pinned host buffers allocated afterwards land on the GPU's NUMA node and host<->device copies
+    do not cross the socket interconnect.  Returns a one-line description of what was done; never
+    raises (placement is an optimisation, results do not depend on it)."""
+    import os
+
+    if os.environ.get("AB_NO_NUMA_BIND"):
+        return "off (AB_NO_NUMA_BIND)"
+    try:
+        import pynvml as n
+        import torch
+
+        n.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            h = n.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            h = n.nvmlDeviceGetHandleByIndex(device_index)
+        words = n.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "unchanged (no local CPUs inside the current affinity mask)"
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} CPUs local to GPU {device_index} (NVML cpu affinity)"
+    except Exception as e:  # no NVML, no permission, ...
+        return f"unchanged ({type(e).__name__})"

@@ -450,6 +450,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from astroburst_b200 import parallel as ab_parallel
+    all_cpus = os.sched_getaffinity(0)
+    placement = ab_parallel.bind_to_gpu_numa(local)   # before any pinned allocation
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -556,7 +559,8 @@ def main():
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "Mpix/s",
                     "h2d_bytes_per_step": N_FRAMES * npix * 4, "d2h_bytes_per_step": npix * 4 + 8,
-                    "steps": args.e2e_steps, "matches_device_path": e2e_same},
+                    "steps": args.e2e_steps, "matches_device_path": e2e_same,
+                    "host_placement": placement},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": _ncu_traffic(),
                          "traffic_source": "committed ncu --set full capture of this command "
@@ -566,6 +570,7 @@ def main():
                          "kernel_ms": kern_ms, "algorithmic_bytes": ALGO_BYTES},
         }
         if not args.no_cpu_baseline and world == 1:
+            os.sched_setaffinity(0, all_cpus)   # the CPU leg gets every host core back
             sample_rows = ROWS  # the whole stack: ~1 s on 16 host cores (~15 core-seconds)
             r0 = 0
             band = [f[r0:r0 + sample_rows].cpu().numpy() for f in frames]

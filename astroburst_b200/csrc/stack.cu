@@ -17,7 +17,7 @@ namespace abk {
 // [P, npix] f32 view of the frame cube, box = box_px pixels x P frames, no swizzle: the tile lands
 // in shared memory as stage[f][pixel], exactly what the per-thread column reads expect.
 bool ab_make_stack_tmap(ab_ctx *ctx, const float *base, size_t npix, size_t plane_stride_elems,
-                        int P, int box_px, TmapParam *out) {
+                        int P, int box_px, TmapParam *out, int n_rows) {
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -32,7 +32,9 @@ bool ab_make_stack_tmap(ab_ctx *ctx, const float *base, size_t npix, size_t plan
         ctx->encode_tmap_fn = fn;
     }
     static_assert(sizeof(CUtensorMap) == sizeof(TmapParam), "CUtensorMap is 128 bytes");
-    const cuuint64_t gdim[2] = {(cuuint64_t)npix, (cuuint64_t)P};
+    // n_rows < P: the cube holds fewer frames than the kernel's box; the missing rows arrive as NaN
+    // (out-of-bounds fill), i.e. as samples the finite filter drops
+    const cuuint64_t gdim[2] = {(cuuint64_t)npix, (cuuint64_t)n_rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)plane_stride_elems * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)box_px, (cuuint32_t)P};
     const cuuint32_t estride[2] = {1, 1};
@@ -40,7 +42,7 @@ bool ab_make_stack_tmap(ab_ctx *ctx, const float *base, size_t npix, size_t plan
         reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
         const_cast<float *>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        n_rows < P ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -82,6 +84,28 @@ ab_status ab_stack_launch(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_
             break;
     }
 #undef AB_CASE
+    // 33..63 frames without a kernel of their own: the next register kernel up, its missing frames
+    // delivered as NaN by the tensor map (frames the finite filter drops, combine.rs:170-175, so
+    // the result is the same stack).  Needs the frames as one aligned constant-stride cube; the
+    // kernel falls back to the deep path itself when the tensor map cannot be built.
+    if (n_frames > 32 && n_frames < 64 && !peer_frames && npix < ((size_t)1 << 31)) {
+        const ptrdiff_t stride = ft.p[1] - ft.p[0];
+        bool cube = stride > 0 && (stride % 4) == 0 && (size_t)stride >= npix && ctx->stack_variant != 2;
+        for (int f = 0; cube && f < n_frames; ++f)
+            cube = (reinterpret_cast<uintptr_t>(ft.p[f]) & 15) == 0 && (f == 0 || ft.p[f] - ft.p[f - 1] == stride);
+        if (cube) {
+            const int padded = n_frames <= 36 ? 36 : n_frames <= 40 ? 40 : n_frames <= 48 ? 48 : n_frames <= 56 ? 56 : 64;
+            FrameTable pt;
+            for (int f = 0; f < AB_MAX_FRAMES; ++f) pt.p[f] = f < n_frames ? ft.p[f] : nullptr;  // null = padding
+            switch (padded) {
+                case 36: return abk::launch_tile<36>(ctx, pt, npix, sigma_low, sigma_high, max_iter, d_out, d_rejected, stream);
+                case 40: return abk::launch_tile<40>(ctx, pt, npix, sigma_low, sigma_high, max_iter, d_out, d_rejected, stream);
+                case 48: return abk::launch_tile<48>(ctx, pt, npix, sigma_low, sigma_high, max_iter, d_out, d_rejected, stream);
+                case 56: return abk::launch_tile<56>(ctx, pt, npix, sigma_low, sigma_high, max_iter, d_out, d_rejected, stream);
+                default: return abk::launch_tile<64>(ctx, pt, npix, sigma_low, sigma_high, max_iter, d_out, d_rejected, stream);
+            }
+        }
+    }
     AB_CUDA(ctx, cudaMemsetAsync(d_rejected, 0, sizeof(unsigned long long), stream));
     DeepPre pre{};
     pre.peer_frames = peer_frames ? 1 : 0;

@@ -1011,22 +1011,39 @@ ab_status launch_ldg(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, f
 
 // Host side of the tensor map (stack.cu): encodes a [P, npix] f32 view with a box_px x P box.
 bool ab_make_stack_tmap(ab_ctx *ctx, const float *base, size_t npix, size_t plane_stride_elems,
-                        int P, int box_px, TmapParam *out);
+                        int P, int box_px, TmapParam *out, int n_rows);
 
 template <int P, int MN, int MD>
 ab_status launch_mix(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, float sh,
                      unsigned max_iter, float *d_out, unsigned long long *d_rej,
                      cudaStream_t stream) {
+    // trailing null frames = padding (ab_stack_launch, 33..63 frames on the next kernel up): the
+    // cube has n_real rows, the tensor map fills the box's other rows with NaN
+    int n_real = P;
+    while (n_real > 1 && !ft.p[n_real - 1]) --n_real;
+    const bool padded = n_real < P;
+    auto deep = [&](const FrameTable &t, size_t n, float *o) {  // padded mode's way out
+        DeepPre pre{};
+        return ab_stack_launch_deep(ctx, t, n_real, n, sl, sh, max_iter, pre, o, d_rej, stream);
+    };
     bool al = ctx->stack_variant != 2;  // AB_STACK_VARIANT=2: plain loads everywhere
-    for (int f = 0; f < P; ++f) al = al && ((reinterpret_cast<uintptr_t>(ft.p[f]) & 15) == 0);
+    for (int f = 0; f < n_real; ++f) al = al && ((reinterpret_cast<uintptr_t>(ft.p[f]) & 15) == 0);
     const size_t groups = al && npix < ((size_t)1 << 31) ? npix / 32 : 0;
+    if (padded && !groups) {
+        AB_CUDA(ctx, cudaMemsetAsync(d_rej, 0, sizeof(unsigned long long), stream));
+        return deep(ft, npix, d_out);
+    }
     if (groups) {
-        bool cube = P > 1 && !ctx->force_tma1d;
+        bool cube = P > 1 && (!ctx->force_tma1d || padded);
         const ptrdiff_t stride = P > 1 ? ft.p[1] - ft.p[0] : 0;
-        for (int f = 1; cube && f < P; ++f) cube = (ft.p[f] - ft.p[f - 1]) == stride;
+        for (int f = 1; cube && f < n_real; ++f) cube = (ft.p[f] - ft.p[f - 1]) == stride;
         cube = cube && stride > 0 && (stride % 4) == 0 && (size_t)stride >= npix;
         TmapParam tm{};
-        if (cube) cube = ab_make_stack_tmap(ctx, ft.p[0], npix, (size_t)stride, P, 32, &tm);
+        if (cube) cube = ab_make_stack_tmap(ctx, ft.p[0], npix, (size_t)stride, P, 32, &tm, n_real);
+        if (padded && !cube) {
+            AB_CUDA(ctx, cudaMemsetAsync(d_rej, 0, sizeof(unsigned long long), stream));
+            return deep(ft, npix, d_out);
+        }
         // scattered frames: P small bulk copies per group measured slower (1.18 ms) than plain
         // coalesced loads (0.92 ms) -> only the tensor-map form is used unless forced
         if (!cube && !ctx->force_tma1d) {
@@ -1055,6 +1072,11 @@ ab_status launch_mix(ab_ctx *ctx, const FrameTable &ft, size_t npix, float sl, f
         AB_CUDA(ctx, cudaMemsetAsync(d_rej, 0, sizeof(unsigned long long), stream));
     }
     const size_t done = groups * 32;
+    if (padded && done < npix) {  // ragged tail of a padded launch: the deep kernel adds its rejects
+        FrameTable tail;
+        for (int f = 0; f < AB_MAX_FRAMES; ++f) tail.p[f] = f < n_real ? ft.p[f] + done : nullptr;
+        return deep(tail, npix - done, d_out + done);
+    }
     if (done < npix) {  // ragged tail (or everything, for unaligned frames): plain loads
         FrameTable tail;
         for (int f = 0; f < AB_MAX_FRAMES; ++f) tail.p[f] = f < P ? ft.p[f] + done : nullptr;

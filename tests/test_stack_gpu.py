@@ -260,6 +260,45 @@ def test_deep_ragged_unaligned_and_gaps(ab, orc, n_frames, rows, cols):
     assert int(rej) == want_rej and np.array_equal(out.cpu().numpy().reshape(rows, cols), want)
 
 
+@pytest.mark.parametrize("n_frames", [33, 35, 37, 39, 41, 47, 49, 50, 55, 57, 63])
+def test_frame_counts_between_register_kernels(ab, orc, n_frames):
+    """33..63 frames without a kernel of their own run the next register kernel up, the missing
+    frames delivered as NaN by the tensor map: same image and reject count as the oracle, on a
+    constant-stride cube (the padded route), with a ragged tail, a padded plane stride, per-pixel
+    gaps beyond the 8 the specialised tails cover, and all-NaN pixels."""
+    import torch
+    from astroburst_b200 import synth
+
+    rows, cols = 21, 101                    # 2,121 px = 66 tiles + 9 px
+    fr = synth.stack_frames(n_frames, rows, cols, seed=1000 + n_frames, nan_border=2, cosmic_fraction=3e-3)
+    rng = np.random.default_rng(n_frames)
+    fr[rng.random(fr.shape) < 0.03] = np.nan
+    fr[rng.random(fr.shape) < 0.001] = np.inf
+    fr[:, 5, 6] = np.nan
+    fr[: n_frames - 1, 6, 7] = np.nan
+    fr[::2, 7, :] = np.nan                  # half the frames missing along a row
+    fr[: n_frames - 20, 8, :50] = np.nan    # many missing
+    want, want_rej = orc.stack_images(list(fr), 3.0, 3.0, 5)
+    dev = torch.device("cuda:0")
+    npix = rows * cols
+    cfg = ab.StackConfig(3.0, 3.0, 5, False)
+    stream = torch.cuda.current_stream().cuda_stream
+    for stride in (npix + (-npix) % 4, npix + 4 * 37):       # tight (16-byte aligned planes) and padded
+        cube = torch.full((n_frames, stride), 7.0, dtype=torch.float32, device=dev)
+        cube[:, :npix] = torch.from_numpy(fr.reshape(n_frames, -1))
+        if (stride * 4) % 16:
+            continue
+        ptrs = [cube[f].data_ptr() for f in range(n_frames)]
+        assert all(p % 16 == 0 for p in ptrs)
+        out = torch.empty(npix, dtype=torch.float32, device=dev)
+        rej = torch.full((1,), 12345, dtype=torch.int64, device=dev)   # stale value: the launch must overwrite it
+        ab.stack_images_device(ptrs, npix, cfg, out.data_ptr(), rej.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert int(rej) == want_rej and np.array_equal(out.cpu().numpy().reshape(rows, cols), want), stride
+    res = ab.stack_images(list(fr), cfg)    # host buffers
+    assert res.rejected_pixels == want_rej and np.array_equal(res.image, want)
+
+
 def test_deep_band_properties_at_config5_size(ab, orc):
     """256 frames x (64 x 4096) band (1/64 of BASELINE config 5): oracle on sampled rows,
     frame-order invariance, sigma / iteration sweep."""

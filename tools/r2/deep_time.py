@@ -8,7 +8,7 @@ from oracle import oracle
 dev = torch.device("cuda:0"); ctx = ab.default_context(0)
 stream = torch.cuda.current_stream().cuda_stream
 lines = []
-for n_frames, rows in ((256, 512), (225, 512), (200, 512), (128, 512), (100, 512), (64, 512), (33, 512)):
+for n_frames, rows in ((256, 512), (225, 512), (200, 512), (128, 512), (100, 512), (65, 512), (64, 512), (63, 512), (50, 512), (48, 512), (33, 512), (32, 512)):
     fr = synth.stack_frames_torch(n_frames, rows, 4096, dev, seed=5)
     cube = torch.stack(fr); del fr
     out = torch.empty((rows, 4096), dtype=torch.float32, device=dev)

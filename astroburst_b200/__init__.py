@@ -12,6 +12,7 @@ from .core import (  # noqa: F401
     StackConfig,
     StackResult,
     sigma_clip_combine,
+    stack_fits_units,
     stack_images,
     stack_images_device,
 )

@@ -169,6 +169,8 @@ SIGNATURES = {
     "ab_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, _sz]),
     "ab_stack_sigma_clip": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz, _sz,
                                       C.POINTER(StackConfigC), _vp, _u64p]),
+    "ab_stack_fits_units": (C.c_int, [_vp, C.POINTER(_vp), _vp, _vp, _vp, _sz, _sz, _sz,
+                                      C.POINTER(StackConfigC), _vp, _u64p]),
     "ab_stack_sigma_clip_dev": (C.c_int, [_vp, C.POINTER(_vp), _sz, _sz,
                                           C.POINTER(StackConfigC), _vp, _vp, _vp]),
     "ab_sigma_clip_combine": (C.c_int, [_vp, _vp, _sz, C.c_float, C.c_float, C.c_uint32,

@@ -78,6 +78,36 @@ def stack_images(images: Sequence[np.ndarray], config: StackConfig,
     return StackResult(out, len(frames), int(rej.value), [(int(a), int(b)) for a, b in offs])
 
 
+def stack_fits_units(units: Sequence[np.ndarray], bitpix, bscale, bzero, rows: int, cols: int,
+                     config: StackConfig, ctx: Context | None = None, out: np.ndarray | None = None) -> StackResult:
+    """stack_images on FITS data units as read from the files (load_fits_image -> decode_pixels,
+    infra/fits/reader.rs:37-101, then combine.rs:94-193, align=False).  units[f]: uint8 array of
+    rows*cols big-endian samples of BITPIX bitpix[f]; bscale / bzero per frame (scalars broadcast).
+    The planes cross PCIe in the file's sample type and are decoded on the device."""
+    ctx = ctx or default_context()
+    n = len(units)
+    if n == 0:
+        raise AstroBurstError(_lib.AB_ERR_INVALID, "No images to stack")
+    bp = np.ascontiguousarray(np.broadcast_to(np.asarray(bitpix, np.int32), (n,)))
+    bs = np.ascontiguousarray(np.broadcast_to(np.asarray(bscale, np.float64), (n,)))
+    bz = np.ascontiguousarray(np.broadcast_to(np.asarray(bzero, np.float64), (n,)))
+    raw = []
+    for u, b in zip(units, bp):
+        a = np.ascontiguousarray(u).view(np.uint8).reshape(-1)
+        if a.size != rows * cols * (abs(int(b)) // 8):
+            raise AstroBurstError(_lib.AB_ERR_INVALID, f"data unit of {a.size} bytes for {rows}x{cols} BITPIX {b}")
+        raw.append(a)
+    if out is None:
+        out = np.empty((rows, cols), np.float32)
+    assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (rows, cols)
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in raw])
+    cfg = config.to_c()
+    rej = C.c_uint64(0)
+    ctx.check(lib().ab_stack_fits_units(ctx.handle, ptrs, bp.ctypes.data, bs.ctypes.data, bz.ctypes.data, n, rows,
+                                        cols, C.byref(cfg), out.ctypes.data, C.byref(rej)))
+    return StackResult(out, n, int(rej.value), [(0, 0)] * n)
+
+
 def stack_images_device(frame_ptrs: Sequence[int], npix: int, config: StackConfig, out_ptr: int,
                         rejected_ptr: int, stream: int = 0, ctx: Context | None = None) -> None:
     """Device-resident stack: raw device pointers (e.g. torch `data_ptr()`), enqueued on

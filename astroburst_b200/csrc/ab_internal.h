@@ -152,6 +152,10 @@ ab_status ab_stack_launch_deep(ab_ctx *ctx, const FrameTable &ft, int n_frames, 
                                float sigma_low, float sigma_high, unsigned max_iter,
                                const DeepPre &pre, float *d_out, unsigned long long *d_rejected,
                                cudaStream_t stream);
+// fits.cu: decode_pixels (reader.rs:37-101) of a device-resident data unit, enqueued on `s`
+ab_status ab_fits_decode_on(ab_ctx *ctx, const unsigned char *d, size_t n, int bitpix, double bscale,
+                            double bzero, float *out, cudaStream_t s);
+size_t ab_fits_bytes_per_pixel(int bitpix);  // 0 for an unsupported BITPIX
 ab_status ab_stack_launch(ab_ctx *ctx, const FrameTable &ft, int n_frames, size_t npix,
                           float sigma_low, float sigma_high, unsigned max_iter, float *d_out,
                           unsigned long long *d_rejected, cudaStream_t stream, bool peer_frames = false);

@@ -291,6 +291,82 @@ ab_status ab_stack_sigma_clip(ab_ctx *ctx, const float *const *frames, size_t n_
     return AB_OK;
 }
 
+// The same call on FITS data units as they sit in the files: every band crosses PCIe in the file's
+// sample type (2 bytes per pixel for BITPIX 16 instead of the 4 of the decoded f32 plane) and
+// decode_pixels (reader.rs:37-101) runs on the device right behind the copy, into the plane the
+// stack kernel reads.  Same banding / three-stream pipeline as ab_stack_sigma_clip.
+ab_status ab_stack_fits_units(ab_ctx *ctx, const uint8_t *const *units, const int32_t *bitpix,
+                              const double *bscale, const double *bzero, size_t n_frames, size_t rows,
+                              size_t cols, const ab_stack_config *cfg, float *out,
+                              uint64_t *rejected_pixels) {
+    ab_status st = check_stack_args(ctx, units, n_frames, cfg, out);
+    if (st != AB_OK) return st;
+    if (!bitpix || !bscale || !bzero) return ab_fail(ctx, AB_ERR_INVALID, "null argument");
+    size_t max_bpp = 0;
+    for (size_t f = 0; f < n_frames; ++f) {
+        if (!units[f]) return ab_fail(ctx, AB_ERR_INVALID, "null data unit %zu", f);
+        const size_t bpp = ab_fits_bytes_per_pixel(bitpix[f]);
+        if (!bpp) return ab_fail(ctx, AB_ERR_UNSUPPORTED, "BITPIX %d (frame %zu)", (int)bitpix[f], f);
+        max_bpp = std::max(max_bpp, bpp);
+    }
+    CtxLock lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    if (rejected_pixels) *rejected_pixels = 0;
+    const size_t npix = rows * cols;
+    if (npix == 0) return AB_OK;
+
+    const size_t target_px = std::max<size_t>((96u << 20) / (n_frames * sizeof(float)), 1);
+    size_t band_rows = std::min(std::max<size_t>(target_px / cols, 1), rows);
+    const size_t band_px_max = band_rows * cols;
+    const size_t n_bands = (rows + band_rows - 1) / band_rows;
+    const int n_slots = (int)std::min<size_t>(AB_NUM_COPY_STREAMS, n_bands);
+    // per slot: n_frames decoded planes + 1 output plane + two raw staging planes (frame f's copy
+    // lands in staging f % 2 while frame f-1 is being decoded out of the other one)
+    const size_t plane_bytes = ((band_px_max * sizeof(float) + 255) / 256) * 256;
+    const size_t raw_bytes = ((band_px_max * max_bpp + 255) / 256) * 256;
+    for (int s = 0; s < n_slots; ++s) {
+        st = ab_scratch_reserve(ctx, s, plane_bytes * (n_frames + 1) + 2 * raw_bytes);
+        if (st != AB_OK) return st;
+    }
+    unsigned long long *d_rej = reinterpret_cast<unsigned long long *>(ctx->d_small);
+    unsigned long long *h_rej = reinterpret_cast<unsigned long long *>(ctx->h_small);
+    if (n_bands * sizeof(unsigned long long) > 4096)
+        return ab_fail(ctx, AB_ERR_UNSUPPORTED, "too many bands (%zu)", n_bands);
+
+    for (size_t b = 0; b < n_bands; ++b) {
+        const int slot = (int)(b % n_slots);
+        cudaStream_t s = ctx->copy_streams[slot];
+        const size_t r0 = b * band_rows;
+        const size_t nr = std::min(band_rows, rows - r0);
+        const size_t off = r0 * cols, px = nr * cols;
+        char *base = static_cast<char *>(ctx->d_scratch[slot]);
+        unsigned char *raw = reinterpret_cast<unsigned char *>(base + plane_bytes * (n_frames + 1));
+        FrameTable ft;
+        for (size_t f = 0; f < n_frames; ++f) {
+            float *d = reinterpret_cast<float *>(base + f * plane_bytes);
+            const size_t bpp = ab_fits_bytes_per_pixel(bitpix[f]);
+            unsigned char *stage = raw + (f & 1) * raw_bytes;
+            AB_CUDA(ctx, cudaMemcpyAsync(stage, units[f] + off * bpp, px * bpp, cudaMemcpyHostToDevice, s));
+            st = ab_fits_decode_on(ctx, stage, px, bitpix[f], bscale[f], bzero[f], d, s);
+            if (st != AB_OK) return st;
+            ft.p[f] = d;
+        }
+        for (size_t f = n_frames; f < AB_MAX_FRAMES; ++f) ft.p[f] = nullptr;
+        float *d_out = reinterpret_cast<float *>(base + n_frames * plane_bytes);
+        st = ab_stack_launch(ctx, ft, (int)n_frames, px, cfg->sigma_low, cfg->sigma_high,
+                             cfg->max_iterations, d_out, d_rej + b, s);
+        if (st != AB_OK) return st;
+        AB_CUDA(ctx, cudaMemcpyAsync(out + off, d_out, px * sizeof(float), cudaMemcpyDeviceToHost, s));
+        AB_CUDA(ctx, cudaMemcpyAsync(h_rej + b, d_rej + b, sizeof(unsigned long long),
+                                     cudaMemcpyDeviceToHost, s));
+    }
+    for (int s = 0; s < n_slots; ++s) AB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_streams[s]));
+    uint64_t total = 0;
+    for (size_t b = 0; b < n_bands; ++b) total += h_rej[b];
+    if (rejected_pixels) *rejected_pixels = total;
+    return AB_OK;
+}
+
 // stack_images with config.align honoured (combine.rs:118-147): frame 0 is the reference, every
 // other frame is phase-correlated against it (align.rs:84-97) and shifted with the bicubic
 // sampler (align.rs:36-57); offsets[i] = (round(dy), round(dx)) like combine.rs:139-141.  All

@@ -120,6 +120,12 @@ ab_status encode_on(ab_ctx *ctx, const float *d, size_t n, int bitpix, double bz
 
 }  // namespace
 
+ab_status ab_fits_decode_on(ab_ctx *ctx, const unsigned char *d, size_t n, int bitpix, double bscale,
+                            double bzero, float *out, cudaStream_t s) {
+    return decode_on(ctx, d, n, bitpix, bscale, bzero, out, s);
+}
+size_t ab_fits_bytes_per_pixel(int bitpix) { return (size_t)bytes_per_pixel(bitpix); }
+
 extern "C" {
 
 ab_status ab_fits_decode_dev(ab_ctx *ctx, const uint8_t *d_data, size_t n_pixels, int bitpix,

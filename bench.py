@@ -539,7 +539,38 @@ def main():
     e2e_s = time.perf_counter() - t0
     e2e_max = float(_max_over_ranks(torch, dist, world, dev, [e2e_s])[0])
     e2e_value = world * npix * args.e2e_steps / e2e_max / 1e6
-    del host, host_np, host_out
+    del host, host_np
+
+    # ---- the same call on BITPIX 16 data units (what camera FITS files hold): half the H2D bytes,
+    # decode_pixels on the device behind the copy (ab_stack_fits_units)
+    fits16 = None
+    if not args.no_secondary:
+        units = [torch.empty((ROWS, COLS), dtype=torch.int16, pin_memory=True) for _ in range(N_FRAMES)]
+        for u, f in zip(units, frames):
+            q = torch.nan_to_num(f, nan=0.0, posinf=65535.0, neginf=0.0).sub_(32768.0).round_().clamp_(-32768, 32767)
+            u.copy_(q.to(torch.int16))
+            u.numpy().byteswap(inplace=True)                      # FITS is big-endian
+        units_np = [u.numpy().view(np.uint8).reshape(-1) for u in units]
+        ab.stack_fits_units(units_np, 16, 1.0, 32768.0, ROWS, COLS, cfg, ctx, out=host_out.numpy())  # warm
+        _sync_all(torch, dist, world)
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            r16 = ab.stack_fits_units(units_np, 16, 1.0, 32768.0, ROWS, COLS, cfg, ctx, out=host_out.numpy())
+        f16_s = time.perf_counter() - t0
+        f16_max = float(_max_over_ranks(torch, dist, world, dev, [f16_s])[0])
+        fits16 = {"workload": "the same 32x4096^2 stack from BITPIX 16 data units (BZERO 32768), decoded on the device",
+                  "value": world * npix * args.e2e_steps / f16_max / 1e6, "unit": "Mpix/s",
+                  "h2d_bytes_per_step": N_FRAMES * npix * 2, "d2h_bytes_per_step": npix * 4 + 8,
+                  "steps": args.e2e_steps}
+        if rank == 0:
+            from oracle import oracle as _orc
+            r0 = ROWS // 2
+            dec = [_orc.fits_decode(u.numpy()[r0:r0 + 16].tobytes(), 16, 1.0, 32768.0).reshape(16, COLS) for u in units]
+            want16, _ = _orc.stack_images(dec, SIGMA_LOW, SIGMA_HIGH, MAX_ITER)
+            fits16["matches_oracle_on_sample"] = bool(np.array_equal(want16, r16.image[r0:r0 + 16]))
+            fits16["sample"] = f"rows {r0}..{r0 + 16} through the oracle's decode_pixels + stack_images"
+        del units, units_np
+    del host_out
 
     line = None
     if rank == 0:
@@ -586,6 +617,8 @@ def main():
         del cube, frames, out
         torch.cuda.empty_cache()
         secondary = {}
+        if fits16 is not None:
+            secondary["e2e_bitpix16"] = fits16
         try:
             if world > 1:
                 okp = run_multi_gpu_parity(torch, dist, ab, ctx, dev, rank, world)

@@ -219,6 +219,16 @@ ab_status ab_memcpy_d2h(ab_ctx *ctx, void *dst_host, const void *src_dev, size_t
 ab_status ab_stack_sigma_clip(ab_ctx *ctx, const float *const *frames, size_t n_frames,
                               size_t rows, size_t cols, const ab_stack_config *cfg, float *out,
                               uint64_t *rejected_pixels);
+/* The same stack on FITS data units as they sit in the files (load_fits_image ->
+ * decode_pixels, infra/fits/reader.rs:37-101, then combine.rs:94-193 with align == false): units[f] =
+ * rows*cols big-endian samples of BITPIX bitpix[f] (8 / 16 / 32 / -32 / -64) with that file's
+ * BSCALE / BZERO.  Bands cross PCIe in the file's sample type (half the bytes of the f32 planes for
+ * BITPIX 16) and are decoded on the device behind the copy; the result equals
+ * ab_fits_decode + ab_stack_sigma_clip bit for bit.  cfg->align != 0 -> AB_ERR_UNSUPPORTED. */
+ab_status ab_stack_fits_units(ab_ctx *ctx, const uint8_t *const *units, const int32_t *bitpix,
+                              const double *bscale, const double *bzero, size_t n_frames, size_t rows,
+                              size_t cols, const ab_stack_config *cfg, float *out,
+                              uint64_t *rejected_pixels);
 /* Device-resident variant.  d_frames: HOST array of n_frames DEVICE pointers.  d_rejected:
  * DEVICE u64, overwritten.  npix = rows*cols (pixels are independent, so callers may pass any
  * row band: this is the multi-GPU sharding unit). */

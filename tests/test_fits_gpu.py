@@ -52,3 +52,47 @@ def test_encode_matches_oracle_and_round_trips(fits, orc, bitpix, bzero, bscale)
     else:
         fin = np.isfinite(a) & (np.abs((a - bzero) / bscale) < 32000)
         assert np.max(np.abs(back[fin] - a[fin])) <= 0.5 * abs(bscale) + 1e-2
+
+
+@pytest.mark.parametrize("case", ["i16_bzero", "mixed", "f32_identity", "ragged_many_bands"])
+def test_stack_fits_units_equals_decode_then_stack(fits, orc, case):
+    """ab_stack_fits_units (data units over PCIe in the file's sample type, decoded on the device)
+    against the oracle's decode_pixels + stack_images: same image, same reject count."""
+    import astroburst_b200 as ab
+    from astroburst_b200 import synth
+
+    rng = np.random.default_rng(7)
+    if case == "ragged_many_bands":
+        n, rows, cols = 40, 700, 1031          # several bands, tail pixels, the padded 40-frame kernel
+    else:
+        n, rows, cols = 12, 61, 83
+    fr = synth.stack_frames(n, rows, cols, seed=77, nan_border=0, cosmic_fraction=2e-3)
+    units, bitpix, bscale, bzero = [], [], [], []
+    for f in range(n):
+        kind = {"i16_bzero": 16, "f32_identity": -32, "ragged_many_bands": 16}.get(case) or (8, 16, 32, -32, -64)[f % 5]
+        if kind == 16:
+            bs, bz = 1.0, 32768.0
+            q = np.clip(np.rint((fr[f].astype(np.float64) - bz) / bs), -32768, 32767).astype(">i2")
+        elif kind == 8:
+            bs, bz = 8.0, 0.0
+            q = np.clip(np.rint(fr[f] / bs), 0, 255).astype(np.uint8)
+        elif kind == 32:
+            bs, bz = 0.001, 10.0
+            q = np.rint((fr[f].astype(np.float64) - bz) / bs).astype(">i4")
+        elif kind == -32:
+            bs, bz = 1.0, 0.0
+            q = fr[f].astype(">f4")
+            q.reshape(-1)[rng.integers(0, q.size, 5)] = np.nan       # non-finite samples survive the decode
+        else:
+            bs, bz = 1.0 + 1e-3, -0.5
+            q = fr[f].astype(">f8")
+        units.append(np.frombuffer(q.tobytes(), np.uint8))
+        bitpix.append(kind); bscale.append(bs); bzero.append(bz)
+    decoded = [orc.fits_decode(u.tobytes(), b, s, z).reshape(rows, cols) for u, b, s, z in zip(units, bitpix, bscale, bzero)]
+    want, want_rej = orc.stack_images(decoded, 3.0, 3.0, 5)
+    res = ab.stack_fits_units(units, bitpix, bscale, bzero, rows, cols, ab.StackConfig(3.0, 3.0, 5, False))
+    assert res.rejected_pixels == want_rej and np.array_equal(res.image, want, equal_nan=True)
+    with pytest.raises(ab.AstroBurstError):
+        ab.stack_fits_units(units, [64] * n, bscale, bzero, rows, cols, ab.StackConfig(3.0, 3.0, 5, False))
+    with pytest.raises(ab.AstroBurstError):
+        ab.stack_fits_units(units, bitpix, bscale, bzero, rows, cols, ab.StackConfig(3.0, 3.0, 5, True))

@@ -260,6 +260,7 @@ SIGNATURES = {
     "ab_align_affine_dev": (C.c_int, [_vp, _vp, _vp, _sz, _sz, C.c_int, _vp, _vp]),
     "ab_align_ref_stars_dev": (C.c_int, [_vp, _vp, _sz, _sz, _vp, C.POINTER(C.c_size_t), _vp]),
     "ab_align_affine_with_ref_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _sz, _sz, C.c_int, _vp, _vp]),
+    "ab_align_affine_from_stars_dev": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _sz, _sz, C.c_int, _vp, _vp]),
     "ab_match_stars": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, C.POINTER(C.c_size_t)]),
     "ab_ransac_affine": (C.c_int, [_vp, _sz, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),
     "ab_ransac_affine_gpu": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),

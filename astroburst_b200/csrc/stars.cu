@@ -1897,25 +1897,21 @@ ab_status align_star_points(ab_ctx *ctx, const float *d_img, size_t rows, size_t
     return AB_OK;
 }
 
-// align_channel_affine (affine.rs:129-212) from the reference's star list onwards
-ab_status align_with_ref_points(ab_ctx *ctx, const std::vector<Pt> &rs, const float *d_ref,
-                                const float *d_tgt, size_t rows, size_t cols, int n_threads,
-                                cudaStream_t s, ab_align_result *out) {
+// align_channel_affine (affine.rs:129-212) from both star lists onwards: triangle votes, RANSAC,
+// sanity checks, phase-correlation fallback
+ab_status align_from_star_points(ab_ctx *ctx, const std::vector<Pt> &rs, const std::vector<Pt> &ts,
+                                 const float *d_ref, const float *d_tgt, size_t rows, size_t cols,
+                                 int n_threads, cudaStream_t s, ab_align_result *out, double t_det) {
     const bool trace = std::getenv("AB_TRACE") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<double, std::milli>(now() - t0).count();
     };
-    const auto t0 = now();
-    std::vector<Pt> ts;
-    ab_status st = align_star_points(ctx, d_tgt, rows, cols, s, ts);
-    if (st != AB_OK) return st;
-    const double t_det = ms_since(t0);
     if (rs.size() < MIN_MATCHES_RIGID || ts.size() < MIN_MATCHES_RIGID)
         return fallback(ctx, d_ref, d_tgt, rows, cols, s, out);
     const auto t1 = now();
     std::vector<Match> matches;
-    st = match_stars(ctx, rs, ts, s, matches);
+    ab_status st = match_stars(ctx, rs, ts, s, matches);
     if (st != AB_OK) return st;
     const double t_match = ms_since(t1);
     if (matches.size() < MIN_MATCHES_RIGID) return fallback(ctx, d_ref, d_tgt, rows, cols, s, out);
@@ -1936,6 +1932,17 @@ ab_status align_with_ref_points(ab_ctx *ctx, const std::vector<Pt> &rs, const fl
         return AB_OK;
     }
     return fallback(ctx, d_ref, d_tgt, rows, cols, s, out);
+}
+// ... from the reference's star list onwards (the target's stars are detected here)
+ab_status align_with_ref_points(ab_ctx *ctx, const std::vector<Pt> &rs, const float *d_ref,
+                                const float *d_tgt, size_t rows, size_t cols, int n_threads,
+                                cudaStream_t s, ab_align_result *out) {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<Pt> ts;
+    ab_status st = align_star_points(ctx, d_tgt, rows, cols, s, ts);
+    if (st != AB_OK) return st;
+    const double t_det = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return align_from_star_points(ctx, rs, ts, d_ref, d_tgt, rows, cols, n_threads, s, out, t_det);
 }
 
 ab_status align_on_device(ab_ctx *ctx, const float *d_ref, const float *d_tgt, size_t rows,
@@ -2201,6 +2208,22 @@ ab_status ab_align_affine_with_ref_dev(ab_ctx *ctx, const double *ref_xy, size_t
     std::vector<Pt> rs;
     for (size_t i = 0; i < std::min(n_ref, (size_t)MAX_STARS); ++i) rs.push_back({ref_xy[2 * i], ref_xy[2 * i + 1]});
     return align_with_ref_points(ctx, rs, d_ref, d_tgt, rows, cols, n_threads, (cudaStream_t)stream, out);
+}
+
+// Both star lists given (each from ab_align_ref_stars_dev on its plane): a rank can detect its
+// target frames before the reference's list has arrived.  d_ref / d_tgt feed only the
+// phase-correlation fallback (either NULL: identity, method 3).  Equals ab_align_affine_dev.
+ab_status ab_align_affine_from_stars_dev(ab_ctx *ctx, const double *ref_xy, size_t n_ref, const double *tgt_xy,
+                                         size_t n_tgt, const float *d_ref, const float *d_tgt, size_t rows,
+                                         size_t cols, int n_threads, ab_align_result *out, void *stream) {
+    if (!ctx || !out || (n_ref && !ref_xy) || (n_tgt && !tgt_xy)) return AB_ERR_INVALID;
+    CtxLock lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    std::vector<Pt> rs, ts;
+    for (size_t i = 0; i < std::min(n_ref, (size_t)MAX_STARS); ++i) rs.push_back({ref_xy[2 * i], ref_xy[2 * i + 1]});
+    for (size_t i = 0; i < std::min(n_tgt, (size_t)MAX_STARS); ++i) ts.push_back({tgt_xy[2 * i], tgt_xy[2 * i + 1]});
+    return align_from_star_points(ctx, rs, ts, d_tgt ? d_ref : nullptr, d_tgt, rows, cols, n_threads,
+                                  (cudaStream_t)stream, out, 0.0);
 }
 
 ab_status ab_align_affine(ab_ctx *ctx, const float *ref, const float *tgt, size_t rows, size_t cols,

@@ -182,6 +182,23 @@ def align_ref_stars(ref_ptr: int, rows: int, cols: int, ctx: Context | None = No
     return xy[: n.value].copy()
 
 
+def align_and_warp_from_stars(ref_xy: np.ndarray, tgt_xy: np.ndarray, ref_ptr: Optional[int], tgt_ptr: int,
+                              out_ptr: int, rows: int, cols: int, n_threads: int = 8, ctx: Context | None = None,
+                              stream: int = 0, warp_stream: Optional[int] = None) -> AlignResultC:
+    """align_and_warp with both star lists given (`align_ref_stars` on each plane): the target's
+    detection can run before the reference's list has arrived from the GPU that holds frame 0."""
+    ctx = ctx or default_context()
+    res = AlignResultC()
+    s = stream if stream else None
+    rxy = np.ascontiguousarray(ref_xy, dtype=np.float64)
+    txy = np.ascontiguousarray(tgt_xy, dtype=np.float64)
+    ctx.check(lib().ab_align_affine_from_stars_dev(ctx.handle, rxy.ctypes.data, len(rxy), txy.ctypes.data, len(txy),
+                                                   ref_ptr, tgt_ptr, rows, cols, n_threads, C.addressof(res), s))
+    ctx.check(lib().ab_warp_affine_bicubic_dev(ctx.handle, tgt_ptr, rows, cols, C.addressof(res.transform), rows, cols,
+                                               out_ptr, warp_stream if warp_stream is not None else s))
+    return res
+
+
 def align_and_warp_with_ref(ref_xy: np.ndarray, ref_ptr: Optional[int], tgt_ptr: int, out_ptr: int, rows: int,
                             cols: int, n_threads: int = 8, ctx: Context | None = None, stream: int = 0,
                             warp_stream: Optional[int] = None) -> AlignResultC:

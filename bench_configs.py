@@ -242,7 +242,9 @@ def run_config3(torch, dist, ab, ctx, dev, rank, world, reps=2, n_frames=16, R=8
     warp_side = torch.cuda.Stream(device=dev)   # warps overlap the next frame's detection
 
     def pipeline():
-        # reference star list once, on the rank that holds frame 0, broadcast (<= 1.9 KB) to the others
+        # reference star list once, on the rank that holds frame 0, broadcast (<= 1.9 KB) to the
+        # others -- which detect the stars of their own target frames while it is on its way
+        work = None
         if rank == 0:
             xy = pipelines.align_ref_stars(frames[0].data_ptr(), R, R, ctx, stream)
             xy_dev.zero_()
@@ -250,15 +252,19 @@ def run_config3(torch, dist, ab, ctx, dev, rank, world, reps=2, n_frames=16, R=8
             if len(xy):
                 xy_dev[1:1 + len(xy)].copy_(torch.from_numpy(xy))
         if world > 1:
-            dist.broadcast(xy_dev, src=0)
+            work = dist.broadcast(xy_dev, src=0, async_op=True)
+        tgt_xy = {f: pipelines.align_ref_stars(frames[f].data_ptr(), R, R, ctx, stream) for f in mine if f != 0}
+        if work is not None:
+            work.wait()
         h = xy_dev.cpu().numpy()
         ref_xy = h[1:1 + int(h[0, 0])]
         for f in mine:
             if f == 0:
                 continue
             ref_ptr = frames[0].data_ptr() if 0 in frames else None
-            results[f] = pipelines.align_and_warp_with_ref(ref_xy, ref_ptr, frames[f].data_ptr(), outs[f].data_ptr(),
-                                                           R, R, 16, ctx, stream, warp_stream=warp_side.cuda_stream)
+            results[f] = pipelines.align_and_warp_from_stars(ref_xy, tgt_xy[f], ref_ptr, frames[f].data_ptr(),
+                                                             outs[f].data_ptr(), R, R, 16, ctx, stream,
+                                                             warp_stream=warp_side.cuda_stream)
 
     pipeline()
     ms = _wall_max(torch, dist, world, dev, pipeline, reps)

@@ -575,6 +575,14 @@ ab_status ab_align_affine_with_ref_dev(ab_ctx *ctx, const double *ref_xy, size_t
                                        const float *d_ref, const float *d_tgt, size_t rows,
                                        size_t cols, int n_threads, ab_align_result *out,
                                        void *stream);
+/* Both star lists given, each the output of ab_align_ref_stars_dev on its own plane (the function
+ * is the aligner's view of ANY plane: normalisation, detection at 3.5 sigma, 120 brightest).  A
+ * rank of a frames-across-GPUs run can therefore detect its target frames before the reference's
+ * list has been broadcast.  d_ref / d_tgt feed only the phase-correlation fallback (either NULL:
+ * identity, method 3).  Same result as ab_align_affine_dev(ref, tgt). */
+ab_status ab_align_affine_from_stars_dev(ab_ctx *ctx, const double *ref_xy, size_t n_ref, const double *tgt_xy,
+                                         size_t n_tgt, const float *d_ref, const float *d_tgt, size_t rows,
+                                         size_t cols, int n_threads, ab_align_result *out, void *stream);
 /* build_triangles + match_triangles, affine.rs:279-384, on (x, y) star lists (<= 120 each);
  * matches_out receives (ref x, ref y, tgt x, tgt y) per match */
 ab_status ab_match_stars(ab_ctx *ctx, const double *ref_xy, size_t n_ref, const double *tgt_xy,

@@ -92,3 +92,18 @@ def test_align_with_shared_reference_star_list_equals_pairwise_align(orc):
         # without the reference plane on this GPU only the phase-correlation fallback is lost
         got2 = pipelines.align_and_warp_with_ref(xy, None, d_t.data_ptr(), out.data_ptr(), rows, cols, 8, ctx, s)
         assert tup(got2) == tup(got)
+        # both star lists detected up front (the target's before the reference's list "arrives")
+        txy = pipelines.align_ref_stars(d_t.data_ptr(), rows, cols, ctx, s)
+        out3 = torch.empty_like(d_t)
+        got3 = pipelines.align_and_warp_from_stars(xy, txy, d_ref.data_ptr(), d_t.data_ptr(), out3.data_ptr(), rows, cols, 8, ctx, s)
+        torch.cuda.synchronize()
+        assert tup(got3) == tup(pair) and np.array_equal(out3.cpu().numpy(), want)
+    # too few stars on one side: the phase-correlation fallback, exactly as the pairwise call
+    flat = torch.full((rows, cols), 0.25, device=dev)
+    fxy = pipelines.align_ref_stars(flat.data_ptr(), rows, cols, ctx, s)
+    assert len(fxy) < 4
+    out4 = torch.empty_like(flat)
+    got4 = pipelines.align_and_warp_from_stars(xy, fxy, d_ref.data_ptr(), flat.data_ptr(), out4.data_ptr(), rows, cols, 8, ctx, s)
+    pair4 = AlignResultC()
+    ctx.check(lib().ab_align_affine_dev(ctx.handle, d_ref.data_ptr(), flat.data_ptr(), rows, cols, 8, C.addressof(pair4), s))
+    assert tup(got4) == tup(pair4) and got4.method in (2, 3)

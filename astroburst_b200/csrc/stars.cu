@@ -281,17 +281,20 @@ __device__ __forceinline__ unsigned hist_find_warp(const unsigned *hist, unsigne
     return b;
 }
 // k-th smallest (0-based) of the bracket (every warp scans its own segment of `mine` keys);
-// *less = keys strictly below it
+// *less = keys strictly below it.  The bracket's keys lie in [base, base + range]: the radix select
+// runs on key - base and starts at the highest byte `range` reaches (typically 2 passes instead of
+// 4, and the first pass already spreads the keys over the bins instead of one hot bin).
 __device__ __forceinline__ unsigned bracket_select(const unsigned *seg, unsigned mine, Sel &s, unsigned k,
-                                                   unsigned *less) {
+                                                   unsigned base, unsigned range, unsigned *less) {
     unsigned prefix = 0, mask = 0, below = 0;
     const unsigned lane = threadIdx.x & 31;
+    const int shift0 = ((31 - __clz((int)(range | 1u))) >> 3) << 3;
 #pragma unroll 1
-    for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int shift = shift0; shift >= 0; shift -= 8) {
         if (threadIdx.x < 256) s.hist[threadIdx.x] = 0;
         __syncthreads();
         for (unsigned i = lane; i < mine; i += 32) {
-            const unsigned key = seg[i];
+            const unsigned key = seg[i] - base;
             if ((key & mask) == prefix) atomicAdd(&s.hist[(key >> shift) & 255u], 1u);
         }
         __syncthreads();
@@ -308,10 +311,24 @@ __device__ __forceinline__ unsigned bracket_select(const unsigned *seg, unsigned
         below += s.cum;
         prefix |= s.bin << shift;
         mask |= 0xffu << shift;
-        __syncthreads();
     }
     *less = below;
-    return prefix;
+    return prefix + base;
+}
+// largest bracket key strictly below `bound` (exists by construction when called)
+__device__ __forceinline__ unsigned bracket_max_below(const unsigned *seg, unsigned mine, Sel &s, unsigned bound) {
+    __syncthreads();
+    if (threadIdx.x == 0) s.maxkey = 0;
+    __syncthreads();
+    unsigned m = 0;
+    for (unsigned i = threadIdx.x & 31; i < mine; i += 32) {
+        const unsigned key = seg[i];
+        if (key < bound) m = max(m, key);
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&s.maxkey, m);
+    __syncthreads();
+    return s.maxkey;
 }
 // ascending bitonic sort of FS_SAMPLES u32 in shared memory, one comparator per thread and stage
 __device__ __forceinline__ void sort_samples(unsigned *sk) {
@@ -392,19 +409,36 @@ __device__ __forceinline__ bool tile_pair_fast(const Src &src, Sel &s, double me
                 if (i + d < (int)m) hi_key = __float_as_uint(s.samp_v[a + i + d]);
             }
             __syncthreads();
-        } else {  // |v - median| keys of the retained samples, sorted in the bracket's space
-            unsigned *sk = s.bracket;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const unsigned j = threadIdx.x + h * OC_THREADS;
-                sk[j] = (j >= a && j < b) ? key_of(s.samp_v[j]) : 0xffffffffu;
+        } else {
+            // |v - median| over the value-sorted sample is V-shaped: descending up to the first sample
+            // >= median (index c), ascending from there.  The k-th smallest key of the two monotone
+            // halves comes from a binary search over how many of the k + 1 smallest sit on the left.
+            unsigned c = a;
+            {
+                unsigned l = a, r = b;
+                while (l < r) {
+                    const unsigned mdl = (l + r) >> 1;
+                    if ((double)s.samp_v[mdl] < median) l = mdl + 1; else r = mdl;
+                }
+                c = l;
             }
-            sort_samples(sk);
+            const int nL = (int)(c - a), nR = (int)(b - c);
+            auto Lk = [&](int j) { return key_of(s.samp_v[c - 1 - j]); };  // ascending in j
+            auto Rk = [&](int j) { return key_of(s.samp_v[c + j]); };
+            auto kth = [&](int k) -> unsigned {
+                int lo = max(0, k + 1 - nR), hi = min(k + 1, nL);
+                while (lo < hi) {
+                    const int t = (lo + hi) >> 1;  // t from the left, k + 1 - t from the right
+                    if (Lk(t) < Rk(k - t)) lo = t + 1; else hi = t;
+                }
+                const unsigned x = lo > 0 ? Lk(lo - 1) : 0u, y = k + 1 - lo > 0 ? Rk(k - lo) : 0u;
+                return max(x, y);
+            };
             if (m >= 64) {
-                if (i - d >= 0) lo_key = sk[i - d];
-                if (i + d < (int)m) hi_key = sk[i + d];
+                if (i - d >= 0) lo_key = kth(i - d);
+                if (i + d < (int)m) hi_key = kth(i + d);
             }
-            __syncthreads();  // the sample's keys are dead from here: the bracket reuses their space
+            __syncthreads();
         }
     }
     // ---- one pass: retained keys in total, keys below the bracket, the bracket's keys
@@ -446,10 +480,10 @@ __device__ __forceinline__ bool tile_pair_fast(const Src &src, Sel &s, double me
         return false;
     }
     unsigned less;
-    const unsigned rk = bracket_select(seg, mine, s, mid - n_lo, &less);
+    const unsigned rk = bracket_select(seg, mine, s, mid - n_lo, lo_key, hi_key - lo_key, &less);
     unsigned lk = rk;
-    if (!(n & 1u) && less == mid - n_lo)  // the lower middle is a smaller key: the next one down
-        lk = bracket_select(seg, mine, s, mid - n_lo - 1, &less);
+    if (!(n & 1u) && less == mid - n_lo)  // the lower middle is a smaller key: the largest one below
+        lk = bracket_max_below(seg, mine, s, rk);
     *left = __uint_as_float(lk);
     *right = __uint_as_float(rk);
     return true;

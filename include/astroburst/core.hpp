@@ -95,6 +95,38 @@ inline StackResult stack_images(const Context &ctx, const std::vector<Image> &im
     return res;
 }
 
+// The same stack straight from FITS data units (load_fits_image -> decode_pixels,
+// infra/fits/reader.rs:37-101, then stack_images with align == false): the planes cross PCIe in
+// the file's sample type and are decoded on the device (ab_stack_fits_units).
+struct FitsUnit {
+    const uint8_t *data = nullptr;  // rows * cols big-endian samples
+    int bitpix = -32;               // 8 / 16 / 32 / -32 / -64
+    double bscale = 1.0, bzero = 0.0;
+};
+inline StackResult stack_fits_units(const Context &ctx, const std::vector<FitsUnit> &units, size_t rows,
+                                    size_t cols, const StackConfig &config) {
+    if (units.empty()) throw Error(AB_ERR_INVALID, "No images to stack");
+    std::vector<const uint8_t *> ptrs;
+    std::vector<int32_t> bitpix;
+    std::vector<double> bscale, bzero;
+    for (const FitsUnit &u : units) {
+        ptrs.push_back(u.data);
+        bitpix.push_back(u.bitpix);
+        bscale.push_back(u.bscale);
+        bzero.push_back(u.bzero);
+    }
+    StackResult res;
+    res.image = Image(rows, cols);
+    res.frame_count = units.size();
+    res.offsets.assign(units.size(), {0, 0});
+    const ab_stack_config cfg{config.sigma_low, config.sigma_high, (uint32_t)config.max_iterations,
+                              config.align ? 1u : 0u};
+    ctx.check(ab_stack_fits_units(ctx.get(), ptrs.data(), bitpix.data(), bscale.data(), bzero.data(),
+                                  units.size(), rows, cols, &cfg, res.image.data.data(),
+                                  &res.rejected_pixels));
+    return res;
+}
+
 // core/stacking/calibration.rs (frames arrive loaded; FITS I/O stays with the caller)
 namespace calibration {
 struct CalibrationConfig {  // :8-13

@@ -36,6 +36,24 @@ int main(int argc, char **argv) {
         FILE *fp = fopen(argv[1], "wb");
         fwrite(r.image.data.data(), 4, r.image.data.size(), fp);
         fwrite(&r.rejected_pixels, 8, 1, fp);
+        // the same frames as BITPIX 16 data units (BZERO 32768, big-endian), decoded on the device
+        std::vector<std::vector<uint8_t>> raw(n);
+        std::vector<core::stacking::FitsUnit> units(n);
+        for (size_t f = 0; f < n; ++f) {
+            raw[f].resize(rows * cols * 2);
+            for (size_t i = 0; i < rows * cols; ++i) {
+                const int q = (int)frames[f].data[i] - 32768;                      // truncating: any i16 will do
+                const uint16_t u = (uint16_t)(int16_t)(q < -32768 ? -32768 : q > 32767 ? 32767 : q);
+                raw[f][2 * i] = (uint8_t)(u >> 8);
+                raw[f][2 * i + 1] = (uint8_t)(u & 0xff);
+            }
+            units[f].data = raw[f].data();
+            units[f].bitpix = 16;
+            units[f].bzero = 32768.0;
+        }
+        core::stacking::StackResult r16 = core::stacking::stack_fits_units(ctx, units, rows, cols, cfg);
+        fwrite(r16.image.data.data(), 4, r16.image.data.size(), fp);
+        fwrite(&r16.rejected_pixels, 8, 1, fp);
         fclose(fp);
         try {  // error behaviour: bail!("No images to stack")
             core::stacking::stack_images(ctx, {}, cfg);
@@ -75,7 +93,14 @@ def test_core_hpp_runs_on_the_gpu_and_matches_the_oracle(orc):
         r = subprocess.run([exe, out], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr
         raw = open(out, "rb").read()
-    got = np.frombuffer(raw[: rows * cols * 4], np.float32).reshape(rows, cols)
-    rej = int(np.frombuffer(raw[rows * cols * 4:], np.uint64)[0])
+    nb = rows * cols * 4
+    got = np.frombuffer(raw[:nb], np.float32).reshape(rows, cols)
+    rej = int(np.frombuffer(raw[nb:nb + 8], np.uint64)[0])
     assert rej == want_rej and want_rej > 0
     assert np.array_equal(got, want)
+    # stack_fits_units: truncated i16 samples + 32768, stacked
+    q = [(np.clip(f.astype(np.int64) - 32768, -32768, 32767) + 32768).astype(np.float32) for f in frames]
+    want16, want16_rej = orc.stack_images(q, 3.0, 3.0, 5)
+    got16 = np.frombuffer(raw[nb + 8:2 * nb + 8], np.float32).reshape(rows, cols)
+    rej16 = int(np.frombuffer(raw[2 * nb + 8:], np.uint64)[0])
+    assert rej16 == want16_rej and np.array_equal(got16, want16)

@@ -188,6 +188,15 @@ ab_status ab_memcpy_d2h(ab_ctx *ctx, void *dst, const void *src, size_t bytes) {
 }
 
 // ------------------------------------------------------------------------------- stacking
+// Input bytes per band of the host-buffer pipelines (AB_BAND_MB overrides, for measurements).
+// Measured on B200 / PCIe Gen5 with 32 pinned 4096^2 frames: 32 MiB bands 342 Mpix/s, 96 MiB 395,
+// 192 MiB 407, 384 MiB 417, 768 MiB 420 -- the per-frame copies of a band (band / n_frames bytes
+// each) want to be >= 10 MB; three slots of 384 MiB are 1.2 GB of scratch.
+static size_t ab_band_bytes() {
+    const char *e = std::getenv("AB_BAND_MB");
+    const long mb = e ? std::atol(e) : 0;
+    return (size_t)(mb > 0 && mb <= 4096 ? mb : 384) << 20;
+}
 static ab_status check_stack_args(ab_ctx *ctx, const void *frames, size_t n_frames,
                                   const ab_stack_config *cfg, const void *out,
                                   bool align_ok = false) {
@@ -241,8 +250,8 @@ ab_status ab_stack_sigma_clip(ab_ctx *ctx, const float *const *frames, size_t n_
     const size_t npix = rows * cols;
     if (npix == 0) return AB_OK;
 
-    // band size: ~96 MiB of input per band, whole rows, at least one row
-    const size_t target_px = std::max<size_t>((96u << 20) / (n_frames * sizeof(float)), 1);
+    // band size: ~384 MiB of input per band (ab_band_bytes), whole rows, at least one row
+    const size_t target_px = std::max<size_t>(ab_band_bytes() / (n_frames * sizeof(float)), 1);
     size_t band_rows = std::max<size_t>(target_px / cols, 1);
     band_rows = std::min(band_rows, rows);
     const size_t band_px_max = band_rows * cols;
@@ -315,7 +324,7 @@ ab_status ab_stack_fits_units(ab_ctx *ctx, const uint8_t *const *units, const in
     const size_t npix = rows * cols;
     if (npix == 0) return AB_OK;
 
-    const size_t target_px = std::max<size_t>((96u << 20) / (n_frames * sizeof(float)), 1);
+    const size_t target_px = std::max<size_t>(ab_band_bytes() / (n_frames * sizeof(float)), 1);
     size_t band_rows = std::min(std::max<size_t>(target_px / cols, 1), rows);
     const size_t band_px_max = band_rows * cols;
     const size_t n_bands = (rows + band_rows - 1) / band_rows;

@@ -55,7 +55,7 @@ def test_encode_matches_oracle_and_round_trips(fits, orc, bitpix, bzero, bscale)
 
 
 @pytest.mark.parametrize("case", ["i16_bzero", "mixed", "f32_identity", "ragged_many_bands"])
-def test_stack_fits_units_equals_decode_then_stack(fits, orc, case):
+def test_stack_fits_units_equals_decode_then_stack(fits, orc, case, monkeypatch):
     """ab_stack_fits_units (data units over PCIe in the file's sample type, decoded on the device)
     against the oracle's decode_pixels + stack_images: same image, same reject count."""
     import astroburst_b200 as ab
@@ -63,6 +63,7 @@ def test_stack_fits_units_equals_decode_then_stack(fits, orc, case):
 
     rng = np.random.default_rng(7)
     if case == "ragged_many_bands":
+        monkeypatch.setenv("AB_BAND_MB", "16")  # (default 384 MiB: this stack would be one band)
         n, rows, cols = 40, 700, 1031          # several bands, tail pixels, the padded 40-frame kernel
     else:
         n, rows, cols = 12, 61, 83
@@ -92,6 +93,9 @@ def test_stack_fits_units_equals_decode_then_stack(fits, orc, case):
     want, want_rej = orc.stack_images(decoded, 3.0, 3.0, 5)
     res = ab.stack_fits_units(units, bitpix, bscale, bzero, rows, cols, ab.StackConfig(3.0, 3.0, 5, False))
     assert res.rejected_pixels == want_rej and np.array_equal(res.image, want, equal_nan=True)
+    if case == "ragged_many_bands":         # the f32 host-buffer call over the same 8 bands
+        res32 = ab.stack_images(decoded, ab.StackConfig(3.0, 3.0, 5, False))
+        assert res32.rejected_pixels == want_rej and np.array_equal(res32.image, want, equal_nan=True)
     with pytest.raises(ab.AstroBurstError):
         ab.stack_fits_units(units, [64] * n, bscale, bzero, rows, cols, ab.StackConfig(3.0, 3.0, 5, False))
     with pytest.raises(ab.AstroBurstError):

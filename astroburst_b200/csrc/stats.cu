@@ -40,6 +40,22 @@ constexpr unsigned HIST_BINS = 65536;       // stats.rs:8
 constexpr int ST_THREADS = 512;
 constexpr int HT_THREADS = 1024;            // histogram passes: one block per SM
 constexpr unsigned HALF_FLUSH = 0x8000u;    // packed u16 counter -> global u32 bin hand-over
+// One increment of packed half `a` (shared-window address of the table in `pbase`): a
+// shared-space atomic on a precomputed 32-bit address -- the generic-pointer form re-derives the
+// shared window base (S2R + 3 integer instructions) for every pixel.
+__device__ __forceinline__ void packed_inc(unsigned pbase, unsigned a, unsigned *__restrict__ histA) {
+    const unsigned addr = pbase + ((a & ~1u) << 1);
+    const unsigned odd = a & 1u;
+    const unsigned inc = odd ? 0x10000u : 1u;
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(inc) : "memory");
+    const unsigned half = odd ? (old >> 16) : (old & 0xffffu);
+    if (half == HALF_FLUSH - 1u) {
+        atomicAdd(&histA[a], HALF_FLUSH);
+        const unsigned dec = 0u - (odd ? (HALF_FLUSH << 16) : HALF_FLUSH);
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(dec) : "memory");
+    }
+}
 
 __device__ __forceinline__ bool valid_px(float v) {
     return (fabsf(v) < CUDART_INF_F) && v > PADDING_THRESHOLD;
@@ -124,6 +140,7 @@ hist_kernel(const float *__restrict__ data, size_t len, F f, unsigned *__restric
     extern __shared__ unsigned packed[];
     for (unsigned i = threadIdx.x; i < HIST_BINS / 2; i += HT_THREADS) packed[i] = 0;
     __syncthreads();
+    const unsigned pbase = (unsigned)__cvta_generic_to_shared(packed);
 
     const bool vec_ok = (reinterpret_cast<uintptr_t>(data) & 15) == 0;
     const size_t n4 = vec_ok ? len / 4 : 0;
@@ -143,12 +160,7 @@ hist_kernel(const float *__restrict__ data, size_t len, F f, unsigned *__restric
         }
         if constexpr (F::kA) {
             const unsigned a = f.bin_a(v, dv);
-            const unsigned sh = (a & 1u) << 4;
-            const unsigned old = atomicAdd(&packed[a >> 1], 1u << sh);
-            if (((old >> sh) & 0xffffu) == HALF_FLUSH - 1u) {
-                atomicAdd(&histA[a], HALF_FLUSH);
-                atomicSub(&packed[a >> 1], HALF_FLUSH << sh);
-            }
+            packed_inc(pbase, a, histA);
         }
         if constexpr (F::kB) {
             unsigned b;
@@ -260,6 +272,7 @@ hist_ctl_kernel(const float *__restrict__ data, size_t len, const F *__restrict_
     const F f = *f_dev;
     for (unsigned i = threadIdx.x; i < HIST_BINS / 2; i += HT_THREADS) packed[i] = 0;
     __syncthreads();
+    const unsigned pbase = (unsigned)__cvta_generic_to_shared(packed);
     const bool vec_ok = (reinterpret_cast<uintptr_t>(data) & 15) == 0;
     const size_t n4 = vec_ok ? len / 4 : 0;
     const size_t stride = (size_t)gridDim.x * HT_THREADS;
@@ -275,12 +288,7 @@ hist_ctl_kernel(const float *__restrict__ data, size_t len, const F *__restrict_
         }
         if constexpr (F::kA) {
             const unsigned a = f.bin_a(v, dv);
-            const unsigned sh = (a & 1u) << 4;
-            const unsigned old = atomicAdd(&packed[a >> 1], 1u << sh);
-            if (((old >> sh) & 0xffffu) == HALF_FLUSH - 1u) {
-                atomicAdd(&histA[a], HALF_FLUSH);
-                atomicSub(&packed[a >> 1], HALF_FLUSH << sh);
-            }
+            packed_inc(pbase, a, histA);
         }
         if constexpr (F::kB) {
             unsigned b;

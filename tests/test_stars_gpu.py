@@ -83,6 +83,42 @@ def test_background_matches_oracle(al, orc, shape, tile):
     assert al.estimate_background(img, tile) == orc.estimate_background(img, tile)
 
 
+@pytest.mark.parametrize("kind", ["integer", "integer/65535", "8 levels", "two values", "constant + outliers",
+                                  "mostly invalid", "ramp"])
+def test_background_sampled_selection_on_tie_heavy_and_odd_tiles(al, orc, kind):
+    """The sampled-bracket selection of the 256^2 on-chip tiles where the bracket degenerates:
+    massive ties (integer ADU planes: a handful of distinct keys around the median), two-valued and
+    constant tiles, tiles with few valid pixels (thin samples), monotone ramps -- and the radix-select
+    fallback they force.  Medians / MADs / clip rounds must equal the oracle's bit for bit."""
+    rng = np.random.default_rng(11)
+    n = 1024                                  # 16 tiles of 256 x 256 (the detector's tile size here)
+    base = 1000.0 + rng.normal(0.0, 12.0, (n, n))
+    base[rng.random((n, n)) < 2e-3] += 20000.0
+    if kind == "integer":
+        img = np.rint(base)
+    elif kind == "integer/65535":
+        img = np.rint(base) / 65535.0
+    elif kind == "8 levels":
+        img = np.rint(base / 8.0) * 8.0
+    elif kind == "two values":
+        img = np.where(rng.random((n, n)) < 0.5, 1000.0, 1001.0)
+    elif kind == "constant + outliers":
+        img = np.full((n, n), 777.0)
+        img[rng.random((n, n)) < 1e-3] = 5000.0
+    elif kind == "mostly invalid":
+        img = base.copy()
+        img[rng.random((n, n)) < 0.98] = 0.0          # ~1,300 valid pixels per tile
+        img[:256, :256] = 0.0                          # one empty tile
+        img[:256, 256:512][rng.random((256, 256)) < 0.9995] = 0.0   # a tile with ~30 valid pixels
+        img[256:512, :256] = np.nan
+        img[256:263, :1] = base[256:263, :1]           # 7 valid pixels: below the n >= 8 gate
+    else:
+        img = np.add.outer(np.arange(n), np.arange(n)).astype(np.float64) * 0.01 + 1.0
+    img = img.astype(np.float32)
+    assert al.estimate_background(img, 256) == orc.estimate_background(img, 256)
+    same_detection(al.detect_stars(img, 4.0), orc.detect_stars(img, 4.0))
+
+
 @pytest.mark.parametrize("shape,n,sigma", [((512, 512), 80, 5.0), ((700, 900), 300, 3.5), ((1500, 1100), 500, 4.0)])
 def test_detect_matches_oracle(al, orc, shape, n, sigma):
     img = star_field(*shape, n_stars=n, seed=n)

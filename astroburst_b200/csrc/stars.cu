@@ -81,6 +81,7 @@ __device__ __forceinline__ float tile_load(const TileCtx &t, unsigned i) {
 struct FromGlobal {
     TileCtx t;
     __device__ __forceinline__ int slots() const { return 1; }
+    __device__ __forceinline__ bool presampled(float &, float &) const { return false; }
     template <typename Fn>
     __device__ __forceinline__ void for_each(Fn fn) const {
         const unsigned n_px = (unsigned)(t.th * t.tw);
@@ -92,14 +93,26 @@ struct OnChip {
     float rv[OC_REG];
     const float *sm;  // [OC_SMEM][OC_THREADS], slot-major: conflict-free
     int n_slots;      // ceil(n_px / OC_THREADS); empty positions hold NaN (never valid)
+    float samp0, samp1;  // this thread's two samples for the bracket selection (+inf = none)
     __device__ __forceinline__ void fill(const TileCtx &t, float *smw) {
         const unsigned n_px = (unsigned)(t.th * t.tw);
         n_slots = (int)((n_px + OC_THREADS - 1) / OC_THREADS);
         sm = smw;
+        // the sample is taken while the tile streams in: the first valid value at or after two
+        // pseudo-random slots of this thread's column (a spatially spread sample, no extra pass)
+        const unsigned ns = (unsigned)max(n_slots, 1);
+        const unsigned w0 = (threadIdx.x * 2654435761u >> 16) % ns, w1 = (w0 + (ns >> 1)) % ns;
+        float p0 = CUDART_INF_F, p1 = CUDART_INF_F;
+        auto note = [&](float v, unsigned j) {
+            const bool ok = v > 1e-7f && v < CUDART_INF_F;
+            if (ok && j >= w0 && p0 == CUDART_INF_F) p0 = v;
+            if (ok && j >= w1 && j != w0 && p1 == CUDART_INF_F) p1 = v;
+        };
 #pragma unroll
         for (int j = 0; j < OC_REG; ++j) {
             const unsigned i = (unsigned)j * OC_THREADS + threadIdx.x;
             rv[j] = i < n_px ? tile_load(t, i) : CUDART_NAN_F;
+            note(rv[j], (unsigned)j);
         }
         int j = OC_REG;
         for (; j + 8 <= n_slots; j += 8) {  // 8 loads in flight per thread
@@ -110,12 +123,24 @@ struct OnChip {
                 v[u] = i < n_px ? tile_load(t, i) : CUDART_NAN_F;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) smw[(j + u - OC_REG) * OC_THREADS + threadIdx.x] = v[u];
+            for (int u = 0; u < 8; ++u) {
+                smw[(j + u - OC_REG) * OC_THREADS + threadIdx.x] = v[u];
+                note(v[u], (unsigned)(j + u));
+            }
         }
         for (; j < n_slots; ++j) {
             const unsigned i = (unsigned)j * OC_THREADS + threadIdx.x;
-            smw[(j - OC_REG) * OC_THREADS + threadIdx.x] = i < n_px ? tile_load(t, i) : CUDART_NAN_F;
+            const float v = i < n_px ? tile_load(t, i) : CUDART_NAN_F;
+            smw[(j - OC_REG) * OC_THREADS + threadIdx.x] = v;
+            note(v, (unsigned)j);
         }
+        samp0 = p0;
+        samp1 = ns > 1 ? p1 : CUDART_INF_F;
+    }
+    __device__ __forceinline__ bool presampled(float &a, float &b) const {
+        a = samp0;
+        b = samp1;
+        return true;
     }
     __device__ __forceinline__ int slots() const { return n_slots; }
     template <typename Fn>
@@ -350,17 +375,19 @@ __device__ __forceinline__ void sort_samples(unsigned *sk) {
 template <typename Src>
 __device__ __forceinline__ void tile_sample(const Src &src, Sel &s) {
     if (!s.samp_v) return;
-    const unsigned ns = (unsigned)max(src.slots(), 1);
-    const unsigned w0 = (threadIdx.x * 2654435761u >> 16) % ns, w1 = (w0 + (ns >> 1)) % ns;
-    unsigned idx = 0;
     float p0 = CUDART_INF_F, p1 = CUDART_INF_F;
-    src.for_each([&](float v) {
-        const bool ok = v > 1e-7f && v < CUDART_INF_F;
-        if (ok && idx >= w0 && p0 == CUDART_INF_F) p0 = v;
-        if (ok && idx >= w1 && idx != w0 && p1 == CUDART_INF_F) p1 = v;
-        ++idx;
-    });
-    if (ns < 2) p1 = CUDART_INF_F;
+    if (!src.presampled(p0, p1)) {  // (sources that did not sample while loading: one pass)
+        const unsigned ns = (unsigned)max(src.slots(), 1);
+        const unsigned w0 = (threadIdx.x * 2654435761u >> 16) % ns, w1 = (w0 + (ns >> 1)) % ns;
+        unsigned idx = 0;
+        src.for_each([&](float v) {
+            const bool ok = v > 1e-7f && v < CUDART_INF_F;
+            if (ok && idx >= w0 && p0 == CUDART_INF_F) p0 = v;
+            if (ok && idx >= w1 && idx != w0 && p1 == CUDART_INF_F) p1 = v;
+            ++idx;
+        });
+        if (ns < 2) p1 = CUDART_INF_F;
+    }
     if (threadIdx.x == 0) s.n_samp = 0;
     __syncthreads();
     unsigned c = (p0 < CUDART_INF_F) + (p1 < CUDART_INF_F);

@@ -9,6 +9,9 @@ with linked STF + curves (cmd/processing/curves.rs:58-191).  Works on a ROW BAND
 sweeps need nothing from other bands, the statistics come from `stats_fn`, which is either the
 single-GPU ab_image_stats_dev or the sharded, NCCL-reduced variant (parallel.py).
 
+`process_fits`: the mono branch of process_fits / process_fits_full (cmd/io/mod.rs:23-31,103-170) from
+the file's data unit to the u8 preview plane and the display histogram.
+
 config 3 (`align_and_warp`): align_channels_cmd with alignMethod = "affine"
 (cmd/compose/blend.rs:226-348): every target frame is registered against the reference frame
 (align_channel_affine, affine.rs:129-212) and resampled with warp_image (affine.rs:663-690).
@@ -155,6 +158,55 @@ def color_chain(ch_ptrs: Sequence[int], n: int, rows: int, cols: int, weights, c
     tc.apply_scnr, tc.scnr = 0, ScnrConfigC(0, 0.0, 0)
     ctx.check(lib().ab_tone_composite_dev(h, r_ptr, g_ptr, b_ptr, n, C.addressof(tc), r_ptr, g_ptr, b_ptr, s))
     return ColorChainResult(stats_blend, tuple(float(f) for f in fac), tuple(bal), stf, ctx.launch_count - l0, lut)
+
+
+# ------------------------------------------------------------------------------------- process_fits
+@dataclass
+class ProcessFitsResult:
+    stats: ImageStatsC
+    stf: StfParamsC
+    preview_u8: np.ndarray                 # rows x cols, what save_preview_png receives
+    histogram_bins: Optional[np.ndarray]   # 512 display bins (process_fits_full), else None
+
+
+def process_fits(unit, bitpix: int, bscale: float, bzero: float, rows: int, cols: int, full: bool = False,
+                 ctx: Context | None = None) -> ProcessFitsResult:
+    """The mono branch of process_fits / process_fits_full (cmd/io/mod.rs:23-31,103-170) between the
+    file read and the PNG encoder, with the plane resident in HBM: the data unit is uploaded as bytes,
+    decode_pixels (infra/fits/reader.rs:37-101), compute_image_stats, apply_stf and -- for the full
+    command -- compute_histogram_with_stats run on the device; auto_stf and downsample_histogram are the
+    scalar / 65,536-element host code.  One upload of the file's bytes, one download of the u8 preview."""
+    import torch
+
+    ctx = ctx or default_context()
+    h = ctx.handle
+    n = rows * cols
+    raw = np.frombuffer(unit, np.uint8) if isinstance(unit, (bytes, bytearray, memoryview)) else np.ascontiguousarray(unit).view(np.uint8).reshape(-1)
+    bpp = abs(int(bitpix)) // 8
+    if bpp == 0 or raw.size < n * bpp:
+        raise ValueError(f"data unit of {raw.size} bytes for {rows}x{cols} BITPIX {bitpix}")
+    dev = torch.device("cuda", ctx.device)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    s = stream if stream else None
+    d_raw = torch.from_numpy(raw[: n * bpp].copy()).to(dev, non_blocking=True)
+    plane = torch.empty(n, dtype=torch.float32, device=dev)
+    ctx.check(lib().ab_fits_decode_dev(h, d_raw.data_ptr(), n, int(bitpix), float(bscale), float(bzero), plane.data_ptr(), s))
+    st = ImageStatsC()
+    ctx.check(lib().ab_image_stats_dev(h, plane.data_ptr(), n, 0, 0.0, 0.0, C.addressof(st), s))
+    cfg = AutoStfConfigC(0.25, -2.8)
+    stf = StfParamsC()
+    lib().ab_auto_stf(C.addressof(st), C.addressof(cfg), C.addressof(stf))
+    u8 = torch.empty(n, dtype=torch.uint8, device=dev)
+    ctx.check(lib().ab_apply_stf_u8_dev(h, plane.data_ptr(), n, C.addressof(stf), C.addressof(st), u8.data_ptr(), s))
+    bins = None
+    if full:
+        hist = np.zeros(65536, np.uint32)
+        edges = np.zeros(65537, np.float64)
+        ctx.check(lib().ab_histogram_u32_dev(h, plane.data_ptr(), n, 65536, st.min, st.max, hist.ctypes.data,
+                                             edges.ctypes.data, s))
+        bins = np.zeros(512, np.uint32)
+        ctx.check(lib().ab_downsample_histogram(hist.ctypes.data, hist.size, 512, bins.ctypes.data))
+    return ProcessFitsResult(st, stf, u8.cpu().numpy().reshape(rows, cols), bins)
 
 
 # ------------------------------------------------------------------------------------- config 3

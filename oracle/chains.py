@@ -62,3 +62,18 @@ def color_chain(chans, weights, curve_points, scnr_after_wb=("average", 0.5, Fal
     return out, stats_blend, tuple(bal), stf
 
 
+
+
+def process_fits(unit: bytes, bitpix: int, bscale: float, bzero: float, rows: int, cols: int, full: bool = False):
+    """process_fits / process_fits_full for a mono image, cmd/io/mod.rs:23-31,103-170 (after the file
+    read, before the PNG encoder): decode_pixels -> compute_image_stats -> auto_stf(default) ->
+    apply_stf (u8) [-> compute_histogram_with_stats -> downsample_histogram(512)]."""
+    img = oracle.fits_decode(unit, bitpix, bscale, bzero).reshape(rows, cols)
+    stats = oracle.compute_image_stats(img)
+    stf = oracle.auto_stf(stats)
+    u8 = oracle.apply_stf(img, stf, stats)
+    bins = None
+    if full:
+        hist, _ = oracle.build_histogram(img, 65536, stats.min, stats.max)
+        bins = oracle.downsample_histogram(hist, 512)
+    return stats, stf, u8, bins

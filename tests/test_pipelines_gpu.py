@@ -107,3 +107,33 @@ def test_align_with_shared_reference_star_list_equals_pairwise_align(orc):
     pair4 = AlignResultC()
     ctx.check(lib().ab_align_affine_dev(ctx.handle, d_ref.data_ptr(), flat.data_ptr(), rows, cols, 8, C.addressof(pair4), s))
     assert tup(got4) == tup(pair4) and got4.method in (2, 3)
+
+
+@pytest.mark.parametrize("bitpix,shape", [(16, (700, 900)), (-32, (2100, 2000)), (16, (2100, 2000)), (8, (300, 301)), (-64, (257, 129))])
+def test_process_fits_chain_matches_oracle_chain(orc, bitpix, shape):
+    """pipelines.process_fits (mono branch of process_fits_full, cmd/io/mod.rs:23-31,103-170) against the
+    same composition of the oracle: statistics (exact-select and histogram sizes), auto-STF, the u8
+    preview plane and the 512 display bins, bit for bit."""
+    from astroburst_b200 import pipelines
+    from oracle import chains
+
+    rows, cols = shape
+    rng = np.random.default_rng(abs(bitpix) + rows)
+    sky = 900.0 + rng.normal(0.0, 15.0, shape)
+    sky[rng.random(shape) < 1e-3] += rng.uniform(500, 30000)
+    sky[: rows // 25] = 0.0                                   # padding strip (invalid: <= 1e-7)
+    if bitpix == 16:
+        unit, bscale, bzero = np.clip(np.rint(sky - 32768.0), -32768, 32767).astype(">i2").tobytes(), 1.0, 32768.0
+    elif bitpix == 8:
+        unit, bscale, bzero = np.clip(np.rint(sky / 128.0), 0, 255).astype(np.uint8).tobytes(), 128.0, 0.0
+    elif bitpix == -32:
+        unit, bscale, bzero = sky.astype(">f4").tobytes(), 1.0, 0.0
+    else:
+        unit, bscale, bzero = sky.astype(">f8").tobytes(), 0.5, 3.0
+    got = pipelines.process_fits(unit, bitpix, bscale, bzero, rows, cols, full=True)
+    stats, stf, u8, bins = chains.process_fits(unit, bitpix, bscale, bzero, rows, cols, full=True)
+    key = lambda s: (s.min, s.max, s.median, s.mad, s.sigma, int(s.valid_count))
+    assert key(got.stats) == key(stats) and abs(got.stats.mean - stats.mean) <= 1e-12 * abs(stats.mean)
+    assert (got.stf.shadow, got.stf.midtone, got.stf.highlight) == (stf.shadow, stf.midtone, stf.highlight)
+    assert np.array_equal(got.preview_u8, np.asarray(u8).reshape(rows, cols))
+    assert np.array_equal(got.histogram_bins, bins)

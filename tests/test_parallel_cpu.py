@@ -176,3 +176,19 @@ def test_c_abi_partition_rules_match_the_python_mirror():
     for n in (1, 3, 8, 40, 255, 256):
         for world in (1, 2, 5, 8):
             assert [lib.ab_frame_owner(f, n, world) for f in range(n)] == [frame_owner(f, n, world) for f in range(n)]
+
+
+def test_bind_to_gpu_numa_never_raises_and_keeps_a_usable_mask(monkeypatch):
+    """Host placement is an optimisation: without NVML / a GPU it must leave the affinity mask alone
+    and say so; with AB_NO_NUMA_BIND it must do nothing."""
+    import os
+    from astroburst_b200 import parallel
+
+    before = os.sched_getaffinity(0)
+    msg = parallel.bind_to_gpu_numa(0)
+    assert isinstance(msg, str) and msg
+    assert os.sched_getaffinity(0) and os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)
+    monkeypatch.setenv("AB_NO_NUMA_BIND", "1")
+    assert parallel.bind_to_gpu_numa(0).startswith("off")
+    assert os.sched_getaffinity(0) == before

@@ -137,3 +137,40 @@ def test_process_fits_chain_matches_oracle_chain(orc, bitpix, shape):
     assert (got.stf.shadow, got.stf.midtone, got.stf.highlight) == (stf.shadow, stf.midtone, stf.highlight)
     assert np.array_equal(got.preview_u8, np.asarray(u8).reshape(rows, cols))
     assert np.array_equal(got.histogram_bins, bins)
+
+
+def test_align_channels_with_lanes_equals_pairwise_align(orc):
+    """pipelines.align_channels (several host threads / contexts feeding one GPU) returns, for every
+    target, exactly what the per-pair aligner returns, and the warped planes equal the oracle's."""
+    import importlib, os, sys
+    import torch
+    import astroburst_b200 as ab
+    from astroburst_b200 import pipelines
+    from astroburst_b200._lib import AlignResultC, lib
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    star_field = importlib.import_module("test_stars_gpu").star_field
+    rows = cols = 768
+    dev = torch.device("cuda:0")
+    ctx = ab.default_context(0)
+    s = torch.cuda.current_stream().cuda_stream
+    ref = star_field(rows, cols, 220, seed=21)
+    tfs = []
+    for k in range(5):
+        th = math.radians(0.3 * (k + 1))
+        tfs.append((math.cos(th), -math.sin(th), 3.5 * k - 4.0, math.sin(th), math.cos(th), 2.25 - 1.5 * k))
+    tgts = [star_field(rows, cols, 220, seed=21, transform=t, noise_seed=40 + k) for k, t in enumerate(tfs)]
+    tgts.append(np.full((rows, cols), 0.5, np.float32))            # no stars: the fallback path inside a lane
+    d_ref = torch.from_numpy(ref).to(dev)
+    d_t = [torch.from_numpy(t).to(dev) for t in tgts]
+    outs = [torch.empty_like(x) for x in d_t]
+    tup = lambda r: tuple(getattr(r.transform, k) for k in "a b tx c d ty".split()) + (r.method, r.inliers, r.residual_px)
+    for lanes in (1, 3):
+        res = pipelines.align_channels(d_ref.data_ptr(), [x.data_ptr() for x in d_t], [o.data_ptr() for o in outs],
+                                       rows, cols, 8, lanes, ctx)
+        for k, (r, x, o) in enumerate(zip(res, d_t, outs)):
+            pair = AlignResultC()
+            ctx.check(lib().ab_align_affine_dev(ctx.handle, d_ref.data_ptr(), x.data_ptr(), rows, cols, 8, C.addressof(pair), s))
+            assert tup(r) == tup(pair), (lanes, k)
+            want = orc.warp_image(tgts[k], tup(r)[:6], rows, cols)
+            assert np.array_equal(o.cpu().numpy(), want), (lanes, k)

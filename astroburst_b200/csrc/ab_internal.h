@@ -134,7 +134,7 @@ struct PeerScalarOp {  // up to 8 scalars per call: kind 0 f64 sum, 1 u64 sum, 2
 // `count` u32 words (0 = none) and the scalars of `op` under ONE barrier pair
 ab_status ab_peer_allreduce(ab_ctx *ctx, size_t src_off, size_t dst_off, size_t count,
                             const PeerScalarOp &op, cudaStream_t s);
-ab_status ab_peer_check(ab_ctx *ctx);  // after a synchronisation: did a barrier time out?
+ab_status ab_peer_check(ab_ctx *ctx, cudaStream_t s);  // after a synchronisation: did a barrier time out?
 
 // ---- stack.cu
 struct FrameTable {

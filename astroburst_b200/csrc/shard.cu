@@ -165,11 +165,15 @@ ab_status ab_peer_allreduce(ab_ctx *ctx, size_t src_off, size_t dst_off, size_t 
     }
     return peer_barrier(ctx, s);  // every rank has read every source: they may be overwritten
 }
-ab_status ab_peer_check(ab_ctx *ctx) {
+ab_status ab_peer_check(ab_ctx *ctx, cudaStream_t s) {
     if (ctx->peer_world < 1) return AB_OK;
     unsigned err = 0;
-    AB_CUDA(ctx, cudaMemcpy(&err, ctx->peer_small[ctx->peer_rank] + AB_SMALL_PEER_FLAGS + AB_MAX_RANKS * 8, 4,
-                            cudaMemcpyDeviceToHost));
+    // on the caller's stream: a synchronous cudaMemcpy is a NULL-stream command, which would order
+    // this thread behind kernels other host threads have in the NULL stream (a spinning barrier
+    // of another context's peer group, say) -- a cross-rank deadlock with several contexts per GPU
+    AB_CUDA(ctx, cudaMemcpyAsync(&err, ctx->peer_small[ctx->peer_rank] + AB_SMALL_PEER_FLAGS + AB_MAX_RANKS * 8, 4,
+                                 cudaMemcpyDeviceToHost, s));
+    AB_CUDA(ctx, cudaStreamSynchronize(s));
     if (err) return ab_fail(ctx, AB_ERR_CUDA, "peer barrier timed out (a rank of the peer group did not arrive)");
     return AB_OK;
 }

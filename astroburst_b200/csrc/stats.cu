@@ -1035,7 +1035,7 @@ ab_status stats_hist_chained(ab_ctx *ctx, const float *d, size_t len, bool known
     AB_CUDA(ctx, cudaMemcpyAsync(h_out, &ctl->out, sizeof(ab_image_stats), cudaMemcpyDeviceToHost, s));
     AB_CUDA(ctx, cudaStreamSynchronize(s));
     *out = *h_out;
-    return rd.peer ? ab_peer_check(ctx) : AB_OK;
+    return rd.peer ? ab_peer_check(ctx, s) : AB_OK;
 }
 
 // stats.rs:43-73

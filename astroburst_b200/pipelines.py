@@ -91,6 +91,24 @@ def auto_wb_factors(sr: ImageStatsC, sg: ImageStatsC, sb: ImageStatsC):
     return m / max(sr.median, 1e-10), 1.0, m / max(sb.median, 1e-10)
 
 
+def _sync_stream(stream: int) -> None:
+    import torch
+
+    if stream:
+        torch.cuda.ExternalStream(stream).synchronize()
+    else:
+        torch.cuda.synchronize()
+
+
+@dataclass
+class StatsLane:
+    """One of the host threads that compute the three channel statistics of a colour-chain stage
+    side by side: its own context (scratch, peer group), its stream and its stats_fn."""
+    ctx: Context
+    stream: int
+    stats_fn: Callable
+
+
 @dataclass
 class ColorChainResult:
     stats_blend: tuple          # ImageStats of the blended R, G, B (blend.rs:187-193)
@@ -103,38 +121,64 @@ class ColorChainResult:
 
 def color_chain(ch_ptrs: Sequence[int], n: int, rows: int, cols: int, weights, curve_points,
                 r_ptr: int, g_ptr: int, b_ptr: int, stats_fn: Callable, total_pixels: Optional[int] = None,
-                scnr_after_wb=(0, 0.5, 0), ctx: Context | None = None, stream: int = 0) -> ColorChainResult:
+                scnr_after_wb=(0, 0.5, 0), ctx: Context | None = None, stream: int = 0,
+                lanes: Optional[Sequence[StatsLane]] = None, pool=None) -> ColorChainResult:
     """The config-4 colour chain on `n` = rows * cols pixels (one row band, or the whole image).
     ch_ptrs: device planes of the input channels; r/g/b_ptr: three device planes that receive the
     result (they are also the working planes).  weights: [(channel_idx, r, g, b), ...].
-    scnr_after_wb: (method, amount, preserve_luminance) of calibrate_and_scnr_cmd."""
+    scnr_after_wb: (method, amount, preserve_luminance) of calibrate_and_scnr_cmd.
+    lanes (three StatsLane) + pool (a 3-thread executor): the R, G, B statistics of a stage -- and
+    the white-balance scale in front of them -- run side by side on three contexts; every statistic
+    ends in a small read-back, and the other channels' sweeps fill the GPU meanwhile."""
     ctx = ctx or default_context()
     h = ctx.handle
     s = stream if stream else None
-    l0 = ctx.launch_count
+    all_ctx = list({id(c): c for c in [ctx] + ([l.ctx for l in lanes] if lanes else [])}.values())
+    l0 = sum(c.launch_count for c in all_ctx)
     total_pixels = total_pixels or n
+    use_lanes = bool(lanes) and pool is not None and len(lanes) == 3
+
+    def per_channel(fn):
+        """fn(k, lane) for k = 0, 1, 2 on the three lanes -> [result_r, result_g, result_b]"""
+        futs = [pool.submit(fn, k, lanes[k]) for k in (1, 2)]
+        first = fn(0, lanes[0])
+        return [first] + [f.result() for f in futs]
     # ---- blend_channels_cmd: blend + 3 x compute_image_stats
     w = (BlendWeightC * len(weights))(*[BlendWeightC(*x) for x in weights])
     ptrs = (C.c_void_p * len(ch_ptrs))(*[int(p) for p in ch_ptrs])
     lens = (C.c_size_t * len(ch_ptrs))(*([n] * len(ch_ptrs)))
     ctx.check(lib().ab_blend_channels_dev(h, ptrs, lens, len(ch_ptrs), w, len(weights), rows, cols, r_ptr, g_ptr,
                                           b_ptr, s))
-    s_r, s_g, s_b = stats_fn(r_ptr, n), stats_fn(g_ptr, n), stats_fn(b_ptr, n)
+    planes = (r_ptr, g_ptr, b_ptr)
+    if use_lanes:
+        _sync_stream(stream)     # the blend has finished before the other lanes' streams read its planes
+        s_r, s_g, s_b = per_channel(lambda k, lane: lane.stats_fn(planes[k], n))
+    else:
+        s_r, s_g, s_b = stats_fn(r_ptr, n), stats_fn(g_ptr, n), stats_fn(b_ptr, n)
     stats_blend = (s_r, s_g, s_b)
     # ---- compute_auto_wb_cmd -> calibrate_and_scnr_cmd
     fac = [max(np.float32(f), np.float32(1e-6)) for f in auto_wb_factors(s_r, s_g, s_b)]   # color.rs:115-117
-    bal = []
-    for ptr, f, st in ((r_ptr, fac[0], s_r), (g_ptr, fac[1], s_g), (b_ptr, fac[2], s_b)):
-        ctx.check(lib().ab_scale_dev(h, ptr, n, C.c_float(float(f)), ptr, s))             # calibrate_channel :21-49
+    def calibrate_channel(ptr, f, st, c, cs, fn):   # calibrate_channel, color.rs:21-49
+        c.check(lib().ab_scale_dev(c.handle, ptr, n, C.c_float(float(f)), ptr, cs if cs else None))
         if total_pixels <= PAR_THRESHOLD:
-            bal.append(stats_fn(ptr, n))
-        else:  # factor >= 0 here (floored at 1e-6): known range = orig range * factor (f64)
-            bal.append(stats_fn(ptr, n, (st.min * float(f), st.max * float(f))))
+            return fn(ptr, n)
+        # factor >= 0 here (floored at 1e-6): known range = orig range * factor (f64)
+        return fn(ptr, n, (st.min * float(f), st.max * float(f)))
+
+    before = (s_r, s_g, s_b)
+    if use_lanes:
+        bal = per_channel(lambda k, lane: calibrate_channel(planes[k], fac[k], before[k], lane.ctx, lane.stream,
+                                                            lane.stats_fn))
+    else:
+        bal = [calibrate_channel(planes[k], fac[k], before[k], ctx, stream, stats_fn) for k in range(3)]
     method, amount, preserve = scnr_after_wb
     if amount > 1e-7:
         cfg = ScnrConfigC(method, amount, preserve)
         ctx.check(lib().ab_apply_scnr_dev(h, r_ptr, g_ptr, b_ptr, n, C.addressof(cfg), s))
-        if preserve:
+        if preserve and use_lanes:
+            _sync_stream(stream)
+            bal = per_channel(lambda k, lane: lane.stats_fn(planes[k], n))
+        elif preserve:
             bal = [stats_fn(r_ptr, n), stats_fn(g_ptr, n), stats_fn(b_ptr, n)]
         else:
             bal[1] = stats_fn(g_ptr, n)
@@ -157,7 +201,8 @@ def color_chain(ch_ptrs: Sequence[int], n: int, rows: int, cols: int, weights, c
         tc.lut[k] = lut.data_ptr()
     tc.apply_scnr, tc.scnr = 0, ScnrConfigC(0, 0.0, 0)
     ctx.check(lib().ab_tone_composite_dev(h, r_ptr, g_ptr, b_ptr, n, C.addressof(tc), r_ptr, g_ptr, b_ptr, s))
-    return ColorChainResult(stats_blend, tuple(float(f) for f in fac), tuple(bal), stf, ctx.launch_count - l0, lut)
+    l1 = sum(c.launch_count for c in all_ctx)
+    return ColorChainResult(stats_blend, tuple(float(f) for f in fac), tuple(bal), stf, l1 - l0, lut)
 
 
 # ------------------------------------------------------------------------------------- process_fits

@@ -89,32 +89,61 @@ def run_config4(torch, dist, ab, ctx, dev, rank, world, reps=3, rows=13759, cols
     ms_nccl = None
     res_box = [None]
 
-    def chain(stats_fn):
+    # Three lanes (host threads with their own context + stream) compute the R, G, B statistics of a
+    # stage side by side (AB_C4_LANES=1: one after the other): every statistic ends in a read-back,
+    # and at N > 1 in four peer reductions, which the other channels' sweeps overlap.
+    from concurrent.futures import ThreadPoolExecutor
+
+    # One GPU only: with a peer group per lane, barrier kernels of different lanes spin on the GPU at the
+    # same time, and two streams that share a hardware queue then order one lane's sweep behind another
+    # lane's barrier -- across ranks that is a cycle (measured: 1 in 5 runs timed out at N = 2).
+    use_lanes = world == 1 and os.environ.get("AB_C4_LANES", "3") != "1"
+    lane_ctx = [ctx] + ([ab.Context(dev.index), ab.Context(dev.index)] if use_lanes else [])
+    # every lane on a stream of its own (never the NULL stream: its implicit ordering against other
+    # streams would couple the lanes, and across ranks the peer barriers could then wait in a cycle)
+    lane_stream_objs = [torch.cuda.Stream(device=dev) for _ in range(3 if use_lanes else 1)]   # (kept alive)
+    lane_streams = [o.cuda_stream for o in lane_stream_objs]
+    stream = lane_streams[0]
+    torch.cuda.synchronize()   # the source planes (made on the current stream) exist before the lanes read them
+    pool = ThreadPoolExecutor(3) if use_lanes else None
+
+    def chain(stats_fns):
+        lanes = [pipelines.StatsLane(c, st, fn) for c, st, fn in zip(lane_ctx, lane_streams, stats_fns)] if use_lanes else None
         res_box[0] = pipelines.color_chain([s.data_ptr() for s in src], n, r1 - r0, cols, C4_WEIGHTS, C4_CURVE,
-                                           out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), stats_fn,
-                                           total_pixels=total, ctx=ctx, stream=stream)
+                                           out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), stats_fns[0],
+                                           total_pixels=total, ctx=ctx, stream=stream, lanes=lanes, pool=pool)
 
     if world > 1:
-        # statistics reduced (a) by NCCL through the device callback, (b) by the library's own
-        # kernels over peer memory (NVLink) -- (b) is the product path, (a) is timed beside it
+        # statistics reduced (a) by NCCL through the device callback (one lane: NCCL calls from several
+        # host threads would have to be ordered across ranks), (b) by the library's own kernels over
+        # peer memory (NVLink) -- (b) is the product path, (a) is timed beside it
         cb = parallel.make_allreduce_dev(dev)
         fn_nccl = pipelines.stats_sharded(ctx, stream, cb, total)
-        chain(fn_nccl)
-        ms_nccl = _wall_max(torch, dist, world, dev, lambda: chain(fn_nccl), max(reps - 1, 1))
-        parallel.connect_peer_group(ctx)
-        stats_fn = pipelines.stats_peer(ctx, stream, total)
+        lanes_saved, use_lanes = use_lanes, False
+        chain([fn_nccl])
+        ms_nccl = _wall_max(torch, dist, world, dev, lambda: chain([fn_nccl]), max(reps - 1, 1))
+        use_lanes = lanes_saved
+        for c in lane_ctx:
+            parallel.connect_peer_group(c)
+        stats_fns = [pipelines.stats_peer(c, st, total) for c, st in zip(lane_ctx, lane_streams)]
     else:
-        stats_fn = pipelines.stats_single_gpu(ctx, stream)
-    chain(stats_fn)  # warm-up
-    ms = _wall_max(torch, dist, world, dev, lambda: chain(stats_fn), reps)
+        stats_fns = [pipelines.stats_single_gpu(c, st) for c, st in zip(lane_ctx, lane_streams)]
+    chain(stats_fns)  # warm-up
+    ms = _wall_max(torch, dist, world, dev, lambda: chain(stats_fns), reps)
     res = res_box[0]
     if world > 1:
-        parallel.disconnect_peer_group(ctx)
+        for c in lane_ctx:
+            parallel.disconnect_peer_group(c)
+    if pool is not None:
+        pool.shutdown()
+    for c in lane_ctx[1:]:
+        c.close()
     algo = 20.56e9 * (total / (13759 * 12451))  # 20.56 GB at the full size
     peak = _peak()
     info = {"workload": f"3-channel blend + WB + SCNR + linked STF + curve, {rows}x{cols} f32, row-banded over "
                         f"{world} GPU(s); 7 image statistics (3 blend, 3 WB known-range, G re-stat)"
-                        + (" reduced inside kernels over peer memory (NVLink), no NCCL" if world > 1 else ""),
+                        + (" reduced inside kernels over peer memory (NVLink), no NCCL" if world > 1 else "")
+                        + (", the three channel statistics of a stage on three host threads / contexts" if use_lanes else ""),
             "ms_total": ms, "value": total / (ms * 1e-3) / 1e6, "unit": "Mpix/s",
             "algorithmic_bytes": int(algo), "ideal_ms_at_measured_peak": algo / peak / 1e6 / world,
             "frac_of_roofline": algo / (ms * 1e-3) / 1e9 / (peak * world), "gpu_launches": int(res.launches),

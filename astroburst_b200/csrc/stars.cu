@@ -55,11 +55,12 @@ __device__ __forceinline__ float norm_px(const Norm &nm, float v) {
 
 // ------------------------------------------------------------------------- background tiles
 // One block per tile runs sigma_clipped_stats (sigma_clip.rs:4-34) as a sequence of exact
-// selections (MSB-first radix select on the float bit patterns).  The ~30 passes of a tile read
-// its pixels from a pixel source: `OnChip` holds the whole tile (<= 65,536 px, every tile the
-// detector makes) in the SM -- 48 values per thread in shared memory plus 16 in registers at
-// 1,024 threads -- so HBM/L2 is read once per tile; `FromGlobal` re-reads global memory and serves
-// caller-chosen tile sizes beyond that (ab_estimate_background).
+// selections over a pixel source.  `OnChip` holds the whole tile (<= 65,536 px, every tile the
+// detector makes) in the SM -- 48 values per thread in shared memory plus 16 thread-local at
+// 1,024 threads -- so HBM/L2 is read once per tile, and selects with sampled brackets (one pass
+// per statistic, see below) with the MSB-first radix select on the float bit patterns as the
+// exact way out; `FromGlobal` re-reads global memory (radix select only) and serves caller-chosen
+// tile sizes beyond the on-chip capacity (ab_estimate_background).
 struct TileCtx {
     const float *img;
     size_t cols;

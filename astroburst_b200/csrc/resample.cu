@@ -73,13 +73,17 @@ __device__ __forceinline__ double cr_far(double a) { return a * (a * (2.5 - 0.5 
 // The same value on the common path: coordinates inside a plane of < 2^31 pixels per side, so the
 // tap indices are 32-bit, the fractional parts are x - floor(x) (== x - (double)(i64)floor(x)) and
 // interior pixels need no clamping.  Everything else goes to bicubic_sample_generic.
+// kInBounds: the caller has already established -1 <= x <= cols and -1 <= y <= rows (the warp's and
+// the shift's own bounds rules), so floor() and the fractions need no range test (8 f64 compares).
+template <bool kInBounds>
 __device__ __forceinline__ float bicubic_sample(const float *__restrict__ s, size_t rows,
                                                 size_t cols, double y, double x) {
     const double fxf = floor(x), fyf = floor(y);
     const double fx = x - fxf, fy = y - fyf;
-    const bool plain = fxf >= -2.0 && fyf >= -2.0 && fxf <= (double)cols && fyf <= (double)rows &&
-                       fx >= 0.0 && fx <= 1.0 && fy >= 0.0 && fy <= 1.0 && rows < 0x7ffffff0u &&
-                       cols < 0x7ffffff0u;
+    bool plain = rows < 0x7ffffff0u && cols < 0x7ffffff0u;
+    if (!kInBounds)
+        plain = plain && fxf >= -2.0 && fyf >= -2.0 && fxf <= (double)cols && fyf <= (double)rows &&
+                fx >= 0.0 && fx <= 1.0 && fy >= 0.0 && fy <= 1.0;
     if (!plain) return bicubic_sample_generic(s, rows, cols, y, x);
     const int ix = (int)fxf, iy = (int)fyf, nc = (int)cols, nr = (int)rows;
     const double wx0 = cr_far(fx + 1.0), wx1 = cr_near(fx), wx2 = cr_near(fabs(fx - 1.0)),
@@ -139,17 +143,20 @@ gather_kernel(const float *__restrict__ src, size_t src_rows, size_t src_cols,
             const double sx = gp.a * (double)x + gp.b * (double)y + gp.tx;
             const double sy = gp.c * (double)x + gp.d * (double)y + gp.ty;
             if (sx >= 0.0 && sy >= 0.0 && sx < (double)(src_cols - 1) && sy < (double)(src_rows - 1))
-                r = bicubic_sample(src, src_rows, src_cols, sy, sx);
+                r = bicubic_sample<true>(src, src_rows, src_cols, sy, sx);
         } else if (MODE == MODE_SHIFT) {
             const double sy = (double)y + gp.dy;
             const double sx = (double)x + gp.dx;
+            // (a NaN shift passes the reference's bounds rule -- every comparison is false -- and must
+            // reach the literal transcription: its NaN weights come out as 0, not NaN)
             if (!(sy < -0.5 || sy > (double)src_rows - 0.5 || sx < -0.5 ||
                   sx > (double)src_cols - 0.5))
-                r = bicubic_sample(src, src_rows, src_cols, sy, sx);
+                r = (gp.dy == gp.dy && gp.dx == gp.dx) ? bicubic_sample<true>(src, src_rows, src_cols, sy, sx)
+                                                       : bicubic_sample<false>(src, src_rows, src_cols, sy, sx);
         } else {
             const double sy = (double)y * gp.scale_y + gp.hy;
             const double sx = (double)x * gp.scale_x + gp.hx;
-            r = bicubic_sample(src, src_rows, src_cols, sy, sx);
+            r = bicubic_sample<false>(src, src_rows, src_cols, sy, sx);
         }
         __stcs(out + y * out_cols + x, r);
     }

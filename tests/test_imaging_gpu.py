@@ -277,6 +277,9 @@ def test_bicubic_weight_joints_and_odd_inputs(im, orc):
     for dy, dx in ((-1e-20, -1e-20), (-eps / 4, eps / 4), (1 - eps / 2, 1 - eps / 2), (-0.5, -0.5), (2.0, 3.0),
                    (1e-300, -1e-300), (0.5 - eps, 63.5), (-0.49999999999999994, 79.49999999999999)):
         assert np.array_equal(im.shift_image_subpixel(img, dy, dx), orc.shift_image_subpixel(img, dy, dx)), (dy, dx)
+    for dy, dx in ((float("nan"), 0.25), (0.25, float("nan")), (float("inf"), 0.0), (0.0, float("-inf"))):
+        a, b = im.shift_image_subpixel(img, dy, dx), orc.shift_image_subpixel(img, dy, dx)   # NaN shifts pass the bounds rule
+        assert np.array_equal(a, b, equal_nan=True) and np.array_equal(np.signbit(a), np.signbit(b)), (dy, dx)
     for t in ((1, 0, 1e-17, 0, 1, 1e-17), (1, 0, 1 - eps / 2, 0, 1, 2 - eps), (1, 1e-18, 0, 1e-18, 1, 0),
               (1, 0, float("nan"), 0, 1, 0), (float("inf"), 0, 0, 0, 1, 0), (0, 0, 5.0, 0, 0, 7.0), (-1, 0, 70.0, 0, -1, 60.0)):
         a, b = im.warp_image(img, t, 64, 80), orc.warp_image(img, t, 64, 80)

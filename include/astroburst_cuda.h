@@ -485,7 +485,11 @@ ab_status ab_image_stats_sharded_chained_dev(ab_ctx *ctx, const float *d_data, s
                                              int use_known_range, double known_min, double known_max,
                                              ab_image_stats *out, void *stream);
 /* The same over the peer group (ab_peer_connect): reductions are kernels that sum the peers'
- * counters / histograms over NVLink in rank order -- no callback, no NCCL, one synchronisation. */
+ * counters / histograms over NVLink in rank order -- no callback, no NCCL, one synchronisation.
+ * The barrier kernels spin until every rank has arrived: keep the peer collectives of ONE context
+ * per GPU in flight at a time (several contexts' barriers spinning on one GPU can wait on each other
+ * across ranks through streams that share a hardware queue) and enqueue them on a real stream,
+ * not the NULL stream. */
 ab_status ab_image_stats_peer_dev(ab_ctx *ctx, const float *d_data, size_t len, int use_known_range,
                                   double known_min, double known_max, ab_image_stats *out,
                                   void *stream);

@@ -958,19 +958,48 @@ __global__ void ccl_emit_kernel(const unsigned *__restrict__ flag, const unsigne
     if (p < n && flag[p]) comps[slot[p]] = {p, off[p], size[p], 0u};
 }
 
+// nbr[8 p + j] = index (in the sparse list) of neighbour j of pixel p in the reference's order
+// N, S, W, E, NW, NE, SW, SE, or 0xffffffff when that pixel is not above the threshold.  All
+// lookups of the BFS replay done up front, fully parallel: the replay itself is a serial walk per
+// component, and a step then costs one table read instead of a binary search per lane.
+__global__ void __launch_bounds__(256)
+ccl_neighbours_kernel(const unsigned *__restrict__ col, const unsigned *__restrict__ rowi,
+                      const unsigned long long *__restrict__ ro, unsigned n, unsigned rows, unsigned cols,
+                      unsigned *__restrict__ nbr) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned cur = t >> 3, j = t & 7;
+    if (cur >= n) return;
+    const int dr = (j == 0 || j == 4 || j == 5) ? -1 : ((j == 1 || j == 6 || j == 7) ? 1 : 0);
+    const int dc = (j == 2 || j == 4 || j == 6) ? -1 : ((j == 3 || j == 5 || j == 7) ? 1 : 0);
+    const unsigned r = __ldg(rowi + cur), c = __ldg(col + cur);
+    const long long nr = (long long)r + dr, nc = (long long)c + dc;
+    unsigned q = 0xffffffffu;
+    if (nr >= 0 && nc >= 0 && nr < (long long)rows && nc < (long long)cols) {
+        if (dr == 0) {
+            const long long cand = (long long)cur + dc;
+            if (cand >= (long long)__ldg(ro + r) && cand < (long long)__ldg(ro + r + 1) &&
+                __ldg(col + cand) == (unsigned)nc)
+                q = (unsigned)cand;
+        } else {
+            const unsigned long long lb = row_lower_bound(col, ro, (size_t)nr, (unsigned)nc);
+            if (lb < __ldg(ro + nr + 1) && __ldg(col + lb) == (unsigned)nc) q = (unsigned)lb;
+        }
+    }
+    nbr[t] = q;
+}
+
 // One 8-lane group per component: BFS replay + moments.  keys[k] = ~bits(flux) (ascending radix
 // sort = flux descending), all ones for components the reference drops (:177-179, :199-201).
 __global__ void __launch_bounds__(128)
 ccl_measure_kernel(const unsigned *__restrict__ col, const unsigned *__restrict__ rowi,
                    const float *__restrict__ val, const unsigned long long *__restrict__ ro,
                    const CompRec *__restrict__ comps, unsigned n_comp, unsigned rows, unsigned cols,
-                   double bg_median, double bg_sigma, unsigned *queue, unsigned char *vis,
-                   StarRec *stars, unsigned long long *keys, unsigned *order, unsigned *n_valid) {
+                   double bg_median, double bg_sigma, const unsigned *__restrict__ nbr, unsigned *queue,
+                   unsigned char *vis, StarRec *stars, unsigned long long *keys, unsigned *order,
+                   unsigned *n_valid) {
     const unsigned lane = threadIdx.x & 31, j = lane & 7, g = lane >> 3;
     const unsigned gmask = 0xffu << (8 * g);
     const unsigned groups = gridDim.x * (blockDim.x >> 3);
-    const int dr = (j == 0 || j == 4 || j == 5) ? -1 : ((j == 1 || j == 6 || j == 7) ? 1 : 0);
-    const int dc = (j == 2 || j == 4 || j == 6) ? -1 : ((j == 3 || j == 5 || j == 7) ? 1 : 0);
     for (unsigned k = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; k < n_comp; k += groups) {
         const CompRec cr = comps[k];
         unsigned *qu = queue + cr.off;
@@ -982,20 +1011,7 @@ ccl_measure_kernel(const unsigned *__restrict__ col, const unsigned *__restrict_
         unsigned head = 0, tail = 1;
         while (head < tail) {
             const unsigned cur = __ldcg(qu + head);
-            const unsigned r = __ldg(rowi + cur), c = __ldg(col + cur);
-            const long long nr = (long long)r + dr, nc = (long long)c + dc;
-            unsigned q = 0xffffffffu;
-            if (nr >= 0 && nc >= 0 && nr < (long long)rows && nc < (long long)cols) {
-                if (dr == 0) {
-                    const long long cand = (long long)cur + dc;
-                    if (cand >= (long long)__ldg(ro + r) && cand < (long long)__ldg(ro + r + 1) &&
-                        __ldg(col + cand) == (unsigned)nc)
-                        q = (unsigned)cand;
-                } else {
-                    const unsigned long long lb = row_lower_bound(col, ro, (size_t)nr, (unsigned)nc);
-                    if (lb < __ldg(ro + nr + 1) && __ldg(col + lb) == (unsigned)nc) q = (unsigned)lb;
-                }
-            }
+            const unsigned q = __ldg(nbr + 8 * (size_t)cur + j);
             const bool fresh = q != 0xffffffffu && __ldcg(vis + q) == 0;
             const unsigned bal = (__ballot_sync(gmask, fresh) >> (8 * g)) & 0xffu;
             if (fresh) {
@@ -1185,7 +1201,7 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
     AB_CUDA(ctx, cudaStreamSynchronize(s));
     const double t_count = ms_since(t1);
     const auto t2 = now();
-    if (nfg64 >= 0xffffffffull)
+    if (nfg64 >= (1ull << 29))  // (8 neighbour slots per pixel are indexed with 32 bits)
         return ab_fail(ctx, AB_ERR_UNSUPPORTED, "detector: %llu pixels above the threshold", nfg64);
     const unsigned nfg = (unsigned)nfg64;
     std::vector<ab_star> sorted;
@@ -1204,7 +1220,7 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
                                         (unsigned long long *)nullptr, (unsigned *)nullptr,
                                         (unsigned *)nullptr, (int)max_comp, 0, 64, s);
         const size_t b_tmp = (std::max(tmp_scan, tmp_sort) + 255) / 256 * 256;
-        const size_t total = 12 * a4 + b_comp + 2 * b_star + 2 * b_k8 + 2 * b_k4 + b_tmp + 256;
+        const size_t total = 20 * a4 + b_comp + 2 * b_star + 2 * b_k8 + 2 * b_k4 + b_tmp + 256;  // (+ 8 a4: neighbour table)
         st = ab_scratch_reserve(ctx, 2, total);
         if (st != AB_OK) return st;
         char *q = static_cast<char *>(ctx->d_scratch[2]);
@@ -1221,6 +1237,7 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
         unsigned *d_slot = (unsigned *)take(a4), *d_off = (unsigned *)take(a4);
         unsigned *d_queue = (unsigned *)take(a4);
         unsigned char *d_vis = (unsigned char *)take(a4);
+        unsigned *d_nbr = (unsigned *)take(8 * a4);
         CompRec *d_comps = (CompRec *)take(b_comp);
         StarRec *d_stars = (StarRec *)take(b_star);
         ab_star *d_sorted = (ab_star *)take(b_star);
@@ -1256,9 +1273,12 @@ ab_status detect_on_device(ab_ctx *ctx, const float *d_img, size_t rows, size_t 
         if (n_comp) {
             ccl_emit_kernel<<<nb, 256, 0, s>>>(d_flag, d_size, d_slot, d_off, d_comps, nfg);
             AB_LAUNCH_CHECK(ctx);
+            ccl_neighbours_kernel<<<(unsigned)(((size_t)nfg * 8 + 255) / 256), 256, 0, s>>>(
+                d_col, d_row, d_ro, nfg, (unsigned)rows, (unsigned)cols, d_nbr);
+            AB_LAUNCH_CHECK(ctx);
             const unsigned mb = (unsigned)std::min<size_t>(((size_t)n_comp + 15) / 16, (size_t)ctx->sm_count * 16);
             ccl_measure_kernel<<<mb, 128, 0, s>>>(d_col, d_row, d_val, d_ro, d_comps, n_comp, (unsigned)rows,
-                                                 (unsigned)cols, bg_median, bg_sigma, d_queue, d_vis,
+                                                 (unsigned)cols, bg_median, bg_sigma, d_nbr, d_queue, d_vis,
                                                  d_stars, d_keys, d_order, d_nvalid);
             AB_LAUNCH_CHECK(ctx);
             tb = b_tmp;
